@@ -1,0 +1,428 @@
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+//
+// C-ABI harness around the *reference's own* classes (compiled in place from /root/reference by
+// oracle/build_ref.sh into oracle/_ref/libtrinity_ref.so).  It is the parity oracle and the CPU
+// baseline ("cpu_baseline.kind" = "reference"):
+//   * builds in-memory indexes through the reference Encoders      (codecs.h:176-200)
+//   * decodes postings through the reference PostingsListIterator  (codecs.h:211-246)
+//   * runs the reference Trinity::exec_query()                     (exec.h:50-52)
+//   * exposes the reference BM25 scorer                            (similarity.h:165-255)
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+#include "exec.h"
+#include "google_codec.h"
+#include "lucene_codec.h"
+#include "similarity.h"
+#include <atomic>
+#include <chrono>
+#include <queue>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+using namespace Trinity;
+
+namespace {
+        thread_local std::string g_err;
+
+        struct MemSrc final : public IndexSource {
+                Codecs::AccessProxy *                           ap{nullptr};
+                std::unordered_map<std::string, term_index_ctx> terms;
+                field_statistics                                fs;
+
+                term_index_ctx resolve_term_ctx(const str8_t term) override {
+                        auto it = terms.find(std::string(term.data(), term.size()));
+                        if (it == terms.end())
+                                return {};
+                        return it->second;
+                }
+
+                Codecs::Decoder *new_postings_decoder(const str8_t, const term_index_ctx ctx) override {
+                        return ap->new_decoder(ctx);
+                }
+
+                field_statistics default_field_stats() override {
+                        return fs;
+                }
+
+                bool index_empty() const override {
+                        return false;
+                }
+        };
+
+        struct RefIndex {
+                int                                   codec{0};
+                std::unique_ptr<Codecs::IndexSession> sess;
+                std::unique_ptr<Codecs::Encoder>      enc;
+                std::vector<uint8_t>                  index, hits;
+                std::vector<term_index_ctx>           tctx;
+                std::vector<std::string>              names;
+                std::unique_ptr<Codecs::AccessProxy>  ap;
+                MemSrc *                              src{nullptr};
+                std::unique_ptr<IndexSourcesCollection> col;
+                uint64_t                              sumHits{0};
+
+                ~RefIndex() {
+                        col.reset(); // releases src
+                }
+
+                void open(uint64_t docsCnt) {
+                        if (codec == 0)
+                                ap.reset(new Codecs::Google::AccessProxy("/tmp", index.data()));
+                        else
+                                ap.reset(new Codecs::Lucene::AccessProxy("/tmp", index.data(), hits.empty() ? (const uint8_t *)"" : hits.data()));
+                        src     = new MemSrc();
+                        src->ap = ap.get();
+                        uint64_t sumDocs{0};
+                        for (size_t i = 0; i < names.size(); ++i) {
+                                src->terms.emplace(names[i], tctx[i]);
+                                sumDocs += tctx[i].documents;
+                        }
+                        src->fs.docsCnt      = docsCnt;
+                        src->fs.sumTermsDocs = sumDocs;
+                        src->fs.totalTerms   = names.size();
+                        src->fs.sumTermHits  = sumHits;
+                        col.reset(new IndexSourcesCollection());
+                        col->insert(src); // Retain()
+                        src->Release();   // collection now holds the only ref
+                        col->commit();
+                }
+        };
+
+        struct CollectSink final : public MatchedIndexDocumentsFilter {
+                std::vector<uint32_t> ids;
+                std::vector<double>   scores;
+                bool                  wantScores{false};
+                uint64_t              n{0}, cap{0};
+
+                void consider(const docid_t id) override {
+                        if (n < cap)
+                                ids.push_back(id);
+                        ++n;
+                }
+                void consider(const docid_t id, const double score) override {
+                        if (n < cap) {
+                                ids.push_back(id);
+                                scores.push_back(score);
+                        }
+                        ++n;
+                }
+        };
+
+        // top-k sink: score desc, docID asc (the tie rule this repo defines; the reference leaves top-k to the app, matches.h:139-186)
+        struct TopKSink final : public MatchedIndexDocumentsFilter {
+                struct E {
+                        double   s;
+                        uint32_t id;
+                };
+                struct Worse {
+                        // priority_queue top = the WORST kept element
+                        bool operator()(const E &a, const E &b) const noexcept {
+                                if (a.s != b.s)
+                                        return a.s > b.s;
+                                return a.id < b.id;
+                        }
+                };
+                std::priority_queue<E, std::vector<E>, Worse> pq;
+                uint32_t                                    k{100};
+                uint64_t                                    n{0};
+
+                void consider(const docid_t id, const double score) override {
+                        ++n;
+                        if (pq.size() < k)
+                                pq.push({score, uint32_t(id)});
+                        else {
+                                const auto &w = pq.top();
+                                if (score > w.s || (score == w.s && id < w.id)) {
+                                        pq.pop();
+                                        pq.push({score, uint32_t(id)});
+                                }
+                        }
+                }
+                void consider(const docid_t) override {
+                        ++n;
+                }
+        };
+
+        struct IdsSink final : public MatchedIndexDocumentsFilter {
+                std::vector<uint32_t> ids;
+                uint64_t              sum{0};
+                void                  consider(const docid_t id) override {
+                        ids.push_back(id);
+                        sum += id;
+                }
+        };
+
+        template <typename F>
+        int guarded(F &&f) {
+                try {
+                        f();
+                        return 0;
+                } catch (const std::exception &e) {
+                        g_err = e.what();
+                } catch (...) {
+                        g_err = "unknown exception";
+                }
+                return -1;
+        }
+} // namespace
+
+extern "C" {
+const char *tref_last_error() {
+        return g_err.c_str();
+}
+
+// codec: 0 = GOOGLE, 1 = LUCENE (FastPFor<4>, the reference's compile-time default lucene_codec.h:21-29)
+void *tref_new(int codec) {
+        auto x   = new RefIndex();
+        x->codec = codec;
+        if (codec == 0)
+                x->sess.reset(new Codecs::Google::IndexSession("/tmp"));
+        else
+                x->sess.reset(new Codecs::Lucene::IndexSession("/tmp"));
+        x->sess->begin();
+        x->enc.reset(x->sess->new_encoder());
+        return x;
+}
+
+void tref_free(void *h) {
+        delete static_cast<RefIndex *>(h);
+}
+
+// positions: absolute positions per hit, concatenated over documents (sum(freqs) entries); may be null => 1..freq
+int tref_add_term(void *h, const char *name, const uint32_t *docids, const uint32_t *freqs, uint32_t n, const uint32_t *positions) {
+        auto x = static_cast<RefIndex *>(h);
+        int  idx{-1};
+        if (guarded([&] {
+                    term_index_ctx t;
+                    size_t         pi{0};
+                    x->enc->begin_term();
+                    for (uint32_t i = 0; i < n; ++i) {
+                            x->enc->begin_document(docids[i]);
+                            for (uint32_t k = 0; k < freqs[i]; ++k) {
+                                    const uint32_t pos = positions ? positions[pi++] : k + 1;
+                                    x->enc->new_hit(pos, {});
+                            }
+                            x->sumHits += freqs[i];
+                            x->enc->end_document();
+                    }
+                    x->enc->end_term(&t);
+                    idx = int(x->tctx.size());
+                    x->tctx.push_back(t);
+                    x->names.emplace_back(name);
+            }))
+                return -1;
+        return idx;
+}
+
+int tref_finish(void *h, uint64_t docsCnt) {
+        auto x = static_cast<RefIndex *>(h);
+        return guarded([&] {
+                x->index.assign((const uint8_t *)x->sess->indexOut.data(), (const uint8_t *)x->sess->indexOut.data() + x->sess->indexOut.size());
+                if (x->codec == 1) {
+                        // take the hits.data bytes straight from the session buffer (IndexSession::end() would persist them to basePath/hits.data)
+                        auto ls = static_cast<Codecs::Lucene::IndexSession *>(x->sess.get());
+                        x->hits.assign((const uint8_t *)ls->positionsOut.data(), (const uint8_t *)ls->positionsOut.data() + ls->positionsOut.size());
+                }
+                x->enc.reset();
+                x->sess.reset();
+                x->open(docsCnt);
+        });
+}
+
+void *tref_from_bytes(int codec, const uint8_t *index, uint64_t n, const uint8_t *hits, uint64_t nh, const char *const *names, const uint32_t *docs,
+                      const uint32_t *off, const uint32_t *len, uint32_t nterms, uint64_t docsCnt, uint64_t sumHits) {
+        auto x   = new RefIndex();
+        x->codec = codec;
+        x->index.assign(index, index + n);
+        if (hits && nh)
+                x->hits.assign(hits, hits + nh);
+        for (uint32_t i = 0; i < nterms; ++i) {
+                x->names.emplace_back(names[i]);
+                x->tctx.emplace_back(docs[i], range32_t{off[i], len[i]});
+        }
+        x->sumHits = sumHits;
+        if (guarded([&] { x->open(docsCnt); })) {
+                delete x;
+                return nullptr;
+        }
+        return x;
+}
+
+uint64_t tref_index_size(void *h) {
+        return static_cast<RefIndex *>(h)->index.size();
+}
+const uint8_t *tref_index_data(void *h) {
+        return static_cast<RefIndex *>(h)->index.data();
+}
+uint64_t tref_hits_size(void *h) {
+        return static_cast<RefIndex *>(h)->hits.size();
+}
+const uint8_t *tref_hits_data(void *h) {
+        return static_cast<RefIndex *>(h)->hits.data();
+}
+uint32_t tref_num_terms(void *h) {
+        return static_cast<RefIndex *>(h)->tctx.size();
+}
+void tref_term(void *h, uint32_t idx, uint32_t *docs, uint32_t *off, uint32_t *len) {
+        const auto &t = static_cast<RefIndex *>(h)->tctx[idx];
+        *docs         = t.documents;
+        *off          = t.indexChunk.offset;
+        *len          = t.indexChunk.size();
+}
+
+// full decode through PostingsListIterator::next(); returns number of postings (<= cap stored)
+int64_t tref_decode(void *h, uint32_t termIdx, uint32_t *docids, uint32_t *freqs, uint64_t cap) {
+        auto    x = static_cast<RefIndex *>(h);
+        int64_t n{0};
+        if (guarded([&] {
+                    std::unique_ptr<Codecs::Decoder>              dec(x->ap->new_decoder(x->tctx[termIdx]));
+                    std::unique_ptr<Codecs::PostingsListIterator> it(dec->new_iterator());
+                    for (auto id = it->next(); id != DocIDsEND; id = it->next()) {
+                            if (uint64_t(n) < cap) {
+                                    docids[n] = id;
+                                    freqs[n]  = it->freq;
+                            }
+                            ++n;
+                    }
+            }))
+                return -1;
+        return n;
+}
+
+// advance() probe: for each (ascending) target returns first docID >= target (DocIDsEND = UINT32_MAX when exhausted)
+int tref_advance(void *h, uint32_t termIdx, const uint32_t *targets, uint32_t n, uint32_t *out) {
+        auto x = static_cast<RefIndex *>(h);
+        return guarded([&] {
+                std::unique_ptr<Codecs::Decoder>              dec(x->ap->new_decoder(x->tctx[termIdx]));
+                std::unique_ptr<Codecs::PostingsListIterator> it(dec->new_iterator());
+                for (uint32_t i = 0; i < n; ++i) {
+                        if (it->current() < targets[i] || it->current() == 0)
+                                it->advance(targets[i]);
+                        out[i] = it->current();
+                }
+        });
+}
+
+// reference BM25 score for (term, freq): similarity.h:209-235
+double tref_bm25(void *h, uint32_t termIdx, uint32_t freq) {
+        auto   x = static_cast<RefIndex *>(h);
+        double r{-1};
+        guarded([&] {
+                Similarity::IndexSourcesCollectionBM25Scorer        cs;
+                cs.reset(x->col.get());
+                std::unique_ptr<Similarity::IndexSourceTermsScorer> sc(cs.new_source_scorer(x->src));
+                str8_t                                              t(x->names[termIdx].data(), x->names[termIdx].size());
+                std::unique_ptr<Similarity::ScorerWeight>           w(sc->new_scorer_weight(&t, 1));
+                r = sc->score(1, uint16_t(freq), w.get());
+        });
+        return r;
+}
+
+// mode 0: ExecFlags::DocumentsOnly ; mode 1: ExecFlags::AccumulatedScoreScheme + BM25.  Returns #matches (ids/scores filled up to cap)
+int64_t tref_exec(void *h, const char *q, int mode, uint32_t *ids, double *scores, uint64_t cap) {
+        auto    x = static_cast<RefIndex *>(h);
+        int64_t n{-1};
+        guarded([&] {
+                query       qq(str32_t(q, strlen(q)));
+                CollectSink sink;
+                sink.cap  = cap;
+                auto reg  = masked_documents_registry::make(nullptr, 0);
+                if (mode == 0) {
+                        exec_query(qq, x->src, reg.get(), &sink, nullptr, uint32_t(ExecFlags::DocumentsOnly));
+                } else {
+                        Similarity::IndexSourcesCollectionBM25Scorer        cs;
+                        cs.reset(x->col.get());
+                        std::unique_ptr<Similarity::IndexSourceTermsScorer> sc(cs.new_source_scorer(x->src));
+                        exec_query(qq, x->src, reg.get(), &sink, nullptr, uint32_t(ExecFlags::AccumulatedScoreScheme), sc.get());
+                }
+                memcpy(ids, sink.ids.data(), sink.ids.size() * sizeof(uint32_t));
+                if (mode == 1 && scores)
+                        memcpy(scores, sink.scores.data(), sink.scores.size() * sizeof(double));
+                n = int64_t(sink.n);
+        });
+        return n;
+}
+
+// CPU baseline: run nq queries over `threads` host threads (one query per thread at a time; exec_query is re-entrant, exec.cpp:12).
+// mode 0: collect every matched docID (DocumentsOnly); mode 1: BM25 top-k heap in consider(id, score).
+// Outputs per query: match count, sum of matched ids (mode 0) , top-k (mode 1: ids/scores, k per query, padded with 0).
+// Returns elapsed wall seconds for the whole batch (steady_clock), < 0 on error.
+double tref_exec_batch(void *h, const char *const *qs, uint32_t nq, int mode, uint32_t k, int threads, uint64_t *matchCounts, uint64_t *idSums,
+                       uint32_t *topkIds, double *topkScores) {
+        auto                  x = static_cast<RefIndex *>(h);
+        std::atomic<uint32_t> next{0};
+        std::atomic<int>      failed{0};
+        std::string           err;
+        std::mutex            errLock;
+        const auto            t0 = std::chrono::steady_clock::now();
+        auto                  worker = [&] {
+                try {
+                        IdsSink                                             ids;
+                        Similarity::IndexSourcesCollectionBM25Scorer        cs;
+                        std::unique_ptr<Similarity::IndexSourceTermsScorer> sc;
+                        if (mode == 1) {
+                                cs.reset(x->col.get());
+                                sc.reset(cs.new_source_scorer(x->src));
+                        }
+                        auto reg = masked_documents_registry::make(nullptr, 0);
+                        for (;;) {
+                                const auto i = next.fetch_add(1);
+                                if (i >= nq)
+                                        break;
+                                query qq(str32_t(qs[i], strlen(qs[i])));
+                                if (mode == 0) {
+                                        ids.ids.clear();
+                                        ids.sum = 0;
+                                        exec_query(qq, x->src, reg.get(), &ids, nullptr, uint32_t(ExecFlags::DocumentsOnly));
+                                        if (matchCounts)
+                                                matchCounts[i] = ids.ids.size();
+                                        if (idSums)
+                                                idSums[i] = ids.sum;
+                                } else {
+                                        TopKSink sink;
+                                        sink.k = k;
+                                        exec_query(qq, x->src, reg.get(), &sink, nullptr, uint32_t(ExecFlags::AccumulatedScoreScheme), sc.get());
+                                        if (matchCounts)
+                                                matchCounts[i] = sink.n;
+                                        size_t cnt = sink.pq.size();
+                                        for (uint32_t j = 0; j < k; ++j) {
+                                                if (topkIds)
+                                                        topkIds[size_t(i) * k + j] = 0;
+                                                if (topkScores)
+                                                        topkScores[size_t(i) * k + j] = 0;
+                                        }
+                                        while (cnt) {
+                                                --cnt;
+                                                if (topkIds)
+                                                        topkIds[size_t(i) * k + cnt] = sink.pq.top().id;
+                                                if (topkScores)
+                                                        topkScores[size_t(i) * k + cnt] = sink.pq.top().s;
+                                                sink.pq.pop();
+                                        }
+                                }
+                        }
+                } catch (const std::exception &e) {
+                        std::lock_guard<std::mutex> g(errLock);
+                        err = e.what();
+                        failed.store(1);
+                } catch (...) {
+                        failed.store(1);
+                }
+        };
+        std::vector<std::thread> ths;
+        if (threads < 1)
+                threads = 1;
+        for (int i = 1; i < threads; ++i)
+                ths.emplace_back(worker);
+        worker();
+        for (auto &t : ths)
+                t.join();
+        const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (failed.load()) {
+                g_err = err.empty() ? "exec_query failed" : err;
+                return -1.0;
+        }
+        return el;
+}
+}
