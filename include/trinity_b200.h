@@ -1,0 +1,180 @@
+/*
+ * trinity_b200 — C ABI of the B200-native execution engine for Trinity's inverted-index hot path
+ * (postings-block decode -> docset AND/OR/NOT -> per-doc BM25 -> top-k).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int return codes (0 = ok, <0 = error; the message is
+ * available from trn_last_error()), no exceptions cross it, no torch types.  Each entry point cites the
+ * reference interface it stands in for (file:line under the reference tree); INTEGRATION.md shows the
+ * reference-side C++ binding (GpuAccessProxy / GpuDocsSetSpan) a Trinity maintainer would add on top.
+ */
+#ifndef TRINITY_B200_H
+#define TRINITY_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRN_OK 0
+#define TRN_ERR_ARG (-1)
+#define TRN_ERR_CUDA (-2)
+#define TRN_ERR_FORMAT (-3)
+#define TRN_ERR_STATE (-4)
+#define TRN_ERR_PARSE (-5)
+#define TRN_ERR_CAPACITY (-6)
+
+/* codec identifiers == AccessProxy::codec_identifier() "GOOGLE" / "LUCENE" (codecs.h:312, google_codec.h:101, lucene_codec.h:213) */
+#define TRN_CODEC_GOOGLE 0
+#define TRN_CODEC_LUCENE 1
+
+/* == Trinity::term_index_ctx {documents, indexChunk{offset,len}} (codecs.h:17-55) */
+typedef struct trn_term {
+        uint32_t documents;
+        uint32_t chunk_off;
+        uint32_t chunk_len;
+} trn_term;
+
+/* ------------------------------------------------------------------------------------------------ index build
+ * == Codecs::IndexSession + Codecs::Encoder (codecs.h:66-200; google_codec.cpp:9-176; lucene_codec.cpp:163-388).
+ * Host code; produces bytes identical to the reference encoders'. */
+typedef struct trn_builder trn_builder;
+int  trn_builder_create(int codec, trn_builder **out);
+void trn_builder_destroy(trn_builder *);
+/* streaming interface == Encoder::{begin_term,begin_document,new_hit,end_document,end_term} */
+int trn_builder_begin_term(trn_builder *);
+int trn_builder_begin_document(trn_builder *, uint32_t docid);
+int trn_builder_new_hit(trn_builder *, uint32_t position, const uint8_t *payload, uint8_t payload_len);
+int trn_builder_end_document(trn_builder *);
+int trn_builder_end_term(trn_builder *, trn_term *out);
+/* whole-term convenience: positions = absolute positions of every hit, concatenated (sum(freqs) entries); NULL => 1..freq */
+int trn_builder_add_term(trn_builder *, const uint32_t *docids, const uint32_t *freqs, uint32_t n, const uint32_t *positions, trn_term *out);
+/* Google only: the encoder's skiplist countdown is session state that survives end_term (google_codec.h:57) */
+int trn_builder_set_google_skiplist_countdown(trn_builder *, uint32_t countdown);
+/* buffers stay owned by the builder */
+int trn_builder_index(trn_builder *, const uint8_t **index, uint64_t *nbytes);
+int trn_builder_hits(trn_builder *, const uint8_t **hits, uint64_t *nbytes); /* Lucene hits.data; 0 bytes for Google */
+const char *trn_builder_last_error(trn_builder *);
+
+/* ------------------------------------------------------------------------------------------------ synthetic index
+ * The BASELINE.md workload generator: V terms, df_r = max(min_df, floor(0.5*N/r)), geometric docID gaps
+ * from splitmix64(seed ^ r), freq = 1 + min(7, Geom(1/2)), positions cumulative 1+u(1..16).  Multi-threaded over terms;
+ * byte-identical to feeding the same postings to one reference encoder term after term. */
+typedef struct trn_synth trn_synth;
+int  trn_synth_build(int codec, uint32_t ndocs, uint32_t nterms, uint32_t min_df, uint64_t seed, int with_hits, int threads, trn_synth **out);
+void trn_synth_destroy(trn_synth *);
+int  trn_synth_index(trn_synth *, const uint8_t **index, uint64_t *nbytes);
+int  trn_synth_hits(trn_synth *, const uint8_t **hits, uint64_t *nbytes);
+int  trn_synth_terms(trn_synth *, const trn_term **terms, uint32_t *nterms);
+uint64_t trn_synth_sum_hits(trn_synth *);
+/* regenerate the raw postings of term rank r (1-based) — used by tests to feed the reference encoder the same input */
+int trn_synth_postings(uint32_t ndocs, uint32_t rank, uint32_t min_df, uint64_t seed, uint32_t *docids, uint32_t *freqs, uint32_t cap, uint32_t *n);
+int trn_synth_positions(uint32_t ndocs, uint32_t rank, uint32_t min_df, uint64_t seed, uint32_t *positions, uint64_t cap, uint64_t *n);
+
+/* ------------------------------------------------------------------------------------------------ query plans
+ * A query is a flat node array == the reference's compiled exec_node tree (compilation_ctx.h:8-30 ENT::*) after
+ * queryexec_ctx::build_iterator's flattening (exec.cpp:253-449):
+ *   TERM      -> PostingsListIterator          AND -> Conjuction / ConjuctionAllPLI
+ *   OR        -> Disjunction / DisjunctionAllPLI
+ *   NOT       -> Filter(req = child 0, excl = child 1)           (docset_iterators.cpp:652-677)
+ *   OPTIONAL  -> Optional(main = child 0, opt = child 1)         (docset_iterators.h:174-206)
+ * children of node i are nodes[first_child .. first_child + nchildren). */
+#define TRN_NODE_TERM 0
+#define TRN_NODE_AND 1
+#define TRN_NODE_OR 2
+#define TRN_NODE_NOT 3
+#define TRN_NODE_OPTIONAL 4
+
+typedef struct trn_qnode {
+        uint8_t  kind;
+        uint8_t  nchildren;
+        uint16_t first_child;
+        uint32_t term;  /* TERM: index into the uploaded terms table */
+        double   weight; /* TERM: BM25 idf weight == ScorerWeight::idf (similarity.h:190-222); ignored in docs-only mode */
+} trn_qnode;
+
+typedef struct trn_query {
+        const trn_qnode *nodes;
+        uint32_t         nnodes;
+        uint32_t         root;
+} trn_query;
+
+/* Host-side front-end for the operator subset of the reference query language (queries.cpp:11-27,150-218,477-520:
+ * AND / OR / '|' / NOT / '-' / parentheses / juxtaposition = AND; OR binds tighter than AND/NOT; left-assoc), followed by the
+ * same flattening build_iterator applies.  term names are resolved through `names` (nterms C strings).
+ * Writes at most cap nodes; *nnodes receives the count, *root the root index. */
+int trn_parse_query(const char *text, const char *const *names, uint32_t nterms, trn_qnode *nodes, uint32_t cap, uint32_t *nnodes, uint32_t *root,
+                    char *err, size_t errcap);
+
+/* BM25 weight of one term == IndexSourcesCollectionBM25Scorer::Scorer::idf evaluated in float (similarity.h:179-181) */
+double trn_bm25_idf(uint32_t doc_freq, uint64_t docs_cnt);
+/* == Scorer::score(id, freq, weight) (similarity.h:228-235): float(idf * float(freq) / double(freq + 1.2f)) */
+float trn_bm25_score(double idf, uint16_t freq);
+
+/* ------------------------------------------------------------------------------------------------ engine
+ * trn_ctx == one device-resident IndexSource (index_source.h:18-155) + its AccessProxy (codecs.h:290-317). */
+typedef struct trn_ctx trn_ctx;
+
+int         trn_create(int device, trn_ctx **out);
+void        trn_destroy(trn_ctx *);
+const char *trn_last_error(trn_ctx *);
+/* run on this cudaStream_t (default: the legacy default stream). Lets callers time with their own events. */
+int trn_set_stream(trn_ctx *, void *cuda_stream);
+
+/* == AccessProxy(basePath, indexPtr) + Decoder::init for every term (google_codec.cpp:936-983, lucene_codec.cpp:877-932):
+ * copies the raw, unmodified index bytes to HBM and builds the block directory.  max_docid = upper bound of the docID space. */
+int trn_upload_index(trn_ctx *, int codec, const uint8_t *index, uint64_t nbytes, const trn_term *terms, uint32_t nterms, uint32_t max_docid);
+
+typedef struct trn_index_info {
+        int      codec;
+        uint32_t nterms, max_docid, tile_docs, ntiles;
+        uint64_t index_bytes, directory_bytes, total_blocks, total_postings;
+} trn_index_info;
+int trn_index_info_get(trn_ctx *, trn_index_info *out);
+
+/* execution modes == ExecFlags (exec.h:12-43) + where top-k lives */
+#define TRN_MODE_DOCS_ONLY 0    /* ExecFlags::DocumentsOnly: matched docIDs ascending == consider(docid_t) stream        */
+#define TRN_MODE_SCORED_ALL 1   /* ExecFlags::AccumulatedScoreScheme: every (docID, score) ascending == consider(id,score) */
+#define TRN_MODE_SCORED_TOPK 2  /* AccumulatedScoreScheme + the application's top-k sink fused on device                 */
+
+/* Result of a batch. Host pointers are pinned buffers owned by the ctx, valid until the next exec call.
+ * DOCS_ONLY / SCORED_ALL: query q owns [offsets[q], offsets[q+1]) of docids (ascending) (+ scores).
+ * SCORED_TOPK: query q owns [offsets[q], offsets[q+1]) with at most k entries ordered by (score desc, docID asc);
+ * match_counts[q] = total number of matching documents. */
+typedef struct trn_result {
+        uint32_t        nq;
+        uint64_t        total;
+        const uint64_t *offsets;
+        const uint32_t *docids;
+        const float *   scores;
+        const uint64_t *match_counts;
+        uint64_t        postings_scanned; /* sum over queries of sum over leaf terms of term.documents (full-scan accounting) */
+        uint64_t        index_bytes_touched; /* sum over queries of sum over leaf terms of chunk_len (algorithmic bytes)        */
+        uint32_t        kernel_launches;
+        float           device_ms; /* CUDA-event time of the device part of this call */
+} trn_result;
+
+/* == exec_query(query, IndexSource*, masked_documents_registry*, MatchedIndexDocumentsFilter*, ..., flags, scorer) (exec.h:50-52),
+ * batched (gpu_exec_queries).  H2D of the plans and D2H of the results are part of the call. */
+int trn_exec_batch(trn_ctx *, const trn_query *queries, uint32_t nq, int mode, uint32_t k, trn_result *out);
+
+/* Split form used by bench.py / multi-GPU: run on device only, results stay in HBM ... */
+int trn_exec_batch_device(trn_ctx *, const trn_query *queries, uint32_t nq, int mode, uint32_t k, trn_result *out_counts_only);
+/* ... device pointers of the last SCORED_TOPK run: nq*k u32 docids, nq*k f32 scores (unused slots: docid 0, score -inf), nq u32 counts */
+int trn_last_topk_device(trn_ctx *, void **docids, void **scores, void **counts);
+/* merge `nshards` gathered top-k lists (layout [shard][nq][k]) into one; the one exchange step of the multi-GPU path.
+ * All pointers are device pointers; docid_base[shard] is added to the docids of that shard (0 if docIDs are already global). */
+int trn_merge_topk(trn_ctx *, const void *docids, const void *scores, uint32_t nshards, uint32_t nq, uint32_t k, void *out_docids, void *out_scores);
+/* copy the last device results to the pinned host buffers (the D2H leg) and fill `out` */
+int trn_fetch_results(trn_ctx *, trn_result *out);
+
+/* Decode microbench / parity probe == PostingsListIterator::next() over whole lists (google_codec.cpp:777-819, lucene_codec.cpp:568-594).
+ * materialise != 0: writes docids/freqs (host pointers, sum(documents) entries, terms concatenated in the given order);
+ * materialise == 0: fused checksum only (sum of docids and sum of freqs per term into sums[2*i], sums[2*i+1]). */
+int trn_decode_terms(trn_ctx *, const uint32_t *term_ids, uint32_t nterms, int materialise, uint32_t *docids, uint32_t *freqs, uint64_t *sums,
+                     float *device_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,28 @@
+import os
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _native_built():
+    # build (or reuse) the in-tree native library; no CPU fallback exists
+    from trinity_b200.build import build_native
+    build_native()
+    yield
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The reference oracle (oracle/_ref/libtrinity_ref.so == the reference's own code).  TEST-ONLY."""
+    from refharness import load_ref
+    return load_ref()

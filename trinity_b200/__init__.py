@@ -1,0 +1,335 @@
+"""trinity_b200 — B200-native execution engine for Trinity's inverted-index hot path.
+
+Thin Python plumbing over the C ABI (include/trinity_b200.h).  Class and method names follow the reference's
+domain vocabulary (IndexSession/Encoder, IndexSource, exec_query, term_index_ctx, postings, docsets);
+all decode / docset / scoring work happens in the sm_100a kernels of libtrinity_b200.so — there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from ._ffi import QNODE_DTYPE, TERM_DTYPE, TrnIndexInfo, TrnQuery, TrnResult, TrnTerm, lib
+
+CODEC_GOOGLE, CODEC_LUCENE = 0, 1
+MODE_DOCS_ONLY, MODE_SCORED_ALL, MODE_SCORED_TOPK = 0, 1, 2  # == ExecFlags::DocumentsOnly / AccumulatedScoreScheme (+ fused top-k sink)
+NODE_TERM, NODE_AND, NODE_OR, NODE_NOT, NODE_OPTIONAL = 0, 1, 2, 3, 4
+EMPTY_TERM = 0xFFFFFFFF
+DOC_IDS_END = 0xFFFFFFFF  # DocIDsEND, common.h:43
+
+
+class TrinityError(RuntimeError):
+    pass
+
+
+def _u32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ----------------------------------------------------------------------------------------------- index build (host)
+class IndexBuilder:
+    """== Codecs::IndexSession + Codecs::Encoder (codecs.h:66-200).  Bytes are identical to the reference encoders'."""
+
+    def __init__(self, codec: int):
+        self._L = lib()
+        self.codec = codec
+        h = C.c_void_p()
+        if self._L.trn_builder_create(codec, C.byref(h)) != 0:
+            raise TrinityError("trn_builder_create failed")
+        self._h = h
+        self.terms: List[tuple] = []
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TrinityError(self._L.trn_builder_last_error(self._h).decode())
+
+    def set_google_skiplist_countdown(self, n: int):
+        self._ck(self._L.trn_builder_set_google_skiplist_countdown(self._h, n))
+
+    def begin_term(self):
+        self._ck(self._L.trn_builder_begin_term(self._h))
+
+    def begin_document(self, docid: int):
+        self._ck(self._L.trn_builder_begin_document(self._h, docid))
+
+    def new_hit(self, position: int, payload: bytes = b""):
+        buf = (C.c_uint8 * len(payload)).from_buffer_copy(payload) if payload else None
+        self._ck(self._L.trn_builder_new_hit(self._h, position, buf, len(payload)))
+
+    def end_document(self):
+        self._ck(self._L.trn_builder_end_document(self._h))
+
+    def end_term(self) -> tuple:
+        t = TrnTerm()
+        self._ck(self._L.trn_builder_end_term(self._h, C.byref(t)))
+        self.terms.append((t.documents, t.chunk_off, t.chunk_len))
+        return self.terms[-1]
+
+    def add_term(self, docids, freqs, positions=None) -> tuple:
+        d, f = _u32(docids), _u32(freqs)
+        p = None if positions is None else _u32(positions)
+        t = TrnTerm()
+        self._ck(self._L.trn_builder_add_term(self._h, _ptr(d), _ptr(f), len(d), _ptr(p), C.byref(t)))
+        self.terms.append((t.documents, t.chunk_off, t.chunk_len))
+        return self.terms[-1]
+
+    def _bytes(self, fn) -> np.ndarray:
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(fn(self._h, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=np.uint8)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,)).copy()
+
+    def index(self) -> np.ndarray:
+        return self._bytes(self._L.trn_builder_index)
+
+    def hits(self) -> np.ndarray:
+        return self._bytes(self._L.trn_builder_hits)
+
+    def terms_array(self) -> np.ndarray:
+        return np.array(self.terms, dtype=TERM_DTYPE)
+
+    def __del__(self):
+        try:
+            self._L.trn_builder_destroy(self._h)
+        except Exception:
+            pass
+
+
+class SynthIndex:
+    """The BASELINE.md synthetic Zipfian index, built multi-threaded through the host encoders."""
+
+    def __init__(self, codec: int, ndocs: int, nterms: int = 4096, min_df: int = 1000, seed: int = 0x5EED,
+                 with_hits: bool = True, threads: int = 0):
+        self._L = lib()
+        self.codec, self.ndocs, self.nterms, self.min_df, self.seed = codec, ndocs, nterms, min_df, seed
+        h = C.c_void_p()
+        rc = self._L.trn_synth_build(codec, ndocs, nterms, min_df, seed, int(with_hits), threads, C.byref(h))
+        if rc != 0:
+            raise TrinityError(f"trn_synth_build failed rc={rc}")
+        self._h = h
+        p, n = C.c_void_p(), C.c_uint64()
+        self._L.trn_synth_index(h, C.byref(p), C.byref(n))
+        self.index = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,))
+        self._L.trn_synth_hits(h, C.byref(p), C.byref(n))
+        self.hits = (np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,)) if n.value
+                     else np.zeros(0, dtype=np.uint8))
+        tp, tn = C.c_void_p(), C.c_uint32()
+        self._L.trn_synth_terms(h, C.byref(tp), C.byref(tn))
+        raw = np.ctypeslib.as_array(C.cast(tp, C.POINTER(C.c_uint8)), shape=(tn.value * 12,))
+        self.terms = raw.view(TERM_DTYPE)
+        self.sum_hits = int(self._L.trn_synth_sum_hits(h))
+        self.names = [f"t{r:04d}" for r in range(1, nterms + 1)]
+
+    @staticmethod
+    def postings(ndocs: int, rank: int, min_df: int = 1000, seed: int = 0x5EED):
+        L = lib()
+        n = C.c_uint32()
+        L.trn_synth_postings(ndocs, rank, min_df, seed, None, None, 0, C.byref(n))
+        d, f = np.zeros(n.value, np.uint32), np.zeros(n.value, np.uint32)
+        L.trn_synth_postings(ndocs, rank, min_df, seed, _ptr(d), _ptr(f), n.value, C.byref(n))
+        return d, f
+
+    @staticmethod
+    def positions(ndocs: int, rank: int, min_df: int = 1000, seed: int = 0x5EED):
+        L = lib()
+        n = C.c_uint64()
+        L.trn_synth_positions(ndocs, rank, min_df, seed, None, 0, C.byref(n))
+        p = np.zeros(n.value, np.uint32)
+        L.trn_synth_positions(ndocs, rank, min_df, seed, _ptr(p), n.value, C.byref(n))
+        return p
+
+    def __del__(self):
+        try:
+            self._L.trn_synth_destroy(self._h)
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------------------------- query front-end
+class TermDictionary:
+    """term name -> term id; the host-side stand-in for IndexSource::resolve_term_ctx (index_source.h:118)."""
+
+    def __init__(self, names: Sequence[str]):
+        self.names = list(names)
+        self._enc = [s.encode() for s in self.names]
+        self._arr = (C.c_char_p * len(self._enc))(*self._enc)
+
+    def __len__(self):
+        return len(self.names)
+
+
+def parse_query(text: str, tdict: TermDictionary) -> np.ndarray:
+    """Query string -> flat trn_qnode array (see include/trinity_b200.h).  Mirrors the reference's operator subset and
+    precedence (queries.cpp:11-27,477-520) followed by build_iterator's flattening (exec.cpp:328-400)."""
+    L = lib()
+    nodes = np.zeros(256, dtype=QNODE_DTYPE)
+    nn, root = C.c_uint32(), C.c_uint32()
+    err = C.create_string_buffer(256)
+    rc = L.trn_parse_query(text.encode(), C.cast(tdict._arr, C.c_void_p), len(tdict), _ptr(nodes), len(nodes),
+                           C.byref(nn), C.byref(root), err, 256)
+    if rc != 0:
+        raise TrinityError(f"parse error: {err.value.decode()}")
+    assert root.value == 0
+    return nodes[: nn.value].copy()
+
+
+def bm25_idf(doc_freq: int, docs_cnt: int) -> float:
+    return float(lib().trn_bm25_idf(doc_freq, docs_cnt))
+
+
+def bm25_score(idf: float, freq: int) -> float:
+    return float(lib().trn_bm25_score(idf, freq))
+
+
+# ----------------------------------------------------------------------------------------------- engine
+@dataclass
+class BatchResult:
+    nq: int
+    mode: int
+    k: int
+    offsets: np.ndarray       # nq+1
+    docids: np.ndarray
+    scores: Optional[np.ndarray]
+    match_counts: np.ndarray  # nq
+    postings_scanned: int
+    index_bytes_touched: int
+    kernel_launches: int
+    device_ms: float
+
+    def query(self, q: int):
+        """(docids, scores) of query q.  top-k mode: only the valid entries, (score desc, docID asc)."""
+        a, b = int(self.offsets[q]), int(self.offsets[q + 1])
+        d = self.docids[a:b]
+        s = None if self.scores is None else self.scores[a:b]
+        if self.mode == MODE_SCORED_TOPK:
+            keep = s >= 0
+            return d[keep], s[keep]
+        return d, s
+
+
+class GpuIndexSource:
+    """== one device-resident IndexSource + AccessProxy (index_source.h:18-155, codecs.h:290-317) and the batch form of
+    exec_query() (exec.h:50-52) over it."""
+
+    def __init__(self, device: int = 0):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.trn_create(device, C.byref(h))
+        self._h = h
+        if rc != 0:
+            msg = self._L.trn_last_error(h).decode() if h else "trn_create failed"
+            raise TrinityError(msg)
+        self.terms: Optional[np.ndarray] = None
+        self.docs_cnt = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TrinityError(f"rc={rc}: " + self._L.trn_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._ck(self._L.trn_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def upload(self, codec: int, index: np.ndarray, terms: np.ndarray, max_docid: int):
+        index = np.ascontiguousarray(index, dtype=np.uint8)
+        terms = np.ascontiguousarray(terms, dtype=TERM_DTYPE)
+        self._ck(self._L.trn_upload_index(self._h, codec, _ptr(index), index.size, _ptr(terms), len(terms), max_docid))
+        self.terms = terms.copy()
+        self.docs_cnt = max_docid
+        self.codec = codec
+
+    def info(self) -> dict:
+        i = TrnIndexInfo()
+        self._ck(self._L.trn_index_info_get(self._h, C.byref(i)))
+        return {f: getattr(i, f) for f, _ in TrnIndexInfo._fields_}
+
+    def set_bm25_weights(self, nodes: np.ndarray, docs_cnt: Optional[int] = None) -> np.ndarray:
+        """fills TERM weights with ScorerWeight::idf (similarity.h:190-222) from the uploaded terms' document counts"""
+        n = docs_cnt or self.docs_cnt
+        for x in nodes:
+            if x["kind"] == NODE_TERM and x["term"] != EMPTY_TERM:
+                x["weight"] = bm25_idf(int(self.terms["documents"][x["term"]]), n)
+        return nodes
+
+    def _pack(self, queries: Sequence[np.ndarray]):
+        arr = (TrnQuery * len(queries))()
+        keep = []
+        for i, q in enumerate(queries):
+            q = np.ascontiguousarray(q, dtype=QNODE_DTYPE)
+            keep.append(q)
+            arr[i].nodes = q.ctypes.data
+            arr[i].nnodes = len(q)
+            arr[i].root = 0
+        return arr, keep
+
+    def exec_batch_device(self, queries: Sequence[np.ndarray], mode: int, k: int = 100):
+        arr, keep = self._pack(queries)
+        r = TrnResult()
+        self._ck(self._L.trn_exec_batch_device(self._h, C.cast(arr, C.c_void_p), len(queries), mode, k, C.byref(r)))
+        self._last = (mode, k, len(queries))
+        return r
+
+    def fetch(self) -> BatchResult:
+        r = TrnResult()
+        self._ck(self._L.trn_fetch_results(self._h, C.byref(r)))
+        mode, k, nq = self._last
+        return self._wrap(r, mode, k)
+
+    def _wrap(self, r: TrnResult, mode: int, k: int) -> BatchResult:
+        nq = r.nq
+        offsets = np.ctypeslib.as_array(r.offsets, shape=(nq + 1,)).copy()
+        n = int(offsets[nq])
+        docids = np.ctypeslib.as_array(r.docids, shape=(max(n, 1),))[:n].copy()
+        scores = None
+        if mode != MODE_DOCS_ONLY:
+            scores = np.ctypeslib.as_array(r.scores, shape=(max(n, 1),))[:n].copy()
+        counts = np.ctypeslib.as_array(r.match_counts, shape=(nq,)).copy()
+        return BatchResult(nq, mode, k, offsets, docids, scores, counts, int(r.postings_scanned), int(r.index_bytes_touched),
+                           int(r.kernel_launches), float(r.device_ms))
+
+    def exec_batch(self, queries: Sequence[np.ndarray], mode: int, k: int = 100) -> BatchResult:
+        """== exec_query() for a batch: plans H2D, fused kernels, results D2H."""
+        arr, keep = self._pack(queries)
+        r = TrnResult()
+        self._ck(self._L.trn_exec_batch(self._h, C.cast(arr, C.c_void_p), len(queries), mode, k, C.byref(r)))
+        self._last = (mode, k, len(queries))
+        return self._wrap(r, mode, k)
+
+    def last_topk_device(self):
+        d, s, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self._L.trn_last_topk_device(self._h, C.byref(d), C.byref(s), C.byref(c)))
+        return d.value, s.value, c.value
+
+    def merge_topk(self, docids_ptr: int, scores_ptr: int, nshards: int, nq: int, k: int, out_docids_ptr: int, out_scores_ptr: int):
+        self._ck(self._L.trn_merge_topk(self._h, C.c_void_p(docids_ptr), C.c_void_p(scores_ptr), nshards, nq, k,
+                                        C.c_void_p(out_docids_ptr), C.c_void_p(out_scores_ptr)))
+
+    def decode_terms(self, term_ids: Iterable[int], materialise: bool = True):
+        """== PostingsListIterator::next() over whole lists.  Returns (docids, freqs, sums[nterms,2], device_ms)."""
+        t = _u32(list(term_ids))
+        total = int(self.terms["documents"][t].sum())
+        d = np.zeros(total if materialise else 0, np.uint32)
+        f = np.zeros(total if materialise else 0, np.uint32)
+        sums = np.zeros((len(t), 2), np.uint64)
+        ms = C.c_float()
+        self._ck(self._L.trn_decode_terms(self._h, _ptr(t), len(t), int(materialise), _ptr(d) if materialise else None,
+                                          _ptr(f) if materialise else None, _ptr(sums), C.byref(ms)))
+        return d, f, sums, float(ms.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.trn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,608 @@
+// Host-side encoders for the GOOGLE and LUCENE(FastPFor<4>) postings layouts + the load-time block directory.
+// See codecs.h for the reference citations.  Written from the format description,
+// byte-exactness pinned against the reference encoders by tests/test_codecs_cpu.py.
+#include "codecs.h"
+#include "varbyte.h"
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <thread>
+
+namespace trn {
+namespace Codecs {
+
+        // ======================================================================================= GOOGLE
+        namespace Google {
+                void Encoder::begin_term() {
+                        auto &out               = sess->indexOut;
+                        curBlockSize            = 0;
+                        lastCommitedDocID       = 0;
+                        prevBlockLastDocumentID = 0;
+                        hitsData.clear();
+                        skipListData.clear();
+                        termDocuments = 0;
+                        curTermOffset = uint32_t(out.size());
+                        put_u16(out, 0); // skiplist entry count, patched in end_term()
+                }
+
+                void Encoder::begin_document(uint32_t documentID) {
+                        if (documentID == 0 || documentID <= lastCommitedDocID)
+                                throw std::invalid_argument("google encoder: document IDs must be > 0 and strictly ascending");
+                        curDocID                 = documentID;
+                        lastPos                  = 0;
+                        curPayloadSize           = 0;
+                        blockFreqs[curBlockSize] = 0;
+                }
+
+                void Encoder::new_hit(uint32_t pos, const uint8_t *payload, uint8_t payloadSize) {
+                        if (!pos && !payloadSize)
+                                return; // valid: a document with no positional hit (freq stays 0)
+                        if (pos < lastPos || payloadSize > 8)
+                                throw std::invalid_argument("google encoder: positions must be non-decreasing, payload <= 8 bytes");
+                        const uint32_t delta = pos - lastPos;
+                        ++blockFreqs[curBlockSize];
+                        // TRACK_PAYLOADS layout: varbyte((delta<<1)|sizeChanged) [u8 newSize] payload
+                        if (payloadSize != curPayloadSize) {
+                                varbyte_put(hitsData, (delta << 1) | 1u);
+                                hitsData.push_back(payloadSize);
+                                curPayloadSize = payloadSize;
+                        } else
+                                varbyte_put(hitsData, delta << 1);
+                        if (payloadSize)
+                                hitsData.insert(hitsData.end(), payload, payload + payloadSize);
+                        lastPos = pos;
+                }
+
+                void Encoder::end_document() {
+                        docDeltas[curBlockSize++] = curDocID - lastCommitedDocID;
+                        if (curBlockSize == N)
+                                commit_block();
+                        lastCommitedDocID = curDocID;
+                        ++termDocuments;
+                }
+
+                void Encoder::commit_block() {
+                        auto &         out   = sess->indexOut;
+                        const uint32_t delta = curDocID - prevBlockLastDocumentID;
+
+                        block.clear();
+                        for (uint32_t i = 0; i + 1 < curBlockSize; ++i) // the last doc is implied by the header
+                                varbyte_put(block, docDeltas[i]);
+                        for (uint32_t i = 0; i < curBlockSize; ++i)
+                                varbyte_put(block, blockFreqs[i]);
+
+                        const uint32_t blockLength = uint32_t(block.size() + hitsData.size());
+
+                        if (--skiplistEntryCountdown == 0) {
+                                if (skipListData.size() / 8 < UINT16_MAX) {
+                                        put_u32(skipListData, prevBlockLastDocumentID);
+                                        put_u32(skipListData, uint32_t(out.size()) - curTermOffset);
+                                }
+                                skiplistEntryCountdown = SKIPLIST_STEP;
+                        }
+
+                        varbyte_put(out, delta);
+                        varbyte_put(out, blockLength);
+                        out.push_back(uint8_t(curBlockSize));
+                        out.insert(out.end(), block.begin(), block.end());
+                        out.insert(out.end(), hitsData.begin(), hitsData.end());
+                        hitsData.clear();
+
+                        prevBlockLastDocumentID = curDocID;
+                        curBlockSize            = 0;
+                }
+
+                void Encoder::end_term(term_index_ctx *tctx) {
+                        auto &out = sess->indexOut;
+                        if (curBlockSize)
+                                commit_block();
+                        const uint16_t entries = uint16_t(skipListData.size() / 8);
+                        out.insert(out.end(), skipListData.begin(), skipListData.end());
+                        out[curTermOffset]     = uint8_t(entries);
+                        out[curTermOffset + 1] = uint8_t(entries >> 8);
+                        tctx->offset           = curTermOffset;
+                        tctx->size             = uint32_t(out.size()) - curTermOffset;
+                        tctx->documents        = termDocuments;
+                        skipListData.clear();
+                }
+        } // namespace Google
+
+        // ======================================================================================= LUCENE
+        namespace Lucene {
+                namespace {
+                        inline uint32_t bits_of(uint32_t v) {
+                                return v ? 32 - uint32_t(__builtin_clz(v)) : 0;
+                        }
+
+                        // LSB-first packing of 32 values at `bit` bits into `bit` words
+                        void pack32(const uint32_t *in, uint32_t *out, uint32_t bit, bool mask) {
+                                for (uint32_t i = 0; i < bit; ++i)
+                                        out[i] = 0;
+                                if (!bit)
+                                        return;
+                                const uint32_t m = bit == 32 ? 0xffffffffu : ((1u << bit) - 1);
+                                for (uint32_t i = 0; i < 32; ++i) {
+                                        const uint32_t v  = mask ? (in[i] & m) : in[i];
+                                        const uint32_t bp = i * bit, w = bp >> 5, sh = bp & 31;
+                                        out[w] |= v << sh;
+                                        if (sh + bit > 32)
+                                                out[w + 1] |= v >> (32 - sh);
+                                }
+                        }
+
+                        // FastPFor<4>::getBestBFromData cost model (fastpfor.h:143-171)
+                        void best_b(const uint32_t *in, uint8_t &bestb, uint8_t &bestcexcept, uint8_t &maxb) {
+                                uint32_t freqs[33] = {0};
+                                for (uint32_t k = 0; k < BLOCK_SIZE; ++k)
+                                        freqs[bits_of(in[k])]++;
+                                uint32_t b = 32;
+                                while (freqs[b] == 0)
+                                        b--;
+                                bestb             = uint8_t(b);
+                                maxb              = uint8_t(b);
+                                uint32_t bestcost = b * BLOCK_SIZE;
+                                uint32_t cexcept  = 0;
+                                bestcexcept       = 0;
+                                for (int32_t bb = int32_t(b) - 1; bb >= 0; --bb) {
+                                        cexcept += freqs[bb + 1];
+                                        uint32_t thiscost = cexcept * 8 /*overheadofeachexcept*/ + cexcept * (maxb - bb) + uint32_t(bb) * BLOCK_SIZE + 8;
+                                        if (maxb - bb == 1)
+                                                thiscost -= cexcept;
+                                        if (thiscost < bestcost) {
+                                                bestcost    = thiscost;
+                                                bestb       = uint8_t(bb);
+                                                bestcexcept = uint8_t(cexcept);
+                                        }
+                                }
+                        }
+                } // namespace
+
+                // FastPFor<4>::encodeArray of exactly one 128-value block (one "page" per call, lucene_codec.cpp:57-64)
+                static uint32_t pfor_encode_page(const uint32_t *in, uint32_t *out) {
+                        uint32_t *const initout = out;
+                        *out++                  = BLOCK_SIZE; // length word (fastpfor.h:107)
+                        uint32_t *const headerout = out++;    // wheremeta
+                        uint8_t         bytes[4 + BLOCK_SIZE];
+                        uint32_t        nb{0};
+                        uint8_t         b, cexcept, maxb;
+                        uint32_t        exceptions[BLOCK_SIZE];
+                        uint32_t        nexc{0};
+
+                        best_b(in, b, cexcept, maxb);
+                        bytes[nb++] = b;
+                        bytes[nb++] = cexcept;
+                        if (cexcept > 0) {
+                                bytes[nb++]            = maxb;
+                                const uint32_t maxval = uint32_t(1ull << b);
+                                for (uint32_t k = 0; k < BLOCK_SIZE; ++k) {
+                                        if (in[k] >= maxval) {
+                                                exceptions[nexc++] = in[k] >> b;
+                                                bytes[nb++]        = uint8_t(k);
+                                        }
+                                }
+                        }
+                        for (uint32_t j = 0; j < BLOCK_SIZE; j += 32) {
+                                pack32(in + j, out, b, true);
+                                out += b;
+                        }
+                        headerout[0] = uint32_t(out - headerout);
+                        *out++       = nb;
+                        std::memset(out, 0, ((nb + 3) / 4) * 4); // deterministic padding (the reference leaves stale bytes; see note in tests)
+                        std::memcpy(out, bytes, nb);
+                        out += (nb + 3) / 4;
+
+                        const uint32_t k      = uint32_t(maxb) - b; // exception width; k==1 carries no stream
+                        uint32_t       bitmap = 0;
+                        if (nexc && k >= 2)
+                                bitmap |= 1u << (k - 1);
+                        *out++ = bitmap;
+                        if (bitmap) {
+                                uint32_t padded[BLOCK_SIZE + 32] = {0};
+                                std::memcpy(padded, exceptions, nexc * sizeof(uint32_t));
+                                *out++ = nexc;
+                                uint32_t j{0};
+                                for (; j < nexc; j += 32) {
+                                        pack32(padded + j, out, k, false);
+                                        out += k;
+                                }
+                                out -= (j - nexc) * k / 32;
+                        }
+                        return uint32_t(out - initout);
+                }
+
+                void ints_encode(const uint32_t *values, std::vector<uint8_t> &out) {
+                        bool eq{true};
+                        for (uint32_t i = 1; i < BLOCK_SIZE; ++i)
+                                if (values[i] != values[0]) {
+                                        eq = false;
+                                        break;
+                                }
+                        if (eq) {
+                                out.push_back(0);
+                                varbyte_put(out, values[0]);
+                                return;
+                        }
+                        uint32_t       page[2 * BLOCK_SIZE + 64];
+                        const uint32_t l = pfor_encode_page(values, page);
+                        out.push_back(uint8_t(l));
+                        const auto *bytes = reinterpret_cast<const uint8_t *>(page);
+                        out.insert(out.end(), bytes, bytes + size_t(l) * 4);
+                }
+
+                void Encoder::begin_term() {
+                        lastDocID = totalHits = sumHits = buffered = termDocuments = 0;
+                        termIndexOffset        = uint32_t(sess->indexOut.size());
+                        termPositionsOffset    = uint32_t(sess->positionsOut.size());
+                        lastHitsBlockOffset    = 0;
+                        lastHitsBlockTotalHits = 0;
+                        skiplistCountdown      = SKIPLIST_STEP;
+                        skiplist.clear();
+                        payloadsBuf.clear();
+                        // chunk header: u32 hitsDataOffset, u32 sumHits, u32 positionsChunkSize, u16 skiplistSize (patched in end_term)
+                        put_u32(sess->indexOut, termPositionsOffset);
+                        put_u32(sess->indexOut, 0);
+                        put_u32(sess->indexOut, 0);
+                        put_u16(sess->indexOut, 0);
+                }
+
+                void Encoder::output_block() {
+                        if (--skiplistCountdown == 0) {
+                                if (skiplist.size() < UINT16_MAX)
+                                        skiplist.push_back(cur_block);
+                                skiplistCountdown = SKIPLIST_STEP;
+                        }
+                        ints_encode(docDeltas, sess->indexOut);
+                        ints_encode(docFreqs, sess->indexOut);
+                        buffered = 0;
+                }
+
+                void Encoder::begin_document(uint32_t documentID) {
+                        if (documentID <= lastDocID)
+                                throw std::invalid_argument("lucene encoder: document IDs must be > 0 and strictly ascending");
+                        if (buffered == BLOCK_SIZE)
+                                output_block();
+                        if (!buffered) {
+                                cur_block.indexOffset            = uint32_t(sess->indexOut.size()) - termIndexOffset;
+                                cur_block.lastDocID              = lastDocID;
+                                cur_block.totalDocumentsSoFar    = termDocuments;
+                                cur_block.lastHitsBlockOffset    = lastHitsBlockOffset;
+                                cur_block.lastHitsBlockTotalHits = lastHitsBlockTotalHits;
+                                cur_block.curHitsBlockHits       = uint16_t(totalHits);
+                        }
+                        docDeltas[buffered] = documentID - lastDocID;
+                        docFreqs[buffered]  = 0;
+                        ++termDocuments;
+                        lastDocID    = documentID;
+                        lastPosition = 0;
+                }
+
+                void Encoder::new_hit(uint32_t pos, const uint8_t *payload, uint8_t payloadSize) {
+                        if (!pos && !payloadSize)
+                                return;
+                        if (pos < lastPosition || payloadSize > 8)
+                                throw std::invalid_argument("lucene encoder: positions must be non-decreasing, payload <= 8 bytes");
+                        ++docFreqs[buffered];
+                        hitPosDeltas[totalHits]    = pos - lastPosition;
+                        hitPayloadSizes[totalHits] = payloadSize;
+                        lastPosition               = pos;
+                        if (payloadSize)
+                                payloadsBuf.insert(payloadsBuf.end(), payload, payload + payloadSize);
+                        if (++totalHits == BLOCK_SIZE) {
+                                auto &po = sess->positionsOut;
+                                sumHits += totalHits;
+                                ints_encode(hitPosDeltas, po);
+                                ints_encode(hitPayloadSizes, po);
+                                varbyte_put(po, uint32_t(payloadsBuf.size()));
+                                po.insert(po.end(), payloadsBuf.begin(), payloadsBuf.end());
+                                payloadsBuf.clear();
+                                lastHitsBlockTotalHits = sumHits;
+                                lastHitsBlockOffset    = uint32_t(po.size()) - termPositionsOffset;
+                                totalHits              = 0;
+                        }
+                }
+
+                void Encoder::end_document() {
+                        ++buffered;
+                }
+
+                void Encoder::end_term(term_index_ctx *out) {
+                        auto &io = sess->indexOut;
+                        auto &po = sess->positionsOut;
+                        sumHits += totalHits;
+                        if (buffered == BLOCK_SIZE)
+                                output_block();
+                        else {
+                                for (uint32_t i = 0; i < buffered; ++i) {
+                                        varbyte_put(io, docDeltas[i]);
+                                        varbyte_put(io, docFreqs[i]);
+                                }
+                        }
+                        if (totalHits) {
+                                uint8_t lastPayloadLen{0};
+                                for (uint32_t i = 0; i < totalHits; ++i) {
+                                        const uint8_t pl = uint8_t(hitPayloadSizes[i]);
+                                        if (pl != lastPayloadLen) {
+                                                lastPayloadLen = pl;
+                                                varbyte_put(po, (hitPosDeltas[i] << 1) | 1u);
+                                                po.push_back(pl);
+                                        } else
+                                                varbyte_put(po, hitPosDeltas[i] << 1);
+                                }
+                                po.insert(po.end(), payloadsBuf.begin(), payloadsBuf.end());
+                                payloadsBuf.clear();
+                        }
+                        auto patch32 = [&](uint32_t at, uint32_t v) {
+                                io[at]     = uint8_t(v);
+                                io[at + 1] = uint8_t(v >> 8);
+                                io[at + 2] = uint8_t(v >> 16);
+                                io[at + 3] = uint8_t(v >> 24);
+                        };
+                        const uint16_t skiplistSize = uint16_t(skiplist.size());
+                        patch32(termIndexOffset + 4, sumHits);
+                        patch32(termIndexOffset + 8, uint32_t(po.size()) - termPositionsOffset);
+                        io[termIndexOffset + 12] = uint8_t(skiplistSize);
+                        io[termIndexOffset + 13] = uint8_t(skiplistSize >> 8);
+                        for (const auto &e : skiplist) {
+                                put_u32(io, e.indexOffset);
+                                put_u32(io, e.lastDocID);
+                                put_u32(io, e.lastHitsBlockOffset);
+                                put_u32(io, e.totalDocumentsSoFar);
+                                put_u32(io, e.lastHitsBlockTotalHits);
+                                put_u16(io, e.curHitsBlockHits);
+                        }
+                        skiplist.clear();
+                        out->documents = termDocuments;
+                        out->offset    = termIndexOffset;
+                        out->size      = uint32_t(io.size()) - termIndexOffset;
+                }
+        } // namespace Lucene
+
+        Encoder *new_encoder(IndexSession *s) {
+                if (s->codec == Codec::Google)
+                        return new Google::Encoder(s);
+                return new Lucene::Encoder(s);
+        }
+} // namespace Codecs
+
+// =========================================================================================== block directory
+namespace {
+        // host decode of one Lucene int-block (sum only is needed for the directory; full values for tests)
+        const uint8_t *lucene_ints_decode(const uint8_t *p, const uint8_t *end, uint32_t *values) {
+                using Codecs::Lucene::BLOCK_SIZE;
+                if (p >= end)
+                        throw std::runtime_error("lucene: int-block past chunk end");
+                const uint32_t L = *p++;
+                if (L == 0) {
+                        const uint32_t v = varbyte_get(p);
+                        for (uint32_t i = 0; i < BLOCK_SIZE; ++i)
+                                values[i] = v;
+                        return p;
+                }
+                if (p + size_t(L) * 4 > end)
+                        throw std::runtime_error("lucene: PFor page past chunk end");
+                auto w = [&](uint32_t i) { return get_u32(p + size_t(i) * 4); };
+                if (w(0) != BLOCK_SIZE)
+                        throw std::runtime_error("lucene: PFor page length word != 128");
+                const uint32_t wheremeta = w(1);
+                const uint32_t b         = (wheremeta - 1) / 4;
+                if (wheremeta != 1 + 4 * b || b > 32 || 2 + wheremeta > L)
+                        throw std::runtime_error("lucene: malformed PFor page header");
+                for (uint32_t i = 0; i < BLOCK_SIZE; ++i) {
+                        if (!b) {
+                                values[i] = 0;
+                                continue;
+                        }
+                        const uint32_t g = i >> 5, j = i & 31, bp = j * b, wi = 2 + g * b + (bp >> 5), sh = bp & 31;
+                        uint64_t       x = w(wi);
+                        if (sh + b > 32)
+                                x |= uint64_t(w(wi + 1)) << 32;
+                        values[i] = uint32_t((x >> sh) & (b == 32 ? 0xffffffffull : ((1ull << b) - 1)));
+                }
+                const uint32_t meta     = 1 + wheremeta;
+                const uint32_t bytesize = w(meta);
+                const uint8_t *bytes    = p + size_t(meta + 1) * 4;
+                if (bytes[0] != b)
+                        throw std::runtime_error("lucene: PFor b mismatch");
+                const uint32_t cexcept = bytes[1];
+                if (cexcept) {
+                        const uint32_t maxbits = bytes[2];
+                        const uint32_t k       = maxbits - b;
+                        const uint32_t excw    = meta + 1 + (bytesize + 3) / 4; // bitmap word
+                        for (uint32_t e = 0; e < cexcept; ++e) {
+                                const uint32_t pos = bytes[3 + e];
+                                uint32_t       ev{1};
+                                if (k > 1) {
+                                        const uint32_t base = excw + 2; // after bitmap + count
+                                        const uint32_t bp = e * k, wi = base + (bp >> 5), sh = bp & 31;
+                                        uint64_t       x = w(wi);
+                                        if (sh + k > 32)
+                                                x |= uint64_t(w(wi + 1)) << 32;
+                                        ev = uint32_t((x >> sh) & (k == 32 ? 0xffffffffull : ((1ull << k) - 1)));
+                                }
+                                values[pos] |= ev << b;
+                        }
+                }
+                return p + size_t(L) * 4;
+        }
+
+        void dir_google_term(const uint8_t *index, const term_index_ctx &t, std::vector<uint32_t> &last, std::vector<uint32_t> &off, uint32_t &firstDoc) {
+                using Codecs::Google::N;
+                firstDoc = 0;
+                if (!t.size) {
+                        if (t.documents)
+                                throw std::runtime_error("google: term with documents but empty chunk");
+                        return;
+                }
+                const uint8_t *base     = index + t.offset;
+                const uint32_t entries  = get_u16(base);
+                const uint8_t *chunkEnd = base + t.size - size_t(entries) * 8;
+                const uint8_t *p        = base + 2;
+                uint32_t       prev{0}, docs{0};
+                while (p < chunkEnd) {
+                        const uint32_t delta = varbyte_get(p);
+                        const uint32_t blen  = varbyte_get(p);
+                        const uint32_t n     = *p++;
+                        if (n == 0 || n > N)
+                                throw std::runtime_error("google: bad block doc count");
+                        if (last.empty()) {
+                                const uint8_t *q = p;
+                                firstDoc         = n > 1 ? varbyte_get(q) : delta;
+                        }
+                        prev += delta;
+                        last.push_back(prev);
+                        off.push_back(uint32_t(p - index));
+                        docs += n;
+                        if (n != N && docs != t.documents)
+                                throw std::runtime_error("google: non-final block is not full (unsupported by the GPU directory)");
+                        p += blen;
+                }
+                if (p != chunkEnd || docs != t.documents)
+                        throw std::runtime_error("google: chunk walk did not end at chunkEnd / documents mismatch");
+                last.push_back(UINT32_MAX);
+                off.push_back(uint32_t(chunkEnd - index));
+        }
+
+        void dir_lucene_term(const uint8_t *index, const term_index_ctx &t, std::vector<uint32_t> &last, std::vector<uint32_t> &off, uint32_t &firstDoc) {
+                using Codecs::Lucene::BLOCK_SIZE;
+                firstDoc = 0;
+                if (!t.size) {
+                        if (t.documents)
+                                throw std::runtime_error("lucene: term with documents but empty chunk");
+                        return;
+                }
+                const uint8_t *base = index + t.offset;
+                if (t.size < 14)
+                        throw std::runtime_error("lucene: chunk shorter than its header");
+                const uint32_t skipn    = get_u16(base + 12);
+                const uint8_t *chunkEnd = base + t.size - size_t(skipn) * 22;
+                const uint8_t *skip     = chunkEnd;
+                const uint8_t *p        = base + 14;
+                const uint32_t nfull    = t.documents / BLOCK_SIZE;
+                const uint32_t tail     = t.documents % BLOCK_SIZE;
+                uint32_t       prev{0};
+                uint32_t       vals[BLOCK_SIZE];
+                for (uint32_t blk = 0; blk < nfull; ++blk) {
+                        off.push_back(uint32_t(p - index));
+                        const bool haveNext = blk + 1 < skipn; // skiplist entry blk+1 holds this block's last docID
+                        if (blk < skipn) {
+                                // cross-check the on-disk skiplist entry for this block
+                                if (get_u32(skip + size_t(blk) * 22) != uint32_t(p - base) || get_u32(skip + size_t(blk) * 22 + 4) != prev)
+                                        throw std::runtime_error("lucene: skiplist entry disagrees with block walk");
+                        }
+                        if (haveNext && blk != 0) {
+                                // fast path: skip the two int-blocks by their length bytes
+                                for (int k = 0; k < 2; ++k) {
+                                        const uint32_t L = *p++;
+                                        if (L == 0)
+                                                (void)varbyte_get(p);
+                                        else
+                                                p += size_t(L) * 4;
+                                }
+                                prev = get_u32(skip + size_t(blk + 1) * 22 + 4);
+                        } else {
+                                p = lucene_ints_decode(p, chunkEnd, vals);
+                                if (blk == 0)
+                                        firstDoc = vals[0];
+                                uint32_t s{0};
+                                for (uint32_t i = 0; i < BLOCK_SIZE; ++i)
+                                        s += vals[i];
+                                prev += s;
+                                // skip freqs block
+                                const uint32_t L = *p++;
+                                if (L == 0)
+                                        (void)varbyte_get(p);
+                                else
+                                        p += size_t(L) * 4;
+                        }
+                        last.push_back(prev);
+                }
+                if (tail) {
+                        off.push_back(uint32_t(p - index));
+                        for (uint32_t i = 0; i < tail; ++i) {
+                                const uint32_t d = varbyte_get(p);
+                                (void)varbyte_get(p);
+                                prev += d;
+                                if (nfull == 0 && i == 0)
+                                        firstDoc = d;
+                        }
+                        last.push_back(prev);
+                }
+                if (p != chunkEnd)
+                        throw std::runtime_error("lucene: chunk walk did not end at the skiplist");
+                last.push_back(UINT32_MAX);
+                off.push_back(uint32_t(chunkEnd - index));
+        }
+} // namespace
+
+// exposed for tests (host decode of a Lucene int-block)
+const uint8_t *lucene_ints_decode_host(const uint8_t *p, const uint8_t *end, uint32_t *values) {
+        return lucene_ints_decode(p, end, values);
+}
+
+void build_block_directory(Codec codec, const uint8_t *index, uint64_t nbytes, const term_index_ctx *terms, uint32_t nterms, int threads, BlockDirectory &out) {
+        struct PerTerm {
+                std::vector<uint32_t> last, off;
+                uint32_t              firstDoc{0};
+        };
+        std::vector<PerTerm>  per(nterms);
+        std::atomic<uint32_t> next{0};
+        std::string           err;
+        std::atomic<bool>     failed{false};
+        auto                  worker = [&] {
+                for (;;) {
+                        const uint32_t i = next.fetch_add(1);
+                        if (i >= nterms || failed.load())
+                                break;
+                        try {
+                                if (uint64_t(terms[i].offset) + terms[i].size > nbytes)
+                                        throw std::runtime_error("term chunk exceeds index size");
+                                if (codec == Codec::Google)
+                                        dir_google_term(index, terms[i], per[i].last, per[i].off, per[i].firstDoc);
+                                else
+                                        dir_lucene_term(index, terms[i], per[i].last, per[i].off, per[i].firstDoc);
+                        } catch (const std::exception &e) {
+                                bool exp{false};
+                                if (failed.compare_exchange_strong(exp, true))
+                                        err = std::string("term ") + std::to_string(i) + ": " + e.what();
+                        }
+                }
+        };
+        if (threads < 1)
+                threads = 1;
+        std::vector<std::thread> ths;
+        for (int i = 1; i < threads; ++i)
+                ths.emplace_back(worker);
+        worker();
+        for (auto &t : ths)
+                t.join();
+        if (failed.load())
+                throw std::runtime_error("build_block_directory: " + err);
+
+        size_t total{0};
+        for (auto &p : per)
+                total += p.last.size();
+        if (total >= (1ull << 32))
+                throw std::runtime_error("block directory exceeds 2^32 entries");
+        out.blk_last.resize(total);
+        out.blk_off.resize(total);
+        out.terms.resize(nterms);
+        size_t at{0};
+        for (uint32_t i = 0; i < nterms; ++i) {
+                auto &p  = per[i];
+                auto &td = out.terms[i];
+                td.documents = terms[i].documents;
+                td.dir_begin = uint32_t(at);
+                td.nblocks   = p.last.empty() ? 0 : uint32_t(p.last.size() - 1);
+                td.first_doc = p.firstDoc;
+                td.last_doc  = td.nblocks ? p.last[td.nblocks - 1] : 0;
+                std::copy(p.last.begin(), p.last.end(), out.blk_last.begin() + at);
+                std::copy(p.off.begin(), p.off.end(), out.blk_off.begin() + at);
+                at += p.last.size();
+                std::vector<uint32_t>().swap(p.last);
+                std::vector<uint32_t>().swap(p.off);
+        }
+}
+
+} // namespace trn

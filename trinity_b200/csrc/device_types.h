@@ -1,0 +1,85 @@
+// Device-side data layout shared by engine.cu (host) and kernels.cu (device).
+#pragma once
+#include <cstdint>
+
+namespace trn {
+
+static constexpr uint32_t kEmptyTerm = 0xffffffffu;
+
+// one per dictionary term (16 B + 8)
+struct DevTerm {
+        uint32_t documents;
+        uint32_t dir_begin; // first entry in blk_last / blk_off (nblocks + 1 entries incl. sentinel)
+        uint32_t nblocks;
+        uint32_t first_doc;
+        uint32_t last_doc;
+        uint32_t chunk_len;
+};
+
+struct DevIndex {
+        const uint8_t * index;    // raw reference-format bytes (google index / lucene index), 256B aligned, 64B tail padding
+        const uint32_t *blk_last; // last docID per block (+ sentinel UINT32_MAX per term)
+        const uint32_t *blk_off;  // payload byte offset per block (+ sentinel = end of block area)
+        const DevTerm * terms;
+        const uint32_t *tile_first; // [nterms][ntiles + 1]: first block whose last docID >= tile * tile_docs
+        uint32_t        nterms;
+        uint32_t        ntiles;
+        uint32_t        tile_shift; // tile_docs = 1 << tile_shift
+        uint32_t        max_docid;
+        int             codec;
+};
+
+// ---- per-query step program (built on the host from the trn_qnode tree) ----
+enum StepOp : uint8_t {
+        OP_LEAF      = 0, // decode term, combine its docset into slot dst (mode), optionally accumulate BM25 (flag SCORE)
+        OP_SLOT      = 1, // combine slot src into slot dst (mode)
+        OP_CLEAR     = 2, // dst = 0
+        OP_LEAFSCORE = 3, // second pass: decode term, accumulate BM25 where slot src (mask) has the doc's bit
+};
+enum StepMode : uint8_t { M_SET = 0, M_OR = 1, M_AND = 2, M_ANDNOT = 3, M_NONE = 4 };
+enum StepFlags : uint8_t { F_SCORE = 1, F_BREAK_IF_EMPTY = 2 };
+
+struct DevStep {
+        uint8_t  op, mode, dst, src;
+        uint8_t  flags, pad[3];
+        uint32_t term;
+        uint32_t pad2;
+        double   idf;
+};
+static_assert(sizeof(DevStep) == 24, "DevStep layout");
+
+struct DevQuery {
+        uint32_t step_begin, nsteps;
+        uint32_t tile_lo, ntiles; // tiles [tile_lo, tile_lo + ntiles)
+        uint32_t item_base;       // first work item of this query
+        uint32_t root_slot;
+        uint32_t cand_base; // SCORED_TOPK: first candidate slot of this query
+        uint32_t cand_cap;
+};
+
+struct ExecParams {
+        DevIndex        ix;
+        const DevQuery *queries;
+        const DevStep * steps;
+        uint32_t        nq;
+        uint32_t        total_items;
+        uint32_t        nslots; // bitmap slots per CTA
+        int             mode;   // TRN_MODE_*
+        uint32_t        k;
+        uint32_t *      ticket; // work-item dispenser
+        // docs-only / scored-all outputs: segments allocated by atomicAdd on seg_cursor
+        unsigned long long *seg_cursor;
+        uint64_t            seg_capacity;
+        uint32_t *          seg_docids;
+        float *             seg_scores;
+        uint64_t *          item_off; // per work item: offset of its segment
+        uint32_t *          item_cnt; // per work item: number of matches
+        // top-k
+        unsigned long long *match_counts; // per query
+        uint32_t *          theta;        // per query: lower bound (float bits) of the k-th best score
+        uint32_t *          cand_cursor;  // per query
+        uint2 *             cand;         // (score bits, docid)
+        uint32_t *          overflow;     // set to 1 if seg_capacity was exceeded
+};
+
+} // namespace trn

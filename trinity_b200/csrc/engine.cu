@@ -1,0 +1,888 @@
+// trn_ctx: the device-resident index source + batch executor behind the C ABI (include/trinity_b200.h).
+// Host responsibilities mirror the host side of the reference's exec path:
+//   * upload == AccessProxy construction + Decoder::init for every term (google_codec.cpp:936-983, lucene_codec.cpp:877-932)
+//   * plan compile == queryexec_ctx::build_iterator + build_span (exec.cpp:253-505): operator tree -> per-tile step program,
+//     including the IteratorScorer combination rules of docset_iterators_scorers.cpp:8-242 (which leaves contribute to a
+//     document's score is structural; see compile_node()).
+// There is NO CPU execution fallback: every docset/score operation runs in kernels.cu.
+#include "../../include/trinity_b200.h"
+#include "codecs.h"
+#include "device_types.h"
+#include "kernels.h"
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace trn;
+
+namespace {
+struct DevBuf {
+        void * p{nullptr};
+        size_t cap{0};
+        cudaError_t ensure(size_t bytes) {
+                if (bytes <= cap)
+                        return cudaSuccess;
+                if (p)
+                        cudaFree(p);
+                p   = nullptr;
+                cap = 0;
+                size_t want = bytes + bytes / 8 + 256;
+                cudaError_t e = cudaMalloc(&p, want);
+                if (e == cudaSuccess)
+                        cap = want;
+                return e;
+        }
+        void release() {
+                if (p)
+                        cudaFree(p);
+                p   = nullptr;
+                cap = 0;
+        }
+        template <class T> T *as() const {
+                return static_cast<T *>(p);
+        }
+};
+struct PinBuf {
+        void * p{nullptr};
+        size_t cap{0};
+        cudaError_t ensure(size_t bytes) {
+                if (bytes <= cap)
+                        return cudaSuccess;
+                if (p)
+                        cudaFreeHost(p);
+                p   = nullptr;
+                cap = 0;
+                size_t want = bytes + bytes / 8 + 256;
+                cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+                if (e == cudaSuccess)
+                        cap = want;
+                return e;
+        }
+        void release() {
+                if (p)
+                        cudaFreeHost(p);
+                p   = nullptr;
+                cap = 0;
+        }
+        template <class T> T *as() const {
+                return static_cast<T *>(p);
+        }
+};
+} // namespace
+
+struct trn_ctx {
+        int          device{0};
+        cudaStream_t stream{nullptr};
+        std::string  err;
+        int          num_sms{148};
+        // index
+        bool                 have_index{false};
+        int                  codec{0};
+        uint32_t             nterms{0}, max_docid{0}, tile_shift{14}, ntiles{0};
+        uint64_t             index_bytes{0}, dir_bytes{0}, total_blocks{0}, total_postings{0};
+        DevBuf               d_index, d_blk_last, d_blk_off, d_terms, d_tile_first;
+        std::vector<DevTerm> h_terms;
+        // batch scratch (grow-only)
+        DevBuf d_queries, d_steps, d_small, d_item_off, d_item_cnt, d_item_dst, d_seg_docids, d_seg_scores, d_out_docids, d_out_scores, d_q_offsets, d_cand,
+            d_topk_docids, d_topk_scores, d_topk_counts, d_dec_a, d_dec_b, d_dec_c, d_dec_docids, d_dec_freqs, d_dec_sums, d_merge_docids, d_merge_scores;
+        PinBuf h_offsets, h_docids, h_scores, h_counts, h_small;
+        cudaEvent_t ev0{nullptr}, ev1{nullptr};
+        // last batch
+        int      last_mode{-1};
+        uint32_t last_nq{0}, last_k{0}, last_launches{0};
+        uint64_t last_postings{0}, last_bytes{0};
+        float    last_ms{0};
+};
+
+#define CK(call)                                                                                                                                               \
+        do {                                                                                                                                                   \
+                cudaError_t e__ = (call);                                                                                                                      \
+                if (e__ != cudaSuccess) {                                                                                                                      \
+                        c->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                                                          \
+                        return TRN_ERR_CUDA;                                                                                                                   \
+                }                                                                                                                                              \
+        } while (0)
+
+static int fail(trn_ctx *c, int code, const std::string &m) {
+        c->err = m;
+        return code;
+}
+
+// =================================================================================================== plan compiler
+namespace {
+struct Range {
+        uint32_t lo{1}, hi{0}; // inclusive docIDs; empty when lo > hi
+        bool     empty() const {
+                return lo > hi;
+        }
+};
+
+struct Compiler {
+        const trn_qnode *           n;
+        uint32_t                    nn;
+        const std::vector<DevTerm> &terms;
+        bool                        scored;
+        uint32_t                    root;
+        std::vector<DevStep> &      steps;
+        uint32_t                    next_slot{0};
+        uint64_t                    postings{0}, bytes{0};
+        struct Deferred {
+                uint32_t              term;
+                double                idf;
+                std::vector<uint8_t> cond;
+        };
+        std::vector<Deferred> deferred;
+        std::string           err;
+
+        Compiler(const trn_qnode *nodes, uint32_t cnt, const std::vector<DevTerm> &t, bool sc, uint32_t r, std::vector<DevStep> &s)
+            : n{nodes}, nn{cnt}, terms{t}, scored{sc}, root{r}, steps{s} {
+        }
+
+        bool is_leaf(uint32_t i) const {
+                return n[i].kind == TRN_NODE_TERM;
+        }
+        uint32_t df(uint32_t i) const {
+                const auto t = n[i].term;
+                return t == kEmptyTerm ? 0u : terms[t].documents;
+        }
+        void push(uint8_t op, uint8_t mode, uint32_t dst, uint32_t src, uint8_t flags, uint32_t term, double idf) {
+                DevStep s;
+                std::memset(&s, 0, sizeof(s));
+                s.op    = op;
+                s.mode  = mode;
+                s.dst   = uint8_t(dst);
+                s.src   = uint8_t(src);
+                s.flags = flags;
+                s.term  = term;
+                s.idf   = idf;
+                steps.push_back(s);
+        }
+        void account(uint32_t i) {
+                const auto t = n[i].term;
+                if (t != kEmptyTerm) {
+                        postings += terms[t].documents;
+                        bytes += terms[t].chunk_len;
+                }
+        }
+        // leaf combined into dst with `mode`; scoring per the structural rules
+        void leaf(uint32_t i, uint8_t mode, uint32_t dst, bool scoring, const std::vector<uint8_t> &cond, uint8_t extraFlags) {
+                account(i);
+                uint8_t flags = extraFlags;
+                if (scored && scoring) {
+                        if (cond.empty())
+                                flags |= F_SCORE;
+                        else
+                                deferred.push_back({n[i].term, n[i].weight, cond});
+                }
+                if (mode == M_NONE && !(flags & F_SCORE))
+                        return; // nothing to do in this pass
+                push(OP_LEAF, mode, dst, 0, flags, n[i].term, n[i].weight);
+        }
+
+        // compiles internal node i into its own slot; returns the slot
+        int node(uint32_t i, bool scoring, const std::vector<uint8_t> &cond) {
+                if (next_slot >= 14) {
+                        err = "query needs more than 14 docset slots";
+                        return -1;
+                }
+                const uint32_t s    = next_slot++;
+                const auto &   X    = n[i];
+                const bool     isRoot = i == root;
+                if (X.nchildren == 0 || uint32_t(X.first_child) + X.nchildren > nn) {
+                        err = "operator node without (valid) children";
+                        return -1;
+                }
+                std::vector<uint32_t> kids(X.nchildren);
+                for (uint32_t c = 0; c < X.nchildren; ++c)
+                        kids[c] = X.first_child + c;
+                auto child_cond = [&](uint32_t slotOfChild) {
+                        auto v = cond;
+                        v.push_back(uint8_t(slotOfChild));
+                        return v;
+                };
+                switch (X.kind) {
+                        case TRN_NODE_AND: {
+                                // leaves first, rarest first (== prepare_tree's df sort exec.cpp:154-170 and reorder_execnodes :216)
+                                std::stable_sort(kids.begin(), kids.end(), [&](uint32_t a, uint32_t b) {
+                                        const bool la = is_leaf(a), lb = is_leaf(b);
+                                        if (la != lb)
+                                                return la;
+                                        if (la)
+                                                return df(a) < df(b);
+                                        return false;
+                                });
+                                bool first{true};
+                                for (auto c : kids) {
+                                        const uint8_t fl = isRoot ? F_BREAK_IF_EMPTY : 0;
+                                        if (is_leaf(c))
+                                                leaf(c, first ? M_SET : M_AND, s, scoring, cond, fl);
+                                        else {
+                                                const int cs = node(c, scoring, cond);
+                                                if (cs < 0)
+                                                        return -1;
+                                                push(OP_SLOT, first ? M_SET : M_AND, s, uint32_t(cs), fl, 0, 0);
+                                        }
+                                        first = false;
+                                }
+                        } break;
+                        case TRN_NODE_OR: {
+                                push(OP_CLEAR, 0, s, 0, 0, 0, 0);
+                                for (auto c : kids) {
+                                        if (is_leaf(c))
+                                                leaf(c, M_OR, s, scoring, cond, 0);
+                                        else {
+                                                // a non-leaf child of a disjunction contributes its score only for documents it matches itself
+                                                // (Disjunction scorer sums children positioned on the doc, docset_iterators_scorers.cpp)
+                                                const uint32_t willBe = next_slot;
+                                                const int      cs     = node(c, scoring, child_cond(willBe));
+                                                if (cs < 0)
+                                                        return -1;
+                                                push(OP_SLOT, M_OR, s, uint32_t(cs), 0, 0, 0);
+                                        }
+                                }
+                        } break;
+                        case TRN_NODE_NOT:
+                        case TRN_NODE_OPTIONAL: {
+                                if (X.nchildren != 2) {
+                                        err = "NOT / OPTIONAL need exactly two children";
+                                        return -1;
+                                }
+                                const uint8_t fl = isRoot ? F_BREAK_IF_EMPTY : 0;
+                                if (is_leaf(kids[0]))
+                                        leaf(kids[0], M_SET, s, scoring, cond, fl);
+                                else {
+                                        const int cs = node(kids[0], scoring, cond);
+                                        if (cs < 0)
+                                                return -1;
+                                        push(OP_SLOT, M_SET, s, uint32_t(cs), fl, 0, 0);
+                                }
+                                if (X.kind == TRN_NODE_NOT) {
+                                        // Filter: excluded side never scores (docset_iterators_scorers.cpp Filter -> req only)
+                                        if (is_leaf(kids[1]))
+                                                leaf(kids[1], M_ANDNOT, s, false, cond, 0);
+                                        else {
+                                                const int cs = node(kids[1], false, cond);
+                                                if (cs < 0)
+                                                        return -1;
+                                                push(OP_SLOT, M_ANDNOT, s, uint32_t(cs), 0, 0, 0);
+                                        }
+                                } else if (scored && scoring) {
+                                        // Optional: main drives; opt only adds its score when it is on the document
+                                        if (is_leaf(kids[1]))
+                                                leaf(kids[1], M_NONE, s, true, cond, 0);
+                                        else {
+                                                const uint32_t willBe = next_slot;
+                                                if (node(kids[1], true, child_cond(willBe)) < 0)
+                                                        return -1;
+                                        }
+                                } else {
+                                        // docs-only: the optional side cannot change the match set, but it is still "touched" by the reference
+                                        // (Optional::next advances opt lazily); we do not read it at all.
+                                }
+                        } break;
+                        default:
+                                err = "unknown node kind";
+                                return -1;
+                }
+                return int(s);
+        }
+
+        Range range(uint32_t i) const {
+                const auto &X = n[i];
+                Range       r;
+                if (X.kind == TRN_NODE_TERM) {
+                        if (X.term != kEmptyTerm && terms[X.term].documents) {
+                                r.lo = terms[X.term].first_doc;
+                                r.hi = terms[X.term].last_doc;
+                        }
+                        return r;
+                }
+                if (X.kind == TRN_NODE_NOT || X.kind == TRN_NODE_OPTIONAL)
+                        return range(X.first_child);
+                bool first{true};
+                for (uint32_t c = 0; c < X.nchildren; ++c) {
+                        const Range cr = range(X.first_child + c);
+                        if (X.kind == TRN_NODE_AND) {
+                                if (cr.empty())
+                                        return Range{};
+                                if (first)
+                                        r = cr;
+                                else {
+                                        r.lo = std::max(r.lo, cr.lo);
+                                        r.hi = std::min(r.hi, cr.hi);
+                                        if (r.empty())
+                                                return Range{};
+                                }
+                                first = false;
+                        } else {
+                                if (cr.empty())
+                                        continue;
+                                if (first)
+                                        r = cr;
+                                else {
+                                        r.lo = std::min(r.lo, cr.lo);
+                                        r.hi = std::max(r.hi, cr.hi);
+                                }
+                                first = false;
+                        }
+                }
+                return r;
+        }
+
+        uint64_t bound(uint32_t i) const {
+                const auto &X = n[i];
+                if (X.kind == TRN_NODE_TERM)
+                        return df(i);
+                if (X.kind == TRN_NODE_NOT || X.kind == TRN_NODE_OPTIONAL)
+                        return bound(X.first_child);
+                uint64_t b = X.kind == TRN_NODE_AND ? ~0ull : 0ull;
+                for (uint32_t c = 0; c < X.nchildren; ++c) {
+                        const uint64_t cb = bound(X.first_child + c);
+                        b                 = X.kind == TRN_NODE_AND ? std::min(b, cb) : b + cb;
+                }
+                return b;
+        }
+
+        bool validate() {
+                if (root >= nn) {
+                        err = "root out of range";
+                        return false;
+                }
+                for (uint32_t i = 0; i < nn; ++i) {
+                        if (n[i].kind == TRN_NODE_TERM) {
+                                if (n[i].term != kEmptyTerm && n[i].term >= terms.size()) {
+                                        err = "term id out of range";
+                                        return false;
+                                }
+                        } else if (n[i].kind > TRN_NODE_OPTIONAL) {
+                                err = "unknown node kind";
+                                return false;
+                        } else {
+                                // children must come after their parent (guarantees an acyclic tree)
+                                if (n[i].nchildren == 0 || n[i].first_child <= i || uint32_t(n[i].first_child) + n[i].nchildren > nn) {
+                                        err = "children must follow their parent in the node array";
+                                        return false;
+                                }
+                        }
+                }
+                return true;
+        }
+
+        // returns root slot or -1
+        int run() {
+                if (!validate())
+                        return -1;
+                int rs;
+                if (is_leaf(root)) {
+                        rs = int(next_slot++);
+                        leaf(root, M_SET, uint32_t(rs), true, {}, 0);
+                } else
+                        rs = node(root, true, {});
+                if (rs < 0)
+                        return -1;
+                // second pass for leaves whose contribution is conditional on a disjunction branch matching
+                for (auto &d : deferred) {
+                        uint32_t mask = d.cond[0];
+                        if (d.cond.size() > 1) {
+                                if (next_slot >= 14) {
+                                        err = "query needs more than 14 docset slots";
+                                        return -1;
+                                }
+                                mask = next_slot++;
+                                push(OP_SLOT, M_SET, mask, d.cond[0], 0, 0, 0);
+                                for (size_t j = 1; j < d.cond.size(); ++j)
+                                        push(OP_SLOT, M_AND, mask, d.cond[j], 0, 0, 0);
+                        }
+                        push(OP_LEAFSCORE, M_NONE, 0, mask, 0, d.term, d.idf);
+                }
+                return rs;
+        }
+};
+} // namespace
+
+// =================================================================================================== C ABI: lifecycle
+extern "C" int trn_create(int device, trn_ctx **out) {
+        if (!out)
+                return TRN_ERR_ARG;
+        auto c    = new trn_ctx();
+        c->device = device;
+        *out      = c;
+        int ndev{0};
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || device < 0 || device >= ndev) {
+                // No silent CPU fallback: the context is unusable without a CUDA device.
+                c->err = std::string("trn_create: no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range") + ")";
+                return TRN_ERR_CUDA;
+        }
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        c->num_sms = prop.multiProcessorCount;
+        CK(cudaEventCreate(&c->ev0));
+        CK(cudaEventCreate(&c->ev1));
+        return TRN_OK;
+}
+
+extern "C" void trn_destroy(trn_ctx *c) {
+        if (!c)
+                return;
+        cudaSetDevice(c->device);
+        for (DevBuf *b : {&c->d_index, &c->d_blk_last, &c->d_blk_off, &c->d_terms, &c->d_tile_first, &c->d_queries, &c->d_steps, &c->d_small, &c->d_item_off,
+                          &c->d_item_cnt, &c->d_item_dst, &c->d_seg_docids, &c->d_seg_scores, &c->d_out_docids, &c->d_out_scores, &c->d_q_offsets, &c->d_cand,
+                          &c->d_topk_docids, &c->d_topk_scores, &c->d_topk_counts, &c->d_dec_a, &c->d_dec_b, &c->d_dec_c, &c->d_dec_docids, &c->d_dec_freqs,
+                          &c->d_dec_sums, &c->d_merge_docids, &c->d_merge_scores})
+                b->release();
+        for (PinBuf *b : {&c->h_offsets, &c->h_docids, &c->h_scores, &c->h_counts, &c->h_small})
+                b->release();
+        if (c->ev0)
+                cudaEventDestroy(c->ev0);
+        if (c->ev1)
+                cudaEventDestroy(c->ev1);
+        delete c;
+}
+
+extern "C" const char *trn_last_error(trn_ctx *c) {
+        return c ? c->err.c_str() : "null ctx";
+}
+
+extern "C" int trn_set_stream(trn_ctx *c, void *s) {
+        if (!c)
+                return TRN_ERR_ARG;
+        c->stream = static_cast<cudaStream_t>(s);
+        return TRN_OK;
+}
+
+// =================================================================================================== upload
+extern "C" int trn_upload_index(trn_ctx *c, int codec, const uint8_t *index, uint64_t nbytes, const trn_term *terms, uint32_t nterms, uint32_t max_docid) {
+        if (!c || !index || !terms || (codec != TRN_CODEC_GOOGLE && codec != TRN_CODEC_LUCENE))
+                return c ? fail(c, TRN_ERR_ARG, "trn_upload_index: bad arguments") : TRN_ERR_ARG;
+        if (nbytes >= (1ull << 32))
+                return fail(c, TRN_ERR_ARG, "index larger than 4 GiB: one IndexSource is limited to range32_t offsets (codecs.h:17-55); shard it");
+        CK(cudaSetDevice(c->device));
+        BlockDirectory dir;
+        try {
+                std::vector<term_index_ctx> t(nterms);
+                for (uint32_t i = 0; i < nterms; ++i) {
+                        t[i].documents = terms[i].documents;
+                        t[i].offset    = terms[i].chunk_off;
+                        t[i].size      = terms[i].chunk_len;
+                }
+                const int threads = int(std::max(1u, std::min(64u, std::thread::hardware_concurrency())));
+                build_block_directory(codec == TRN_CODEC_GOOGLE ? Codec::Google : Codec::Lucene, index, nbytes, t.data(), nterms, threads, dir);
+        } catch (const std::exception &e) {
+                return fail(c, TRN_ERR_FORMAT, e.what());
+        }
+        c->codec      = codec;
+        c->nterms     = nterms;
+        c->max_docid  = max_docid;
+        const uint32_t W = 1u << c->tile_shift;
+        c->ntiles     = uint32_t((uint64_t(max_docid) + 1 + W - 1) >> c->tile_shift);
+        c->h_terms.resize(nterms);
+        c->total_blocks   = 0;
+        c->total_postings = 0;
+        for (uint32_t i = 0; i < nterms; ++i) {
+                auto &d     = c->h_terms[i];
+                d.documents = dir.terms[i].documents;
+                d.dir_begin = dir.terms[i].dir_begin;
+                d.nblocks   = dir.terms[i].nblocks;
+                d.first_doc = dir.terms[i].first_doc;
+                d.last_doc  = dir.terms[i].last_doc;
+                d.chunk_len = terms[i].chunk_len;
+                c->total_blocks += d.nblocks;
+                c->total_postings += d.documents;
+                if (d.nblocks && d.last_doc > max_docid)
+                        return fail(c, TRN_ERR_ARG, "a term holds a docID above max_docid");
+        }
+        // tile directory: first block of every term whose last docID reaches the tile (O(1) replacement for skiplist_search,
+        // google_codec.cpp:464-495 / lucene_codec.cpp:596-656)
+        std::vector<uint32_t> tf(size_t(nterms) * (c->ntiles + 1));
+        {
+                const uint32_t nthreads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+                auto           work     = [&](uint32_t tid) {
+                        for (uint32_t t = tid; t < nterms; t += nthreads) {
+                                const auto &    d  = c->h_terms[t];
+                                const uint32_t *bl = dir.blk_last.data() + d.dir_begin;
+                                uint32_t *      o  = tf.data() + size_t(t) * (c->ntiles + 1);
+                                uint32_t        b  = 0;
+                                for (uint32_t j = 0; j <= c->ntiles; ++j) {
+                                        const uint64_t lo = uint64_t(j) << c->tile_shift;
+                                        while (b < d.nblocks && bl[b] < lo)
+                                                ++b;
+                                        o[j] = b;
+                                }
+                        }
+                };
+                std::vector<std::thread> ths;
+                for (uint32_t i = 1; i < nthreads; ++i)
+                        ths.emplace_back(work, i);
+                work(0);
+                for (auto &t : ths)
+                        t.join();
+        }
+        CK(c->d_index.ensure(nbytes + 64));
+        CK(cudaMemsetAsync(c->d_index.p, 0, nbytes + 64, c->stream));
+        CK(cudaMemcpyAsync(c->d_index.p, index, nbytes, cudaMemcpyHostToDevice, c->stream));
+        const size_t nent = dir.blk_last.size();
+        CK(c->d_blk_last.ensure(std::max<size_t>(4, nent * 4)));
+        CK(c->d_blk_off.ensure(std::max<size_t>(4, nent * 4)));
+        CK(cudaMemcpyAsync(c->d_blk_last.p, dir.blk_last.data(), nent * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_blk_off.p, dir.blk_off.data(), nent * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(c->d_terms.ensure(std::max<size_t>(4, nterms * sizeof(DevTerm))));
+        CK(cudaMemcpyAsync(c->d_terms.p, c->h_terms.data(), nterms * sizeof(DevTerm), cudaMemcpyHostToDevice, c->stream));
+        CK(c->d_tile_first.ensure(std::max<size_t>(4, tf.size() * 4)));
+        CK(cudaMemcpyAsync(c->d_tile_first.p, tf.data(), tf.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->index_bytes = nbytes;
+        c->dir_bytes   = nent * 8 + tf.size() * 4 + nterms * sizeof(DevTerm);
+        c->have_index  = true;
+        return TRN_OK;
+}
+
+extern "C" int trn_index_info_get(trn_ctx *c, trn_index_info *o) {
+        if (!c || !o)
+                return TRN_ERR_ARG;
+        if (!c->have_index)
+                return fail(c, TRN_ERR_STATE, "no index uploaded");
+        o->codec           = c->codec;
+        o->nterms          = c->nterms;
+        o->max_docid       = c->max_docid;
+        o->tile_docs       = 1u << c->tile_shift;
+        o->ntiles          = c->ntiles;
+        o->index_bytes     = c->index_bytes;
+        o->directory_bytes = c->dir_bytes;
+        o->total_blocks    = c->total_blocks;
+        o->total_postings  = c->total_postings;
+        return TRN_OK;
+}
+
+static DevIndex dev_index(trn_ctx *c) {
+        DevIndex ix;
+        ix.index      = c->d_index.as<uint8_t>();
+        ix.blk_last   = c->d_blk_last.as<uint32_t>();
+        ix.blk_off    = c->d_blk_off.as<uint32_t>();
+        ix.terms      = c->d_terms.as<DevTerm>();
+        ix.tile_first = c->d_tile_first.as<uint32_t>();
+        ix.nterms     = c->nterms;
+        ix.ntiles     = c->ntiles;
+        ix.tile_shift = c->tile_shift;
+        ix.max_docid  = c->max_docid;
+        ix.codec      = c->codec;
+        return ix;
+}
+
+// =================================================================================================== exec
+// small device scratch layout (d_small): [0] ticket u32, [2..3] seg_cursor u64, [4] overflow u32, then per-query arrays
+extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint32_t nq, int mode, uint32_t k, trn_result *out) {
+        if (!c)
+                return TRN_ERR_ARG;
+        if (!c->have_index)
+                return fail(c, TRN_ERR_STATE, "no index uploaded");
+        if (!queries || !nq || mode < 0 || mode > 2)
+                return fail(c, TRN_ERR_ARG, "trn_exec_batch: bad arguments");
+        if (mode == TRN_MODE_SCORED_TOPK && (k == 0 || k > kernel_max_k()))
+                return fail(c, TRN_ERR_ARG, "top-k: k must be in [1, 512]");
+        CK(cudaSetDevice(c->device));
+        const bool scored = mode != TRN_MODE_DOCS_ONLY;
+
+        std::vector<DevQuery> hq(nq);
+        std::vector<DevStep>  steps;
+        uint32_t              maxSlots{1};
+        uint64_t              items{0}, segCap{0}, candTotal{0}, postings{0}, bytes{0};
+        for (uint32_t q = 0; q < nq; ++q) {
+                const auto &Q = queries[q];
+                if (!Q.nodes || !Q.nnodes)
+                        return fail(c, TRN_ERR_ARG, "empty query");
+                Compiler cc(Q.nodes, Q.nnodes, c->h_terms, scored, Q.root, steps);
+                auto &   dq     = hq[q];
+                dq.step_begin   = uint32_t(steps.size());
+                const int rs    = cc.run();
+                if (rs < 0)
+                        return fail(c, TRN_ERR_ARG, "query " + std::to_string(q) + ": " + cc.err);
+                dq.nsteps    = uint32_t(steps.size()) - dq.step_begin;
+                dq.root_slot = uint32_t(rs);
+                maxSlots     = std::max(maxSlots, cc.next_slot + 1); // + scratch slot
+                postings += cc.postings;
+                bytes += cc.bytes;
+                const Range r = cc.range(Q.root);
+                if (r.empty()) {
+                        dq.tile_lo = 0;
+                        dq.ntiles  = 0;
+                } else {
+                        dq.tile_lo = r.lo >> c->tile_shift;
+                        dq.ntiles  = (r.hi >> c->tile_shift) - dq.tile_lo + 1;
+                }
+                dq.item_base = uint32_t(items);
+                items += dq.ntiles;
+                if (items >= (1ull << 32))
+                        return fail(c, TRN_ERR_CAPACITY, "batch has more than 2^32 (query, tile) work items; split it");
+                const uint64_t width = r.empty() ? 0 : uint64_t(r.hi) - r.lo + 1;
+                segCap += std::min(cc.bound(Q.root), width);
+                dq.cand_base = uint32_t(candTotal);
+                dq.cand_cap  = uint32_t(std::min<uint64_t>(uint64_t(dq.ntiles) * k, 0xffffffffull));
+                if (mode == TRN_MODE_SCORED_TOPK) {
+                        candTotal += dq.cand_cap;
+                        if (candTotal >= (1ull << 32))
+                                return fail(c, TRN_ERR_CAPACITY, "top-k candidate space exceeds 2^32 entries; split the batch");
+                }
+        }
+        const uint32_t totalItems = uint32_t(items);
+
+        // ---- device buffers
+        CK(c->d_queries.ensure(nq * sizeof(DevQuery)));
+        CK(c->d_steps.ensure(std::max<size_t>(sizeof(DevStep), steps.size() * sizeof(DevStep))));
+        const size_t smallBytes = 64 + size_t(nq) * (8 + 4 + 4);
+        CK(c->d_small.ensure(smallBytes));
+        CK(c->d_q_offsets.ensure((size_t(nq) + 1) * 8));
+        if (mode != TRN_MODE_SCORED_TOPK) {
+                CK(c->d_item_off.ensure(std::max<size_t>(8, size_t(totalItems) * 8)));
+                CK(c->d_item_cnt.ensure(std::max<size_t>(4, size_t(totalItems) * 4)));
+                CK(c->d_item_dst.ensure(std::max<size_t>(8, size_t(totalItems) * 8)));
+                CK(c->d_seg_docids.ensure(std::max<size_t>(4, segCap * 4)));
+                CK(c->d_out_docids.ensure(std::max<size_t>(4, segCap * 4)));
+                if (scored) {
+                        CK(c->d_seg_scores.ensure(std::max<size_t>(4, segCap * 4)));
+                        CK(c->d_out_scores.ensure(std::max<size_t>(4, segCap * 4)));
+                }
+        } else {
+                CK(c->d_cand.ensure(std::max<size_t>(8, candTotal * 8)));
+                CK(c->d_topk_docids.ensure(size_t(nq) * k * 4));
+                CK(c->d_topk_scores.ensure(size_t(nq) * k * 4));
+                CK(c->d_topk_counts.ensure(size_t(nq) * 4));
+        }
+        uint8_t *small        = c->d_small.as<uint8_t>();
+        auto *   ticket       = reinterpret_cast<uint32_t *>(small);
+        auto *   seg_cursor   = reinterpret_cast<unsigned long long *>(small + 8);
+        auto *   overflow     = reinterpret_cast<uint32_t *>(small + 16);
+        auto *   match_counts = reinterpret_cast<unsigned long long *>(small + 64);
+        auto *   theta        = reinterpret_cast<uint32_t *>(small + 64 + size_t(nq) * 8);
+        auto *   cand_cursor  = reinterpret_cast<uint32_t *>(small + 64 + size_t(nq) * 12);
+
+        CK(cudaEventRecord(c->ev0, c->stream));
+        CK(cudaMemcpyAsync(c->d_queries.p, hq.data(), nq * sizeof(DevQuery), cudaMemcpyHostToDevice, c->stream));
+        if (!steps.empty())
+                CK(cudaMemcpyAsync(c->d_steps.p, steps.data(), steps.size() * sizeof(DevStep), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(small, 0, smallBytes, c->stream));
+
+        ExecParams P;
+        std::memset(&P, 0, sizeof(P));
+        P.ix           = dev_index(c);
+        P.queries      = c->d_queries.as<DevQuery>();
+        P.steps        = c->d_steps.as<DevStep>();
+        P.nq           = nq;
+        P.total_items  = totalItems;
+        P.nslots       = maxSlots;
+        P.mode         = mode;
+        P.k            = k;
+        P.ticket       = ticket;
+        P.seg_cursor   = seg_cursor;
+        P.seg_capacity = segCap;
+        P.seg_docids   = c->d_seg_docids.as<uint32_t>();
+        P.seg_scores   = scored ? c->d_seg_scores.as<float>() : nullptr;
+        P.item_off     = c->d_item_off.as<uint64_t>();
+        P.item_cnt     = c->d_item_cnt.as<uint32_t>();
+        P.match_counts = match_counts;
+        P.theta        = theta;
+        P.cand_cursor  = cand_cursor;
+        P.cand         = c->d_cand.as<uint2>();
+        P.overflow     = overflow;
+
+        uint32_t launches{0};
+        if (totalItems) {
+                const int perSM = exec_max_ctas_per_sm(c->tile_shift, maxSlots, mode);
+                if (perSM <= 0)
+                        return fail(c, TRN_ERR_CUDA, "k_exec_tiles does not fit on an SM with this many docset slots");
+                const int grid = int(std::min<uint64_t>(uint64_t(c->num_sms) * perSM, totalItems));
+                CK(launch_exec_tiles(P, grid, c->stream));
+                ++launches;
+        }
+        if (mode != TRN_MODE_SCORED_TOPK) {
+                CK(launch_query_scan(match_counts, nq, c->d_q_offsets.as<uint64_t>(), c->stream));
+                ++launches;
+                if (totalItems) {
+                        CK(launch_item_scan(P.queries, nq, P.item_cnt, c->d_q_offsets.as<uint64_t>(), c->d_item_dst.as<uint64_t>(), c->stream));
+                        CK(launch_gather(totalItems, P.item_off, P.item_cnt, c->d_item_dst.as<uint64_t>(), P.seg_docids, P.seg_scores,
+                                         c->d_out_docids.as<uint32_t>(), scored ? c->d_out_scores.as<float>() : nullptr, c->stream));
+                        launches += 2;
+                }
+        } else {
+                CK(launch_topk_select(P.queries, nq, P.cand, cand_cursor, k, c->d_topk_docids.as<uint32_t>(), c->d_topk_scores.as<float>(),
+                                      c->d_topk_counts.as<uint32_t>(), c->stream));
+                ++launches;
+        }
+        CK(cudaEventRecord(c->ev1, c->stream));
+        c->last_mode     = mode;
+        c->last_nq       = nq;
+        c->last_k        = k;
+        c->last_launches = launches;
+        c->last_postings = postings;
+        c->last_bytes    = bytes;
+        if (out) {
+                std::memset(out, 0, sizeof(*out));
+                out->nq                  = nq;
+                out->postings_scanned    = postings;
+                out->index_bytes_touched = bytes;
+                out->kernel_launches     = launches;
+        }
+        return TRN_OK;
+}
+
+extern "C" int trn_fetch_results(trn_ctx *c, trn_result *out) {
+        if (!c || !out)
+                return TRN_ERR_ARG;
+        if (c->last_mode < 0)
+                return fail(c, TRN_ERR_STATE, "no batch executed");
+        CK(cudaSetDevice(c->device));
+        const uint32_t nq = c->last_nq;
+        const uint8_t *small        = c->d_small.as<uint8_t>();
+        const auto *   match_counts = reinterpret_cast<const unsigned long long *>(small + 64);
+        CK(c->h_offsets.ensure((size_t(nq) + 1) * 8));
+        CK(c->h_counts.ensure(size_t(nq) * 8));
+        CK(c->h_small.ensure(64 + size_t(nq) * 4));
+        CK(cudaMemcpyAsync(c->h_counts.p, match_counts, size_t(nq) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(c->h_small.p, small, 64, cudaMemcpyDeviceToHost, c->stream));
+        std::memset(out, 0, sizeof(*out));
+        out->nq = nq;
+        if (c->last_mode != TRN_MODE_SCORED_TOPK) {
+                CK(cudaMemcpyAsync(c->h_offsets.p, c->d_q_offsets.p, (size_t(nq) + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+                if (c->h_small.as<uint32_t>()[4])
+                        return fail(c, TRN_ERR_CAPACITY, "segment buffer overflow (internal bound violated)");
+                const uint64_t total = c->h_offsets.as<uint64_t>()[nq];
+                CK(c->h_docids.ensure(std::max<size_t>(4, total * 4)));
+                if (total)
+                        CK(cudaMemcpyAsync(c->h_docids.p, c->d_out_docids.p, total * 4, cudaMemcpyDeviceToHost, c->stream));
+                if (c->last_mode == TRN_MODE_SCORED_ALL) {
+                        CK(c->h_scores.ensure(std::max<size_t>(4, total * 4)));
+                        if (total)
+                                CK(cudaMemcpyAsync(c->h_scores.p, c->d_out_scores.p, total * 4, cudaMemcpyDeviceToHost, c->stream));
+                        out->scores = c->h_scores.as<float>();
+                }
+                CK(cudaStreamSynchronize(c->stream));
+                out->total  = total;
+                out->docids = c->h_docids.as<uint32_t>();
+        } else {
+                const uint32_t k = c->last_k;
+                CK(c->h_docids.ensure(size_t(nq) * k * 4));
+                CK(c->h_scores.ensure(size_t(nq) * k * 4));
+                uint32_t *hc = c->h_small.as<uint32_t>() + 16;
+                CK(cudaMemcpyAsync(c->h_docids.p, c->d_topk_docids.p, size_t(nq) * k * 4, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaMemcpyAsync(c->h_scores.p, c->d_topk_scores.p, size_t(nq) * k * 4, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaMemcpyAsync(hc, c->d_topk_counts.p, size_t(nq) * 4, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+                // fixed stride k per query: offsets[q] = q*k, valid entries = counts
+                uint64_t *off = c->h_offsets.as<uint64_t>();
+                uint64_t  tot{0};
+                for (uint32_t q = 0; q < nq; ++q) {
+                        off[q] = uint64_t(q) * k;
+                        tot += hc[q];
+                }
+                off[nq]     = uint64_t(nq) * k;
+                out->total  = tot;
+                out->docids = c->h_docids.as<uint32_t>();
+                out->scores = c->h_scores.as<float>();
+        }
+        out->offsets             = c->h_offsets.as<uint64_t>();
+        out->match_counts        = c->h_counts.as<uint64_t>();
+        out->postings_scanned    = c->last_postings;
+        out->index_bytes_touched = c->last_bytes;
+        out->kernel_launches     = c->last_launches;
+        float ms{0};
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
+                out->device_ms = ms;
+        c->last_ms = ms;
+        return TRN_OK;
+}
+
+extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq, int mode, uint32_t k, trn_result *out) {
+        const int r = trn_exec_batch_device(c, queries, nq, mode, k, nullptr);
+        if (r != TRN_OK)
+                return r;
+        return trn_fetch_results(c, out);
+}
+
+extern "C" int trn_last_topk_device(trn_ctx *c, void **docids, void **scores, void **counts) {
+        if (!c)
+                return TRN_ERR_ARG;
+        if (c->last_mode != TRN_MODE_SCORED_TOPK)
+                return fail(c, TRN_ERR_STATE, "last batch was not SCORED_TOPK");
+        if (docids)
+                *docids = c->d_topk_docids.p;
+        if (scores)
+                *scores = c->d_topk_scores.p;
+        if (counts)
+                *counts = c->d_topk_counts.p;
+        return TRN_OK;
+}
+
+extern "C" int trn_merge_topk(trn_ctx *c, const void *docids, const void *scores, uint32_t nshards, uint32_t nq, uint32_t k, void *out_docids, void *out_scores) {
+        if (!c || !docids || !scores || !out_docids || !out_scores || !nshards || !nq || !k || k > kernel_max_k())
+                return c ? fail(c, TRN_ERR_ARG, "trn_merge_topk: bad arguments") : TRN_ERR_ARG;
+        CK(cudaSetDevice(c->device));
+        CK(launch_topk_merge(static_cast<const uint32_t *>(docids), static_cast<const float *>(scores), nshards, nq, k, static_cast<uint32_t *>(out_docids),
+                             static_cast<float *>(out_scores), c->stream));
+        return TRN_OK;
+}
+
+// =================================================================================================== decode probe
+extern "C" int trn_decode_terms(trn_ctx *c, const uint32_t *term_ids, uint32_t nterms, int materialise, uint32_t *docids, uint32_t *freqs, uint64_t *sums,
+                                float *device_ms) {
+        if (!c)
+                return TRN_ERR_ARG;
+        if (!c->have_index)
+                return fail(c, TRN_ERR_STATE, "no index uploaded");
+        if (!term_ids || !nterms || (materialise && (!docids || !freqs)))
+                return fail(c, TRN_ERR_ARG, "trn_decode_terms: bad arguments");
+        CK(cudaSetDevice(c->device));
+        std::vector<uint32_t> unit_base(nterms + 1);
+        std::vector<uint64_t> out_base(nterms + 1);
+        uint64_t              units{0}, posts{0};
+        for (uint32_t i = 0; i < nterms; ++i) {
+                if (term_ids[i] >= c->nterms)
+                        return fail(c, TRN_ERR_ARG, "term id out of range");
+                const auto &t = c->h_terms[term_ids[i]];
+                unit_base[i]  = uint32_t(units);
+                out_base[i]   = posts;
+                units += c->codec == TRN_CODEC_GOOGLE ? (t.nblocks + 31) / 32 : t.nblocks;
+                posts += t.documents;
+                if (units >= (1ull << 32))
+                        return fail(c, TRN_ERR_CAPACITY, "too many decode units");
+        }
+        unit_base[nterms] = uint32_t(units);
+        out_base[nterms]  = posts;
+        CK(c->d_dec_a.ensure(nterms * 4));
+        CK(c->d_dec_b.ensure((nterms + 1) * 4));
+        CK(c->d_dec_c.ensure((nterms + 1) * 8));
+        CK(c->d_dec_sums.ensure(size_t(nterms) * 16));
+        if (materialise) {
+                CK(c->d_dec_docids.ensure(std::max<size_t>(4, posts * 4)));
+                CK(c->d_dec_freqs.ensure(std::max<size_t>(4, posts * 4)));
+        }
+        CK(cudaMemcpyAsync(c->d_dec_a.p, term_ids, nterms * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_dec_b.p, unit_base.data(), (nterms + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_dec_c.p, out_base.data(), (nterms + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(c->d_dec_sums.p, 0, size_t(nterms) * 16, c->stream));
+        CK(cudaEventRecord(c->ev0, c->stream));
+        if (units) {
+                const int grid = int(std::min<uint64_t>(uint64_t(c->num_sms) * 8, (units + 3) / 4));
+                CK(launch_decode_terms(dev_index(c), c->d_dec_a.as<uint32_t>(), c->d_dec_b.as<uint32_t>(), c->d_dec_c.as<uint64_t>(), nterms, uint32_t(units),
+                                       materialise ? c->d_dec_docids.as<uint32_t>() : nullptr, materialise ? c->d_dec_freqs.as<uint32_t>() : nullptr,
+                                       c->d_dec_sums.as<unsigned long long>(), grid, c->stream));
+        }
+        CK(cudaEventRecord(c->ev1, c->stream));
+        if (materialise && posts) {
+                CK(cudaMemcpyAsync(docids, c->d_dec_docids.p, posts * 4, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaMemcpyAsync(freqs, c->d_dec_freqs.p, posts * 4, cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (sums)
+                CK(cudaMemcpyAsync(sums, c->d_dec_sums.p, size_t(nterms) * 16, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (device_ms) {
+                float ms{0};
+                CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+                *device_ms = ms;
+        }
+        return TRN_OK;
+}

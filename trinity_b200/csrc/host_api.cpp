@@ -1,0 +1,580 @@
+// Host-side half of the C ABI: index builder, synthetic workload generator, query front-end, BM25 weights.
+// (The device half lives in engine.cu.)  No reference code is linked here; formats are pinned by tests against oracle/_ref.
+#include "../../include/trinity_b200.h"
+#include "codecs.h"
+#include "varbyte.h"
+#include <algorithm>
+#include <atomic>
+#include <cctype>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+using namespace trn;
+
+static constexpr uint32_t kEmptyTerm = 0xffffffffu; // == device_types.h
+
+// =================================================================================================== builder
+struct trn_builder {
+        Codecs::IndexSession             sess;
+        std::unique_ptr<Codecs::Encoder> enc;
+        std::string                      err;
+        explicit trn_builder(Codec c)
+            : sess{c}, enc{Codecs::new_encoder(&sess)} {
+        }
+};
+
+template <class F> static int guarded(trn_builder *b, F &&f) {
+        if (!b)
+                return TRN_ERR_ARG;
+        try {
+                f();
+                return TRN_OK;
+        } catch (const std::exception &e) {
+                b->err = e.what();
+        } catch (...) {
+                b->err = "unknown error";
+        }
+        return TRN_ERR_ARG;
+}
+
+extern "C" int trn_builder_create(int codec, trn_builder **out) {
+        if (!out || (codec != TRN_CODEC_GOOGLE && codec != TRN_CODEC_LUCENE))
+                return TRN_ERR_ARG;
+        *out = new trn_builder(codec == TRN_CODEC_GOOGLE ? Codec::Google : Codec::Lucene);
+        return TRN_OK;
+}
+extern "C" void trn_builder_destroy(trn_builder *b) {
+        delete b;
+}
+extern "C" const char *trn_builder_last_error(trn_builder *b) {
+        return b ? b->err.c_str() : "null builder";
+}
+extern "C" int trn_builder_begin_term(trn_builder *b) {
+        return guarded(b, [&] { b->enc->begin_term(); });
+}
+extern "C" int trn_builder_begin_document(trn_builder *b, uint32_t docid) {
+        return guarded(b, [&] { b->enc->begin_document(docid); });
+}
+extern "C" int trn_builder_new_hit(trn_builder *b, uint32_t position, const uint8_t *payload, uint8_t payload_len) {
+        return guarded(b, [&] { b->enc->new_hit(position, payload, payload_len); });
+}
+extern "C" int trn_builder_end_document(trn_builder *b) {
+        return guarded(b, [&] { b->enc->end_document(); });
+}
+extern "C" int trn_builder_end_term(trn_builder *b, trn_term *out) {
+        return guarded(b, [&] {
+                term_index_ctx t;
+                b->enc->end_term(&t);
+                if (out) {
+                        out->documents = t.documents;
+                        out->chunk_off = t.offset;
+                        out->chunk_len = t.size;
+                }
+        });
+}
+extern "C" int trn_builder_add_term(trn_builder *b, const uint32_t *docids, const uint32_t *freqs, uint32_t n, const uint32_t *positions, trn_term *out) {
+        return guarded(b, [&] {
+                size_t pi{0};
+                b->enc->begin_term();
+                for (uint32_t i = 0; i < n; ++i) {
+                        b->enc->begin_document(docids[i]);
+                        for (uint32_t k = 0; k < freqs[i]; ++k)
+                                b->enc->new_hit(positions ? positions[pi++] : k + 1);
+                        b->enc->end_document();
+                }
+                term_index_ctx t;
+                b->enc->end_term(&t);
+                if (out) {
+                        out->documents = t.documents;
+                        out->chunk_off = t.offset;
+                        out->chunk_len = t.size;
+                }
+        });
+}
+extern "C" int trn_builder_set_google_skiplist_countdown(trn_builder *b, uint32_t countdown) {
+        return guarded(b, [&] {
+                if (b->sess.codec != Codec::Google || countdown == 0 || countdown > Codecs::Google::SKIPLIST_STEP)
+                        throw std::invalid_argument("countdown only applies to the GOOGLE codec, range 1..8");
+                static_cast<Codecs::Google::Encoder *>(b->enc.get())->skiplistEntryCountdown = countdown;
+        });
+}
+extern "C" int trn_builder_index(trn_builder *b, const uint8_t **index, uint64_t *nbytes) {
+        if (!b || !index || !nbytes)
+                return TRN_ERR_ARG;
+        *index  = b->sess.indexOut.data();
+        *nbytes = b->sess.indexOut.size();
+        return TRN_OK;
+}
+extern "C" int trn_builder_hits(trn_builder *b, const uint8_t **hits, uint64_t *nbytes) {
+        if (!b || !hits || !nbytes)
+                return TRN_ERR_ARG;
+        *hits   = b->sess.positionsOut.data();
+        *nbytes = b->sess.positionsOut.size();
+        return TRN_OK;
+}
+
+// =================================================================================================== synthetic index
+namespace {
+inline uint64_t splitmix64(uint64_t &s) {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z          = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z          = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+}
+
+inline uint32_t synth_df(uint32_t ndocs, uint32_t rank, uint32_t min_df) {
+        const uint64_t z = uint64_t(ndocs) / (2ull * rank); // floor(0.5 * N / r)
+        return uint32_t(std::min<uint64_t>(ndocs, std::max<uint64_t>(min_df, z)));
+}
+
+// Calls f(docid, freq, stateForPositions) for each posting of term `rank`
+template <class F> void synth_term(uint32_t ndocs, uint32_t rank, uint32_t min_df, uint64_t seed, F &&f) {
+        const uint32_t df = synth_df(ndocs, rank, min_df);
+        uint64_t       s  = seed ^ uint64_t(rank);
+        uint64_t       s2 = (seed ^ uint64_t(rank)) * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull;
+        const double   p  = double(df) / double(ndocs);
+        const double   il = p < 1.0 ? 1.0 / std::log1p(-p) : 0.0;
+        uint64_t       doc{0};
+        for (uint32_t i = 0; i < df; ++i) {
+                const uint64_t x = splitmix64(s);
+                uint64_t       gap{1};
+                if (p < 1.0) {
+                        const double u = double((x >> 11) + 1) * (1.0 / 9007199254740992.0); // (0, 1]
+                        const double g = std::floor(std::log(u) * il);
+                        gap            = 1 + uint64_t(std::min(g, 4.0e9));
+                }
+                const uint64_t maxdoc = uint64_t(ndocs) - (df - 1 - i);
+                doc                   = std::min(doc + gap, maxdoc);
+                const uint32_t geo    = uint32_t(__builtin_ctzll((x & 0x7ffull) | 0x800ull));
+                const uint32_t freq   = 1 + std::min<uint32_t>(7, geo);
+                f(uint32_t(doc), freq, splitmix64(s2));
+        }
+}
+
+// positions of one document: cumulative steps 2..17 (== 1 + u(1..16)), < Limits::MaxPosition (trinity_limits.h:15)
+inline uint32_t synth_pos_step(uint64_t y, uint32_t h) {
+        return 2u + uint32_t((y >> (4u * h)) & 15u);
+}
+} // namespace
+
+struct trn_synth {
+        Codec                 codec;
+        std::vector<uint8_t>  index, hits;
+        std::vector<trn_term> terms;
+        uint64_t              sumHits{0};
+};
+
+extern "C" int trn_synth_build(int codec, uint32_t ndocs, uint32_t nterms, uint32_t min_df, uint64_t seed, int with_hits, int threads, trn_synth **out) {
+        if (!out || !ndocs || !nterms || (codec != TRN_CODEC_GOOGLE && codec != TRN_CODEC_LUCENE))
+                return TRN_ERR_ARG;
+        const Codec cd = codec == TRN_CODEC_GOOGLE ? Codec::Google : Codec::Lucene;
+        struct Part {
+                std::vector<uint8_t> index, hits;
+                term_index_ctx       t;
+                uint64_t             hitsCnt{0};
+        };
+        std::vector<Part> parts(nterms);
+        // Google: the skiplist countdown carries over between terms (google_codec.h:57): phase = committed blocks so far mod 8
+        std::vector<uint32_t> countdown(nterms, Codecs::Google::SKIPLIST_STEP);
+        {
+                uint64_t blocks{0};
+                for (uint32_t r = 1; r <= nterms; ++r) {
+                        countdown[r - 1] = Codecs::Google::SKIPLIST_STEP - uint32_t(blocks % Codecs::Google::SKIPLIST_STEP);
+                        blocks += (synth_df(ndocs, r, min_df) + Codecs::Google::N - 1) / Codecs::Google::N;
+                }
+        }
+        std::atomic<uint32_t> next{0};
+        std::atomic<bool>     failed{false};
+        auto                  worker = [&] {
+                for (;;) {
+                        const uint32_t i = next.fetch_add(1);
+                        if (i >= nterms || failed.load())
+                                break;
+                        try {
+                                Codecs::IndexSession             sess(cd);
+                                std::unique_ptr<Codecs::Encoder> enc(Codecs::new_encoder(&sess));
+                                if (cd == Codec::Google)
+                                        static_cast<Codecs::Google::Encoder *>(enc.get())->skiplistEntryCountdown = countdown[i];
+                                auto &P = parts[i];
+                                enc->begin_term();
+                                synth_term(ndocs, i + 1, min_df, seed, [&](uint32_t doc, uint32_t freq, uint64_t y) {
+                                        enc->begin_document(doc);
+                                        if (with_hits) {
+                                                uint32_t pos{0};
+                                                for (uint32_t h = 0; h < freq; ++h) {
+                                                        pos += synth_pos_step(y, h);
+                                                        enc->new_hit(pos);
+                                                }
+                                        } else {
+                                                for (uint32_t h = 0; h < freq; ++h)
+                                                        enc->new_hit(h + 1);
+                                        }
+                                        P.hitsCnt += freq;
+                                        enc->end_document();
+                                });
+                                enc->end_term(&P.t);
+                                P.index.swap(sess.indexOut);
+                                P.hits.swap(sess.positionsOut);
+                        } catch (...) {
+                                failed.store(true);
+                        }
+                }
+        };
+        if (threads < 1)
+                threads = int(std::max(1u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> ths;
+        for (int i = 1; i < threads; ++i)
+                ths.emplace_back(worker);
+        worker();
+        for (auto &t : ths)
+                t.join();
+        if (failed.load())
+                return TRN_ERR_FORMAT;
+        uint64_t ib{0}, hb{0};
+        for (auto &p : parts) {
+                ib += p.index.size();
+                hb += p.hits.size();
+        }
+        if (ib >= (1ull << 32) || hb >= (1ull << 32))
+                return TRN_ERR_CAPACITY; // range32_t limit of one IndexSource (codecs.h:17-55)
+        auto s   = new trn_synth();
+        s->codec = cd;
+        s->index.resize(ib);
+        s->hits.resize(hb);
+        s->terms.resize(nterms);
+        uint64_t io{0}, ho{0};
+        for (uint32_t i = 0; i < nterms; ++i) {
+                auto &p = parts[i];
+                std::memcpy(s->index.data() + io, p.index.data(), p.index.size());
+                if (cd == Codec::Lucene) {
+                        // the chunk header's first u32 is the term's absolute offset into hits.data (lucene_codec.cpp:178)
+                        const uint32_t v   = uint32_t(ho);
+                        s->index[io]       = uint8_t(v);
+                        s->index[io + 1]   = uint8_t(v >> 8);
+                        s->index[io + 2]   = uint8_t(v >> 16);
+                        s->index[io + 3]   = uint8_t(v >> 24);
+                        if (!p.hits.empty())
+                                std::memcpy(s->hits.data() + ho, p.hits.data(), p.hits.size());
+                }
+                s->terms[i].documents = p.t.documents;
+                s->terms[i].chunk_off = uint32_t(io);
+                s->terms[i].chunk_len = p.t.size;
+                s->sumHits += p.hitsCnt;
+                io += p.index.size();
+                ho += p.hits.size();
+                std::vector<uint8_t>().swap(p.index);
+                std::vector<uint8_t>().swap(p.hits);
+        }
+        *out = s;
+        return TRN_OK;
+}
+extern "C" void trn_synth_destroy(trn_synth *s) {
+        delete s;
+}
+extern "C" int trn_synth_index(trn_synth *s, const uint8_t **index, uint64_t *nbytes) {
+        if (!s || !index || !nbytes)
+                return TRN_ERR_ARG;
+        *index  = s->index.data();
+        *nbytes = s->index.size();
+        return TRN_OK;
+}
+extern "C" int trn_synth_hits(trn_synth *s, const uint8_t **hits, uint64_t *nbytes) {
+        if (!s || !hits || !nbytes)
+                return TRN_ERR_ARG;
+        *hits   = s->hits.data();
+        *nbytes = s->hits.size();
+        return TRN_OK;
+}
+extern "C" int trn_synth_terms(trn_synth *s, const trn_term **terms, uint32_t *nterms) {
+        if (!s || !terms || !nterms)
+                return TRN_ERR_ARG;
+        *terms  = s->terms.data();
+        *nterms = uint32_t(s->terms.size());
+        return TRN_OK;
+}
+extern "C" uint64_t trn_synth_sum_hits(trn_synth *s) {
+        return s ? s->sumHits : 0;
+}
+extern "C" int trn_synth_postings(uint32_t ndocs, uint32_t rank, uint32_t min_df, uint64_t seed, uint32_t *docids, uint32_t *freqs, uint32_t cap, uint32_t *n) {
+        if (!ndocs || !rank || !n)
+                return TRN_ERR_ARG;
+        uint32_t k{0};
+        synth_term(ndocs, rank, min_df, seed, [&](uint32_t doc, uint32_t freq, uint64_t) {
+                if (k < cap) {
+                        if (docids)
+                                docids[k] = doc;
+                        if (freqs)
+                                freqs[k] = freq;
+                }
+                ++k;
+        });
+        *n = k;
+        return TRN_OK;
+}
+extern "C" int trn_synth_positions(uint32_t ndocs, uint32_t rank, uint32_t min_df, uint64_t seed, uint32_t *positions, uint64_t cap, uint64_t *n) {
+        if (!ndocs || !rank || !n)
+                return TRN_ERR_ARG;
+        uint64_t k{0};
+        synth_term(ndocs, rank, min_df, seed, [&](uint32_t, uint32_t freq, uint64_t y) {
+                uint32_t pos{0};
+                for (uint32_t h = 0; h < freq; ++h) {
+                        pos += synth_pos_step(y, h);
+                        if (k < cap && positions)
+                                positions[k] = pos;
+                        ++k;
+                }
+        });
+        *n = k;
+        return TRN_OK;
+}
+
+// =================================================================================================== BM25 weights
+extern "C" double trn_bm25_idf(uint32_t doc_freq, uint64_t docs_cnt) {
+        // similarity.h:179-181: std::log(1 + (docsCnt - docFreq + 0.5f) / (docFreq + 0.5f)), evaluated in float
+        const float a = float(uint64_t(docs_cnt - doc_freq)) + 0.5f;
+        const float b = float(doc_freq) + 0.5f;
+        const float q = a / b;
+        return double(std::log(1.0f + q));
+}
+extern "C" float trn_bm25_score(double idf, uint16_t freq) {
+        const float f = float(freq);
+        return float(idf * double(f) / double(f + 1.2f));
+}
+
+// =================================================================================================== query front-end
+namespace {
+struct Ast {
+        int                  kind; // TRN_NODE_*
+        uint32_t             term{0};
+        std::vector<int>     kids;
+};
+
+struct Parser {
+        const char *                                     p, *e;
+        const std::unordered_map<std::string, uint32_t> &dict;
+        std::vector<Ast>                                 nodes;
+        std::string                                      err;
+
+        enum Op { NONE, AND, OR, NOT };
+        static int prio(Op o) {
+                // queries.cpp:11-27: STRICT_AND / AND / NOT = 8, OR = 7
+                return o == OR ? 7 : (o == NONE ? 0 : 8);
+        }
+        void ws() {
+                while (p < e && (*p == ' ' || *p == '\t' || *p == '\n'))
+                        ++p;
+        }
+        static bool isterm(char c) {
+                return std::isalnum(static_cast<unsigned char>(c)) || c == '_' || c == ':';
+        }
+        bool keyword(const char *kw, size_t n) const {
+                if (size_t(e - p) < n || std::strncmp(p, kw, n))
+                        return false;
+                if (p + n == e)
+                        return true;
+                const char c = p[n];
+                return c == ' ' || c == '\t' || c == '(' || c == ')' || c == '-' || c == '+' || c == '.';
+        }
+        // peeks the operator at the cursor; *len = bytes to consume
+        Op peek(size_t *len) {
+                ws();
+                *len = 0;
+                if (p >= e || *p == ')')
+                        return NONE;
+                if (keyword("AND", 3)) {
+                        *len = 3;
+                        return AND;
+                }
+                if (keyword("OR", 2)) {
+                        *len = 2;
+                        return OR;
+                }
+                if (keyword("NOT", 3)) {
+                        *len = 3;
+                        return NOT;
+                }
+                if (*p == '|') {
+                        size_t n = 0;
+                        while (p + n < e && p[n] == '|')
+                                ++n;
+                        *len = n;
+                        return OR;
+                }
+                if (*p == '-' && p + 1 < e && std::isalnum(static_cast<unsigned char>(p[1]))) {
+                        *len = 1;
+                        return NOT;
+                }
+                if (isterm(*p) || *p == '(')
+                        return AND; // juxtaposition
+                return NONE;
+        }
+        int add(int kind) {
+                nodes.push_back(Ast{kind});
+                return int(nodes.size()) - 1;
+        }
+        int unary() {
+                ws();
+                if (p < e && *p == '(') {
+                        ++p;
+                        const int x = subexpr(255);
+                        if (x < 0)
+                                return -1;
+                        ws();
+                        if (p >= e || *p != ')') {
+                                err = "expected ')'";
+                                return -1;
+                        }
+                        ++p;
+                        return x;
+                }
+                const char *b = p;
+                while (p < e && isterm(*p))
+                        ++p;
+                if (p == b) {
+                        err = "expected a term";
+                        return -1;
+                }
+                const std::string name(b, p);
+                if (name == "AND" || name == "OR" || name == "NOT") {
+                        err = "operator where a term was expected";
+                        return -1;
+                }
+                const int  x  = add(TRN_NODE_TERM);
+                const auto it = dict.find(name);
+                nodes[x].term = it == dict.end() ? kEmptyTerm : it->second;
+                return x;
+        }
+        // precedence climbing exactly as parse_subexpr (queries.cpp:477-520): continue while prio(op) < limit, rhs = subexpr(prio(op)),
+        // which makes OR bind tighter than AND/NOT and equal priorities left-associative
+        int subexpr(int limit) {
+                int cur = unary();
+                if (cur < 0)
+                        return -1;
+                for (;;) {
+                        size_t   len;
+                        const Op op = peek(&len);
+                        if (op == NONE || prio(op) >= limit)
+                                break;
+                        p += len;
+                        const int v = subexpr(prio(op));
+                        if (v < 0)
+                                return -1;
+                        const int kind = op == AND ? TRN_NODE_AND : (op == OR ? TRN_NODE_OR : TRN_NODE_NOT);
+                        const int x    = add(kind);
+                        nodes[x].kids  = {cur, v};
+                        cur            = x;
+                }
+                return cur;
+        }
+};
+
+// flatten chains of the same associative operator (build_iterator exec.cpp:328-400) and drop duplicate term operands
+void flatten(std::vector<Ast> &n, int i) {
+        auto &X = n[i];
+        if (X.kind == TRN_NODE_TERM)
+                return;
+        for (int k : X.kids)
+                flatten(n, k);
+        if (X.kind == TRN_NODE_AND || X.kind == TRN_NODE_OR) {
+                std::vector<int> out;
+                for (int k : n[i].kids) {
+                        if (n[k].kind == n[i].kind)
+                                out.insert(out.end(), n[k].kids.begin(), n[k].kids.end());
+                        else
+                                out.push_back(k);
+                }
+                std::vector<int> ded;
+                for (int k : out) {
+                        bool dup{false};
+                        if (n[k].kind == TRN_NODE_TERM)
+                                for (int j : ded)
+                                        if (n[j].kind == TRN_NODE_TERM && n[j].term == n[k].term)
+                                                dup = true;
+                        if (!dup)
+                                ded.push_back(k);
+                }
+                n[i].kids = ded;
+        }
+}
+} // namespace
+
+extern "C" int trn_parse_query(const char *text, const char *const *names, uint32_t nterms, trn_qnode *nodes, uint32_t cap, uint32_t *nnodes, uint32_t *root,
+                               char *err, size_t errcap) {
+        auto seterr = [&](const std::string &m) {
+                if (err && errcap) {
+                        std::strncpy(err, m.c_str(), errcap - 1);
+                        err[errcap - 1] = 0;
+                }
+                return TRN_ERR_PARSE;
+        };
+        if (!text || !nodes || !nnodes || !root)
+                return TRN_ERR_ARG;
+        // the dictionary is rebuilt per call only for small inputs; callers with big vocabularies use trn_dict_* below
+        static thread_local const char *const *                   cachedNames{nullptr};
+        static thread_local uint32_t                              cachedN{0};
+        static thread_local std::unordered_map<std::string, uint32_t> dict;
+        if (cachedNames != names || cachedN != nterms) {
+                dict.clear();
+                dict.reserve(nterms * 2);
+                for (uint32_t i = 0; i < nterms; ++i)
+                        dict.emplace(names[i], i);
+                cachedNames = names;
+                cachedN     = nterms;
+        }
+        Parser ps{text, text + std::strlen(text), dict, {}, {}};
+        const int r = ps.subexpr(255);
+        if (r < 0)
+                return seterr(ps.err);
+        ps.ws();
+        if (ps.p != ps.e)
+                return seterr("trailing input at offset " + std::to_string(ps.p - text));
+        flatten(ps.nodes, r);
+        // single-child AND/OR after de-duplication collapse to the child
+        int rr = r;
+        while (ps.nodes[rr].kind != TRN_NODE_TERM && ps.nodes[rr].kids.size() == 1 && (ps.nodes[rr].kind == TRN_NODE_AND || ps.nodes[rr].kind == TRN_NODE_OR))
+                rr = ps.nodes[rr].kids[0];
+        // emit breadth-first so that children are contiguous and follow their parent
+        std::vector<int> order{rr};
+        std::vector<trn_qnode> out;
+        out.reserve(32);
+        out.push_back(trn_qnode{});
+        for (size_t qi = 0; qi < order.size(); ++qi) {
+                const Ast &A = ps.nodes[order[qi]];
+                trn_qnode  q;
+                std::memset(&q, 0, sizeof(q));
+                q.kind = uint8_t(A.kind);
+                if (A.kind == TRN_NODE_TERM)
+                        q.term = A.term;
+                else {
+                        std::vector<int> kids;
+                        for (int k : A.kids) {
+                                int kk = k;
+                                while (ps.nodes[kk].kind != TRN_NODE_TERM && ps.nodes[kk].kids.size() == 1 &&
+                                       (ps.nodes[kk].kind == TRN_NODE_AND || ps.nodes[kk].kind == TRN_NODE_OR))
+                                        kk = ps.nodes[kk].kids[0];
+                                kids.push_back(kk);
+                        }
+                        if (kids.size() > 255 || out.size() + kids.size() > 65535)
+                                return seterr("query too large");
+                        q.nchildren   = uint8_t(kids.size());
+                        q.first_child = uint16_t(out.size());
+                        for (int k : kids) {
+                                order.push_back(k);
+                                out.push_back(trn_qnode{});
+                        }
+                }
+                out[qi] = q;
+        }
+        if (out.size() > cap)
+                return seterr("node buffer too small");
+        std::memcpy(nodes, out.data(), out.size() * sizeof(trn_qnode));
+        *nnodes = uint32_t(out.size());
+        *root   = 0;
+        return TRN_OK;
+}
