@@ -71,6 +71,12 @@ uint64_t trn_synth_sum_hits(trn_synth *);
 int trn_synth_postings(uint32_t ndocs, uint32_t rank, uint32_t min_df, uint64_t seed, uint32_t *docids, uint32_t *freqs, uint32_t cap, uint32_t *n);
 int trn_synth_positions(uint32_t ndocs, uint32_t rank, uint32_t min_df, uint64_t seed, uint32_t *positions, uint64_t cap, uint64_t *n);
 
+/* Load-time block directory of one term (host; what trn_upload_index builds for every term): last docID and payload byte
+ * offset of each block (+ one sentinel entry).  == the skiplist parse of Decoder::init (google_codec.cpp:936-983,
+ * lucene_codec.cpp:877-932) extended to every block.  Exposed for tests / tooling. */
+int trn_directory_probe(int codec, const uint8_t *index, uint64_t nbytes, const trn_term *term, uint32_t *blk_last, uint32_t *blk_off, uint32_t cap,
+                        uint32_t *nblocks, uint32_t *first_doc, char *err, size_t errcap);
+
 /* ------------------------------------------------------------------------------------------------ query plans
  * A query is a flat node array == the reference's compiled exec_node tree (compilation_ctx.h:8-30 ENT::*) after
  * queryexec_ctx::build_iterator's flattening (exec.cpp:253-449):
@@ -151,7 +157,8 @@ typedef struct trn_result {
         uint64_t        postings_scanned; /* sum over queries of sum over leaf terms of term.documents (full-scan accounting) */
         uint64_t        index_bytes_touched; /* sum over queries of sum over leaf terms of chunk_len (algorithmic bytes)        */
         uint32_t        kernel_launches;
-        float           device_ms; /* CUDA-event time of the device part of this call */
+        float           device_ms; /* CUDA-event time of the device part of this call (plan H2D + all kernels) */
+        float           exec_kernel_ms; /* CUDA-event time of the fused k_exec_tiles launch alone (roofline denominator) */
 } trn_result;
 
 /* == exec_query(query, IndexSource*, masked_documents_registry*, MatchedIndexDocumentsFilter*, ..., flags, scorer) (exec.h:50-52),

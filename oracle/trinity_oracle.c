@@ -1,0 +1,330 @@
+/*
+ * TEST INFRASTRUCTURE — NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this.
+ *
+ * Plain-C CPU restatement of the reference's hot path (postings decode -> docset algebra -> BM25), written from the
+ * reference's behaviour, every function citing the reference file:line it follows.  It is PINNED against the reference
+ * itself: tests/test_oracle_cpu.py checks every function here against oracle/_ref/libtrinity_ref.so (the reference's own
+ * code compiled in place by oracle/build_ref.sh) and against the golden vectors in tests/golden/ that were generated from it.
+ * The reference ships no tests or golden vectors of its own for this path, so "pinned" here means
+ * "pinned by executing the reference".
+ *
+ * The docset algebra is restated the simplest possible way (one byte + one double per document) because its job is to be
+ * obviously right, not fast: it is the checker, never the thing measured.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- prefix varbyte: Switch/switch_compiler_aux.h:53-81 (varbyte_get32) ---- */
+static uint32_t vb_get(const uint8_t **pp) {
+        const uint8_t *p = *pp;
+        uint32_t       x = *p++;
+        if (!(x & 0x80u)) {
+        } else if (!(x & 0x40u)) {
+                x = ((x & 0x3fu) << 8) | p[0];
+                p += 1;
+        } else if (!(x & 0x20u)) {
+                x = ((x & 0x1fu) << 16) | p[0] | ((uint32_t)p[1] << 8);
+                p += 2;
+        } else if (!(x & 0x10u)) {
+                x = ((x & 0x0fu) << 24) | ((uint32_t)p[0] << 16) | ((uint32_t)p[1] << 8) | p[2];
+                p += 3;
+        } else {
+                x = p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+                p += 4;
+        }
+        *pp = p;
+        return x;
+}
+static uint32_t rd32(const uint8_t *p) {
+        return p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+static uint32_t rd16(const uint8_t *p) {
+        return p[0] | ((uint32_t)p[1] << 8);
+}
+
+/* ---- GOOGLE codec: Decoder::init (google_codec.cpp:936-983), unpack_block (:596-639), next (:777-819), skip_block_doc (:497-531).
+ * Walks the chunk exactly like a sequence of next() calls, INCLUDING the varbyte walk over every document's hits that the
+ * reference needs to find the next block (TRACK_PAYLOADS layout, google_codec.cpp:58-71).  Returns #postings or -1. */
+int64_t orc_decode_google(const uint8_t *chunk, uint32_t len, uint32_t *docids, uint32_t *freqs, uint64_t cap) {
+        if (len == 0)
+                return 0;
+        const uint32_t entries  = rd16(chunk);
+        const uint8_t *end      = chunk + len - (size_t)entries * 8; /* chunkEnd = start of skiplist */
+        const uint8_t *p        = chunk + 2;
+        uint32_t       prevLast = 0;
+        uint64_t       n        = 0;
+        uint32_t       docs[32], fr[32];
+        while (p < end) {
+                const uint32_t last = prevLast + vb_get(&p);
+                (void)vb_get(&p); /* block length: the reference's next() does not use it, it walks the hits */
+                const uint32_t cnt = *p++;
+                if (cnt == 0 || cnt > 32)
+                        return -1;
+                uint32_t id = prevLast;
+                for (uint32_t i = 0; i + 1 < cnt; ++i) {
+                        id += vb_get(&p);
+                        docs[i] = id;
+                }
+                docs[cnt - 1] = last;
+                for (uint32_t i = 0; i < cnt; ++i)
+                        fr[i] = vb_get(&p);
+                for (uint32_t i = 0; i < cnt; ++i) {
+                        if (n < cap) {
+                                docids[n] = docs[i];
+                                freqs[n]  = fr[i] & 0xffffu; /* PostingsListIterator::freq is tokenpos_t = uint16_t (codecs.h:217, common.h:46) */
+                        }
+                        ++n;
+                        uint8_t payloadSize = 0;
+                        for (uint32_t h = 0; h < fr[i]; ++h) { /* skip_block_doc */
+                                const uint32_t step = vb_get(&p);
+                                if (step & 1u)
+                                        payloadSize = *p++;
+                                p += payloadSize;
+                        }
+                }
+                prevLast = last;
+        }
+        return p == end ? (int64_t)n : -1;
+}
+
+/* ---- LUCENE codec int-block: ints_decode (lucene_codec.cpp:69-100) + FastPFor<4>::__decodeArray (fastpfor.h:222-270),
+ * fastunpack (bitpackinghelpers.h:15-120: value i of a 32-value group sits at bits [i*b, (i+1)*b) LSB-first) and
+ * packingvector<32>::unpackmetight (packingvectors.h:34-58) for the exception stream. */
+static uint32_t bits_at(const uint8_t *words, uint32_t bitpos, uint32_t nbits) {
+        if (nbits == 0)
+                return 0;
+        uint64_t       x  = rd32(words + (size_t)(bitpos >> 5) * 4);
+        const uint32_t sh = bitpos & 31u;
+        if (sh + nbits > 32)
+                x |= (uint64_t)rd32(words + (size_t)(bitpos >> 5) * 4 + 4) << 32;
+        x >>= sh;
+        return nbits == 32 ? (uint32_t)x : (uint32_t)(x & ((1ull << nbits) - 1));
+}
+
+static const uint8_t *orc_ints_decode(const uint8_t *p, uint32_t *values) {
+        const uint32_t L = *p++;
+        if (L == 0) {
+                const uint32_t v = vb_get(&p);
+                for (int i = 0; i < 128; ++i)
+                        values[i] = v;
+                return p;
+        }
+        /* page words: [0]=nvalue(128) [1]=wheremeta [2..] 4 groups x b packed words ; meta at word 1+wheremeta */
+        const uint32_t wheremeta = rd32(p + 4);
+        const uint8_t *meta      = p + (size_t)(1 + wheremeta) * 4;
+        const uint32_t bytesize  = rd32(meta);
+        const uint8_t *bytep     = meta + 4;
+        const uint8_t *inexcept  = bytep + (size_t)((bytesize + 3) / 4) * 4;
+        const uint32_t bitmap    = rd32(inexcept);
+        inexcept += 4;
+        /* exception streams, one per set bit k-1 (k = maxbits - b in 2..32): u32 count, then count values at k bits, tight */
+        const uint8_t *excStream[33] = {0};
+        uint32_t       excIdx[33]    = {0};
+        for (uint32_t k = 2; k <= 32; ++k) {
+                if (bitmap & (1u << (k - 1))) {
+                        const uint32_t cnt = rd32(inexcept);
+                        excStream[k]       = inexcept + 4;
+                        inexcept += 4 + (size_t)((cnt * k + 31) / 32) * 4;
+                }
+        }
+        const uint32_t b       = *bytep++;
+        const uint32_t cexcept = *bytep++;
+        for (uint32_t g = 0; g < 4; ++g)
+                for (uint32_t j = 0; j < 32; ++j)
+                        values[g * 32 + j] = bits_at(p + 8 + (size_t)g * b * 4, j * b, b);
+        if (cexcept) {
+                const uint32_t maxbits = *bytep++;
+                const uint32_t k       = maxbits - b;
+                for (uint32_t e = 0; e < cexcept; ++e) {
+                        const uint32_t pos = *bytep++;
+                        if (k == 1)
+                                values[pos] |= 1u << b;
+                        else
+                                values[pos] |= bits_at(excStream[k], (excIdx[k]++) * k, k) << b;
+                }
+        }
+        return p + (size_t)L * 4;
+}
+
+/* Lucene::Decoder::init (lucene_codec.cpp:896-932) + refill_documents / next (:515-594): 14-byte header, documents/128 full
+ * blocks (deltas int-block, freqs int-block), then (documents % 128) varbyte (delta, freq) pairs, skiplist at the end. */
+int64_t orc_decode_lucene(const uint8_t *chunk, uint32_t len, uint32_t documents, uint32_t *docids, uint32_t *freqs, uint64_t cap) {
+        if (len == 0)
+                return 0;
+        const uint32_t skipn = rd16(chunk + 12);
+        const uint8_t *end   = chunk + len - (size_t)skipn * 22;
+        const uint8_t *p     = chunk + 14;
+        uint32_t       id = 0, d[128], f[128];
+        uint64_t       n = 0;
+        for (uint32_t blk = 0; blk < documents / 128; ++blk) {
+                p = orc_ints_decode(p, d);
+                p = orc_ints_decode(p, f);
+                for (int i = 0; i < 128; ++i) {
+                        id += d[i];
+                        if (n < cap) {
+                                docids[n] = id;
+                                freqs[n]  = f[i] & 0xffffu;
+                        }
+                        ++n;
+                }
+        }
+        for (uint32_t i = 0; i < documents % 128; ++i) {
+                id += vb_get(&p);
+                const uint32_t fr = vb_get(&p);
+                if (n < cap) {
+                        docids[n] = id;
+                        freqs[n]  = fr & 0xffffu;
+                }
+                ++n;
+        }
+        return p == end ? (int64_t)n : -1;
+}
+
+/* ---- BM25: IndexSourcesCollectionBM25Scorer::Scorer::idf (similarity.h:179-181, float arithmetic) and score (:228-235) ---- */
+double orc_bm25_idf(uint32_t docFreq, uint64_t docsCnt) {
+        const float a = (float)(docsCnt - docFreq) + 0.5f;
+        const float b = (float)docFreq + 0.5f;
+        return (double)logf(1.0f + a / b);
+}
+float orc_bm25_score(double idf, uint16_t freq) {
+        const float f = (float)freq;
+        return (float)(idf * (double)f / (double)(f + 1.2f));
+}
+
+/* ---- docset algebra + structural scoring ----
+ * node layout == trn_qnode of include/trinity_b200.h (kind 0 TERM, 1 AND, 2 OR, 3 NOT(req, excl), 4 OPTIONAL(main, opt)).
+ * Matching: Conjuction / Disjunction / Filter / Optional next()/advance() semantics (docset_iterators.cpp:282-677,
+ * docset_iterators.h:174-206).  Scoring: the IteratorScorer wrappers (docset_iterators_scorers.cpp:8-242): a conjunction sums all
+ * children, a disjunction sums the children positioned on the document, a filter scores its required side only, an optional adds
+ * its optional side when that is on the document.  Per-posting score = float, accumulated in double (docset_spans.cpp:735). */
+typedef struct {
+        uint8_t  kind, nchildren;
+        uint16_t first_child;
+        uint32_t term;
+        double   weight;
+} orc_node;
+typedef struct {
+        uint32_t documents, chunk_off, chunk_len;
+} orc_term;
+
+typedef struct {
+        int             codec;
+        const uint8_t * index;
+        const orc_term *terms;
+        const orc_node *nodes;
+        uint32_t        ndocs;
+        int             scored;
+} orc_ctx;
+
+static int orc_eval_node(const orc_ctx *c, uint32_t i, uint8_t *m, double *s) {
+        const orc_node *X = &c->nodes[i];
+        const size_t    n = (size_t)c->ndocs + 1;
+        memset(m, 0, n);
+        if (c->scored)
+                memset(s, 0, n * sizeof(double));
+        if (X->kind == 0) {
+                if (X->term == 0xffffffffu)
+                        return 0;
+                const orc_term *t   = &c->terms[X->term];
+                uint32_t *      ids = (uint32_t *)malloc(((size_t)t->documents + 1) * 4), *fr = (uint32_t *)malloc(((size_t)t->documents + 1) * 4);
+                const int64_t   k   = c->codec == 0 ? orc_decode_google(c->index + t->chunk_off, t->chunk_len, ids, fr, t->documents)
+                                                : orc_decode_lucene(c->index + t->chunk_off, t->chunk_len, t->documents, ids, fr, t->documents);
+                if (k != (int64_t)t->documents) {
+                        free(ids);
+                        free(fr);
+                        return -1;
+                }
+                for (int64_t j = 0; j < k; ++j) {
+                        if (ids[j] > c->ndocs)
+                                continue;
+                        m[ids[j]] = 1;
+                        if (c->scored)
+                                s[ids[j]] = (double)orc_bm25_score(X->weight, (uint16_t)fr[j]);
+                }
+                free(ids);
+                free(fr);
+                return 0;
+        }
+        uint8_t *cm = (uint8_t *)malloc(n);
+        double * cs = c->scored ? (double *)malloc(n * sizeof(double)) : NULL;
+        int      rc = 0;
+        for (uint32_t k = 0; k < X->nchildren && rc == 0; ++k) {
+                rc = orc_eval_node(c, X->first_child + k, cm, cs);
+                if (rc)
+                        break;
+                for (size_t d = 0; d < n; ++d) {
+                        switch (X->kind) {
+                                case 1: /* AND */
+                                        if (k == 0) {
+                                                m[d] = cm[d];
+                                                if (cs) s[d] = cs[d];
+                                        } else {
+                                                m[d] = m[d] && cm[d];
+                                                if (cs) s[d] += cs[d];
+                                        }
+                                        break;
+                                case 2: /* OR */
+                                        if (cm[d]) {
+                                                m[d] = 1;
+                                                if (cs) s[d] += cs[d];
+                                        }
+                                        break;
+                                case 3: /* NOT: req, then excl */
+                                        if (k == 0) {
+                                                m[d] = cm[d];
+                                                if (cs) s[d] = cs[d];
+                                        } else if (cm[d])
+                                                m[d] = 0;
+                                        break;
+                                default: /* OPTIONAL: main, then opt */
+                                        if (k == 0) {
+                                                m[d] = cm[d];
+                                                if (cs) s[d] = cs[d];
+                                        } else if (cm[d] && cs)
+                                                s[d] += cs[d];
+                                        break;
+                        }
+                }
+        }
+        if (cs)
+                for (size_t d = 0; d < n; ++d)
+                        if (!m[d])
+                                s[d] = 0;
+        free(cm);
+        free(cs);
+        return rc;
+}
+
+/* DocsSetIterators::cost (docset_iterators.cpp:10-64) */
+static uint64_t orc_cost(const orc_ctx *c, uint32_t i) {
+        const orc_node *X = &c->nodes[i];
+        if (X->kind == 0)
+                return X->term == 0xffffffffu ? 0 : c->terms[X->term].documents;
+        if (X->kind == 3 || X->kind == 4)
+                return orc_cost(c, X->first_child);
+        uint64_t r = X->kind == 1 ? ~0ull : 0;
+        for (uint32_t k = 0; k < X->nchildren; ++k) {
+                const uint64_t v = orc_cost(c, X->first_child + k);
+                r                = X->kind == 1 ? (v < r ? v : r) : r + v;
+        }
+        return r;
+}
+
+/* exec_query's general path (exec.cpp:1083-1345) for DocumentsOnly (scored = 0) / AccumulatedScoreScheme (scored = 1).
+ * match[d] = 1 for every matched docID d in 1..ndocs, score[d] = accumulated score.  Includes build_span's behaviour for a root
+ * Filter over a disjunction whose excluded side is not costlier (exec.cpp:488-501 + docset_spans.cpp:98-111,681-694: the
+ * disjunction spans ignore `min`, so the exclusion is not applied) — observed on the reference, see tests. */
+int orc_exec(int codec, const uint8_t *index, const orc_term *terms, const orc_node *nodes, uint32_t ndocs, int scored, uint8_t *match, double *score) {
+        orc_ctx  c    = {codec, index, terms, nodes, ndocs, scored};
+        uint32_t root = 0, cur = 0;
+        int      traversed = 0;
+        while (nodes[cur].kind == 3 && orc_cost(&c, nodes[cur].first_child + 1u) <= orc_cost(&c, nodes[cur].first_child)) {
+                cur       = nodes[cur].first_child;
+                traversed = 1;
+        }
+        if (traversed && nodes[cur].kind == 2)
+                root = cur;
+        return orc_eval_node(&c, root, match, score);
+}

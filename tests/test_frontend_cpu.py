@@ -1,0 +1,74 @@
+"""Host query front-end (parser + flattening) and the structural scoring rules vs the reference's exec_query — CPU only."""
+import numpy as np
+import pytest
+
+import trinity_b200 as tb
+from pyeval import evaluate
+from refharness import RefIndex
+from test_gpu_parity import TEMPLATES
+from util import closed_form_lists
+
+NDOCS = 30_000
+
+
+@pytest.fixture(scope="module")
+def small(ref):
+    lists = closed_form_lists(NDOCS)
+    r = RefIndex(ref, tb.CODEC_GOOGLE)
+    names = [f"t{i + 1}" for i in range(len(lists))]
+    for n, (d, f) in zip(names, lists):
+        r.add_term(n, d, f)
+    r.finish(NDOCS)
+    return r, lists, tb.TermDictionary(names)
+
+
+EXTRA = ["t1 OR t2 AND t3", "t1 AND t2 OR t3", "t1 OR t2 OR t3 AND t4 NOT t5", "(t1 AND t2 AND t3) OR t7",
+         "t1 AND (t2 AND (t3 OR t4))", "(t1 OR (t2 OR t3)) AND t5", "t1 NOT t2 NOT t3", "t5 AND t1 NOT (t2 AND t3)",
+         "(t1 NOT t2) OR (t3 NOT t5)", "t2 -t3 t5", "t7|t9|t10"]
+
+
+@pytest.mark.parametrize("q", TEMPLATES + EXTRA)
+def test_frontend_docs_and_scores_match_reference(small, q):
+    r, lists, tdict = small
+    nodes = tb.parse_query(q, tdict)
+    for x in nodes:
+        if x["kind"] == tb.NODE_TERM and x["term"] != tb.EMPTY_TERM:
+            x["weight"] = tb.bm25_idf(len(lists[int(x["term"])][0]), NDOCS)
+    m, s = evaluate(nodes, lists, NDOCS, weights=True)
+    want, _ = r.exec(q, False, NDOCS + 1)
+    assert np.array_equal(np.flatnonzero(m).astype(np.uint32), want), q
+    if "nosuchterm" in q:
+        return
+    wd, ws = r.exec(q, True, NDOCS + 1)
+    assert np.array_equal(np.flatnonzero(m).astype(np.uint32), wd)
+    got = s[wd]
+    rel = np.abs(got - ws) / np.maximum(np.abs(ws), 1e-30)
+    assert rel.max() <= 1e-5, (q, int(rel.argmax()), got[rel.argmax()], ws[rel.argmax()])
+
+
+def test_bm25_weight_matches_reference_scorer(small):
+    r, lists, _ = small
+    for t in range(len(lists)):
+        idf = tb.bm25_idf(len(lists[t][0]), NDOCS)
+        for freq in (0, 1, 2, 7, 63, 64, 300, 65535):
+            a, b = tb.bm25_score(idf, freq), r.bm25(t, freq)
+            assert abs(a - b) <= 1e-6 * max(abs(b), 1e-30), (t, freq, a, b)
+
+
+def test_parse_errors():
+    td = tb.TermDictionary(["a", "b"])
+    for bad in ["", "(a AND b", "a AND", "AND a", "a )"]:
+        with pytest.raises(tb.TrinityError):
+            tb.parse_query(bad, td)
+
+
+def test_abi_exports_every_declared_symbol():
+    import ctypes, re
+    from pathlib import Path
+    from trinity_b200._ffi import EXPORTS, lib
+    hdr = (Path(__file__).resolve().parent.parent / "include" / "trinity_b200.h").read_text()
+    declared = set(re.findall(r"\b(trn_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(EXPORTS), declared ^ set(EXPORTS)
+    L = lib()
+    for s in EXPORTS:
+        assert hasattr(L, s), s

@@ -203,6 +203,7 @@ class BatchResult:
     index_bytes_touched: int
     kernel_launches: int
     device_ms: float
+    exec_kernel_ms: float = 0.0
 
     def query(self, q: int):
         """(docids, scores) of query q.  top-k mode: only the valid entries, (score desc, docID asc)."""
@@ -292,7 +293,7 @@ class GpuIndexSource:
             scores = np.ctypeslib.as_array(r.scores, shape=(max(n, 1),))[:n].copy()
         counts = np.ctypeslib.as_array(r.match_counts, shape=(nq,)).copy()
         return BatchResult(nq, mode, k, offsets, docids, scores, counts, int(r.postings_scanned), int(r.index_bytes_touched),
-                           int(r.kernel_launches), float(r.device_ms))
+                           int(r.kernel_launches), float(r.device_ms), float(r.exec_kernel_ms))
 
     def exec_batch(self, queries: Sequence[np.ndarray], mode: int, k: int = 100) -> BatchResult:
         """== exec_query() for a batch: plans H2D, fused kernels, results D2H."""
@@ -333,3 +334,19 @@ class GpuIndexSource:
             self.close()
         except Exception:
             pass
+
+
+def directory_probe(codec: int, index: np.ndarray, term: tuple):
+    """Host-side block directory of one term: (blk_last[nblocks+1], blk_off[nblocks+1], first_doc)."""
+    L = lib()
+    index = np.ascontiguousarray(index, dtype=np.uint8)
+    t = TrnTerm(int(term[0]), int(term[1]), int(term[2]))
+    nb, fd = C.c_uint32(), C.c_uint32()
+    err = C.create_string_buffer(256)
+    cap = int(term[0]) // 32 + 4
+    last, off = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+    rc = L.trn_directory_probe(codec, _ptr(index), index.size, C.byref(t), _ptr(last), _ptr(off), cap, C.byref(nb), C.byref(fd), err, 256)
+    if rc != 0:
+        raise TrinityError(err.value.decode())
+    n = nb.value + (1 if nb.value else 0)
+    return last[:n], off[:n], fd.value

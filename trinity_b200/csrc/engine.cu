@@ -89,7 +89,8 @@ struct trn_ctx {
         DevBuf d_queries, d_steps, d_small, d_item_off, d_item_cnt, d_item_dst, d_seg_docids, d_seg_scores, d_out_docids, d_out_scores, d_q_offsets, d_cand,
             d_topk_docids, d_topk_scores, d_topk_counts, d_dec_a, d_dec_b, d_dec_c, d_dec_docids, d_dec_freqs, d_dec_sums, d_merge_docids, d_merge_scores;
         PinBuf h_offsets, h_docids, h_scores, h_counts, h_small;
-        cudaEvent_t ev0{nullptr}, ev1{nullptr};
+        cudaEvent_t ev0{nullptr}, ev1{nullptr}, evk0{nullptr}, evk1{nullptr};
+        bool        have_kernel_events{false};
         // last batch
         int      last_mode{-1};
         uint32_t last_nq{0}, last_k{0}, last_launches{0};
@@ -136,6 +137,7 @@ struct Compiler {
         };
         std::vector<Deferred> deferred;
         std::string           err;
+        bool                  reference_quirks{true};
 
         Compiler(const trn_qnode *nodes, uint32_t cnt, const std::vector<DevTerm> &t, bool sc, uint32_t r, std::vector<DevStep> &s)
             : n{nodes}, nn{cnt}, terms{t}, scored{sc}, root{r}, steps{s} {
@@ -371,10 +373,44 @@ struct Compiler {
                 return true;
         }
 
+        // == DocsSetIterators::cost() (docset_iterators.cpp:10-64); a conjunction's cost is its lead's, which the reference's
+        // reordering passes make the cheapest operand
+        uint64_t cost(uint32_t i) const {
+                const auto &X = n[i];
+                if (X.kind == TRN_NODE_TERM)
+                        return df(i);
+                if (X.kind == TRN_NODE_NOT || X.kind == TRN_NODE_OPTIONAL)
+                        return cost(X.first_child);
+                uint64_t c = X.kind == TRN_NODE_AND ? ~0ull : 0ull;
+                for (uint32_t k = 0; k < X.nchildren; ++k) {
+                        const uint64_t cc = cost(X.first_child + k);
+                        c                 = X.kind == TRN_NODE_AND ? std::min(c, cc) : c + cc;
+                }
+                return c;
+        }
+
+        // REFERENCE QUIRK, mirrored for drop-in parity: build_span() (exec.cpp:488-501) turns a root Filter whose excluded side is not
+        // costlier than its required side into FilteredDocsSetSpan(build_span(req), excl).  When req is a disjunction the inner span is
+        // DocsSetSpanForDisjunctions[WithThreshold], whose process() ignores its `min` argument (docset_spans.cpp:98-111,681-694): the
+        // excluded documents the outer span stepped over are emitted by the next call anyway, so the exclusion has no effect and the
+        // reference returns the plain disjunction.  The same holds through a chain of such root filters.
+        void apply_reference_root_filter_quirk() {
+                uint32_t cur = root;
+                bool     traversed{false};
+                while (n[cur].kind == TRN_NODE_NOT && n[cur].nchildren == 2 && cost(n[cur].first_child + 1u) <= cost(n[cur].first_child)) {
+                        cur       = n[cur].first_child;
+                        traversed = true;
+                }
+                if (traversed && n[cur].kind == TRN_NODE_OR)
+                        root = cur;
+        }
+
         // returns root slot or -1
         int run() {
                 if (!validate())
                         return -1;
+                if (reference_quirks)
+                        apply_reference_root_filter_quirk();
                 int rs;
                 if (is_leaf(root)) {
                         rs = int(next_slot++);
@@ -423,6 +459,8 @@ extern "C" int trn_create(int device, trn_ctx **out) {
         c->num_sms = prop.multiProcessorCount;
         CK(cudaEventCreate(&c->ev0));
         CK(cudaEventCreate(&c->ev1));
+        CK(cudaEventCreate(&c->evk0));
+        CK(cudaEventCreate(&c->evk1));
         return TRN_OK;
 }
 
@@ -606,7 +644,7 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
                 maxSlots     = std::max(maxSlots, cc.next_slot + 1); // + scratch slot
                 postings += cc.postings;
                 bytes += cc.bytes;
-                const Range r = cc.range(Q.root);
+                const Range r = cc.range(cc.root); // cc.root: the effective root (see apply_reference_root_filter_quirk)
                 if (r.empty()) {
                         dq.tile_lo = 0;
                         dq.ntiles  = 0;
@@ -619,7 +657,7 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
                 if (items >= (1ull << 32))
                         return fail(c, TRN_ERR_CAPACITY, "batch has more than 2^32 (query, tile) work items; split it");
                 const uint64_t width = r.empty() ? 0 : uint64_t(r.hi) - r.lo + 1;
-                segCap += std::min(cc.bound(Q.root), width);
+                segCap += std::min(cc.bound(cc.root), width);
                 dq.cand_base = uint32_t(candTotal);
                 dq.cand_cap  = uint32_t(std::min<uint64_t>(uint64_t(dq.ntiles) * k, 0xffffffffull));
                 if (mode == TRN_MODE_SCORED_TOPK) {
@@ -695,7 +733,10 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
                 if (perSM <= 0)
                         return fail(c, TRN_ERR_CUDA, "k_exec_tiles does not fit on an SM with this many docset slots");
                 const int grid = int(std::min<uint64_t>(uint64_t(c->num_sms) * perSM, totalItems));
+                CK(cudaEventRecord(c->evk0, c->stream));
                 CK(launch_exec_tiles(P, grid, c->stream));
+                CK(cudaEventRecord(c->evk1, c->stream));
+                c->have_kernel_events = true;
                 ++launches;
         }
         if (mode != TRN_MODE_SCORED_TOPK) {
@@ -792,6 +833,8 @@ extern "C" int trn_fetch_results(trn_ctx *c, trn_result *out) {
         float ms{0};
         if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
                 out->device_ms = ms;
+        if (c->have_kernel_events && cudaEventElapsedTime(&ms, c->evk0, c->evk1) == cudaSuccess)
+                out->exec_kernel_ms = ms;
         c->last_ms = ms;
         return TRN_OK;
 }

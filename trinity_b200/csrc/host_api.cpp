@@ -119,6 +119,36 @@ extern "C" int trn_builder_hits(trn_builder *b, const uint8_t **hits, uint64_t *
         return TRN_OK;
 }
 
+extern "C" int trn_directory_probe(int codec, const uint8_t *index, uint64_t nbytes, const trn_term *term, uint32_t *blk_last, uint32_t *blk_off, uint32_t cap,
+                                   uint32_t *nblocks, uint32_t *first_doc, char *err, size_t errcap) {
+        if (!index || !term || !nblocks || (codec != TRN_CODEC_GOOGLE && codec != TRN_CODEC_LUCENE))
+                return TRN_ERR_ARG;
+        try {
+                term_index_ctx t;
+                t.documents = term->documents;
+                t.offset    = term->chunk_off;
+                t.size      = term->chunk_len;
+                BlockDirectory d;
+                build_block_directory(codec == TRN_CODEC_GOOGLE ? Codec::Google : Codec::Lucene, index, nbytes, &t, 1, 1, d);
+                *nblocks = d.terms[0].nblocks;
+                if (first_doc)
+                        *first_doc = d.terms[0].first_doc;
+                for (uint32_t i = 0; i < d.blk_last.size() && i < cap; ++i) {
+                        if (blk_last)
+                                blk_last[i] = d.blk_last[i];
+                        if (blk_off)
+                                blk_off[i] = d.blk_off[i];
+                }
+                return TRN_OK;
+        } catch (const std::exception &e) {
+                if (err && errcap) {
+                        std::strncpy(err, e.what(), errcap - 1);
+                        err[errcap - 1] = 0;
+                }
+                return TRN_ERR_FORMAT;
+        }
+}
+
 // =================================================================================================== synthetic index
 namespace {
 inline uint64_t splitmix64(uint64_t &s) {
