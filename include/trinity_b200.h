@@ -62,6 +62,9 @@ const char *trn_builder_last_error(trn_builder *);
  * byte-identical to feeding the same postings to one reference encoder term after term. */
 typedef struct trn_synth trn_synth;
 int  trn_synth_build(int codec, uint32_t ndocs, uint32_t nterms, uint32_t min_df, uint64_t seed, int with_hits, int threads, trn_synth **out);
+/* docID-range shard [doc_lo, doc_hi] of the same index (global docIDs kept): one IndexSource of a docID-partitioned collection */
+int  trn_synth_build_shard(int codec, uint32_t ndocs, uint32_t nterms, uint32_t min_df, uint64_t seed, int with_hits, int threads, uint32_t doc_lo,
+                           uint32_t doc_hi, trn_synth **out);
 void trn_synth_destroy(trn_synth *);
 int  trn_synth_index(trn_synth *, const uint8_t **index, uint64_t *nbytes);
 int  trn_synth_hits(trn_synth *, const uint8_t **hits, uint64_t *nbytes);

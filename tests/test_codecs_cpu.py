@@ -115,3 +115,31 @@ def test_synth_index_equals_reference_encoding_of_same_postings(ref, codec):
         assert diff.size == 0
     else:
         assert np.all(mine[diff] == 0) and diff.size < mine.size // 50
+
+
+@pytest.mark.parametrize("codec", [tb.CODEC_GOOGLE, tb.CODEC_LUCENE])
+def test_synth_docid_shards_partition_the_index(ref, codec):
+    """docID-range shards (multi-GPU layout): every shard is byte-identical to the reference encoding of the
+    postings that fall into its range, and the shards together hold every posting exactly once."""
+    ndocs, nterms, min_df, G = 120_000, 16, 40, 3
+    bounds = [(g * ndocs // G + 1, (g + 1) * ndocs // G) for g in range(G)]
+    counts = np.zeros(nterms, np.int64)
+    for lo, hi in bounds:
+        s = tb.SynthIndex(codec, ndocs, nterms, min_df=min_df, threads=2, doc_range=(lo, hi))
+        r = RefIndex(ref, codec)
+        for rank in range(1, nterms + 1):
+            d, f = tb.SynthIndex.postings(ndocs, rank, min_df)
+            p = tb.SynthIndex.positions(ndocs, rank, min_df)
+            keep = (d >= lo) & (d <= hi)
+            ends = np.cumsum(f)
+            starts = ends - f
+            pk = np.concatenate([p[a:b] for a, b, k in zip(starts, ends, keep) if k]) if keep.any() else np.zeros(0, np.uint32)
+            r.add_term(s.names[rank - 1], d[keep], f[keep], pk)
+            counts[rank - 1] += int(keep.sum())
+        r.finish(ndocs)
+        assert np.array_equal(np.asarray(s.terms), r.terms())
+        mine, theirs = np.asarray(s.index), r.index()
+        diff = np.flatnonzero(mine != theirs)
+        assert np.all(mine[diff] == 0) and (codec == tb.CODEC_LUCENE or diff.size == 0)
+    for rank in range(1, nterms + 1):
+        assert counts[rank - 1] == max(min_df, ndocs // (2 * rank))

@@ -107,11 +107,13 @@ class SynthIndex:
     """The BASELINE.md synthetic Zipfian index, built multi-threaded through the host encoders."""
 
     def __init__(self, codec: int, ndocs: int, nterms: int = 4096, min_df: int = 1000, seed: int = 0x5EED,
-                 with_hits: bool = True, threads: int = 0):
+                 with_hits: bool = True, threads: int = 0, doc_range: Optional[tuple] = None):
         self._L = lib()
         self.codec, self.ndocs, self.nterms, self.min_df, self.seed = codec, ndocs, nterms, min_df, seed
+        self.doc_range = doc_range or (1, ndocs)
         h = C.c_void_p()
-        rc = self._L.trn_synth_build(codec, ndocs, nterms, min_df, seed, int(with_hits), threads, C.byref(h))
+        rc = self._L.trn_synth_build_shard(codec, ndocs, nterms, min_df, seed, int(with_hits), threads,
+                                           self.doc_range[0], self.doc_range[1], C.byref(h))
         if rc != 0:
             raise TrinityError(f"trn_synth_build failed rc={rc}")
         self._h = h

@@ -14,7 +14,7 @@ EXPORTS = [
     "trn_builder_create", "trn_builder_destroy", "trn_builder_begin_term", "trn_builder_begin_document",
     "trn_builder_new_hit", "trn_builder_end_document", "trn_builder_end_term", "trn_builder_add_term",
     "trn_builder_set_google_skiplist_countdown", "trn_builder_index", "trn_builder_hits", "trn_builder_last_error",
-    "trn_synth_build", "trn_synth_destroy", "trn_synth_index", "trn_synth_hits", "trn_synth_terms", "trn_synth_sum_hits",
+    "trn_synth_build", "trn_synth_build_shard", "trn_synth_destroy", "trn_synth_index", "trn_synth_hits", "trn_synth_terms", "trn_synth_sum_hits",
     "trn_synth_postings", "trn_synth_positions",
     "trn_directory_probe", "trn_parse_query", "trn_bm25_idf", "trn_bm25_score",
     "trn_create", "trn_destroy", "trn_last_error", "trn_set_stream", "trn_upload_index", "trn_index_info_get",
@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
     sig("trn_builder_hits", i32, vp, P(vp), P(u64))
     sig("trn_builder_last_error", C.c_char_p, vp)
     sig("trn_synth_build", i32, i32, u32, u32, u32, u64, i32, i32, P(vp))
+    sig("trn_synth_build_shard", i32, i32, u32, u32, u32, u64, i32, i32, u32, u32, P(vp))
     sig("trn_synth_destroy", None, vp)
     sig("trn_synth_index", i32, vp, P(vp), P(u64))
     sig("trn_synth_hits", i32, vp, P(vp), P(u64))

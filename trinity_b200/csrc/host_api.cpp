@@ -201,9 +201,43 @@ struct trn_synth {
 };
 
 extern "C" int trn_synth_build(int codec, uint32_t ndocs, uint32_t nterms, uint32_t min_df, uint64_t seed, int with_hits, int threads, trn_synth **out) {
-        if (!out || !ndocs || !nterms || (codec != TRN_CODEC_GOOGLE && codec != TRN_CODEC_LUCENE))
+        return trn_synth_build_shard(codec, ndocs, nterms, min_df, seed, with_hits, threads, 1, ndocs, out);
+}
+
+// docID-range shard [doc_lo, doc_hi] of the same index: every term keeps only its postings inside the range (== one IndexSource of
+// an IndexSourcesCollection partitioned by docID, index_source.h:191-238).  docIDs stay global.
+extern "C" int trn_synth_build_shard(int codec, uint32_t ndocs, uint32_t nterms, uint32_t min_df, uint64_t seed, int with_hits, int threads, uint32_t doc_lo,
+                                     uint32_t doc_hi, trn_synth **out) {
+        if (!out || !ndocs || !nterms || (codec != TRN_CODEC_GOOGLE && codec != TRN_CODEC_LUCENE) || doc_lo == 0 || doc_lo > doc_hi)
                 return TRN_ERR_ARG;
         const Codec cd = codec == TRN_CODEC_GOOGLE ? Codec::Google : Codec::Lucene;
+        const bool  whole = doc_lo <= 1 && doc_hi >= ndocs;
+        if (threads < 1)
+                threads = int(std::max(1u, std::thread::hardware_concurrency()));
+        // documents of every term inside the range (analytic for the whole index, counted by a generation-only pass otherwise)
+        std::vector<uint32_t> dfIn(nterms);
+        if (whole) {
+                for (uint32_t r = 1; r <= nterms; ++r)
+                        dfIn[r - 1] = synth_df(ndocs, r, min_df);
+        } else {
+                std::atomic<uint32_t> nx{0};
+                auto                  counter = [&] {
+                        for (;;) {
+                                const uint32_t i = nx.fetch_add(1);
+                                if (i >= nterms)
+                                        break;
+                                uint32_t c{0};
+                                synth_term(ndocs, i + 1, min_df, seed, [&](uint32_t doc, uint32_t, uint64_t) { c += doc >= doc_lo && doc <= doc_hi; });
+                                dfIn[i] = c;
+                        }
+                };
+                std::vector<std::thread> ths;
+                for (int i = 1; i < threads; ++i)
+                        ths.emplace_back(counter);
+                counter();
+                for (auto &t : ths)
+                        t.join();
+        }
         struct Part {
                 std::vector<uint8_t> index, hits;
                 term_index_ctx       t;
@@ -216,7 +250,7 @@ extern "C" int trn_synth_build(int codec, uint32_t ndocs, uint32_t nterms, uint3
                 uint64_t blocks{0};
                 for (uint32_t r = 1; r <= nterms; ++r) {
                         countdown[r - 1] = Codecs::Google::SKIPLIST_STEP - uint32_t(blocks % Codecs::Google::SKIPLIST_STEP);
-                        blocks += (synth_df(ndocs, r, min_df) + Codecs::Google::N - 1) / Codecs::Google::N;
+                        blocks += (dfIn[r - 1] + Codecs::Google::N - 1) / Codecs::Google::N;
                 }
         }
         std::atomic<uint32_t> next{0};
@@ -234,6 +268,8 @@ extern "C" int trn_synth_build(int codec, uint32_t ndocs, uint32_t nterms, uint3
                                 auto &P = parts[i];
                                 enc->begin_term();
                                 synth_term(ndocs, i + 1, min_df, seed, [&](uint32_t doc, uint32_t freq, uint64_t y) {
+                                        if (doc < doc_lo || doc > doc_hi)
+                                                return;
                                         enc->begin_document(doc);
                                         if (with_hits) {
                                                 uint32_t pos{0};
@@ -256,8 +292,6 @@ extern "C" int trn_synth_build(int codec, uint32_t ndocs, uint32_t nterms, uint3
                         }
                 }
         };
-        if (threads < 1)
-                threads = int(std::max(1u, std::thread::hardware_concurrency()));
         std::vector<std::thread> ths;
         for (int i = 1; i < threads; ++i)
                 ths.emplace_back(worker);
