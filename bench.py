@@ -307,7 +307,7 @@ def cpu_baseline(synth, texts, args, mode, threads: int | None = None, sample: i
     ref = load_ref()
     cores = threads or (os.cpu_count() or 1)
     r = RefIndex.from_bytes(ref, synth.codec, np.asarray(synth.index), np.asarray(synth.hits), synth.names, np.asarray(synth.terms), args.ndocs, synth.sum_hits)
-    n = sample or args.cpu_sample or min(len(texts), max(cores, 16))
+    n = sample or args.cpu_sample or len(texts)
     qs = texts[:n]
     best = None
     for _ in range(repeats):
@@ -327,7 +327,7 @@ def reference_arm(args, rank, world, wl, K, W):
     synth = tb.SynthIndex(wl["codec"], args.ndocs, args.nterms, threads=os.cpu_count() or 8)
     texts, _ = gen_queries(args.workload, args.nq, args.nterms)
     cores = os.cpu_count() or 1
-    n = args.cpu_sample or min(len(texts), max(cores, 16))
+    n = args.cpu_sample or len(texts)
     sys.path.insert(0, str(ROOT / "tests"))
     from refharness import RefIndex, load_ref
 
