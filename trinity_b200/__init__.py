@@ -272,8 +272,8 @@ class GpuIndexSource:
             arr[i].root = 0
         return arr, keep
 
-    def exec_batch_device(self, queries: Sequence[np.ndarray], mode: int, k: int = 100):
-        arr, keep = self._pack(queries)
+    def exec_batch_device(self, queries: Sequence[np.ndarray], mode: int, k: int = 100, packed=None):
+        arr, keep = packed if packed is not None else self._pack(queries)
         r = TrnResult()
         self._ck(self._L.trn_exec_batch_device(self._h, C.cast(arr, C.c_void_p), len(queries), mode, k, C.byref(r)))
         self._last = (mode, k, len(queries))
@@ -285,25 +285,32 @@ class GpuIndexSource:
         mode, k, nq = self._last
         return self._wrap(r, mode, k)
 
-    def _wrap(self, r: TrnResult, mode: int, k: int) -> BatchResult:
+    def _wrap(self, r: TrnResult, mode: int, k: int, copy: bool = True) -> BatchResult:
+        """copy=False returns views of the ctx-owned pinned host buffers (valid until the next exec call)"""
         nq = r.nq
-        offsets = np.ctypeslib.as_array(r.offsets, shape=(nq + 1,)).copy()
+        keep = (lambda a: a.copy()) if copy else (lambda a: a)
+        offsets = keep(np.ctypeslib.as_array(r.offsets, shape=(nq + 1,)))
         n = int(offsets[nq])
-        docids = np.ctypeslib.as_array(r.docids, shape=(max(n, 1),))[:n].copy()
+        docids = keep(np.ctypeslib.as_array(r.docids, shape=(max(n, 1),))[:n])
         scores = None
         if mode != MODE_DOCS_ONLY:
-            scores = np.ctypeslib.as_array(r.scores, shape=(max(n, 1),))[:n].copy()
-        counts = np.ctypeslib.as_array(r.match_counts, shape=(nq,)).copy()
+            scores = keep(np.ctypeslib.as_array(r.scores, shape=(max(n, 1),))[:n])
+        counts = keep(np.ctypeslib.as_array(r.match_counts, shape=(nq,)))
         return BatchResult(nq, mode, k, offsets, docids, scores, counts, int(r.postings_scanned), int(r.index_bytes_touched),
                            int(r.kernel_launches), float(r.device_ms), float(r.exec_kernel_ms))
 
-    def exec_batch(self, queries: Sequence[np.ndarray], mode: int, k: int = 100) -> BatchResult:
+    def pack(self, queries: Sequence[np.ndarray]):
+        """pre-marshal a batch of plans (trn_query array); pass the result to exec_batch(..., packed=...) to keep ctypes
+        marshalling out of a timed region"""
+        return self._pack(queries)
+
+    def exec_batch(self, queries: Sequence[np.ndarray], mode: int, k: int = 100, copy: bool = True, packed=None) -> BatchResult:
         """== exec_query() for a batch: plans H2D, fused kernels, results D2H."""
-        arr, keep = self._pack(queries)
+        arr, keep = packed if packed is not None else self._pack(queries)
         r = TrnResult()
         self._ck(self._L.trn_exec_batch(self._h, C.cast(arr, C.c_void_p), len(queries), mode, k, C.byref(r)))
         self._last = (mode, k, len(queries))
-        return self._wrap(r, mode, k)
+        return self._wrap(r, mode, k, copy)
 
     def last_topk_device(self):
         d, s, c = C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -63,7 +63,8 @@ struct ExecParams {
         const DevStep * steps;
         uint32_t        nq;
         uint32_t        total_items;
-        uint32_t        nslots; // bitmap slots per CTA
+        uint32_t        nslots; // bitmap slots per worker (CTA for k_exec_tiles, warp for k_exec_docs)
+        uint32_t        exec_shift; // log2 of the docID tile of THIS launch (>= ix.tile_shift; tile_first is indexed at ix.tile_shift granularity)
         int             mode;   // TRN_MODE_*
         uint32_t        k;
         uint32_t *      ticket; // work-item dispenser

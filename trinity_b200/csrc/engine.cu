@@ -10,6 +10,7 @@
 #include "device_types.h"
 #include "kernels.h"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -82,6 +83,7 @@ struct trn_ctx {
         bool                 have_index{false};
         int                  codec{0};
         uint32_t             nterms{0}, max_docid{0}, tile_shift{14}, ntiles{0};
+        uint32_t             docs_shift{15}; // docID tile (log2) of the warp-per-tile DocumentsOnly kernel
         uint64_t             index_bytes{0}, dir_bytes{0}, total_blocks{0}, total_postings{0};
         DevBuf               d_index, d_blk_last, d_blk_off, d_terms, d_tile_first;
         std::vector<DevTerm> h_terms;
@@ -457,6 +459,11 @@ extern "C" int trn_create(int device, trn_ctx **out) {
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         c->num_sms = prop.multiProcessorCount;
+        if (const char *e = getenv("TRN_DOCS_SHIFT")) {
+                const int v = atoi(e);
+                if (v >= 14 && v <= 17)
+                        c->docs_shift = uint32_t(v);
+        }
         CK(cudaEventCreate(&c->ev0));
         CK(cudaEventCreate(&c->ev1));
         CK(cudaEventCreate(&c->evk0));
@@ -624,6 +631,10 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
                 return fail(c, TRN_ERR_ARG, "top-k: k must be in [1, 512]");
         CK(cudaSetDevice(c->device));
         const bool scored = mode != TRN_MODE_DOCS_ONLY;
+        // docID tile of this launch: set queries run one warp per tile (k_exec_docs) on larger tiles; scored queries keep a CTA-wide
+        // fp32 score tile (k_exec_tiles).  Both index the same tile_first table (granularity 2^tile_shift).
+        uint32_t execShift = scored ? c->tile_shift : c->docs_shift;
+        execShift          = std::max(execShift, c->tile_shift);
 
         std::vector<DevQuery> hq(nq);
         std::vector<DevStep>  steps;
@@ -649,8 +660,8 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
                         dq.tile_lo = 0;
                         dq.ntiles  = 0;
                 } else {
-                        dq.tile_lo = r.lo >> c->tile_shift;
-                        dq.ntiles  = (r.hi >> c->tile_shift) - dq.tile_lo + 1;
+                        dq.tile_lo = r.lo >> execShift;
+                        dq.ntiles  = (r.hi >> execShift) - dq.tile_lo + 1;
                 }
                 dq.item_base = uint32_t(items);
                 items += dq.ntiles;
@@ -712,6 +723,7 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
         P.nq           = nq;
         P.total_items  = totalItems;
         P.nslots       = maxSlots;
+        P.exec_shift   = execShift;
         P.mode         = mode;
         P.k            = k;
         P.ticket       = ticket;
@@ -729,12 +741,17 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
 
         uint32_t launches{0};
         if (totalItems) {
-                const int perSM = exec_max_ctas_per_sm(c->tile_shift, maxSlots, mode);
+                const bool warpKernel = !scored;
+                const int  perSM      = warpKernel ? exec_docs_max_ctas_per_sm(execShift, maxSlots) : exec_max_ctas_per_sm(execShift, maxSlots, mode);
                 if (perSM <= 0)
-                        return fail(c, TRN_ERR_CUDA, "k_exec_tiles does not fit on an SM with this many docset slots");
-                const int grid = int(std::min<uint64_t>(uint64_t(c->num_sms) * perSM, totalItems));
+                        return fail(c, TRN_ERR_CUDA, "the exec kernel does not fit on an SM with this many docset slots");
+                const uint64_t workers = warpKernel ? (uint64_t(totalItems) + 3) / 4 : totalItems; // 4 warp-workers per CTA
+                const int      grid    = int(std::min<uint64_t>(uint64_t(c->num_sms) * perSM, std::max<uint64_t>(1, workers)));
                 CK(cudaEventRecord(c->evk0, c->stream));
-                CK(launch_exec_tiles(P, grid, c->stream));
+                if (warpKernel)
+                        CK(launch_exec_docs(P, grid, c->stream));
+                else
+                        CK(launch_exec_tiles(P, grid, c->stream));
                 CK(cudaEventRecord(c->evk1, c->stream));
                 c->have_kernel_events = true;
                 ++launches;

@@ -1,0 +1,397 @@
+// k_exec_docs — DocumentsOnly execution with one WARP per (query, docID tile) work item.  (Included by kernels.cu.)
+//
+// Why a second kernel: the ncu capture of the CTA-per-tile kernel on the 2-term AND workload (profiles/r01_a_*) showed DRAM at 5 % of
+// peak, 37 % issue utilisation and 47 % of all stall samples on CTA barriers — 4 warps waiting for the slowest lane-serial block
+// decode at every step.  Set queries need no score tile, so the whole per-tile state (2-3 slot bitmaps + one staging area) fits a
+// warp: every warp is an independent worker that never waits for another warp (only __syncwarp), and the SM always has
+// as many runnable decode chains as it has resident warps.
+//
+// Same step programs, same decode routines, same output contract as k_exec_tiles (mode TRN_MODE_DOCS_ONLY).
+#pragma once
+
+static constexpr int      kDocsWarps       = 4;   // warps per CTA (independent workers)
+static constexpr uint32_t kSparseThreshold = 192; // candidates per tile below which AND switches to advance()-style skipping
+
+// lower_bound over bl[a..b] (ascending) for the first index with bl[idx] >= v; returns b+1 if none.  Warp-cooperative 32-ary search.
+__device__ __forceinline__ uint32_t warp_lower_bound(const uint32_t *__restrict__ bl, uint32_t a, uint32_t b, uint32_t v, int lane) {
+        // invariant: answer in [a, b+1]
+        while (b - a + 1u > 32u) {
+                const uint32_t n = b - a + 1u, step = (n + 31u) / 32u;
+                const uint32_t p = min(b, a + uint32_t(lane) * step + (step - 1u)); // last element of chunk `lane`
+                const uint32_t c = __popc(__ballot_sync(0xffffffffu, bl[p] < v)); // chunks entirely < v (monotone)
+                if (c == 32u)
+                        return b + 1u;
+                const uint32_t na = a + c * step;
+                b                 = min(b, na + step - 1u);
+                a                 = na;
+        }
+        const uint32_t idx = a + uint32_t(lane);
+        const uint32_t val = idx <= b ? bl[idx] : 0xffffffffu;
+        return a + __popc(__ballot_sync(0xffffffffu, val < v));
+}
+
+// docs-only visitor: word-register bit builder (see BitSink)
+struct DocSink {
+        BitSink bits;
+        __device__ __forceinline__ void visit(uint32_t rel) {
+                bits.add(rel);
+        }
+};
+
+// One lane decodes the doc-delta section of one Google block; INTERIOR = block lies completely inside the tile (no range checks).
+template <bool INTERIOR>
+__device__ __forceinline__ void google_block_docs(const uint8_t *p, uint32_t n, uint32_t prev, uint32_t last, uint32_t lo, uint32_t hi, BitSink &bs) {
+        uint32_t doc = prev;
+        for (uint32_t i = 0; i + 1u < n; ++i) {
+                const uint32_t b0 = *p;
+                if (b0 < 0x80u) {
+                        doc += b0;
+                        p += 1;
+                } else
+                        doc += varbyte_get(p);
+                if (INTERIOR)
+                        bs.add(doc - lo);
+                else {
+                        if (doc >= hi)
+                                return;
+                        if (doc >= lo)
+                                bs.add(doc - lo);
+                }
+        }
+        if (INTERIOR || (last >= lo && last < hi))
+                bs.add(last - lo);
+}
+
+// Decode blocks [bA, bB] of a Google term into the warp's bitmap.  `sparse`: the destination docset holds few candidates — check each
+// block's docID range against it first and skip blocks (and whole groups) without candidates.
+__device__ void google_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t bA, uint32_t bB, uint32_t lo, uint32_t hi, BitSink &bs, const uint32_t *skipfilt,
+                                 uint8_t *stage, int lane) {
+        const uint32_t *bl = ix.blk_last + T.dir_begin;
+        const uint32_t *bo = ix.blk_off + T.dir_begin;
+        for (uint32_t g = bA; g <= bB; g += 32u) {
+                const uint32_t b      = g + uint32_t(lane);
+                const bool     active = b <= bB;
+                uint32_t       off = 0, offn = 0, last = 0, prev = 0, n = 0;
+                if (active) {
+                        off  = bo[b];
+                        offn = bo[b + 1];
+                        last = bl[b];
+                        prev = b ? bl[b - 1] : 0u;
+                        n    = (b + 1u == T.nblocks) ? (T.documents - 32u * (T.nblocks - 1u)) : 32u;
+                }
+                bool need = active;
+                if (need && skipfilt) {
+                        const uint32_t d0 = max(prev + 1u, lo), d1 = min(last, hi - 1u);
+                        if (d1 < d0)
+                                need = false;
+                        else {
+                                const uint32_t r0 = d0 - lo, r1 = d1 - lo, w0 = r0 >> 5, w1 = r1 >> 5;
+                                if (w1 - w0 <= 7u) {
+                                        uint32_t any = 0;
+                                        for (uint32_t w = w0; w <= w1; ++w) {
+                                                uint32_t m = skipfilt[w];
+                                                if (w == w0)
+                                                        m &= 0xffffffffu << (r0 & 31u);
+                                                if (w == w1)
+                                                        m &= 0xffffffffu >> (31u - (r1 & 31u));
+                                                any |= m;
+                                        }
+                                        need = any != 0;
+                                }
+                        }
+                }
+                const uint32_t needMask = __ballot_sync(0xffffffffu, need);
+                if (needMask) {
+                        // stage only the byte span of the lanes that still need their block
+                        const int      l0 = __ffs(int(needMask)) - 1, l1 = 31 - __clz(int(needMask));
+                        const uint32_t first_off = __shfl_sync(0xffffffffu, off, l0);
+                        const uint32_t end_off   = __shfl_sync(0xffffffffu, offn, l1);
+                        const uint32_t span      = end_off - first_off;
+                        const bool     interior  = prev + 1u >= lo && last < hi;
+                        if (span + 32u <= kStageBytes) {
+                                const uint32_t skew = stage_copy(ix.index, first_off, span, stage, lane);
+                                __syncwarp();
+                                if (need) {
+                                        const uint8_t *p = stage + skew + (off - first_off);
+                                        if (interior) google_block_docs<true>(p, n, prev, last, lo, hi, bs);
+                                        else google_block_docs<false>(p, n, prev, last, lo, hi, bs);
+                                }
+                        } else if (need) {
+                                // hits-heavy blocks that do not fit the staging area: decode straight from global memory
+                                if (interior) google_block_docs<true>(ix.index + off, n, prev, last, lo, hi, bs);
+                                else google_block_docs<false>(ix.index + off, n, prev, last, lo, hi, bs);
+                        }
+                }
+                __syncwarp();
+        }
+        bs.flush();
+}
+
+// Lucene: the warp decodes one 128-doc block at a time
+__device__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t bA, uint32_t bB, uint32_t lo, uint32_t hi, BitSink &bs, const uint32_t *skipfilt,
+                                 uint8_t *stage, int lane) {
+        const uint32_t *bl    = ix.blk_last + T.dir_begin;
+        const uint32_t *bo    = ix.blk_off + T.dir_begin;
+        const uint32_t  nfull = T.documents >> 7;
+        for (uint32_t b = bA; b <= bB; ++b) {
+                const uint32_t off = bo[b], offn = bo[b + 1], last = bl[b], prev = b ? bl[b - 1] : 0u;
+                if (skipfilt) {
+                        const uint32_t d0 = max(prev + 1u, lo), d1 = min(last, hi - 1u);
+                        if (d1 < d0)
+                                continue;
+                        const uint32_t r0 = d0 - lo, r1 = d1 - lo, w0 = r0 >> 5, w1 = r1 >> 5;
+                        if (w1 - w0 < 32u) {
+                                uint32_t       m = 0;
+                                const uint32_t w = w0 + uint32_t(lane);
+                                if (w <= w1) {
+                                        m = skipfilt[w];
+                                        if (w == w0)
+                                                m &= 0xffffffffu << (r0 & 31u);
+                                        if (w == w1)
+                                                m &= 0xffffffffu >> (31u - (r1 & 31u));
+                                }
+                                if (!__any_sync(0xffffffffu, m != 0))
+                                        continue;
+                        }
+                }
+                const uint32_t len = offn - off;
+                if (b < nfull) {
+                        const uint32_t skew = stage_copy(ix.index, off, len, stage, lane);
+                        __syncwarp();
+                        uint32_t d[4];
+                        (void)lucene_intblock(stage, skew, lane, d);
+                        d[1] += d[0];
+                        d[2] += d[1];
+                        d[3] += d[2];
+                        const uint32_t incl = warp_incl_scan(d[3], lane);
+                        const uint32_t base = prev + incl - d[3];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                                const uint32_t doc = base + d[t];
+                                if (doc >= lo && doc < hi)
+                                        bs.add(doc - lo);
+                        }
+                } else {
+                        const uint32_t tail = T.documents & 127u;
+                        const uint8_t *p;
+                        if (len + 32u <= kStageBytes) {
+                                const uint32_t skew = stage_copy(ix.index, off, len, stage, lane);
+                                __syncwarp();
+                                p = stage + skew;
+                        } else
+                                p = ix.index + off;
+                        if (lane == 0) {
+                                uint32_t doc = prev;
+                                for (uint32_t i = 0; i < tail; ++i) {
+                                        doc += varbyte_get(p);
+                                        (void)varbyte_get(p);
+                                        if (doc >= hi)
+                                                break;
+                                        if (doc >= lo)
+                                                bs.add(doc - lo);
+                                }
+                        }
+                }
+                __syncwarp();
+        }
+        bs.flush();
+}
+
+__global__ void __launch_bounds__(kDocsWarps * 32) k_exec_docs(ExecParams P) {
+        const uint32_t W  = 1u << P.exec_shift;
+        const uint32_t NW = W >> 5;
+        const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const size_t   perWarp = size_t(P.nslots) * NW * 4 + kStageBytes;
+        uint32_t *     slots = reinterpret_cast<uint32_t *>(dyn_smem + perWarp * warp);
+        uint8_t *      stage = reinterpret_cast<uint8_t *>(slots + size_t(P.nslots) * NW);
+        const uint32_t wpl   = NW >> 5; // bitmap words per lane (contiguous ownership: lane l owns words [l*wpl, (l+1)*wpl))
+        const uint32_t fs    = P.exec_shift - P.ix.tile_shift;
+
+        uint32_t curq = 0xffffffffu;
+        DevQuery Q;
+        Q.item_base = 0;
+        Q.ntiles    = 0;
+
+        for (;;) {
+                uint32_t item = 0;
+                if (lane == 0)
+                        item = atomicAdd(P.ticket, 1u);
+                item = __shfl_sync(0xffffffffu, item, 0);
+                if (item >= P.total_items)
+                        break;
+                if (curq == 0xffffffffu || item < Q.item_base || item - Q.item_base >= Q.ntiles) {
+                        uint32_t qlo = 0, qhi = P.nq;
+                        while (qhi - qlo > 1) {
+                                const uint32_t mid = (qlo + qhi) >> 1;
+                                if (P.queries[mid].item_base <= item) qlo = mid;
+                                else qhi = mid;
+                        }
+                        curq = qlo;
+                        Q    = P.queries[qlo];
+                }
+                const uint32_t tile = Q.tile_lo + (item - Q.item_base);
+                const uint32_t lo = tile << P.exec_shift, hi = lo + W;
+                bool           dead = false;
+
+                for (uint32_t si = 0; si < Q.nsteps && !dead; ++si) {
+                        const DevStep st  = P.steps[Q.step_begin + si];
+                        uint32_t *    dst = slots + size_t(st.dst) * NW;
+                        __syncwarp();
+                        if (st.op == OP_CLEAR) {
+                                for (uint32_t i = lane; i < NW; i += 32)
+                                        dst[i] = 0;
+                        } else if (st.op == OP_SLOT) {
+                                const uint32_t *src = slots + size_t(st.src) * NW;
+                                for (uint32_t i = lane; i < NW; i += 32) {
+                                        const uint32_t s = src[i];
+                                        if (st.mode == M_SET) dst[i] = s;
+                                        else if (st.mode == M_OR) dst[i] |= s;
+                                        else if (st.mode == M_AND) dst[i] &= s;
+                                        else if (st.mode == M_ANDNOT) dst[i] &= ~s;
+                                }
+                        } else if (st.op == OP_LEAF && st.mode != M_NONE) {
+                                uint32_t *tmp      = slots + size_t(P.nslots - 1) * NW;
+                                const int mode     = st.mode;
+                                const bool haveTerm = st.term != kEmptyTerm;
+                                DevTerm    T;
+                                uint32_t   bA = 1, bB = 0;
+                                if (haveTerm) {
+                                        T = P.ix.terms[st.term];
+                                        if (T.nblocks) {
+                                                const uint32_t *tf = P.ix.tile_first + size_t(st.term) * (P.ix.ntiles + 1);
+                                                bA                 = tf[min(tile << fs, P.ix.ntiles)];
+                                                bB                 = min(tf[min((tile + 1u) << fs, P.ix.ntiles)], T.nblocks - 1u);
+                                                if (bA >= T.nblocks) {
+                                                        bA = 1;
+                                                        bB = 0;
+                                                }
+                                        }
+                                }
+                                const uint32_t *skipfilt = nullptr;
+                                BitSink         bs;
+                                if (mode == M_SET) {
+                                        for (uint32_t i = lane; i < NW; i += 32)
+                                                dst[i] = 0;
+                                        bs.init(dst, nullptr, M_OR);
+                                } else if (mode == M_OR) {
+                                        bs.init(dst, nullptr, M_OR);
+                                } else if (mode == M_ANDNOT) {
+                                        bs.init(dst, nullptr, M_ANDNOT);
+                                        skipfilt = dst;
+                                } else { // M_AND
+                                        // candidates alive in dst: count + span (the GPU form of "where would advance() land")
+                                        uint32_t cnt = 0, mn = 0xffffffffu, mx = 0;
+                                        for (uint32_t i = 0; i < wpl; ++i) {
+                                                const uint32_t wi = lane * wpl + i, w = dst[wi];
+                                                tmp[wi]           = 0;
+                                                if (w) {
+                                                        cnt += __popc(w);
+                                                        mn = min(mn, wi * 32u + uint32_t(__ffs(int(w)) - 1));
+                                                        mx = wi * 32u + uint32_t(31 - __clz(int(w)));
+                                                }
+                                        }
+                                        for (int d = 16; d > 0; d >>= 1) {
+                                                cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+                                                mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+                                                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+                                        }
+                                        if (cnt == 0) {
+                                                bA = 1;
+                                                bB = 0;
+                                        } else if (cnt < kSparseThreshold && bA <= bB) {
+                                                const uint32_t *bl = P.ix.blk_last + T.dir_begin;
+                                                const uint32_t  a  = warp_lower_bound(bl, bA, bB, lo + mn, lane);
+                                                if (a > bB) {
+                                                        bA = 1;
+                                                        bB = 0;
+                                                } else {
+                                                        const uint32_t b = warp_lower_bound(bl, a, bB, lo + mx, lane);
+                                                        bA               = a;
+                                                        bB               = min(b, bB);
+                                                }
+                                                skipfilt = dst;
+                                        }
+                                        bs.init(tmp, dst, M_OR);
+                                }
+                                __syncwarp();
+                                if (haveTerm && bA <= bB) {
+                                        if (P.ix.codec == 0) google_leaf_warp(P.ix, T, bA, bB, lo, hi, bs, skipfilt, stage, lane);
+                                        else lucene_leaf_warp(P.ix, T, bA, bB, lo, hi, bs, skipfilt, stage, lane);
+                                }
+                                if (mode == M_AND) {
+                                        __syncwarp();
+                                        for (uint32_t i = lane; i < NW; i += 32)
+                                                dst[i] = tmp[i];
+                                }
+                        }
+                        if (st.flags & F_BREAK_IF_EMPTY) {
+                                __syncwarp();
+                                uint32_t any = 0;
+                                for (uint32_t i = lane; i < NW; i += 32)
+                                        any |= dst[i];
+                                if (!__any_sync(0xffffffffu, any != 0))
+                                        dead = true;
+                        }
+                }
+                __syncwarp();
+
+                // ---- emission: ordered compaction of the root docset
+                uint32_t c = 0;
+                const uint32_t *root = slots + size_t(Q.root_slot) * NW;
+                if (!dead)
+                        for (uint32_t i = 0; i < wpl; ++i)
+                                c += __popc(root[lane * wpl + i]);
+                const uint32_t incl  = warp_incl_scan(c, lane);
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                unsigned long long base = 0;
+                if (lane == 0) {
+                        if (total) {
+                                base = atomicAdd(P.seg_cursor, static_cast<unsigned long long>(total));
+                                atomicAdd(&P.match_counts[curq], static_cast<unsigned long long>(total));
+                                if (base + total > P.seg_capacity) {
+                                        *P.overflow = 1;
+                                        base        = ~0ull;
+                                }
+                        }
+                        P.item_off[item] = base;
+                        P.item_cnt[item] = base == ~0ull ? 0u : total;
+                }
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (total && base != ~0ull) {
+                        unsigned long long pos = base + (incl - c);
+                        for (uint32_t i = 0; i < wpl; ++i) {
+                                const uint32_t wi = lane * wpl + i;
+                                uint32_t       w  = root[wi];
+                                while (w) {
+                                        const uint32_t bit = uint32_t(__ffs(int(w)) - 1);
+                                        w &= w - 1;
+                                        P.seg_docids[pos++] = lo + wi * 32u + bit;
+                                }
+                        }
+                }
+        }
+}
+
+size_t exec_docs_smem_bytes(uint32_t exec_shift, uint32_t nslots) {
+        const size_t NW = (size_t(1) << exec_shift) >> 5;
+        return size_t(kDocsWarps) * (size_t(nslots) * NW * 4 + kStageBytes);
+}
+
+int exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots) {
+        const size_t smem = exec_docs_smem_bytes(exec_shift, nslots);
+        if (cudaFuncSetAttribute(k_exec_docs, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+                return 0;
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_exec_docs, kDocsWarps * 32, smem) != cudaSuccess)
+                return 0;
+        return n;
+}
+
+cudaError_t launch_exec_docs(const ExecParams &P, int grid, cudaStream_t stream) {
+        const size_t smem = exec_docs_smem_bytes(P.exec_shift, P.nslots);
+        cudaError_t  e    = cudaFuncSetAttribute(k_exec_docs, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess)
+                return e;
+        k_exec_docs<<<grid, kDocsWarps * 32, smem, stream>>>(P);
+        return cudaGetLastError();
+}

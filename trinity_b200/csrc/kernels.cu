@@ -419,7 +419,7 @@ __device__ __forceinline__ unsigned long long make_key(float score, uint32_t doc
 extern __shared__ __align__(16) uint8_t dyn_smem[];
 
 __global__ void __launch_bounds__(kThreads) k_exec_tiles(ExecParams P) {
-        const uint32_t W     = 1u << P.ix.tile_shift;
+        const uint32_t W     = 1u << P.exec_shift;
         const uint32_t NW    = W >> 5; // bitmap words per slot
         const bool     scored = P.mode != 0;
         // shared memory carve-up
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(kThreads) k_exec_tiles(ExecParams P) {
                 const uint32_t q    = qlo;
                 const DevQuery Q    = P.queries[q];
                 const uint32_t tile = Q.tile_lo + (item - Q.item_base);
-                const uint32_t lo = tile << P.ix.tile_shift, hi = lo + W;
+                const uint32_t lo = tile << P.exec_shift, hi = lo + W;
 
                 if (scored) {
                         for (uint32_t i = tid; i < W; i += kThreads)
@@ -491,8 +491,9 @@ __global__ void __launch_bounds__(kThreads) k_exec_tiles(ExecParams P) {
                                         T = P.ix.terms[st.term];
                                         if (T.nblocks) {
                                                 const uint32_t *tf = P.ix.tile_first + size_t(st.term) * (P.ix.ntiles + 1);
-                                                bA                 = tf[tile];
-                                                bB                 = min(tf[tile + 1], T.nblocks - 1u);
+                                                const uint32_t  fs = P.exec_shift - P.ix.tile_shift; // exec tile = 2^fs directory tiles
+                                                bA                 = tf[min(tile << fs, P.ix.ntiles)];
+                                                bB                 = min(tf[min((tile + 1u) << fs, P.ix.ntiles)], T.nblocks - 1u);
                                                 if (bA >= T.nblocks) {
                                                         bA = 1;
                                                         bB = 0;
@@ -724,6 +725,8 @@ __global__ void __launch_bounds__(kThreads) k_exec_tiles(ExecParams P) {
                 }
         }
 }
+
+#include "exec_docs.cuh"
 
 // ------------------------------------------------------------------------------------------------ segment ordering
 // one CTA per query: exclusive scan of the per-tile match counts -> destination offset of every tile segment
@@ -1003,7 +1006,7 @@ size_t exec_smem_bytes(uint32_t tile_shift, uint32_t nslots, int mode) {
 }
 
 cudaError_t launch_exec_tiles(const ExecParams &P, int grid, cudaStream_t stream) {
-        const size_t smem = exec_smem_bytes(P.ix.tile_shift, P.nslots, P.mode);
+        const size_t smem = exec_smem_bytes(P.exec_shift, P.nslots, P.mode);
         cudaError_t  e    = cudaFuncSetAttribute(k_exec_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess)
                 return e;

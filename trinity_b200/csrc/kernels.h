@@ -7,6 +7,9 @@ namespace trn {
 size_t      exec_smem_bytes(uint32_t tile_shift, uint32_t nslots, int mode);
 int         exec_max_ctas_per_sm(uint32_t tile_shift, uint32_t nslots, int mode);
 cudaError_t launch_exec_tiles(const ExecParams &P, int grid, cudaStream_t stream);
+size_t      exec_docs_smem_bytes(uint32_t exec_shift, uint32_t nslots);
+int         exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots);
+cudaError_t launch_exec_docs(const ExecParams &P, int grid, cudaStream_t stream);
 cudaError_t launch_query_scan(const unsigned long long *match_counts, uint32_t nq, uint64_t *q_offsets, cudaStream_t stream);
 cudaError_t launch_item_scan(const DevQuery *queries, uint32_t nq, const uint32_t *item_cnt, const uint64_t *q_offsets, uint64_t *item_dst, cudaStream_t stream);
 cudaError_t launch_gather(uint32_t total_items, const uint64_t *item_off, const uint32_t *item_cnt, const uint64_t *item_dst, const uint32_t *seg_docids,
