@@ -652,6 +652,21 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
                         return fail(c, TRN_ERR_ARG, "query " + std::to_string(q) + ": " + cc.err);
                 dq.nsteps    = uint32_t(steps.size()) - dq.step_begin;
                 dq.root_slot = uint32_t(rs);
+                dq.flat      = 0;
+                {
+                        // conjunction / disjunction whose operands are all terms (matchallterms / matchanyterms runs)
+                        const auto &R = Q.nodes[cc.root];
+                        if ((R.kind == TRN_NODE_AND || R.kind == TRN_NODE_OR) && R.nchildren <= 16) {
+                                bool allTerms{true};
+                                for (uint32_t ch = 0; ch < R.nchildren; ++ch)
+                                        allTerms &= Q.nodes[R.first_child + ch].kind == TRN_NODE_TERM;
+                                if (allTerms) {
+                                        dq.flat = R.kind == TRN_NODE_AND ? 1u : 2u;
+                                        if (R.kind == TRN_NODE_AND && R.nchildren <= 3)
+                                                maxSlots = std::max<uint32_t>(maxSlots, R.nchildren); // one bitmap per operand
+                                }
+                        }
+                }
                 maxSlots     = std::max(maxSlots, cc.next_slot + 1); // + scratch slot
                 postings += cc.postings;
                 bytes += cc.bytes;

@@ -259,6 +259,8 @@ __device__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
         bs.flush();
 }
 
+#include "exec_docs_flat.cuh"
+
 __global__ void __launch_bounds__(kDocsWarps * 32) k_exec_docs(ExecParams P) {
         const uint32_t W  = 1u << P.exec_shift;
         const uint32_t NW = W >> 5;
@@ -294,8 +296,13 @@ __global__ void __launch_bounds__(kDocsWarps * 32) k_exec_docs(ExecParams P) {
                 const uint32_t tile = Q.tile_lo + (item - Q.item_base);
                 const uint32_t lo = tile << P.exec_shift, hi = lo + W;
                 bool           dead = false;
+                int            handled = 0;
+                if (Q.flat && P.ix.codec == 0)
+                        handled = flat_exec_google(P, Q, tile, lo, W, NW, fs, slots, stage, lane);
+                if (handled == 2)
+                        dead = true;
 
-                for (uint32_t si = 0; si < Q.nsteps && !dead; ++si) {
+                for (uint32_t si = 0; si < Q.nsteps && !dead && handled == 0; ++si) {
                         const DevStep st  = P.steps[Q.step_begin + si];
                         uint32_t *    dst = slots + size_t(st.dst) * NW;
                         __syncwarp();
