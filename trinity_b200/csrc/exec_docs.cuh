@@ -42,9 +42,41 @@ struct DocSink {
 // (no range checks).  The bytes are consumed through a 64-bit register window that is refilled from aligned 32-bit shared loads issued
 // one step ahead (the load is off the dependency chain), and runs of 1-byte deltas — the common case for the dense lists that carry
 // most postings — are consumed four at a time.
-__device__ __forceinline__ void google_block_docs_smem(const uint8_t *p, uint32_t n, uint32_t prev, uint32_t last, uint32_t lo, uint32_t W, BitSink &bs) {
-        // one unsigned compare covers both tile edges: (doc - lo) < W  <=>  lo <= doc < lo + W.  Interior and boundary blocks run the SAME
-        // instruction stream, so a warp never executes the loop twice for the two kinds of lanes.
+// lean word-register bit builder (or-in only, no filter): one shared atomic per touched 32-doc word
+struct BitAcc {
+        uint32_t *bm;
+        uint32_t  cur_w, cur;
+        __device__ __forceinline__ void init(uint32_t *b) {
+                bm    = b;
+                cur_w = 0;
+                cur   = 0;
+        }
+        __device__ __forceinline__ void add(uint32_t rel) {
+                const uint32_t w = rel >> 5;
+                if (w != cur_w) {
+                        if (cur)
+                                atomicOr(&bm[cur_w], cur);
+                        cur_w = w;
+                        cur   = 0;
+                }
+                cur |= 1u << (rel & 31u);
+        }
+        __device__ __forceinline__ void flush() {
+                if (cur)
+                        atomicOr(&bm[cur_w], cur);
+                cur = 0;
+        }
+};
+
+// One lane decodes the doc-delta section of one Google block from SHARED memory, all participating lanes in LOCKSTEP.
+//  * bytes are consumed through a 64-bit register window refilled from aligned 32-bit shared loads issued one step ahead;
+//  * one unsigned compare covers both tile edges: (doc - lo) < W;
+//  * runs of 1-byte deltas are consumed four at a time, but only when EVERY lane of the warp can do so (warp vote), so the warp never
+//    executes the 4-wide and the 1-wide bodies in the same iteration (the per-lane version of this branch cost half the lanes:
+//    16.7 of 32 threads active per instruction, profiles/r01_c_*).
+// Must be called by all lanes in `m` (the lanes that decode a block in this group).
+template <class SINK>
+__device__ __forceinline__ void google_block_docs_smem(unsigned m, const uint8_t *p, uint32_t n, uint32_t prev, uint32_t last, uint32_t lo, uint32_t W, SINK &bs) {
         const uint32_t  misalign = uint32_t(reinterpret_cast<uintptr_t>(p) & 3u);
         const uint32_t *wp       = reinterpret_cast<const uint32_t *>(p - misalign);
         unsigned long long win   = (static_cast<unsigned long long>(wp[1]) << 32 | wp[0]) >> (misalign * 8u);
@@ -53,56 +85,61 @@ __device__ __forceinline__ void google_block_docs_smem(const uint8_t *p, uint32_
         wp += 3;
         uint32_t doc = prev, i = 0;
         const uint32_t nd = n - 1u; // deltas in the block (the last doc comes from the directory)
-        while (i < nd) {
-                if (avail < 4u) {
+        for (;;) {
+                const bool live = i < nd;
+                if (!__any_sync(m, live))
+                        break;
+                if (live && avail < 4u) {
                         win |= static_cast<unsigned long long>(nxt) << (avail * 8u);
                         avail += 4u;
                         nxt = *wp++;
                 }
                 const uint32_t b = uint32_t(win);
-                if ((b & 0x80808080u) == 0u && i + 4u <= nd) {
-                        // four 1-byte deltas
-                        const uint32_t d0 = doc + (b & 0xffu), d1 = d0 + ((b >> 8) & 0xffu), d2 = d1 + ((b >> 16) & 0xffu), d3 = d2 + (b >> 24);
-                        win >>= 32;
-                        avail -= 4u;
-                        i += 4u;
-                        doc = d3;
-                        if (d0 - lo < W) bs.add(d0 - lo);
-                        if (d1 - lo < W) bs.add(d1 - lo);
-                        if (d2 - lo < W) bs.add(d2 - lo);
-                        if (d3 - lo < W) bs.add(d3 - lo);
-                        continue;
-                }
-                uint32_t v, len;
-                const uint32_t b0 = b & 0xffu;
-                if (b0 < 0x80u) {
-                        v   = b0;
-                        len = 1u;
-                } else if (b0 < 0xc0u) {
-                        v   = ((b0 & 0x3fu) << 8) | ((b >> 8) & 0xffu);
-                        len = 2u;
-                } else if (b0 < 0xe0u) {
-                        v   = ((b0 & 0x1fu) << 16) | ((b >> 8) & 0xffffu);
-                        len = 3u;
-                } else if (b0 < 0xf0u) {
-                        v   = ((b0 & 0x0fu) << 24) | (((b >> 8) & 0xffu) << 16) | (((b >> 16) & 0xffu) << 8) | (b >> 24);
-                        len = 4u;
-                } else {
-                        // 5-byte code: u32le in bytes 1..4 (needs one more byte than the 4 guaranteed)
-                        if (avail < 5u) {
-                                win |= static_cast<unsigned long long>(nxt) << (avail * 8u);
-                                avail += 4u;
-                                nxt = *wp++;
+                if (__all_sync(m, !live || ((b & 0x80808080u) == 0u && i + 4u <= nd))) {
+                        if (live) {
+                                // four 1-byte deltas
+                                const uint32_t d0 = doc + (b & 0xffu), d1 = d0 + ((b >> 8) & 0xffu), d2 = d1 + ((b >> 16) & 0xffu), d3 = d2 + (b >> 24);
+                                win >>= 32;
+                                avail -= 4u;
+                                i += 4u;
+                                doc = d3;
+                                if (d0 - lo < W) bs.add(d0 - lo);
+                                if (d1 - lo < W) bs.add(d1 - lo);
+                                if (d2 - lo < W) bs.add(d2 - lo);
+                                if (d3 - lo < W) bs.add(d3 - lo);
                         }
-                        v   = uint32_t(win >> 8);
-                        len = 5u;
+                } else if (live) {
+                        uint32_t       v, len;
+                        const uint32_t b0 = b & 0xffu;
+                        if (b0 < 0x80u) {
+                                v   = b0;
+                                len = 1u;
+                        } else if (b0 < 0xc0u) {
+                                v   = ((b0 & 0x3fu) << 8) | ((b >> 8) & 0xffu);
+                                len = 2u;
+                        } else if (b0 < 0xe0u) {
+                                v   = ((b0 & 0x1fu) << 16) | ((b >> 8) & 0xffffu);
+                                len = 3u;
+                        } else if (b0 < 0xf0u) {
+                                v   = ((b0 & 0x0fu) << 24) | (((b >> 8) & 0xffu) << 16) | (((b >> 16) & 0xffu) << 8) | (b >> 24);
+                                len = 4u;
+                        } else {
+                                // 5-byte code: u32le in bytes 1..4 (needs one more byte than the 4 guaranteed)
+                                if (avail < 5u) {
+                                        win |= static_cast<unsigned long long>(nxt) << (avail * 8u);
+                                        avail += 4u;
+                                        nxt = *wp++;
+                                }
+                                v   = uint32_t(win >> 8);
+                                len = 5u;
+                        }
+                        win >>= len * 8u;
+                        avail -= len;
+                        ++i;
+                        doc += v;
+                        if (doc - lo < W)
+                                bs.add(doc - lo);
                 }
-                win >>= len * 8u;
-                avail -= len;
-                ++i;
-                doc += v;
-                if (doc - lo < W)
-                        bs.add(doc - lo);
         }
         if (last - lo < W)
                 bs.add(last - lo);
@@ -177,7 +214,7 @@ __device__ void google_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
                                 __syncwarp();
                                 if (need) {
                                         const uint8_t *p = stage + skew + (off - first_off);
-                                        google_block_docs_smem(p, n, prev, last, lo, hi - lo, bs);
+                                        google_block_docs_smem(needMask, p, n, prev, last, lo, hi - lo, bs);
                                 }
                         } else if (need) {
                                 // hits-heavy blocks that do not fit the staging area: decode straight from global memory

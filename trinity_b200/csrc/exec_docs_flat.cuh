@@ -104,13 +104,16 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
                                 direct = true;
                 }
                 __syncwarp();
-                if (active) {
+                const unsigned smemMask = __ballot_sync(0xffffffffu, active && !direct);
+                if (active && !direct) {
+                        BitAcc bs;
+                        bs.init(isAnd ? slots + size_t(j) * NW : root);
+                        google_block_docs_smem(smemMask, p, n, prev, last, lo, W, bs);
+                        bs.flush();
+                } else if (active) {
                         BitSink bs;
                         bs.init(isAnd ? slots + size_t(j) * NW : root, nullptr, M_OR);
-                        if (!direct)
-                                google_block_docs_smem(p, n, prev, last, lo, W, bs);
-                        else
-                                google_block_docs<false>(P.ix.index + off, n, prev, last, lo, lo + W, bs);
+                        google_block_docs<false>(P.ix.index + off, n, prev, last, lo, lo + W, bs);
                         bs.flush();
                 }
                 __syncwarp();
