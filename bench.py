@@ -113,8 +113,19 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def shard_range(ndocs: int, rank: int, world: int):
-    return rank * ndocs // world + 1, (rank + 1) * ndocs // world
+from trinity_b200.sharded import shard_range  # noqa: E402  (host-side sharding plumbing)
+
+
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
+    of this same command (profiles/traffic.json, written from the .ncu-rep by scripts/ncu_summary.py); None if not captured"""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(kernel)
+        except Exception:
+            return None
+    return None
 
 
 def main():
@@ -258,6 +269,8 @@ def main():
     d2h = out_bytes_per_batch + (args.nq + 1) * 8 + args.nq * 8
     peak, peak_src = measured_peak()
     k_ms = float(np.mean(kern_ms)) if kern_ms else None
+    kernel_name = "k_exec_docs" if mode == tb.MODE_DOCS_ONLY else "k_exec_tiles"
+    traffic = ncu_traffic(f"{kernel_name}:{args.workload}") if (world == 1 and args.ndocs == 100_000_000 and args.nq == 1000) else None
     algo_bytes = int(res.index_bytes_touched) + out_bytes_per_batch
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None
 
@@ -287,8 +300,8 @@ def main():
         "e2e": {"value": args.nq * K / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": plan_bytes, "d2h_bytes_per_step": d2h,
                 "decoded_postings_per_s": postings_per_batch * K / e2e_s},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "k_exec_tiles", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms},
         "clocks": clocks,
     }
