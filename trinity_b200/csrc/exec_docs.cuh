@@ -42,28 +42,29 @@ struct DocSink {
 // (no range checks).  The bytes are consumed through a 64-bit register window that is refilled from aligned 32-bit shared loads issued
 // one step ahead (the load is off the dependency chain), and runs of 1-byte deltas — the common case for the dense lists that carry
 // most postings — are consumed four at a time.
-// lean word-register bit builder (or-in only, no filter): one shared atomic per touched 32-doc word
+// lean word-register bit builder (or-in only, no filter): one shared-memory reduction per touched 32-doc word.
+// The flush is a single PREDICATED red.shared.or (no branch): with a branch, the two or three lanes of a warp that cross a word
+// boundary at any given posting made the whole warp execute the flush body at ~2/32 lane occupancy on almost every posting.
 struct BitAcc {
-        uint32_t *bm;
-        uint32_t  cur_w, cur;
+        uint32_t bm;    // shared-state-space address of the bitmap
+        uint32_t cur_w, cur;
         __device__ __forceinline__ void init(uint32_t *b) {
-                bm    = b;
+                bm    = uint32_t(__cvta_generic_to_shared(b));
                 cur_w = 0;
                 cur   = 0;
         }
+        __device__ __forceinline__ void red_if(uint32_t flag) {
+                asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p red.shared.or.b32 [%0], %1; }" ::"r"(bm + cur_w * 4u), "r"(cur), "r"(flag) : "memory");
+        }
         __device__ __forceinline__ void add(uint32_t rel) {
-                const uint32_t w = rel >> 5;
-                if (w != cur_w) {
-                        if (cur)
-                                atomicOr(&bm[cur_w], cur);
-                        cur_w = w;
-                        cur   = 0;
-                }
-                cur |= 1u << (rel & 31u);
+                const uint32_t w = rel >> 5, bit = 1u << (rel & 31u);
+                const bool     nw = w != cur_w;
+                red_if((nw && cur) ? 1u : 0u);
+                cur   = nw ? bit : (cur | bit);
+                cur_w = w;
         }
         __device__ __forceinline__ void flush() {
-                if (cur)
-                        atomicOr(&bm[cur_w], cur);
+                red_if(cur);
                 cur = 0;
         }
 };
