@@ -88,11 +88,16 @@ struct trn_ctx {
         DevBuf               d_index, d_blk_last, d_blk_off, d_terms, d_tile_first;
         std::vector<DevTerm> h_terms;
         // batch scratch (grow-only)
-        DevBuf d_queries, d_steps, d_small, d_item_off, d_item_cnt, d_item_dst, d_seg_docids, d_seg_scores, d_out_docids, d_out_scores, d_q_offsets, d_cand,
+        DevBuf d_queries, d_steps, d_small[2], d_item_off, d_item_cnt, d_item_dst, d_seg_docids, d_seg_scores, d_out_docids[2], d_out_scores[2], d_q_offsets[2], d_cand,
             d_topk_docids, d_topk_scores, d_topk_counts, d_dec_a, d_dec_b, d_dec_c, d_dec_docids, d_dec_freqs, d_dec_sums, d_merge_docids, d_merge_scores;
-        PinBuf h_offsets, h_docids, h_scores, h_counts, h_small;
+        PinBuf h_offsets, h_docids, h_scores, h_counts, h_small, h_chunk;
         cudaEvent_t ev0{nullptr}, ev1{nullptr}, evk0{nullptr}, evk1{nullptr};
         bool        have_kernel_events{false};
+        // pipelined host-buffer path (trn_exec_batch): kernels of chunk i+1 overlap the D2H of chunk i
+        cudaStream_t copy_stream{nullptr};
+        cudaEvent_t  ev_done[2]{nullptr, nullptr}, ev_d2h[2]{nullptr, nullptr}, ev_ck0[16]{}, ev_ck1[16]{};
+        uint32_t     pipeline_chunks{4};
+        uint64_t     last_total_hint{0};
         // last batch
         int      last_mode{-1};
         uint32_t last_nq{0}, last_k{0}, last_launches{0};
@@ -464,6 +469,20 @@ extern "C" int trn_create(int device, trn_ctx **out) {
                 if (v >= 14 && v <= 17)
                         c->docs_shift = uint32_t(v);
         }
+        if (const char *e = getenv("TRN_PIPELINE_CHUNKS")) {
+                const int v = atoi(e);
+                if (v >= 1 && v <= 16)
+                        c->pipeline_chunks = uint32_t(v);
+        }
+        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+                CK(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+        }
+        for (int i = 0; i < 16; ++i) {
+                CK(cudaEventCreate(&c->ev_ck0[i]));
+                CK(cudaEventCreate(&c->ev_ck1[i]));
+        }
         CK(cudaEventCreate(&c->ev0));
         CK(cudaEventCreate(&c->ev1));
         CK(cudaEventCreate(&c->evk0));
@@ -475,12 +494,12 @@ extern "C" void trn_destroy(trn_ctx *c) {
         if (!c)
                 return;
         cudaSetDevice(c->device);
-        for (DevBuf *b : {&c->d_index, &c->d_blk_last, &c->d_blk_off, &c->d_terms, &c->d_tile_first, &c->d_queries, &c->d_steps, &c->d_small, &c->d_item_off,
-                          &c->d_item_cnt, &c->d_item_dst, &c->d_seg_docids, &c->d_seg_scores, &c->d_out_docids, &c->d_out_scores, &c->d_q_offsets, &c->d_cand,
+        for (DevBuf *b : {&c->d_index, &c->d_blk_last, &c->d_blk_off, &c->d_terms, &c->d_tile_first, &c->d_queries, &c->d_steps, &c->d_small[0], &c->d_small[1], &c->d_item_off,
+                          &c->d_item_cnt, &c->d_item_dst, &c->d_seg_docids, &c->d_seg_scores, &c->d_out_docids[0], &c->d_out_docids[1], &c->d_out_scores[0], &c->d_out_scores[1], &c->d_q_offsets[0], &c->d_q_offsets[1], &c->d_cand,
                           &c->d_topk_docids, &c->d_topk_scores, &c->d_topk_counts, &c->d_dec_a, &c->d_dec_b, &c->d_dec_c, &c->d_dec_docids, &c->d_dec_freqs,
                           &c->d_dec_sums, &c->d_merge_docids, &c->d_merge_scores})
                 b->release();
-        for (PinBuf *b : {&c->h_offsets, &c->h_docids, &c->h_scores, &c->h_counts, &c->h_small})
+        for (PinBuf *b : {&c->h_offsets, &c->h_docids, &c->h_scores, &c->h_counts, &c->h_small, &c->h_chunk})
                 b->release();
         if (c->ev0)
                 cudaEventDestroy(c->ev0);
@@ -620,7 +639,7 @@ static DevIndex dev_index(trn_ctx *c) {
 
 // =================================================================================================== exec
 // small device scratch layout (d_small): [0] ticket u32, [2..3] seg_cursor u64, [4] overflow u32, then per-query arrays
-extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint32_t nq, int mode, uint32_t k, trn_result *out) {
+static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, int mode, uint32_t k, trn_result *out, int set, cudaEvent_t k0, cudaEvent_t k1) {
         if (!c)
                 return TRN_ERR_ARG;
         if (!c->have_index)
@@ -698,17 +717,17 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
         CK(c->d_queries.ensure(nq * sizeof(DevQuery)));
         CK(c->d_steps.ensure(std::max<size_t>(sizeof(DevStep), steps.size() * sizeof(DevStep))));
         const size_t smallBytes = 64 + size_t(nq) * (8 + 4 + 4);
-        CK(c->d_small.ensure(smallBytes));
-        CK(c->d_q_offsets.ensure((size_t(nq) + 1) * 8));
+        CK(c->d_small[set].ensure(smallBytes));
+        CK(c->d_q_offsets[set].ensure((size_t(nq) + 1) * 8));
         if (mode != TRN_MODE_SCORED_TOPK) {
                 CK(c->d_item_off.ensure(std::max<size_t>(8, size_t(totalItems) * 8)));
                 CK(c->d_item_cnt.ensure(std::max<size_t>(4, size_t(totalItems) * 4)));
                 CK(c->d_item_dst.ensure(std::max<size_t>(8, size_t(totalItems) * 8)));
                 CK(c->d_seg_docids.ensure(std::max<size_t>(4, segCap * 4)));
-                CK(c->d_out_docids.ensure(std::max<size_t>(4, segCap * 4)));
+                CK(c->d_out_docids[set].ensure(std::max<size_t>(4, segCap * 4)));
                 if (scored) {
                         CK(c->d_seg_scores.ensure(std::max<size_t>(4, segCap * 4)));
-                        CK(c->d_out_scores.ensure(std::max<size_t>(4, segCap * 4)));
+                        CK(c->d_out_scores[set].ensure(std::max<size_t>(4, segCap * 4)));
                 }
         } else {
                 CK(c->d_cand.ensure(std::max<size_t>(8, candTotal * 8)));
@@ -716,7 +735,7 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
                 CK(c->d_topk_scores.ensure(size_t(nq) * k * 4));
                 CK(c->d_topk_counts.ensure(size_t(nq) * 4));
         }
-        uint8_t *small        = c->d_small.as<uint8_t>();
+        uint8_t *small        = c->d_small[set].as<uint8_t>();
         auto *   ticket       = reinterpret_cast<uint32_t *>(small);
         auto *   seg_cursor   = reinterpret_cast<unsigned long long *>(small + 8);
         auto *   overflow     = reinterpret_cast<uint32_t *>(small + 16);
@@ -724,7 +743,8 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
         auto *   theta        = reinterpret_cast<uint32_t *>(small + 64 + size_t(nq) * 8);
         auto *   cand_cursor  = reinterpret_cast<uint32_t *>(small + 64 + size_t(nq) * 12);
 
-        CK(cudaEventRecord(c->ev0, c->stream));
+        if (set < 0 || set > 1)
+                return TRN_ERR_ARG;
         CK(cudaMemcpyAsync(c->d_queries.p, hq.data(), nq * sizeof(DevQuery), cudaMemcpyHostToDevice, c->stream));
         if (!steps.empty())
                 CK(cudaMemcpyAsync(c->d_steps.p, steps.data(), steps.size() * sizeof(DevStep), cudaMemcpyHostToDevice, c->stream));
@@ -762,22 +782,22 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
                         return fail(c, TRN_ERR_CUDA, "the exec kernel does not fit on an SM with this many docset slots");
                 const uint64_t workers = warpKernel ? (uint64_t(totalItems) + 3) / 4 : totalItems; // 4 warp-workers per CTA
                 const int      grid    = int(std::min<uint64_t>(uint64_t(c->num_sms) * perSM, std::max<uint64_t>(1, workers)));
-                CK(cudaEventRecord(c->evk0, c->stream));
+                CK(cudaEventRecord(k0, c->stream));
                 if (warpKernel)
                         CK(launch_exec_docs(P, grid, c->stream));
                 else
                         CK(launch_exec_tiles(P, grid, c->stream));
-                CK(cudaEventRecord(c->evk1, c->stream));
+                CK(cudaEventRecord(k1, c->stream));
                 c->have_kernel_events = true;
                 ++launches;
         }
         if (mode != TRN_MODE_SCORED_TOPK) {
-                CK(launch_query_scan(match_counts, nq, c->d_q_offsets.as<uint64_t>(), c->stream));
+                CK(launch_query_scan(match_counts, nq, c->d_q_offsets[set].as<uint64_t>(), c->stream));
                 ++launches;
                 if (totalItems) {
-                        CK(launch_item_scan(P.queries, nq, P.item_cnt, c->d_q_offsets.as<uint64_t>(), c->d_item_dst.as<uint64_t>(), c->stream));
+                        CK(launch_item_scan(P.queries, nq, P.item_cnt, c->d_q_offsets[set].as<uint64_t>(), c->d_item_dst.as<uint64_t>(), c->stream));
                         CK(launch_gather(totalItems, P.item_off, P.item_cnt, c->d_item_dst.as<uint64_t>(), P.seg_docids, P.seg_scores,
-                                         c->d_out_docids.as<uint32_t>(), scored ? c->d_out_scores.as<float>() : nullptr, c->stream));
+                                         c->d_out_docids[set].as<uint32_t>(), scored ? c->d_out_scores[set].as<float>() : nullptr, c->stream));
                         launches += 2;
                 }
         } else {
@@ -785,7 +805,6 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
                                       c->d_topk_counts.as<uint32_t>(), c->stream));
                 ++launches;
         }
-        CK(cudaEventRecord(c->ev1, c->stream));
         c->last_mode     = mode;
         c->last_nq       = nq;
         c->last_k        = k;
@@ -802,6 +821,19 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
         return TRN_OK;
 }
 
+extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint32_t nq, int mode, uint32_t k, trn_result *out) {
+        if (!c)
+                return TRN_ERR_ARG;
+        CK(cudaSetDevice(c->device));
+        c->have_kernel_events = false;
+        CK(cudaEventRecord(c->ev0, c->stream));
+        const int r = exec_device_impl(c, queries, nq, mode, k, out, 0, c->evk0, c->evk1);
+        if (r != TRN_OK)
+                return r;
+        CK(cudaEventRecord(c->ev1, c->stream));
+        return TRN_OK;
+}
+
 extern "C" int trn_fetch_results(trn_ctx *c, trn_result *out) {
         if (!c || !out)
                 return TRN_ERR_ARG;
@@ -809,7 +841,7 @@ extern "C" int trn_fetch_results(trn_ctx *c, trn_result *out) {
                 return fail(c, TRN_ERR_STATE, "no batch executed");
         CK(cudaSetDevice(c->device));
         const uint32_t nq = c->last_nq;
-        const uint8_t *small        = c->d_small.as<uint8_t>();
+        const uint8_t *small        = c->d_small[0].as<uint8_t>();
         const auto *   match_counts = reinterpret_cast<const unsigned long long *>(small + 64);
         CK(c->h_offsets.ensure((size_t(nq) + 1) * 8));
         CK(c->h_counts.ensure(size_t(nq) * 8));
@@ -819,18 +851,18 @@ extern "C" int trn_fetch_results(trn_ctx *c, trn_result *out) {
         std::memset(out, 0, sizeof(*out));
         out->nq = nq;
         if (c->last_mode != TRN_MODE_SCORED_TOPK) {
-                CK(cudaMemcpyAsync(c->h_offsets.p, c->d_q_offsets.p, (size_t(nq) + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaMemcpyAsync(c->h_offsets.p, c->d_q_offsets[0].p, (size_t(nq) + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
                 CK(cudaStreamSynchronize(c->stream));
                 if (c->h_small.as<uint32_t>()[4])
                         return fail(c, TRN_ERR_CAPACITY, "segment buffer overflow (internal bound violated)");
                 const uint64_t total = c->h_offsets.as<uint64_t>()[nq];
                 CK(c->h_docids.ensure(std::max<size_t>(4, total * 4)));
                 if (total)
-                        CK(cudaMemcpyAsync(c->h_docids.p, c->d_out_docids.p, total * 4, cudaMemcpyDeviceToHost, c->stream));
+                        CK(cudaMemcpyAsync(c->h_docids.p, c->d_out_docids[0].p, total * 4, cudaMemcpyDeviceToHost, c->stream));
                 if (c->last_mode == TRN_MODE_SCORED_ALL) {
                         CK(c->h_scores.ensure(std::max<size_t>(4, total * 4)));
                         if (total)
-                                CK(cudaMemcpyAsync(c->h_scores.p, c->d_out_scores.p, total * 4, cudaMemcpyDeviceToHost, c->stream));
+                                CK(cudaMemcpyAsync(c->h_scores.p, c->d_out_scores[0].p, total * 4, cudaMemcpyDeviceToHost, c->stream));
                         out->scores = c->h_scores.as<float>();
                 }
                 CK(cudaStreamSynchronize(c->stream));
@@ -871,11 +903,136 @@ extern "C" int trn_fetch_results(trn_ctx *c, trn_result *out) {
         return TRN_OK;
 }
 
+// Host-buffer entry point.  DOCS_ONLY / SCORED_ALL batches are split into chunks: the fused kernels of chunk i+1 run while the
+// results of chunk i travel to the (pinned) host buffer on a second stream — the e2e time tends to max(kernels, D2H) instead of
+// their sum.  Output-side device buffers are double-buffered (set = chunk parity); everything else is reused in stream order.
 extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq, int mode, uint32_t k, trn_result *out) {
-        const int r = trn_exec_batch_device(c, queries, nq, mode, k, nullptr);
-        if (r != TRN_OK)
-                return r;
-        return trn_fetch_results(c, out);
+        if (!c || !out)
+                return TRN_ERR_ARG;
+        uint32_t nchunks = c->pipeline_chunks;
+        if (mode == TRN_MODE_SCORED_TOPK || nq < 8 * nchunks || nchunks <= 1) {
+                const int r = trn_exec_batch_device(c, queries, nq, mode, k, nullptr);
+                if (r != TRN_OK)
+                        return r;
+                return trn_fetch_results(c, out);
+        }
+        nchunks = std::min<uint32_t>(nchunks, 16);
+        CK(cudaSetDevice(c->device));
+        const bool scored = mode == TRN_MODE_SCORED_ALL;
+        CK(c->h_offsets.ensure((size_t(nq) + 1) * 8));
+        CK(c->h_counts.ensure(size_t(nq) * 8));
+        const uint32_t per = (nq + nchunks - 1) / nchunks;
+        CK(c->h_chunk.ensure(2 * (64 + (size_t(per) + 1) * 16)));
+        uint64_t *hoff = c->h_offsets.as<uint64_t>(), *hcnt = c->h_counts.as<uint64_t>();
+        uint64_t  running{0}, postings{0}, bytes{0};
+        uint32_t  launches{0};
+        struct Chunk {
+                uint32_t q0, n;
+        };
+        std::vector<Chunk> ch;
+        for (uint32_t q0 = 0; q0 < nq; q0 += per)
+                ch.push_back({q0, std::min(per, nq - q0)});
+        auto grow = [&](PinBuf &b, size_t need, size_t keep) -> cudaError_t {
+                if (need <= b.cap)
+                        return cudaSuccess;
+                void *      np{nullptr};
+                const size_t want = need + need / 4 + 4096;
+                cudaError_t e = cudaHostAlloc(&np, want, cudaHostAllocDefault);
+                if (e != cudaSuccess)
+                        return e;
+                if (b.p && keep) {
+                        // earlier chunks' D2H into the old block must have landed before it is copied
+                        cudaStreamSynchronize(c->copy_stream);
+                        std::memcpy(np, b.p, keep);
+                }
+                if (b.p)
+                        cudaFreeHost(b.p);
+                b.p   = np;
+                b.cap = want;
+                return cudaSuccess;
+        };
+        auto finish = [&](uint32_t j) -> int {
+                const int   set = int(j & 1);
+                const auto &C   = ch[j];
+                uint8_t *   hs  = c->h_chunk.as<uint8_t>() + size_t(set) * (64 + (size_t(per) + 1) * 16);
+                uint64_t *  o   = reinterpret_cast<uint64_t *>(hs + 64);
+                uint64_t *  m   = o + per + 1;
+                const uint8_t *small = c->d_small[set].as<uint8_t>();
+                CK(cudaStreamWaitEvent(c->copy_stream, c->ev_done[set], 0));
+                CK(cudaMemcpyAsync(hs, small, 64, cudaMemcpyDeviceToHost, c->copy_stream));
+                CK(cudaMemcpyAsync(o, c->d_q_offsets[set].p, (size_t(C.n) + 1) * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+                CK(cudaMemcpyAsync(m, small + 64, size_t(C.n) * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+                CK(cudaStreamSynchronize(c->copy_stream));
+                if (reinterpret_cast<uint32_t *>(hs)[4])
+                        return fail(c, TRN_ERR_CAPACITY, "segment buffer overflow (internal bound violated)");
+                const uint64_t total = o[C.n];
+                // grow-only pinned result buffers; after the first batch the previous total is the hint that avoids regrowth
+                const size_t need = std::max<size_t>(4, std::max<uint64_t>(running + total, c->last_total_hint) * 4);
+                CK(grow(c->h_docids, need, running * 4));
+                if (scored)
+                        CK(grow(c->h_scores, need, running * 4));
+                if (total) {
+                        CK(cudaMemcpyAsync(c->h_docids.as<uint32_t>() + running, c->d_out_docids[set].p, total * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+                        if (scored)
+                                CK(cudaMemcpyAsync(c->h_scores.as<float>() + running, c->d_out_scores[set].p, total * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+                }
+                CK(cudaEventRecord(c->ev_d2h[set], c->copy_stream));
+                for (uint32_t i = 0; i < C.n; ++i) {
+                        hoff[C.q0 + i] = running + o[i];
+                        hcnt[C.q0 + i] = m[i];
+                }
+                running += total;
+                return TRN_OK;
+        };
+        CK(cudaEventRecord(c->ev0, c->stream));
+        for (uint32_t i = 0; i < ch.size(); ++i) {
+                const int set = int(i & 1);
+                if (i >= 2)
+                        CK(cudaStreamWaitEvent(c->stream, c->ev_d2h[set], 0)); // the set's previous results have left the device
+                trn_result part;
+                const int  r = exec_device_impl(c, queries + ch[i].q0, ch[i].n, mode, k, &part, set, c->ev_ck0[i], c->ev_ck1[i]);
+                if (r != TRN_OK)
+                        return r;
+                CK(cudaEventRecord(c->ev_done[set], c->stream));
+                postings += part.postings_scanned;
+                bytes += part.index_bytes_touched;
+                launches += part.kernel_launches;
+                if (i >= 1) {
+                        const int fr = finish(i - 1);
+                        if (fr != TRN_OK)
+                                return fr;
+                }
+        }
+        CK(cudaEventRecord(c->ev1, c->stream));
+        {
+                const int fr = finish(uint32_t(ch.size()) - 1);
+                if (fr != TRN_OK)
+                        return fr;
+        }
+        CK(cudaStreamSynchronize(c->copy_stream));
+        CK(cudaStreamSynchronize(c->stream));
+        hoff[nq]           = running;
+        c->last_total_hint = running + running / 16;
+        std::memset(out, 0, sizeof(*out));
+        out->nq                  = nq;
+        out->total               = running;
+        out->offsets             = hoff;
+        out->docids              = c->h_docids.as<uint32_t>();
+        out->scores              = scored ? c->h_scores.as<float>() : nullptr;
+        out->match_counts        = hcnt;
+        out->postings_scanned    = postings;
+        out->index_bytes_touched = bytes;
+        out->kernel_launches     = launches;
+        float ms{0}, ksum{0};
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
+                out->device_ms = ms;
+        for (uint32_t i = 0; i < ch.size(); ++i)
+                if (cudaEventElapsedTime(&ms, c->ev_ck0[i], c->ev_ck1[i]) == cudaSuccess)
+                        ksum += ms;
+        out->exec_kernel_ms = ksum;
+        // the split-form API (trn_fetch_results / trn_last_topk_device) refers to a whole batch; a pipelined call leaves none behind
+        c->last_mode = -1;
+        return TRN_OK;
 }
 
 extern "C" int trn_last_topk_device(trn_ctx *c, void **docids, void **scores, void **counts) {
