@@ -231,6 +231,9 @@ def main():
     for _ in range(W):
         res = g.exec_batch(plans, mode, args.k, copy=False, packed=packed)
         exchange()
+    for _ in range(W):  # the device-resident form has its own (whole-batch) buffers: warm those too
+        g.exec_batch_device(plans, mode, args.k, packed=packed)
+        exchange()
     matches_per_batch = int(res.match_counts.sum())
     out_bytes_per_batch = (matches_per_batch * 4) if mode == tb.MODE_DOCS_ONLY else args.nq * args.k * 8
 

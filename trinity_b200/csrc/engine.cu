@@ -586,8 +586,8 @@ extern "C" int trn_upload_index(trn_ctx *c, int codec, const uint8_t *index, uin
                 for (auto &t : ths)
                         t.join();
         }
-        CK(c->d_index.ensure(nbytes + 64));
-        CK(cudaMemsetAsync(c->d_index.p, 0, nbytes + 64, c->stream));
+        CK(c->d_index.ensure(nbytes + 256));
+        CK(cudaMemsetAsync(c->d_index.p, 0, nbytes + 256, c->stream));
         CK(cudaMemcpyAsync(c->d_index.p, index, nbytes, cudaMemcpyHostToDevice, c->stream));
         const size_t nent = dir.blk_last.size();
         CK(c->d_blk_last.ensure(std::max<size_t>(4, nent * 4)));

@@ -11,6 +11,43 @@
 
 static constexpr int      kDocsWarps       = 4;   // warps per CTA (independent workers)
 static constexpr uint32_t kSparseThreshold = 192; // candidates per tile below which AND switches to advance()-style skipping
+static constexpr uint32_t kGatherBytes     = 80;  // bytes of a block's head each lane stages (5 x 16 B; >= 64 payload bytes after alignment)
+static constexpr uint32_t kGatherWords     = kGatherBytes / 4;
+static constexpr uint32_t kGatherBufBytes  = 32 * kGatherBytes;  // one group
+static constexpr uint32_t kDocsStageBytes  = 2 * kGatherBufBytes; // double-buffered (also hosts one Lucene block: <= 2042 B)
+
+// ---- lane-gather staging with cp.async (LDGSTS): no registers, no L1 allocation, completion tracked per group
+__device__ __forceinline__ void gather_issue(const uint8_t *__restrict__ index, uint32_t off, bool need, uint8_t *buf, int lane) {
+        if (need) {
+                const uint8_t *src = index + (off & ~15u);
+                const uint32_t dst = uint32_t(__cvta_generic_to_shared(buf + lane * kGatherBytes));
+#pragma unroll
+                for (uint32_t c = 0; c < kGatherBytes; c += 16u)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c), "l"(src + c) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void gather_wait() {
+        asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+        __syncwarp();
+}
+
+// word sources for the windowed decoder
+struct SmemWords { // contiguous staged bytes
+        const uint32_t *wp;
+        __device__ __forceinline__ uint32_t next() {
+                return *wp++;
+        }
+};
+struct GatherWords { // the lane's kGatherBytes slot, continued from global memory for the rare longer doc-delta section
+        const uint32_t *slot, *g32;
+        uint32_t        k;
+        __device__ __forceinline__ uint32_t next() {
+                const uint32_t w = k < kGatherWords ? slot[k] : __ldg(g32 + k);
+                ++k;
+                return w;
+        }
+};
 
 // lower_bound over bl[a..b] (ascending) for the first index with bl[idx] >= v; returns b+1 if none.  Warp-cooperative 32-ary search.
 __device__ __forceinline__ uint32_t warp_lower_bound(const uint32_t *__restrict__ bl, uint32_t a, uint32_t b, uint32_t v, int lane) {
@@ -76,14 +113,13 @@ struct BitAcc {
 //    executes the 4-wide and the 1-wide bodies in the same iteration (the per-lane version of this branch cost half the lanes:
 //    16.7 of 32 threads active per instruction, profiles/r01_c_*).
 // Must be called by all lanes in `m` (the lanes that decode a block in this group).
-template <class SINK>
-__device__ __forceinline__ void google_block_docs_smem(unsigned m, const uint8_t *p, uint32_t n, uint32_t prev, uint32_t last, uint32_t lo, uint32_t W, SINK &bs) {
-        const uint32_t  misalign = uint32_t(reinterpret_cast<uintptr_t>(p) & 3u);
-        const uint32_t *wp       = reinterpret_cast<const uint32_t *>(p - misalign);
-        unsigned long long win   = (static_cast<unsigned long long>(wp[1]) << 32 | wp[0]) >> (misalign * 8u);
+template <class SINK, class WORDS>
+__device__ __forceinline__ void google_block_docs_win(unsigned m, WORDS &src, uint32_t misalign, uint32_t n, uint32_t prev, uint32_t last, uint32_t lo, uint32_t W,
+                                                      SINK &bs) {
+        const uint32_t     w0  = src.next(), w1 = src.next();
+        unsigned long long win = (static_cast<unsigned long long>(w1) << 32 | w0) >> (misalign * 8u);
         uint32_t        avail    = 8u - misalign; // valid bytes in win
-        uint32_t        nxt      = wp[2];         // prefetched next word
-        wp += 3;
+        uint32_t        nxt      = src.next();    // prefetched next word
         uint32_t doc = prev, i = 0;
         const uint32_t nd = n - 1u; // deltas in the block (the last doc comes from the directory)
         for (;;) {
@@ -93,7 +129,7 @@ __device__ __forceinline__ void google_block_docs_smem(unsigned m, const uint8_t
                 if (live && avail < 4u) {
                         win |= static_cast<unsigned long long>(nxt) << (avail * 8u);
                         avail += 4u;
-                        nxt = *wp++;
+                        nxt = src.next();
                 }
                 const uint32_t b = uint32_t(win);
                 if (__all_sync(m, !live || ((b & 0x80808080u) == 0u && i + 4u <= nd))) {
@@ -129,7 +165,7 @@ __device__ __forceinline__ void google_block_docs_smem(unsigned m, const uint8_t
                                 if (avail < 5u) {
                                         win |= static_cast<unsigned long long>(nxt) << (avail * 8u);
                                         avail += 4u;
-                                        nxt = *wp++;
+                                        nxt = src.next();
                                 }
                                 v   = uint32_t(win >> 8);
                                 len = 5u;
@@ -144,6 +180,21 @@ __device__ __forceinline__ void google_block_docs_smem(unsigned m, const uint8_t
         }
         if (last - lo < W)
                 bs.add(last - lo);
+}
+
+template <class SINK>
+__device__ __forceinline__ void google_block_docs_smem(unsigned m, const uint8_t *p, uint32_t n, uint32_t prev, uint32_t last, uint32_t lo, uint32_t W, SINK &bs) {
+        const uint32_t misalign = uint32_t(reinterpret_cast<uintptr_t>(p) & 3u);
+        SmemWords      src{reinterpret_cast<const uint32_t *>(p - misalign)};
+        google_block_docs_win(m, src, misalign, n, prev, last, lo, W, bs);
+}
+
+template <class SINK>
+__device__ __forceinline__ void google_block_docs_gather(unsigned m, const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n,
+                                                         uint32_t prev, uint32_t last, uint32_t lo, uint32_t W, SINK &bs) {
+        const uint32_t A = off & ~15u, mis = off - A;
+        GatherWords    src{reinterpret_cast<const uint32_t *>(buf + lane * kGatherBytes), reinterpret_cast<const uint32_t *>(index + A), mis >> 2};
+        google_block_docs_win(m, src, mis & 3u, n, prev, last, lo, W, bs);
 }
 
 // generic-pointer fallback (blocks that do not fit the staging area are read straight from global memory)
@@ -174,10 +225,9 @@ __device__ void google_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
         for (uint32_t g = bA; g <= bB; g += 32u) {
                 const uint32_t b      = g + uint32_t(lane);
                 const bool     active = b <= bB;
-                uint32_t       off = 0, offn = 0, last = 0, prev = 0, n = 0;
+                uint32_t       off = 0, last = 0, prev = 0, n = 0;
                 if (active) {
                         off  = bo[b];
-                        offn = bo[b + 1];
                         last = bl[b];
                         prev = b ? bl[b - 1] : 0u;
                         n    = (b + 1u == T.nblocks) ? (T.documents - 32u * (T.nblocks - 1u)) : 32u;
@@ -205,22 +255,11 @@ __device__ void google_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
                 }
                 const uint32_t needMask = __ballot_sync(0xffffffffu, need);
                 if (needMask) {
-                        // stage only the byte span of the lanes that still need their block
-                        const int      l0 = __ffs(int(needMask)) - 1, l1 = 31 - __clz(int(needMask));
-                        const uint32_t first_off = __shfl_sync(0xffffffffu, off, l0);
-                        const uint32_t end_off   = __shfl_sync(0xffffffffu, offn, l1);
-                        const uint32_t span      = end_off - first_off;
-                        if (span + 32u <= kStageBytes) {
-                                const uint32_t skew = stage_copy(ix.index, first_off, span, stage, lane);
-                                __syncwarp();
-                                if (need) {
-                                        const uint8_t *p = stage + skew + (off - first_off);
-                                        google_block_docs_smem(needMask, p, n, prev, last, lo, hi - lo, bs);
-                                }
-                        } else if (need) {
-                                // hits-heavy blocks that do not fit the staging area: decode straight from global memory
-                                google_block_docs<false>(ix.index + off, n, prev, last, lo, hi, bs);
-                        }
+                        // only the lanes whose block can still hold a candidate fetch (the head of) their block
+                        gather_issue(ix.index, off, need, stage, lane);
+                        gather_wait<0>();
+                        if (need)
+                                google_block_docs_gather(needMask, ix.index, off, stage, lane, n, prev, last, lo, hi - lo, bs);
                 }
                 __syncwarp();
         }
@@ -274,7 +313,7 @@ __device__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
                 } else {
                         const uint32_t tail = T.documents & 127u;
                         const uint8_t *p;
-                        if (len + 32u <= kStageBytes) {
+                        if (len + 32u <= kDocsStageBytes) {
                                 const uint32_t skew = stage_copy(ix.index, off, len, stage, lane);
                                 __syncwarp();
                                 p = stage + skew;
@@ -303,7 +342,7 @@ __global__ void __launch_bounds__(kDocsWarps * 32) k_exec_docs(ExecParams P) {
         const uint32_t W  = 1u << P.exec_shift;
         const uint32_t NW = W >> 5;
         const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const size_t   perWarp = size_t(P.nslots) * NW * 4 + kStageBytes;
+        const size_t   perWarp = size_t(P.nslots) * NW * 4 + kDocsStageBytes;
         uint32_t *     slots = reinterpret_cast<uint32_t *>(dyn_smem + perWarp * warp);
         uint8_t *      stage = reinterpret_cast<uint8_t *>(slots + size_t(P.nslots) * NW);
         const uint32_t wpl   = NW >> 5; // bitmap words per lane (contiguous ownership: lane l owns words [l*wpl, (l+1)*wpl))
@@ -481,7 +520,7 @@ __global__ void __launch_bounds__(kDocsWarps * 32) k_exec_docs(ExecParams P) {
 
 size_t exec_docs_smem_bytes(uint32_t exec_shift, uint32_t nslots) {
         const size_t NW = (size_t(1) << exec_shift) >> 5;
-        return size_t(kDocsWarps) * (size_t(nslots) * NW * 4 + kStageBytes);
+        return size_t(kDocsWarps) * (size_t(nslots) * NW * 4 + kDocsStageBytes);
 }
 
 int exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots) {

@@ -6,9 +6,20 @@
 // another this keeps the lanes full when a term has fewer than 32 blocks in the tile (ncu on the term-at-a-time path: 11.7 of 32
 // lanes active per instruction, profiles/r01_b_*).  When the rarest term is sparse inside the tile the caller falls back to the
 // sequential path, whose advance()-style block skipping then saves more than the lane packing gains.
+//
+// Staging: every lane copies only the head of ITS block (kGatherBytes from the 16B-aligned address below the first doc-delta byte)
+// with cp.async (LDGSTS) into its own slot — the doc-delta section of a 32-doc block is at most 31 x 2 bytes for gaps < 16384, and
+// the inline hits behind it (half of the index bytes) never enter the SM.  Groups are double-buffered: the copies of group g+1 are
+// in flight while group g is decoded.  (The span-copy version kept 6 KB per warp for one group, capped the SM at 20 resident warps
+// and exposed every group's global-load latency: 14 % of all stall samples, profiles/r01_c_*.)
 #pragma once
 
 static constexpr uint32_t kFlatMaxLeaves = 16;
+
+struct FlatLane { // per-lane description of one (term, block) work unit
+        uint32_t j, off, n, prev, last;
+        bool     active;
+};
 
 // returns 0 = not applicable (use the step program), 1 = handled (root docset in slot Q.root_slot), 2 = handled, result empty
 __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t tile, uint32_t lo, uint32_t W, uint32_t NW, uint32_t fs, uint32_t *slots,
@@ -58,65 +69,59 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
         const uint32_t nclear = isAnd ? nleaf : 1u;
         for (uint32_t i = lane; i < nclear * NW; i += 32)
                 (isAnd ? slots : root)[i] = 0;
-        __syncwarp();
 
-        for (uint32_t g = 0; g < total; g += 32u) {
-                const uint32_t f      = g + uint32_t(lane);
-                const bool     active = f < total;
-                uint32_t       j      = 0;
+        // lane assignment of group g
+        auto assign = [&](uint32_t g) {
+                FlatLane       L;
+                const uint32_t f = g + uint32_t(lane);
+                L.active         = f < total;
+                uint32_t j       = 0;
                 for (uint32_t k = 0; k + 1u < nleaf; ++k)
                         j += (f >= __shfl_sync(0xffffffffu, incl, int(k))) ? 1u : 0u;
-                if (!active)
+                if (!L.active)
                         j = nleaf - 1u;
                 const uint32_t jincl = __shfl_sync(0xffffffffu, incl, int(j)), jcnt = __shfl_sync(0xffffffffu, mycnt, int(j));
                 const uint32_t b     = __shfl_sync(0xffffffffu, mybA, int(j)) + (f - (jincl - jcnt));
                 const uint32_t dir   = __shfl_sync(0xffffffffu, mydir, int(j));
                 const uint32_t nb    = __shfl_sync(0xffffffffu, mynb, int(j));
                 const uint32_t docs  = __shfl_sync(0xffffffffu, mydocs, int(j));
-                uint32_t       off = 0, offn = 0, last = 0, prev = 0, n = 0;
-                if (active) {
+                L.j                  = j;
+                L.off = L.n = L.prev = L.last = 0;
+                if (L.active) {
                         const uint32_t *bl = P.ix.blk_last + dir, *bo = P.ix.blk_off + dir;
-                        off  = bo[b];
-                        offn = bo[b + 1];
-                        last = bl[b];
-                        prev = b ? bl[b - 1] : 0u;
-                        n    = (b + 1u == nb) ? (docs - 32u * (nb - 1u)) : 32u;
+                        L.off  = bo[b];
+                        L.last = bl[b];
+                        L.prev = b ? bl[b - 1] : 0u;
+                        L.n    = (b + 1u == nb) ? (docs - 32u * (nb - 1u)) : 32u;
                 }
-                // stage the byte span of every term present in this group (a term's blocks are contiguous in the index)
-                const uint32_t jmin  = __shfl_sync(0xffffffffu, j, 0);
-                const uint32_t jmax  = __shfl_sync(0xffffffffu, j, int(min(31u, total - g - 1u)));
-                uint32_t       sbase = 0;
-                const uint8_t *p     = nullptr;
-                bool           direct = false;
-                for (uint32_t jj = jmin; jj <= jmax; ++jj) {
-                        const uint32_t m = __ballot_sync(0xffffffffu, active && j == jj);
-                        if (!m)
-                                continue;
-                        const int      l0 = __ffs(int(m)) - 1, l1 = 31 - __clz(int(m));
-                        const uint32_t first = __shfl_sync(0xffffffffu, off, l0), end = __shfl_sync(0xffffffffu, offn, l1);
-                        const uint32_t span = end - first, copied = ((first + span + 15u) & ~15u) - (first & ~15u);
-                        if (sbase + copied + 32u <= kStageBytes) {
-                                const uint32_t skew = stage_copy(P.ix.index, first, span, stage + sbase, lane);
-                                if (active && j == jj)
-                                        p = stage + sbase + skew + (off - first);
-                                sbase += copied;
-                        } else if (active && j == jj)
-                                direct = true;
-                }
-                __syncwarp();
-                const unsigned smemMask = __ballot_sync(0xffffffffu, active && !direct);
-                if (active && !direct) {
+                return L;
+        };
+
+        FlatLane cur = assign(0);
+        gather_issue(P.ix.index, cur.off, cur.active, stage, lane);
+        __syncwarp(); // slot clears above are visible before the first reduction
+        uint32_t buf = 0;
+        for (uint32_t g = 0; g < total; g += 32u) {
+                FlatLane nxt;
+                nxt.active = false;
+                nxt.j = nxt.off = nxt.n = nxt.prev = nxt.last = 0;
+                const bool more = g + 32u < total;
+                if (more) {
+                        nxt = assign(g + 32u);
+                        gather_issue(P.ix.index, nxt.off, nxt.active, stage + (buf ^ 1u) * kGatherBufBytes, lane);
+                        gather_wait<1>();
+                } else
+                        gather_wait<0>();
+                const unsigned m = __ballot_sync(0xffffffffu, cur.active);
+                if (cur.active) {
                         BitAcc bs;
-                        bs.init(isAnd ? slots + size_t(j) * NW : root);
-                        google_block_docs_smem(smemMask, p, n, prev, last, lo, W, bs);
-                        bs.flush();
-                } else if (active) {
-                        BitSink bs;
-                        bs.init(isAnd ? slots + size_t(j) * NW : root, nullptr, M_OR);
-                        google_block_docs<false>(P.ix.index + off, n, prev, last, lo, lo + W, bs);
+                        bs.init(isAnd ? slots + size_t(cur.j) * NW : root);
+                        google_block_docs_gather(m, P.ix.index, cur.off, stage + buf * kGatherBufBytes, lane, cur.n, cur.prev, cur.last, lo, W, bs);
                         bs.flush();
                 }
                 __syncwarp();
+                cur = nxt;
+                buf ^= 1u;
         }
         if (isAnd) {
                 // operand i lives in slot i; the root of an all-term conjunction is slot 0
