@@ -320,11 +320,16 @@ double tref_bm25(void *h, uint32_t termIdx, uint32_t freq) {
 }
 
 // mode 0: ExecFlags::DocumentsOnly ; mode 1: ExecFlags::AccumulatedScoreScheme + BM25.  Returns #matches (ids/scores filled up to cap)
+int64_t tref_exec2(void *h, const char *q, int mode, uint32_t parserFlags, uint32_t *ids, double *scores, uint64_t cap);
 int64_t tref_exec(void *h, const char *q, int mode, uint32_t *ids, double *scores, uint64_t cap) {
+        return tref_exec2(h, q, mode, 0, ids, scores, cap);
+}
+// parserFlags: ast_parser::Flags (queries.h:230-240), e.g. ParseConstTrueExpr = 8 enables the <expr> syntax (-> DocsSetIterators::Optional)
+int64_t tref_exec2(void *h, const char *q, int mode, uint32_t parserFlags, uint32_t *ids, double *scores, uint64_t cap) {
         auto    x = static_cast<RefIndex *>(h);
         int64_t n{-1};
         guarded([&] {
-                query       qq(str32_t(q, strlen(q)));
+                query       qq(str32_t(q, strlen(q)), default_token_parser_impl, parserFlags);
                 CollectSink sink;
                 sink.cap  = cap;
                 auto reg  = masked_documents_registry::make(nullptr, 0);

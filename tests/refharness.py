@@ -45,6 +45,8 @@ class RefLib:
         L.tref_bm25.argtypes = [vp, u32, u32]
         L.tref_exec.restype = C.c_int64
         L.tref_exec.argtypes = [vp, C.c_char_p, C.c_int, vp, vp, u64]
+        L.tref_exec2.restype = C.c_int64
+        L.tref_exec2.argtypes = [vp, C.c_char_p, C.c_int, u32, vp, vp, u64]
         L.tref_exec_batch.restype = C.c_double
         L.tref_exec_batch.argtypes = [vp, vp, u32, C.c_int, u32, C.c_int, vp, vp, vp, vp]
         L.tref_last_error.restype = C.c_char_p
@@ -129,10 +131,11 @@ class RefIndex:
     def bm25(self, term_idx, freq):
         return self.rl.L.tref_bm25(self.h, term_idx, freq)
 
-    def exec(self, q: str, scored: bool, cap: int):
+    def exec(self, q: str, scored: bool, cap: int, parser_flags: int = 0):
+        """parser_flags: ast_parser::Flags; 8 = ParseConstTrueExpr (the <expr> syntax -> Optional)"""
         ids = np.zeros(max(cap, 1), np.uint32)
         sc = np.zeros(max(cap, 1), np.float64)
-        n = self.rl.L.tref_exec(self.h, q.encode(), 1 if scored else 0, _p(ids), _p(sc), cap)
+        n = self.rl.L.tref_exec2(self.h, q.encode(), 1 if scored else 0, parser_flags, _p(ids), _p(sc), cap)
         if n < 0:
             raise RuntimeError(self.rl.err())
         assert n <= cap, "reference produced more matches than the capacity given"

@@ -72,3 +72,27 @@ def test_abi_exports_every_declared_symbol():
     L = lib()
     for s in EXPORTS:
         assert hasattr(L, s), s
+
+
+OPTIONAL_QUERIES = ["t3 AND <t5>", "<t2> t7", "t3 AND t4 AND <t5>", "t3 <t5> <t7>", "<t5> t3 <t7> t4", "(t3 OR t4) <t5 OR t2>",
+                    "t9 <t2 AND t3>", "(t3 <t5>) OR t7", "t3 <t5> NOT t2", "t3 <t5> <t7> <t2>"]
+
+
+@pytest.mark.parametrize("q", OPTIONAL_QUERIES)
+def test_optional_semantics_match_reference(small, q):
+    """<expr> (ParseConstTrueExpr) next to a conjunction operand -> DocsSetIterators::Optional: main side decides the match,
+    the optional side only adds its score where it is on the document"""
+    r, lists, tdict = small
+    nodes = tb.parse_query(q, tdict)
+    assert tb.NODE_OPTIONAL in [int(k) for k in nodes["kind"]]
+    for x in nodes:
+        if x["kind"] == tb.NODE_TERM and x["term"] != tb.EMPTY_TERM:
+            x["weight"] = tb.bm25_idf(len(lists[int(x["term"])][0]), NDOCS)
+    m, s = evaluate(nodes, lists, NDOCS, weights=True)
+    ids = np.flatnonzero(m).astype(np.uint32)
+    want, _ = r.exec(q, False, NDOCS + 1, parser_flags=8)
+    assert np.array_equal(ids, want)
+    wd, ws = r.exec(q, True, NDOCS + 1, parser_flags=8)
+    assert np.array_equal(ids, wd)
+    rel = np.abs(s[wd] - ws) / np.maximum(np.abs(ws), 1e-30)
+    assert rel.max() <= 1e-5

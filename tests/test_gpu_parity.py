@@ -99,6 +99,24 @@ def test_topk_matches_reference(closed):
             assert_topk_equal(gd, gs, wd, ws, k, f"[{q}] k={k}")
 
 
+def test_optional_matches_reference(closed):
+    """Optional(main, opt): <expr> beside a conjunction operand (exec.cpp:370-377, docset_iterators.h:174-206)"""
+    from test_frontend_cpu import OPTIONAL_QUERIES
+    qs = OPTIONAL_QUERIES
+    res = closed.gpu.exec_batch([closed.plan(q) for q in qs], tb.MODE_DOCS_ONLY)
+    sres = closed.gpu.exec_batch([closed.plan(q, scored=True) for q in qs], tb.MODE_SCORED_ALL)
+    tres = closed.gpu.exec_batch([closed.plan(q, scored=True) for q in qs], tb.MODE_SCORED_TOPK, k=20)
+    for i, q in enumerate(qs):
+        want, _ = closed.ref.exec(q, False, NDOCS, parser_flags=8)
+        assert_same_docs(res.query(i)[0], want, f"[{q}]")
+        wd, ws = closed.ref.exec(q, True, NDOCS, parser_flags=8)
+        gd, gs = sres.query(i)
+        assert_same_docs(gd, wd, f"[{q}] scored")
+        assert_close_scores(gs, ws, f"[{q}]")
+        td, ts = tres.query(i)
+        assert_topk_equal(td, ts, wd, ws, 20, f"[{q}] top-20")
+
+
 def test_structural_scoring_known_answers(ref):
     """which leaves contribute is structural, not 'all positive terms in the doc'"""
     lists = [(np.array(x, np.uint32), np.ones(len(x), np.uint32)) for x in

@@ -18,6 +18,7 @@
 using namespace trn;
 
 static constexpr uint32_t kEmptyTerm = 0xffffffffu; // == device_types.h
+static constexpr int      kConstTrue = 100;        // parser-internal node kind for <expr>
 
 // =================================================================================================== builder
 struct trn_builder {
@@ -449,7 +450,7 @@ struct Parser {
         Op peek(size_t *len) {
                 ws();
                 *len = 0;
-                if (p >= e || *p == ')')
+                if (p >= e || *p == ')' || *p == '>')
                         return NONE;
                 if (keyword("AND", 3)) {
                         *len = 3;
@@ -474,7 +475,7 @@ struct Parser {
                         *len = 1;
                         return NOT;
                 }
-                if (isterm(*p) || *p == '(')
+                if (isterm(*p) || *p == '(' || *p == '<')
                         return AND; // juxtaposition
                 return NONE;
         }
@@ -484,6 +485,23 @@ struct Parser {
         }
         int unary() {
                 ws();
+                if (p < e && *p == '<') {
+                        // const-true expression (ast_parser::Flags::ParseConstTrueExpr, queries.cpp:378-396): matches like `true`, and, next to
+                        // a conjunction operand, only contributes its score -> DocsSetIterators::Optional (exec.cpp:370-377)
+                        ++p;
+                        const int x = subexpr(255);
+                        if (x < 0)
+                                return -1;
+                        ws();
+                        if (p >= e || *p != '>') {
+                                err = "expected '>'";
+                                return -1;
+                        }
+                        ++p;
+                        const int c   = add(kConstTrue);
+                        nodes[c].kids = {x};
+                        return c;
+                }
                 if (p < e && *p == '(') {
                         ++p;
                         const int x = subexpr(255);
@@ -539,13 +557,27 @@ struct Parser {
 };
 
 // flatten chains of the same associative operator (build_iterator exec.cpp:328-400) and drop duplicate term operands
-void flatten(std::vector<Ast> &n, int i) {
-        auto &X = n[i];
-        if (X.kind == TRN_NODE_TERM)
+void flatten_dedup(std::vector<Ast> &n, int i) {
+        std::vector<int> ded;
+        for (int k : n[i].kids) {
+                bool dup{false};
+                if (n[k].kind == TRN_NODE_TERM)
+                        for (int j : ded)
+                                if (n[j].kind == TRN_NODE_TERM && n[j].term == n[k].term)
+                                        dup = true;
+                if (!dup)
+                        ded.push_back(k);
+        }
+        n[i].kids = ded;
+}
+
+// pass 1: merge chains of the same associative operator (build_iterator exec.cpp:328-400) and drop duplicate term operands
+void merge_chains(std::vector<Ast> &n, int i) {
+        if (n[i].kind == TRN_NODE_TERM)
                 return;
-        for (int k : X.kids)
-                flatten(n, k);
-        if (X.kind == TRN_NODE_AND || X.kind == TRN_NODE_OR) {
+        for (int k : n[i].kids)
+                merge_chains(n, k);
+        if (n[i].kind == TRN_NODE_AND || n[i].kind == TRN_NODE_OR) {
                 std::vector<int> out;
                 for (int k : n[i].kids) {
                         if (n[k].kind == n[i].kind)
@@ -553,18 +585,52 @@ void flatten(std::vector<Ast> &n, int i) {
                         else
                                 out.push_back(k);
                 }
-                std::vector<int> ded;
-                for (int k : out) {
-                        bool dup{false};
-                        if (n[k].kind == TRN_NODE_TERM)
-                                for (int j : ded)
-                                        if (n[j].kind == TRN_NODE_TERM && n[j].term == n[k].term)
-                                                dup = true;
-                        if (!dup)
-                                ded.push_back(k);
-                }
-                n[i].kids = ded;
+                n[i].kids = out;
+                flatten_dedup(n, i);
         }
+}
+
+// pass 2: conjunction operands wrapped in <...> become the optional side of an Optional whose main side is the rest of the chain
+void convert_consttrue(std::vector<Ast> &n, int i) {
+        if (n[i].kind == TRN_NODE_TERM)
+                return;
+        {
+                const std::vector<int> kids = n[i].kids; // n may grow (reallocate) below
+                for (int k : kids)
+                        convert_consttrue(n, k);
+        }
+        if (n[i].kind != TRN_NODE_AND)
+                return;
+        std::vector<int> mains, opts;
+        for (int k : n[i].kids)
+                (n[k].kind == kConstTrue ? opts : mains).push_back(k);
+        if (opts.empty() || mains.empty())
+                return;
+        int mainNode;
+        if (mains.size() == 1)
+                mainNode = mains[0];
+        else {
+                n.push_back(Ast{TRN_NODE_AND, 0, mains});
+                mainNode = int(n.size()) - 1;
+        }
+        // several <...> operands of one conjunction are merged by the reference's compiler into ONE const-true expression over
+        // their conjunction ([<foo> AND <bar>] => [<foo,bar>], compilation_ctx.cpp:371-385)
+        int optExpr = n[opts[0]].kids[0];
+        if (opts.size() > 1) {
+                std::vector<int> es;
+                for (int o : opts)
+                        es.push_back(n[o].kids[0]);
+                n.push_back(Ast{TRN_NODE_AND, 0, es});
+                optExpr = int(n.size()) - 1;
+                merge_chains(n, optExpr);
+        }
+        n[i].kind = TRN_NODE_OPTIONAL;
+        n[i].kids = {mainNode, optExpr};
+}
+
+void flatten(std::vector<Ast> &n, int i) {
+        merge_chains(n, i);
+        convert_consttrue(n, i);
 }
 } // namespace
 
@@ -600,9 +666,14 @@ extern "C" int trn_parse_query(const char *text, const char *const *names, uint3
                 return seterr("trailing input at offset " + std::to_string(ps.p - text));
         flatten(ps.nodes, r);
         // single-child AND/OR after de-duplication collapse to the child
-        int rr = r;
-        while (ps.nodes[rr].kind != TRN_NODE_TERM && ps.nodes[rr].kids.size() == 1 && (ps.nodes[rr].kind == TRN_NODE_AND || ps.nodes[rr].kind == TRN_NODE_OR))
-                rr = ps.nodes[rr].kids[0];
+        // single-operand AND/OR and const-true wrappers that did not end up beside a conjunction operand collapse to their child
+        auto collapse = [&](int x) {
+                while (ps.nodes[x].kind != TRN_NODE_TERM && ps.nodes[x].kids.size() == 1 &&
+                       (ps.nodes[x].kind == TRN_NODE_AND || ps.nodes[x].kind == TRN_NODE_OR || ps.nodes[x].kind == kConstTrue))
+                        x = ps.nodes[x].kids[0];
+                return x;
+        };
+        int rr = collapse(r);
         // emit breadth-first so that children are contiguous and follow their parent
         std::vector<int> order{rr};
         std::vector<trn_qnode> out;
@@ -618,11 +689,7 @@ extern "C" int trn_parse_query(const char *text, const char *const *names, uint3
                 else {
                         std::vector<int> kids;
                         for (int k : A.kids) {
-                                int kk = k;
-                                while (ps.nodes[kk].kind != TRN_NODE_TERM && ps.nodes[kk].kids.size() == 1 &&
-                                       (ps.nodes[kk].kind == TRN_NODE_AND || ps.nodes[kk].kind == TRN_NODE_OR))
-                                        kk = ps.nodes[kk].kids[0];
-                                kids.push_back(kk);
+                                kids.push_back(collapse(k));
                         }
                         if (kids.size() > 255 || out.size() + kids.size() > 65535)
                                 return seterr("query too large");
