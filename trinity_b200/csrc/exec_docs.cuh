@@ -298,7 +298,7 @@ __device__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
                         const uint32_t skew = stage_copy(ix.index, off, len, stage, lane);
                         __syncwarp();
                         uint32_t d[4];
-                        (void)lucene_intblock(stage, skew, lane, d);
+                        (void)lucene_intblock(stage, skew, lane, d, reinterpret_cast<uint32_t *>(stage + 2560));
                         d[1] += d[0];
                         d[2] += d[1];
                         d[3] += d[2];

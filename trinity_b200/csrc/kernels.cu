@@ -23,7 +23,8 @@ namespace trn {
 static constexpr int      kThreads    = 128;
 static constexpr int      kWarps      = kThreads / 32;
 static constexpr uint32_t kStageBytes = 6144; // per-warp staging area for compressed bytes
-static constexpr uint32_t kListCap    = 2048; // smem candidate list (entries) for top-k
+static constexpr uint32_t kListCap    = 2048; // smem candidate list (entries) of the select / merge kernels
+static constexpr uint32_t kTileListCap = 1024; // per-tile candidate list of k_exec_tiles (k <= 512 kept + 512 docs per round)
 static constexpr uint32_t kMaxK       = 512;
 
 // ------------------------------------------------------------------------------------------------ small helpers
@@ -160,9 +161,10 @@ __device__ __forceinline__ void google_block(const uint8_t *p, uint32_t n, uint3
 
 // Decode blocks [bA, bB] of term T that overlap the tile; warps take groups of 32 consecutive blocks.
 template <bool NEED_FREQ>
-__device__ void google_leaf(const DevIndex &ix, const DevTerm &T, uint32_t bA, uint32_t bB, LeafCtx &lc, const uint32_t *skipfilt, uint8_t *stage_all) {
+__device__ void google_leaf(const DevIndex &ix, const DevTerm &T, uint32_t bA, uint32_t bB, LeafCtx &lc, const uint32_t *skipfilt, uint8_t *stage_all,
+                            uint32_t stageBytes) {
         const int       lane  = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        uint8_t *       stage = stage_all + warp * kStageBytes;
+        uint8_t *       stage = stage_all + warp * stageBytes;
         const uint32_t *bl    = ix.blk_last + T.dir_begin;
         const uint32_t *bo    = ix.blk_off + T.dir_begin;
         for (uint32_t g = bA + warp * 32u; g <= bB; g += kWarps * 32u) {
@@ -202,7 +204,7 @@ __device__ void google_leaf(const DevIndex &ix, const DevTerm &T, uint32_t bA, u
                                 }
                         }
                 }
-                if (span + 32u <= kStageBytes) {
+                if (span + 32u <= stageBytes) {
                         if (__any_sync(0xffffffffu, need)) {
                                 const uint32_t skew = stage_copy(ix.index, first_off, span, stage, lane);
                                 __syncwarp();
@@ -223,7 +225,7 @@ __device__ void google_leaf(const DevIndex &ix, const DevTerm &T, uint32_t bA, u
 // One warp decodes one 128-doc block; lane l owns values 4l..4l+3.  int-block format: lucene_codec.cpp:26-100,
 // FastPFor<4> page: fastpfor.h:167-270.  `s` = 4B-aligned shared staging, `o` = byte offset of
 // the int-block's u8 L.  Returns the byte offset just past the int-block.
-__device__ __forceinline__ uint32_t lucene_intblock(const uint8_t *s, uint32_t o, int lane, uint32_t v[4]) {
+__device__ __forceinline__ uint32_t lucene_intblock(const uint8_t *s, uint32_t o, int lane, uint32_t v[4], uint32_t *scratch /*128 words, warp-private*/) {
         const uint32_t L = s[o];
         if (L == 0) {
                 const uint8_t *p  = s + o + 1;
@@ -256,35 +258,42 @@ __device__ __forceinline__ uint32_t lucene_intblock(const uint8_t *s, uint32_t o
         const uint8_t *bytes    = s + meta + 4;
         const uint32_t cexcept  = bytes[1];
         if (cexcept) {
+                // Exception patching (fastpfor.h:248-266): out[pos] |= exc << b.  Lane e owns exception e; the patched values travel through a
+                // warp-private scratch (the first version had EVERY lane walk ALL exceptions: ~15 instructions x cexcept per int-block,
+                // the top instruction hot spot of the OR/BM25 profile profiles/r01_f_*).
                 const uint32_t maxbits = bytes[2];
                 const uint32_t k       = maxbits - b;
                 const uint32_t excw    = meta + 4u + ((bytesize + 3u) & ~3u) + 8u; // past bitmap word and count word
-                for (uint32_t e = 0; e < cexcept; ++e) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                        scratch[lane * 4 + t] = v[t];
+                __syncwarp();
+                for (uint32_t e = uint32_t(lane); e < cexcept; e += 32u) {
                         const uint32_t pos = bytes[3 + e];
-                        if ((pos >> 2) == uint32_t(lane)) {
-                                uint32_t ev = 1;
-                                if (k > 1u) {
-                                        const uint32_t bp = e * k, wi = bp >> 5, sh = bp & 31u;
-                                        uint32_t       x  = lds_u32_unaligned(s, excw + wi * 4u) >> sh;
-                                        if (sh + k > 32u)
-                                                x |= lds_u32_unaligned(s, excw + wi * 4u + 4u) << (32u - sh);
-                                        ev = k == 32u ? x : (x & ((1u << k) - 1u));
-                                }
-                                const uint32_t add = ev << b;
-                                if ((pos & 3u) == 0u) v[0] |= add;
-                                else if ((pos & 3u) == 1u) v[1] |= add;
-                                else if ((pos & 3u) == 2u) v[2] |= add;
-                                else v[3] |= add;
+                        uint32_t       ev  = 1;
+                        if (k > 1u) {
+                                const uint32_t bp = e * k, wi = bp >> 5, sh = bp & 31u;
+                                uint32_t       x  = lds_u32_unaligned(s, excw + wi * 4u) >> sh;
+                                if (sh + k > 32u)
+                                        x |= lds_u32_unaligned(s, excw + wi * 4u + 4u) << (32u - sh);
+                                ev = k == 32u ? x : (x & ((1u << k) - 1u));
                         }
+                        scratch[pos] |= ev << b; // positions are distinct within a block
                 }
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                        v[t] = scratch[lane * 4 + t];
+                __syncwarp();
         }
         return pw + L * 4u;
 }
 
 template <bool NEED_FREQ>
-__device__ void lucene_leaf(const DevIndex &ix, const DevTerm &T, uint32_t bA, uint32_t bB, LeafCtx &lc, const uint32_t *skipfilt, uint8_t *stage_all) {
+__device__ void lucene_leaf(const DevIndex &ix, const DevTerm &T, uint32_t bA, uint32_t bB, LeafCtx &lc, const uint32_t *skipfilt, uint8_t *stage_all,
+                            uint32_t stageBytes) {
         const int       lane  = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        uint8_t *       stage = stage_all + warp * kStageBytes;
+        uint8_t *       stage = stage_all + warp * stageBytes;
         const uint32_t *bl    = ix.blk_last + T.dir_begin;
         const uint32_t *bo    = ix.blk_off + T.dir_begin;
         const uint32_t  nfull = T.documents >> 7;
@@ -319,9 +328,9 @@ __device__ void lucene_leaf(const DevIndex &ix, const DevTerm &T, uint32_t bA, u
                         const uint32_t skew = stage_copy(ix.index, off, len, stage, lane);
                         __syncwarp();
                         uint32_t d[4], f[4] = {0, 0, 0, 0};
-                        const uint32_t o2 = lucene_intblock(stage, skew, lane, d);
+                        const uint32_t o2 = lucene_intblock(stage, skew, lane, d, reinterpret_cast<uint32_t *>(stage + 2560));
                         if (NEED_FREQ)
-                                (void)lucene_intblock(stage, o2, lane, f);
+                                (void)lucene_intblock(stage, o2, lane, f, reinterpret_cast<uint32_t *>(stage + 2560));
                         // docIDs = prev + inclusive prefix sum of deltas (lucene_codec.cpp:568-594 update_curdoc)
                         d[1] += d[0];
                         d[2] += d[1];
@@ -338,7 +347,7 @@ __device__ void lucene_leaf(const DevIndex &ix, const DevTerm &T, uint32_t bA, u
                         // tail block: (varbyte delta, varbyte freq) pairs (lucene_codec.cpp:527-550); lane-strided after a serial boundary walk
                         const uint32_t tail = T.documents & 127u;
                         const uint8_t *p;
-                        if (len + 32u <= kStageBytes) {
+                        if (len + 32u <= stageBytes) {
                                 const uint32_t skew = stage_copy(ix.index, off, len, stage, lane);
                                 __syncwarp();
                                 p = stage + skew;
@@ -425,8 +434,8 @@ __global__ void __launch_bounds__(kThreads) k_exec_tiles(ExecParams P) {
         // shared memory carve-up
         uint32_t *slots = reinterpret_cast<uint32_t *>(dyn_smem);                                   // nslots * NW words
         float *   acc   = reinterpret_cast<float *>(dyn_smem + size_t(P.nslots) * NW * 4);         // W floats (scored only)
-        uint8_t * stage = dyn_smem + size_t(P.nslots) * NW * 4 + (scored ? size_t(W) * 4 : 0);     // kWarps * kStageBytes
-        unsigned long long *list = reinterpret_cast<unsigned long long *>(stage + kWarps * kStageBytes); // kListCap keys (top-k only)
+        uint8_t * stage = dyn_smem + size_t(P.nslots) * NW * 4 + (scored ? size_t(W) * 4 : 0);     // kWarps * P.stage_bytes
+        unsigned long long *list = reinterpret_cast<unsigned long long *>(stage + kWarps * P.stage_bytes); // kTileListCap keys (top-k only)
 
         __shared__ uint32_t s_item, s_warp[kWarps + 1], s_misc[4], s_n;
         __shared__ float    s_lut[64];
@@ -589,11 +598,11 @@ __global__ void __launch_bounds__(kThreads) k_exec_tiles(ExecParams P) {
                                         } else
                                                 lc.bits.init(dst, nullptr, M_OR);
                                         if (P.ix.codec == 0) {
-                                                if (doScore) google_leaf<true>(P.ix, T, bA, bB, lc, skipfilt, stage);
-                                                else google_leaf<false>(P.ix, T, bA, bB, lc, skipfilt, stage);
+                                                if (doScore) google_leaf<true>(P.ix, T, bA, bB, lc, skipfilt, stage, P.stage_bytes);
+                                                else google_leaf<false>(P.ix, T, bA, bB, lc, skipfilt, stage, P.stage_bytes);
                                         } else {
-                                                if (doScore) lucene_leaf<true>(P.ix, T, bA, bB, lc, skipfilt, stage);
-                                                else lucene_leaf<false>(P.ix, T, bA, bB, lc, skipfilt, stage);
+                                                if (doScore) lucene_leaf<true>(P.ix, T, bA, bB, lc, skipfilt, stage, P.stage_bytes);
+                                                else lucene_leaf<false>(P.ix, T, bA, bB, lc, skipfilt, stage, P.stage_bytes);
                                         }
                                 }
                                 if (mode == M_AND) {
@@ -669,17 +678,17 @@ __global__ void __launch_bounds__(kThreads) k_exec_tiles(ExecParams P) {
                                 s_n = 0;
                         unsigned long long thr = static_cast<unsigned long long>(*reinterpret_cast<volatile uint32_t *>(&P.theta[q])) << 32;
                         uint32_t           matches = 0;
-                        const uint32_t     rounds  = W / 1024u;
+                        const uint32_t     rounds  = W / 512u;
                         for (uint32_t r = 0; r < rounds; ++r) {
                                 __syncthreads();
-                                // 1024 docs per round: thread t looks at byte (t&3) of word r*32 + (t>>2)
-                                const uint32_t wi   = r * 32u + (uint32_t(tid) >> 2);
-                                uint32_t       bits = (root[wi] >> ((tid & 3) * 8)) & 0xffu;
+                                // 512 docs per round: thread t looks at nibble (t&7) of word r*16 + (t>>3); list holds <= k + 512 <= kTileListCap keys
+                                const uint32_t wi   = r * 16u + (uint32_t(tid) >> 3);
+                                uint32_t       bits = (root[wi] >> ((tid & 7) * 4)) & 0xfu;
                                 matches += __popc(bits);
                                 while (bits) {
                                         const uint32_t bit = uint32_t(__ffs(int(bits)) - 1);
                                         bits &= bits - 1;
-                                        const uint32_t rel = wi * 32u + (tid & 3) * 8u + bit;
+                                        const uint32_t rel = wi * 32u + (tid & 7) * 4u + bit;
                                         const unsigned long long key = make_key(acc[rel], lo + rel);
                                         if (key >= thr) {
                                                 const uint32_t idx = atomicAdd(&s_n, 1u);
@@ -941,8 +950,8 @@ __global__ void __launch_bounds__(kThreads) k_decode_terms(DevIndex ix, const ui
                                 const uint32_t skew = stage_copy(ix.index, off, len, stage, lane);
                                 __syncwarp();
                                 uint32_t d[4], f[4];
-                                const uint32_t o2 = lucene_intblock(stage, skew, lane, d);
-                                (void)lucene_intblock(stage, o2, lane, f);
+                                const uint32_t o2 = lucene_intblock(stage, skew, lane, d, reinterpret_cast<uint32_t *>(stage + 2560));
+                                (void)lucene_intblock(stage, o2, lane, f, reinterpret_cast<uint32_t *>(stage + 2560));
                                 d[1] += d[0];
                                 d[2] += d[1];
                                 d[3] += d[2];
@@ -995,18 +1004,23 @@ __global__ void __launch_bounds__(kThreads) k_decode_terms(DevIndex ix, const ui
 }
 
 // ------------------------------------------------------------------------------------------------ launch wrappers
-size_t exec_smem_bytes(uint32_t tile_shift, uint32_t nslots, int mode) {
+uint32_t exec_stage_bytes(int codec) {
+        // per-warp staging of k_exec_tiles: Google copies the byte span of 32 blocks; one Lucene block is at most 2*(1+4*255) bytes
+        return codec == 0 ? kStageBytes : 3072u; // 2560 block bytes + 512 exception scratch
+}
+
+size_t exec_smem_bytes(uint32_t tile_shift, uint32_t nslots, int mode, int codec) {
         const size_t W = size_t(1) << tile_shift;
-        size_t       s = size_t(nslots) * (W / 32) * 4 + size_t(kWarps) * kStageBytes;
+        size_t       s = size_t(nslots) * (W / 32) * 4 + size_t(kWarps) * exec_stage_bytes(codec);
         if (mode != 0)
                 s += W * 4;
         if (mode == 2)
-                s += size_t(kListCap) * 8;
+                s += size_t(kTileListCap) * 8;
         return s;
 }
 
 cudaError_t launch_exec_tiles(const ExecParams &P, int grid, cudaStream_t stream) {
-        const size_t smem = exec_smem_bytes(P.exec_shift, P.nslots, P.mode);
+        const size_t smem = exec_smem_bytes(P.exec_shift, P.nslots, P.mode, P.ix.codec);
         cudaError_t  e    = cudaFuncSetAttribute(k_exec_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess)
                 return e;
@@ -1014,8 +1028,8 @@ cudaError_t launch_exec_tiles(const ExecParams &P, int grid, cudaStream_t stream
         return cudaGetLastError();
 }
 
-int exec_max_ctas_per_sm(uint32_t tile_shift, uint32_t nslots, int mode) {
-        const size_t smem = exec_smem_bytes(tile_shift, nslots, mode);
+int exec_max_ctas_per_sm(uint32_t tile_shift, uint32_t nslots, int mode, int codec) {
+        const size_t smem = exec_smem_bytes(tile_shift, nslots, mode, codec);
         if (cudaFuncSetAttribute(k_exec_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
                 return 0;
         int n = 0;

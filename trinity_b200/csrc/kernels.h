@@ -4,8 +4,9 @@
 #include <cuda_runtime.h>
 
 namespace trn {
-size_t      exec_smem_bytes(uint32_t tile_shift, uint32_t nslots, int mode);
-int         exec_max_ctas_per_sm(uint32_t tile_shift, uint32_t nslots, int mode);
+uint32_t    exec_stage_bytes(int codec);
+size_t      exec_smem_bytes(uint32_t tile_shift, uint32_t nslots, int mode, int codec);
+int         exec_max_ctas_per_sm(uint32_t tile_shift, uint32_t nslots, int mode, int codec);
 cudaError_t launch_exec_tiles(const ExecParams &P, int grid, cudaStream_t stream);
 size_t      exec_docs_smem_bytes(uint32_t exec_shift, uint32_t nslots);
 int         exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots);
