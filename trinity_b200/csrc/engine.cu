@@ -1070,28 +1070,31 @@ extern "C" int trn_decode_terms(trn_ctx *c, const uint32_t *term_ids, uint32_t n
                 return fail(c, TRN_ERR_ARG, "trn_decode_terms: bad arguments");
         CK(cudaSetDevice(c->device));
         std::vector<uint32_t> unit_base(nterms + 1);
-        std::vector<uint64_t> out_base(nterms + 1);
-        uint64_t              units{0}, posts{0};
+        std::vector<uint64_t> out_base(nterms + 1), host_base(nterms + 1);
+        uint64_t              units{0}, posts{0}, padded{0};
         for (uint32_t i = 0; i < nterms; ++i) {
                 if (term_ids[i] >= c->nterms)
                         return fail(c, TRN_ERR_ARG, "term id out of range");
                 const auto &t = c->h_terms[term_ids[i]];
                 unit_base[i]  = uint32_t(units);
-                out_base[i]   = posts;
+                out_base[i]   = padded; // device rows start on a 128-entry boundary (16-byte vector stores)
+                host_base[i]  = posts;
                 units += c->codec == TRN_CODEC_GOOGLE ? (t.nblocks + 31) / 32 : t.nblocks;
                 posts += t.documents;
+                padded += (uint64_t(t.documents) + 127) / 128 * 128;
                 if (units >= (1ull << 32))
                         return fail(c, TRN_ERR_CAPACITY, "too many decode units");
         }
         unit_base[nterms] = uint32_t(units);
-        out_base[nterms]  = posts;
+        out_base[nterms]  = padded;
+        host_base[nterms] = posts;
         CK(c->d_dec_a.ensure(nterms * 4));
         CK(c->d_dec_b.ensure((nterms + 1) * 4));
         CK(c->d_dec_c.ensure((nterms + 1) * 8));
         CK(c->d_dec_sums.ensure(size_t(nterms) * 16));
         if (materialise) {
-                CK(c->d_dec_docids.ensure(std::max<size_t>(4, posts * 4)));
-                CK(c->d_dec_freqs.ensure(std::max<size_t>(4, posts * 4)));
+                CK(c->d_dec_docids.ensure(std::max<size_t>(16, padded * 4)));
+                CK(c->d_dec_freqs.ensure(std::max<size_t>(16, padded * 4)));
         }
         CK(cudaMemcpyAsync(c->d_dec_a.p, term_ids, nterms * 4, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(c->d_dec_b.p, unit_base.data(), (nterms + 1) * 4, cudaMemcpyHostToDevice, c->stream));
@@ -1100,14 +1103,24 @@ extern "C" int trn_decode_terms(trn_ctx *c, const uint32_t *term_ids, uint32_t n
         CK(cudaEventRecord(c->ev0, c->stream));
         if (units) {
                 const int grid = int(std::min<uint64_t>(uint64_t(c->num_sms) * 8, (units + 3) / 4));
-                CK(launch_decode_terms(dev_index(c), c->d_dec_a.as<uint32_t>(), c->d_dec_b.as<uint32_t>(), c->d_dec_c.as<uint64_t>(), nterms, uint32_t(units),
-                                       materialise ? c->d_dec_docids.as<uint32_t>() : nullptr, materialise ? c->d_dec_freqs.as<uint32_t>() : nullptr,
-                                       c->d_dec_sums.as<unsigned long long>(), grid, c->stream));
+                if (c->codec == TRN_CODEC_GOOGLE)
+                        CK(launch_decode_google(dev_index(c), c->d_dec_a.as<uint32_t>(), c->d_dec_b.as<uint32_t>(), c->d_dec_c.as<uint64_t>(), nterms,
+                                                uint32_t(units), materialise ? c->d_dec_docids.as<uint32_t>() : nullptr,
+                                                materialise ? c->d_dec_freqs.as<uint32_t>() : nullptr, c->d_dec_sums.as<unsigned long long>(), grid, c->stream));
+                else
+                        CK(launch_decode_terms(dev_index(c), c->d_dec_a.as<uint32_t>(), c->d_dec_b.as<uint32_t>(), c->d_dec_c.as<uint64_t>(), nterms,
+                                               uint32_t(units), materialise ? c->d_dec_docids.as<uint32_t>() : nullptr,
+                                               materialise ? c->d_dec_freqs.as<uint32_t>() : nullptr, c->d_dec_sums.as<unsigned long long>(), grid, c->stream));
         }
         CK(cudaEventRecord(c->ev1, c->stream));
         if (materialise && posts) {
-                CK(cudaMemcpyAsync(docids, c->d_dec_docids.p, posts * 4, cudaMemcpyDeviceToHost, c->stream));
-                CK(cudaMemcpyAsync(freqs, c->d_dec_freqs.p, posts * 4, cudaMemcpyDeviceToHost, c->stream));
+                for (uint32_t i = 0; i < nterms; ++i) {
+                        const uint64_t n = host_base[i + 1] - host_base[i];
+                        if (!n)
+                                continue;
+                        CK(cudaMemcpyAsync(docids + host_base[i], c->d_dec_docids.as<uint32_t>() + out_base[i], n * 4, cudaMemcpyDeviceToHost, c->stream));
+                        CK(cudaMemcpyAsync(freqs + host_base[i], c->d_dec_freqs.as<uint32_t>() + out_base[i], n * 4, cudaMemcpyDeviceToHost, c->stream));
+                }
         }
         if (sums)
                 CK(cudaMemcpyAsync(sums, c->d_dec_sums.p, size_t(nterms) * 16, cudaMemcpyDeviceToHost, c->stream));

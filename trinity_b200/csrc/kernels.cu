@@ -1003,6 +1003,8 @@ __global__ void __launch_bounds__(kThreads) k_decode_terms(DevIndex ix, const ui
         }
 }
 
+#include "decode_google.cuh"
+
 // ------------------------------------------------------------------------------------------------ launch wrappers
 uint32_t exec_stage_bytes(int codec) {
         // per-warp staging of k_exec_tiles: Google copies the byte span of 32 blocks; one Lucene block is at most 2*(1+4*255) bytes

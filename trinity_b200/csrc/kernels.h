@@ -21,5 +21,7 @@ cudaError_t launch_topk_merge(const uint32_t *docids, const float *scores, uint3
                               cudaStream_t stream);
 cudaError_t launch_decode_terms(const DevIndex &ix, const uint32_t *term_ids, const uint32_t *unit_base, const uint64_t *out_base, uint32_t nterms,
                                 uint32_t total_units, uint32_t *docids, uint32_t *freqs, unsigned long long *sums, int grid, cudaStream_t stream);
+cudaError_t launch_decode_google(const DevIndex &ix, const uint32_t *term_ids, const uint32_t *unit_base, const uint64_t *out_base, uint32_t nterms,
+                                 uint32_t total_units, uint32_t *docids, uint32_t *freqs, unsigned long long *sums, int grid, cudaStream_t stream);
 uint32_t    kernel_max_k();
 } // namespace trn
