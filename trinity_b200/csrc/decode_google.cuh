@@ -61,6 +61,7 @@ struct Row4 {
         }
 };
 
+template <bool LOCKSTEP>
 __global__ void __launch_bounds__(kThreads) k_decode_google(DevIndex ix, const uint32_t *term_ids, const uint32_t *unit_base /*nterms+1*/, const uint64_t *out_base,
                                                             uint32_t nterms, uint32_t total_units, uint32_t *docids, uint32_t *freqs, unsigned long long *sums) {
         extern __shared__ __align__(16) uint8_t smem[];
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(kThreads) k_decode_google(DevIndex ix, const u
                         uint32_t       doc = cur.prev, c = 0;
                         for (;;) {
                                 const bool live = c < ncodes;
-                                if (!__any_sync(m, live))
+                                if (LOCKSTEP ? !__any_sync(m, live) : !live)
                                         break;
                                 if (live && avail < 4u) {
                                         win |= static_cast<unsigned long long>(nw) << (avail * 8u);
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(kThreads) k_decode_google(DevIndex ix, const u
                                 const bool inDelta = c < nd;
                                 const uint32_t i   = inDelta ? c : c - nd; // index within docs (for deltas) or within freqs
                                 const bool fast    = (b & 0x80808080u) == 0u && (i & 3u) == 0u && (inDelta ? c + 4u <= nd : c + 4u <= ncodes);
-                                if (__all_sync(m, !live || fast)) {
+                                if (LOCKSTEP ? __all_sync(m, !live || fast) : fast) {
                                         if (live) {
                                                 const uint32_t b0 = b & 0xffu, b1 = (b >> 8) & 0xffu, b2 = (b >> 16) & 0xffu, b3 = b >> 24;
                                                 if (inDelta) {
@@ -217,6 +218,10 @@ __global__ void __launch_bounds__(kThreads) k_decode_google(DevIndex ix, const u
 cudaError_t launch_decode_google(const DevIndex &ix, const uint32_t *term_ids, const uint32_t *unit_base, const uint64_t *out_base, uint32_t nterms,
                                  uint32_t total_units, uint32_t *docids, uint32_t *freqs, unsigned long long *sums, int grid, cudaStream_t stream) {
         const size_t smem = size_t(kWarps) * 2 * kDecBufBytes;
-        k_decode_google<<<grid, kThreads, smem, stream>>>(ix, term_ids, unit_base, out_base, nterms, total_units, docids, freqs, sums);
+        static const bool lockstep = getenv("TRN_DECODE_LOCKSTEP") && atoi(getenv("TRN_DECODE_LOCKSTEP")) != 0;
+        if (lockstep)
+                k_decode_google<true><<<grid, kThreads, smem, stream>>>(ix, term_ids, unit_base, out_base, nterms, total_units, docids, freqs, sums);
+        else
+                k_decode_google<false><<<grid, kThreads, smem, stream>>>(ix, term_ids, unit_base, out_base, nterms, total_units, docids, freqs, sums);
         return cudaGetLastError();
 }

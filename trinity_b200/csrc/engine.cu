@@ -1103,7 +1103,9 @@ extern "C" int trn_decode_terms(trn_ctx *c, const uint32_t *term_ids, uint32_t n
         CK(cudaEventRecord(c->ev0, c->stream));
         if (units) {
                 const int grid = int(std::min<uint64_t>(uint64_t(c->num_sms) * 8, (units + 3) / 4));
-                if (c->codec == TRN_CODEC_GOOGLE)
+                // GOOGLE: the materialising variant uses the single-pass kernel with 16-byte vector stores (k_decode_google); the fused
+                // checksum-only variant is faster with the span-staged kernel (measured, profiles/r01_g_microbench_decode.txt)
+                if (c->codec == TRN_CODEC_GOOGLE && materialise)
                         CK(launch_decode_google(dev_index(c), c->d_dec_a.as<uint32_t>(), c->d_dec_b.as<uint32_t>(), c->d_dec_c.as<uint64_t>(), nterms,
                                                 uint32_t(units), materialise ? c->d_dec_docids.as<uint32_t>() : nullptr,
                                                 materialise ? c->d_dec_freqs.as<uint32_t>() : nullptr, c->d_dec_sums.as<unsigned long long>(), grid, c->stream));

@@ -16,6 +16,7 @@
 #include "device_types.h"
 #include "kernels.h"
 #include "varbyte.h"
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 namespace trn {
