@@ -134,6 +134,11 @@ int trn_set_stream(trn_ctx *, void *cuda_stream);
  * copies the raw, unmodified index bytes to HBM and builds the block directory.  max_docid = upper bound of the docID space. */
 int trn_upload_index(trn_ctx *, int codec, const uint8_t *index, uint64_t nbytes, const trn_term *terms, uint32_t nterms, uint32_t max_docid);
 
+/* == masked_documents_registry (docidupdates.h:90-190): documents deleted/updated by newer index sources.  The reference tests every
+ * match against it in the exec Handlers (exec.cpp:1108-1116, `if (!maskedDocumentsRegistry->test(id)) consider(...)`); here the docIDs are
+ * kept as a device bitmap that is AND-NOTed into every tile's result before emission / top-k.  n == 0 clears the registry. */
+int trn_set_masked_documents(trn_ctx *, const uint32_t *docids, uint64_t n);
+
 typedef struct trn_index_info {
         int      codec;
         uint32_t nterms, max_docid, tile_docs, ntiles;

@@ -349,6 +349,36 @@ int64_t tref_exec2(void *h, const char *q, int mode, uint32_t parserFlags, uint3
         return n;
 }
 
+// exec_query with a masked_documents_registry built from `masked` docIDs through the reference's own pack_updates / unpack_updates
+// (docidupdates.cpp:8-118) — the per-match maskedDocumentsRegistry->test(id) of the exec Handlers (exec.cpp:1108-1116)
+int64_t tref_exec_masked(void *h, const char *q, int mode, const uint32_t *masked, uint32_t nmasked, uint32_t *ids, double *scores, uint64_t cap) {
+        auto    x = static_cast<RefIndex *>(h);
+        int64_t n{-1};
+        guarded([&] {
+                query                qq(str32_t(q, strlen(q)));
+                CollectSink          sink;
+                std::vector<docid_t> v(masked, masked + nmasked);
+                IOBuffer             packed;
+                sink.cap = cap;
+                pack_updates(v, &packed);
+                auto ud  = unpack_updates({reinterpret_cast<const uint8_t *>(packed.data()), uint32_t(packed.size())});
+                auto reg = masked_documents_registry::make(&ud, 1);
+                if (mode == 0) {
+                        exec_query(qq, x->src, reg.get(), &sink, nullptr, uint32_t(ExecFlags::DocumentsOnly));
+                } else {
+                        Similarity::IndexSourcesCollectionBM25Scorer        cs;
+                        cs.reset(x->col.get());
+                        std::unique_ptr<Similarity::IndexSourceTermsScorer> sc(cs.new_source_scorer(x->src));
+                        exec_query(qq, x->src, reg.get(), &sink, nullptr, uint32_t(ExecFlags::AccumulatedScoreScheme), sc.get());
+                }
+                memcpy(ids, sink.ids.data(), sink.ids.size() * sizeof(uint32_t));
+                if (mode == 1 && scores)
+                        memcpy(scores, sink.scores.data(), sink.scores.size() * sizeof(double));
+                n = int64_t(sink.n);
+        });
+        return n;
+}
+
 // CPU baseline: run nq queries over `threads` host threads (one query per thread at a time; exec_query is re-entrant, exec.cpp:12).
 // mode 0: collect every matched docID (DocumentsOnly); mode 1: BM25 top-k heap in consider(id, score).
 // Outputs per query: match count, sum of matched ids (mode 0) , top-k (mode 1: ids/scores, k per query, padded with 0).

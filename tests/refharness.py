@@ -47,6 +47,8 @@ class RefLib:
         L.tref_exec.argtypes = [vp, C.c_char_p, C.c_int, vp, vp, u64]
         L.tref_exec2.restype = C.c_int64
         L.tref_exec2.argtypes = [vp, C.c_char_p, C.c_int, u32, vp, vp, u64]
+        L.tref_exec_masked.restype = C.c_int64
+        L.tref_exec_masked.argtypes = [vp, C.c_char_p, C.c_int, vp, u32, vp, vp, u64]
         L.tref_exec_batch.restype = C.c_double
         L.tref_exec_batch.argtypes = [vp, vp, u32, C.c_int, u32, C.c_int, vp, vp, vp, vp]
         L.tref_last_error.restype = C.c_char_p
@@ -139,6 +141,16 @@ class RefIndex:
         if n < 0:
             raise RuntimeError(self.rl.err())
         assert n <= cap, "reference produced more matches than the capacity given"
+        return ids[:n], (sc[:n] if scored else None)
+
+    def exec_masked(self, q: str, scored: bool, masked, cap: int):
+        """exec_query with the reference's masked_documents_registry holding `masked` docIDs"""
+        mk = np.ascontiguousarray(masked, np.uint32)
+        ids = np.zeros(max(cap, 1), np.uint32)
+        sc = np.zeros(max(cap, 1), np.float64)
+        n = self.rl.L.tref_exec_masked(self.h, q.encode(), 1 if scored else 0, _p(mk), len(mk), _p(ids), _p(sc), cap)
+        if n < 0:
+            raise RuntimeError(self.rl.err())
         return ids[:n], (sc[:n] if scored else None)
 
     def exec_batch(self, queries, scored: bool, k: int, threads: int):

@@ -248,6 +248,11 @@ class GpuIndexSource:
         self.docs_cnt = max_docid
         self.codec = codec
 
+    def set_masked_documents(self, docids=None):
+        """== masked_documents_registry: these docIDs never reach consider() / the top-k (None or empty clears)"""
+        d = _u32([] if docids is None else docids)
+        self._ck(self._L.trn_set_masked_documents(self._h, _ptr(d) if len(d) else None, len(d)))
+
     def info(self) -> dict:
         i = TrnIndexInfo()
         self._ck(self._L.trn_index_info_get(self._h, C.byref(i)))

@@ -17,7 +17,7 @@ EXPORTS = [
     "trn_synth_build", "trn_synth_build_shard", "trn_synth_destroy", "trn_synth_index", "trn_synth_hits", "trn_synth_terms", "trn_synth_sum_hits",
     "trn_synth_postings", "trn_synth_positions",
     "trn_directory_probe", "trn_parse_query", "trn_bm25_idf", "trn_bm25_score",
-    "trn_create", "trn_destroy", "trn_last_error", "trn_set_stream", "trn_upload_index", "trn_index_info_get",
+    "trn_create", "trn_destroy", "trn_last_error", "trn_set_stream", "trn_upload_index", "trn_set_masked_documents", "trn_index_info_get",
     "trn_exec_batch", "trn_exec_batch_device", "trn_last_topk_device", "trn_merge_topk", "trn_fetch_results",
     "trn_decode_terms",
 ]
@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
     sig("trn_last_error", C.c_char_p, vp)
     sig("trn_set_stream", i32, vp, vp)
     sig("trn_upload_index", i32, vp, i32, vp, u64, vp, u32, u32)
+    sig("trn_set_masked_documents", i32, vp, vp, u64)
     sig("trn_index_info_get", i32, vp, P(TrnIndexInfo))
     sig("trn_exec_batch", i32, vp, vp, u32, i32, u32, P(TrnResult))
     sig("trn_exec_batch_device", i32, vp, vp, u32, i32, u32, P(TrnResult))

@@ -21,6 +21,7 @@ struct DevIndex {
         const uint32_t *blk_last; // last docID per block (+ sentinel UINT32_MAX per term)
         const uint32_t *blk_off;  // payload byte offset per block (+ sentinel = end of block area)
         const DevTerm * terms;
+        const uint32_t *masked;     // optional docID bitmap of masked (deleted/updated) documents, word i = docIDs [32i, 32i+32)
         const uint32_t *tile_first; // [nterms][ntiles + 1]: first block whose last docID >= tile * tile_docs
         uint32_t        nterms;
         uint32_t        ntiles;

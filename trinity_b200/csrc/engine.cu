@@ -85,7 +85,8 @@ struct trn_ctx {
         uint32_t             nterms{0}, max_docid{0}, tile_shift{13}, ntiles{0}; // tile_shift: directory granularity == scored tile (8192 docs, the reference's window docset_spans.h:74)
         uint32_t             docs_shift{14}; // docID tile (log2) of the warp-per-tile DocumentsOnly kernel
         uint64_t             index_bytes{0}, dir_bytes{0}, total_blocks{0}, total_postings{0};
-        DevBuf               d_index, d_blk_last, d_blk_off, d_terms, d_tile_first;
+        DevBuf               d_index, d_blk_last, d_blk_off, d_terms, d_tile_first, d_masked;
+        bool                 have_masked{false};
         std::vector<DevTerm> h_terms;
         // batch scratch (grow-only)
         DevBuf d_queries, d_steps, d_small[2], d_item_off, d_item_cnt, d_item_dst, d_seg_docids, d_seg_scores, d_out_docids[2], d_out_scores[2], d_q_offsets[2], d_cand,
@@ -494,7 +495,7 @@ extern "C" void trn_destroy(trn_ctx *c) {
         if (!c)
                 return;
         cudaSetDevice(c->device);
-        for (DevBuf *b : {&c->d_index, &c->d_blk_last, &c->d_blk_off, &c->d_terms, &c->d_tile_first, &c->d_queries, &c->d_steps, &c->d_small[0], &c->d_small[1], &c->d_item_off,
+        for (DevBuf *b : {&c->d_index, &c->d_blk_last, &c->d_blk_off, &c->d_terms, &c->d_tile_first, &c->d_masked, &c->d_queries, &c->d_steps, &c->d_small[0], &c->d_small[1], &c->d_item_off,
                           &c->d_item_cnt, &c->d_item_dst, &c->d_seg_docids, &c->d_seg_scores, &c->d_out_docids[0], &c->d_out_docids[1], &c->d_out_scores[0], &c->d_out_scores[1], &c->d_q_offsets[0], &c->d_q_offsets[1], &c->d_cand,
                           &c->d_topk_docids, &c->d_topk_scores, &c->d_topk_counts, &c->d_dec_a, &c->d_dec_b, &c->d_dec_c, &c->d_dec_docids, &c->d_dec_freqs,
                           &c->d_dec_sums, &c->d_merge_docids, &c->d_merge_scores})
@@ -605,6 +606,33 @@ extern "C" int trn_upload_index(trn_ctx *c, int codec, const uint8_t *index, uin
         return TRN_OK;
 }
 
+extern "C" int trn_set_masked_documents(trn_ctx *c, const uint32_t *docids, uint64_t n) {
+        if (!c)
+                return TRN_ERR_ARG;
+        if (!c->have_index)
+                return fail(c, TRN_ERR_STATE, "no index uploaded");
+        if (n && !docids)
+                return fail(c, TRN_ERR_ARG, "trn_set_masked_documents: null docids");
+        CK(cudaSetDevice(c->device));
+        if (n == 0) {
+                c->have_masked = false;
+                return TRN_OK;
+        }
+        // one bit per docID, padded so that every (largest) tile can read its whole word range
+        const uint64_t        span  = ((uint64_t(c->max_docid) >> 17) + 2) << 17;
+        std::vector<uint32_t> words(span / 32, 0u);
+        for (uint64_t i = 0; i < n; ++i) {
+                if (docids[i] == 0 || docids[i] > c->max_docid)
+                        return fail(c, TRN_ERR_ARG, "masked docID outside 1..max_docid");
+                words[docids[i] >> 5] |= 1u << (docids[i] & 31u);
+        }
+        CK(c->d_masked.ensure(words.size() * 4));
+        CK(cudaMemcpyAsync(c->d_masked.p, words.data(), words.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->have_masked = true;
+        return TRN_OK;
+}
+
 extern "C" int trn_index_info_get(trn_ctx *c, trn_index_info *o) {
         if (!c || !o)
                 return TRN_ERR_ARG;
@@ -629,6 +657,7 @@ static DevIndex dev_index(trn_ctx *c) {
         ix.blk_off    = c->d_blk_off.as<uint32_t>();
         ix.terms      = c->d_terms.as<DevTerm>();
         ix.tile_first = c->d_tile_first.as<uint32_t>();
+        ix.masked     = c->have_masked ? c->d_masked.as<uint32_t>() : nullptr;
         ix.nterms     = c->nterms;
         ix.ntiles     = c->ntiles;
         ix.tile_shift = c->tile_shift;

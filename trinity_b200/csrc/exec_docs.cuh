@@ -481,6 +481,14 @@ __global__ void __launch_bounds__(kDocsWarps * 32) k_exec_docs(ExecParams P) {
                 }
                 __syncwarp();
 
+                // ---- masked documents (docidupdates.h masked_documents_registry::test, exec.cpp:1108-1116) never reach the sink
+                if (!dead && P.ix.masked) {
+                        uint32_t *      r  = slots + size_t(Q.root_slot) * NW;
+                        const uint32_t *mk = P.ix.masked + (lo >> 5);
+                        for (uint32_t i = lane; i < NW; i += 32)
+                                r[i] &= ~mk[i];
+                        __syncwarp();
+                }
                 // ---- emission: ordered compaction of the root docset
                 uint32_t c = 0;
                 const uint32_t *root = slots + size_t(Q.root_slot) * NW;

@@ -623,6 +623,14 @@ __global__ void __launch_bounds__(kThreads) k_exec_tiles(ExecParams P) {
                 }
                 __syncthreads();
 
+                // masked documents (masked_documents_registry::test, exec.cpp:1108-1116) never reach the sink / the top-k
+                if (!dead && P.ix.masked) {
+                        uint32_t *      r  = slots + size_t(Q.root_slot) * NW;
+                        const uint32_t *mk = P.ix.masked + (lo >> 5);
+                        for (uint32_t i = tid; i < NW; i += kThreads)
+                                r[i] &= ~mk[i];
+                        __syncthreads();
+                }
                 // ---------------------------------------------------------------- emission
                 const uint32_t *root = slots + size_t(Q.root_slot) * NW;
                 if (dead) {
