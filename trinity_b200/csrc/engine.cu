@@ -467,7 +467,7 @@ extern "C" int trn_create(int device, trn_ctx **out) {
         c->num_sms = prop.multiProcessorCount;
         if (const char *e = getenv("TRN_DOCS_SHIFT")) {
                 const int v = atoi(e);
-                if (v >= 14 && v <= 17)
+                if (v >= 13 && v <= 17)
                         c->docs_shift = uint32_t(v);
         }
         if (const char *e = getenv("TRN_PIPELINE_CHUNKS")) {

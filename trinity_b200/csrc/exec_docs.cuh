@@ -113,6 +113,8 @@ struct BitAcc {
 //    executes the 4-wide and the 1-wide bodies in the same iteration (the per-lane version of this branch cost half the lanes:
 //    16.7 of 32 threads active per instruction, profiles/r01_c_*).
 // Must be called by all lanes in `m` (the lanes that decode a block in this group).
+__device__ int g_docs_lockstep = 1; // experiment switch (TRN_DOCS_LOCKSTEP): warp-voted vs per-lane choice of the 4-wide path
+
 template <class SINK, class WORDS>
 __device__ __forceinline__ void google_block_docs_win(unsigned m, WORDS &src, uint32_t misalign, uint32_t n, uint32_t prev, uint32_t last, uint32_t lo, uint32_t W,
                                                       SINK &bs) {
@@ -122,9 +124,10 @@ __device__ __forceinline__ void google_block_docs_win(unsigned m, WORDS &src, ui
         uint32_t        nxt      = src.next();    // prefetched next word
         uint32_t doc = prev, i = 0;
         const uint32_t nd = n - 1u; // deltas in the block (the last doc comes from the directory)
+        const bool     lockstep = g_docs_lockstep != 0;
         for (;;) {
                 const bool live = i < nd;
-                if (!__any_sync(m, live))
+                if (lockstep ? !__any_sync(m, live) : !live)
                         break;
                 if (live && avail < 4u) {
                         win |= static_cast<unsigned long long>(nxt) << (avail * 8u);
@@ -132,7 +135,8 @@ __device__ __forceinline__ void google_block_docs_win(unsigned m, WORDS &src, ui
                         nxt = src.next();
                 }
                 const uint32_t b = uint32_t(win);
-                if (__all_sync(m, !live || ((b & 0x80808080u) == 0u && i + 4u <= nd))) {
+                const bool fast4 = (b & 0x80808080u) == 0u && i + 4u <= nd;
+                if (lockstep ? __all_sync(m, !live || fast4) : fast4) {
                         if (live) {
                                 // four 1-byte deltas
                                 const uint32_t d0 = doc + (b & 0xffu), d1 = d0 + ((b >> 8) & 0xffu), d2 = d1 + ((b >> 16) & 0xffu), d3 = d2 + (b >> 24);
@@ -222,46 +226,80 @@ __device__ void google_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
                                  uint8_t *stage, int lane) {
         const uint32_t *bl = ix.blk_last + T.dir_begin;
         const uint32_t *bo = ix.blk_off + T.dir_begin;
-        for (uint32_t g = bA; g <= bB; g += 32u) {
-                const uint32_t b      = g + uint32_t(lane);
-                const bool     active = b <= bB;
-                uint32_t       off = 0, last = 0, prev = 0, n = 0;
-                if (active) {
+        // decode the blocks whose indices are given per lane (b valid where `need`)
+        auto decode_group = [&](uint32_t b, bool need) {
+                uint32_t off = 0, last = 0, prev = 0, n = 0;
+                if (need) {
                         off  = bo[b];
                         last = bl[b];
                         prev = b ? bl[b - 1] : 0u;
                         n    = (b + 1u == T.nblocks) ? (T.documents - 32u * (T.nblocks - 1u)) : 32u;
                 }
-                bool need = active;
-                if (need && skipfilt) {
-                        const uint32_t d0 = max(prev + 1u, lo), d1 = min(last, hi - 1u);
-                        if (d1 < d0)
-                                need = false;
-                        else {
-                                const uint32_t r0 = d0 - lo, r1 = d1 - lo, w0 = r0 >> 5, w1 = r1 >> 5;
-                                if (w1 - w0 <= 7u) {
-                                        uint32_t any = 0;
-                                        for (uint32_t w = w0; w <= w1; ++w) {
-                                                uint32_t m = skipfilt[w];
-                                                if (w == w0)
-                                                        m &= 0xffffffffu << (r0 & 31u);
-                                                if (w == w1)
-                                                        m &= 0xffffffffu >> (31u - (r1 & 31u));
-                                                any |= m;
-                                        }
-                                        need = any != 0;
-                                }
-                        }
-                }
                 const uint32_t needMask = __ballot_sync(0xffffffffu, need);
                 if (needMask) {
-                        // only the lanes whose block can still hold a candidate fetch (the head of) their block
                         gather_issue(ix.index, off, need, stage, lane);
                         gather_wait<0>();
                         if (need)
                                 google_block_docs_gather(needMask, ix.index, off, stage, lane, n, prev, last, lo, hi - lo, bs);
                 }
                 __syncwarp();
+        };
+        if (!skipfilt) {
+                for (uint32_t g = bA; g <= bB; g += 32u) {
+                        const uint32_t b = g + uint32_t(lane);
+                        decode_group(b, b <= bB);
+                }
+        } else {
+                // Sparse destination docset (few candidates): first collect the blocks whose docID range still holds a candidate — the
+                // advance()/skiplist step of the reference (google_codec.cpp:821-934) — THEN decode them 32 at a time.  Decoding inside the
+                // scan loop ran the lane-serial block decoder with ~4 of 32 lanes active (profiles/r01_e_*), which cost as many issue slots
+                // as all the dense tiles together.
+                uint32_t *     list = reinterpret_cast<uint32_t *>(stage + kGatherBufBytes); // second gather buffer: 640 block indices
+                const uint32_t cap  = kGatherBufBytes / 4u - 32u;
+                uint32_t       nlist = 0;
+                auto           drain = [&]() {
+                        __syncwarp();
+                        for (uint32_t i0 = 0; i0 < nlist; i0 += 32u) {
+                                const uint32_t idx = i0 + uint32_t(lane);
+                                const bool     on  = idx < nlist;
+                                decode_group(on ? list[idx] : 0u, on);
+                        }
+                        nlist = 0;
+                        __syncwarp();
+                };
+                for (uint32_t g = bA; g <= bB; g += 32u) {
+                        const uint32_t b    = g + uint32_t(lane);
+                        bool           need = b <= bB;
+                        if (need) {
+                                const uint32_t last = bl[b], prev = b ? bl[b - 1] : 0u;
+                                const uint32_t d0 = max(prev + 1u, lo), d1 = min(last, hi - 1u);
+                                if (d1 < d0)
+                                        need = false;
+                                else {
+                                        const uint32_t r0 = d0 - lo, r1 = d1 - lo, w0 = r0 >> 5, w1 = r1 >> 5;
+                                        if (w1 - w0 <= 7u) {
+                                                uint32_t any = 0;
+                                                for (uint32_t w = w0; w <= w1; ++w) {
+                                                        uint32_t m = skipfilt[w];
+                                                        if (w == w0)
+                                                                m &= 0xffffffffu << (r0 & 31u);
+                                                        if (w == w1)
+                                                                m &= 0xffffffffu >> (31u - (r1 & 31u));
+                                                        any |= m;
+                                                }
+                                                need = any != 0;
+                                        }
+                                }
+                        }
+                        const uint32_t mask = __ballot_sync(0xffffffffu, need);
+                        if (need)
+                                list[nlist + __popc(mask & ((1u << lane) - 1u))] = b;
+                        nlist += __popc(mask);
+                        if (nlist > cap)
+                                drain();
+                }
+                if (nlist)
+                        drain();
         }
         bs.flush();
 }
@@ -542,6 +580,14 @@ int exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots) {
 }
 
 cudaError_t launch_exec_docs(const ExecParams &P, int grid, cudaStream_t stream) {
+        static bool once = false;
+        if (!once) {
+                once = true;
+                if (const char *e = getenv("TRN_DOCS_LOCKSTEP")) {
+                        const int v = atoi(e);
+                        cudaMemcpyToSymbol(g_docs_lockstep, &v, sizeof(int));
+                }
+        }
         const size_t smem = exec_docs_smem_bytes(P.exec_shift, P.nslots);
         cudaError_t  e    = cudaFuncSetAttribute(k_exec_docs, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess)
