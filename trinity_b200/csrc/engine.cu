@@ -465,6 +465,11 @@ extern "C" int trn_create(int device, trn_ctx **out) {
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         c->num_sms = prop.multiProcessorCount;
+        if (const char *e = getenv("TRN_TILE_SHIFT")) { // directory granularity == tile of the scored kernel (experiments)
+                const int v = atoi(e);
+                if (v >= 12 && v <= 14)
+                        c->tile_shift = uint32_t(v);
+        }
         if (const char *e = getenv("TRN_DOCS_SHIFT")) {
                 const int v = atoi(e);
                 if (v >= 13 && v <= 17)
@@ -1134,7 +1139,8 @@ extern "C" int trn_decode_terms(trn_ctx *c, const uint32_t *term_ids, uint32_t n
                 const int grid = int(std::min<uint64_t>(uint64_t(c->num_sms) * 8, (units + 3) / 4));
                 // GOOGLE: the materialising variant uses the single-pass kernel with 16-byte vector stores (k_decode_google); the fused
                 // checksum-only variant is faster with the span-staged kernel (measured, profiles/r01_g_microbench_decode.txt)
-                if (c->codec == TRN_CODEC_GOOGLE && materialise)
+                static const bool forceNew = getenv("TRN_DECODE_KERNEL") && std::string(getenv("TRN_DECODE_KERNEL")) == "single-pass";
+                if (c->codec == TRN_CODEC_GOOGLE && (materialise || forceNew))
                         CK(launch_decode_google(dev_index(c), c->d_dec_a.as<uint32_t>(), c->d_dec_b.as<uint32_t>(), c->d_dec_c.as<uint64_t>(), nterms,
                                                 uint32_t(units), materialise ? c->d_dec_docids.as<uint32_t>() : nullptr,
                                                 materialise ? c->d_dec_freqs.as<uint32_t>() : nullptr, c->d_dec_sums.as<unsigned long long>(), grid, c->stream));
