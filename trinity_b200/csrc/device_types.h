@@ -67,6 +67,7 @@ struct ExecParams {
         uint32_t        total_items;
         uint32_t        nslots; // bitmap slots per worker (CTA for k_exec_tiles, warp for k_exec_docs)
         uint32_t        stage_bytes; // per-warp staging bytes of k_exec_tiles (codec dependent)
+        uint32_t        docs_stage_bytes; // per-warp staging bytes of k_exec_docs (1 or 2 gather buffers)
         uint32_t        exec_shift; // log2 of the docID tile of THIS launch (>= ix.tile_shift; tile_first is indexed at ix.tile_shift granularity)
         int             mode;   // TRN_MODE_*
         uint32_t        k;

@@ -83,6 +83,7 @@ struct trn_ctx {
         bool                 have_index{false};
         int                  codec{0};
         uint32_t             nterms{0}, max_docid{0}, tile_shift{13}, ntiles{0}; // tile_shift: directory granularity == scored tile (8192 docs, the reference's window docset_spans.h:74)
+        int                  docs_bufs{2};   // gather staging buffers per warp in k_exec_docs (TRN_DOCS_BUFS)
         uint32_t             docs_shift{14}; // docID tile (log2) of the warp-per-tile DocumentsOnly kernel
         uint64_t             index_bytes{0}, dir_bytes{0}, total_blocks{0}, total_postings{0};
         DevBuf               d_index, d_blk_last, d_blk_off, d_terms, d_tile_first, d_masked;
@@ -470,6 +471,8 @@ extern "C" int trn_create(int device, trn_ctx **out) {
                 if (v >= 12 && v <= 14)
                         c->tile_shift = uint32_t(v);
         }
+        if (const char *e = getenv("TRN_DOCS_BUFS"))
+                c->docs_bufs = atoi(e) >= 2 ? 2 : 1;
         if (const char *e = getenv("TRN_DOCS_SHIFT")) {
                 const int v = atoi(e);
                 if (v >= 13 && v <= 17)
@@ -794,6 +797,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         P.nslots       = maxSlots;
         P.exec_shift   = execShift;
         P.stage_bytes  = exec_stage_bytes(c->codec);
+        P.docs_stage_bytes = exec_docs_stage_bytes(c->docs_bufs);
         P.mode         = mode;
         P.k            = k;
         P.ticket       = ticket;
@@ -812,7 +816,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         uint32_t launches{0};
         if (totalItems) {
                 const bool warpKernel = !scored;
-                const int  perSM      = warpKernel ? exec_docs_max_ctas_per_sm(execShift, maxSlots) : exec_max_ctas_per_sm(execShift, maxSlots, mode, c->codec);
+                const int  perSM      = warpKernel ? exec_docs_max_ctas_per_sm(execShift, maxSlots, exec_docs_stage_bytes(c->docs_bufs)) : exec_max_ctas_per_sm(execShift, maxSlots, mode, c->codec);
                 if (perSM <= 0)
                         return fail(c, TRN_ERR_CUDA, "the exec kernel does not fit on an SM with this many docset slots");
                 const uint64_t workers = warpKernel ? (uint64_t(totalItems) + 3) / 4 : totalItems; // 4 warp-workers per CTA

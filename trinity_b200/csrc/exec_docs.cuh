@@ -14,7 +14,8 @@ static constexpr uint32_t kSparseThreshold = 192; // candidates per tile below w
 static constexpr uint32_t kGatherBytes     = 80;  // bytes of a block's head each lane stages (5 x 16 B; >= 64 payload bytes after alignment)
 static constexpr uint32_t kGatherWords     = kGatherBytes / 4;
 static constexpr uint32_t kGatherBufBytes  = 32 * kGatherBytes;  // one group
-static constexpr uint32_t kDocsStageBytes  = 2 * kGatherBufBytes; // double-buffered (also hosts one Lucene block: <= 2042 B)
+static constexpr uint32_t kDocsStageBytes  = 2 * kGatherBufBytes; // double-buffered staging (also hosts one Lucene block: <= 2042 B + 512 B scratch)
+static constexpr uint32_t kDocsStageBytes1 = kGatherBufBytes + 512; // single-buffered variant: one group + 128-entry need-list / Lucene scratch
 
 // ---- lane-gather staging with cp.async (LDGSTS): no registers, no L1 allocation, completion tracked per group
 __device__ __forceinline__ void gather_issue(const uint8_t *__restrict__ index, uint32_t off, bool need, uint8_t *buf, int lane) {
@@ -223,7 +224,7 @@ __device__ __forceinline__ void google_block_docs(const uint8_t *p, uint32_t n, 
 // Decode blocks [bA, bB] of a Google term into the warp's bitmap.  `sparse`: the destination docset holds few candidates — check each
 // block's docID range against it first and skip blocks (and whole groups) without candidates.
 __device__ void google_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t bA, uint32_t bB, uint32_t lo, uint32_t hi, BitSink &bs, const uint32_t *skipfilt,
-                                 uint8_t *stage, int lane) {
+                                 uint8_t *stage, uint32_t stageBytes, int lane) {
         const uint32_t *bl = ix.blk_last + T.dir_begin;
         const uint32_t *bo = ix.blk_off + T.dir_begin;
         // decode the blocks whose indices are given per lane (b valid where `need`)
@@ -254,8 +255,8 @@ __device__ void google_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
                 // advance()/skiplist step of the reference (google_codec.cpp:821-934) — THEN decode them 32 at a time.  Decoding inside the
                 // scan loop ran the lane-serial block decoder with ~4 of 32 lanes active (profiles/r01_e_*), which cost as many issue slots
                 // as all the dense tiles together.
-                uint32_t *     list = reinterpret_cast<uint32_t *>(stage + kGatherBufBytes); // second gather buffer: 640 block indices
-                const uint32_t cap  = kGatherBufBytes / 4u - 32u;
+                uint32_t *     list = reinterpret_cast<uint32_t *>(stage + kGatherBufBytes); // behind the first gather buffer
+                const uint32_t cap  = (stageBytes - kGatherBufBytes) / 4u - 32u;
                 uint32_t       nlist = 0;
                 auto           drain = [&]() {
                         __syncwarp();
@@ -351,7 +352,7 @@ __device__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
                 } else {
                         const uint32_t tail = T.documents & 127u;
                         const uint8_t *p;
-                        if (len + 32u <= kDocsStageBytes) {
+                        if (len + 32u <= kGatherBufBytes) {
                                 const uint32_t skew = stage_copy(ix.index, off, len, stage, lane);
                                 __syncwarp();
                                 p = stage + skew;
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(kDocsWarps * 32) k_exec_docs(ExecParams P) {
         const uint32_t W  = 1u << P.exec_shift;
         const uint32_t NW = W >> 5;
         const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const size_t   perWarp = size_t(P.nslots) * NW * 4 + kDocsStageBytes;
+        const size_t   perWarp = size_t(P.nslots) * NW * 4 + P.docs_stage_bytes;
         uint32_t *     slots = reinterpret_cast<uint32_t *>(dyn_smem + perWarp * warp);
         uint8_t *      stage = reinterpret_cast<uint8_t *>(slots + size_t(P.nslots) * NW);
         const uint32_t wpl   = NW >> 5; // bitmap words per lane (contiguous ownership: lane l owns words [l*wpl, (l+1)*wpl))
@@ -499,7 +500,7 @@ __global__ void __launch_bounds__(kDocsWarps * 32) k_exec_docs(ExecParams P) {
                                 }
                                 __syncwarp();
                                 if (haveTerm && bA <= bB) {
-                                        if (P.ix.codec == 0) google_leaf_warp(P.ix, T, bA, bB, lo, hi, bs, skipfilt, stage, lane);
+                                        if (P.ix.codec == 0) google_leaf_warp(P.ix, T, bA, bB, lo, hi, bs, skipfilt, stage, P.docs_stage_bytes, lane);
                                         else lucene_leaf_warp(P.ix, T, bA, bB, lo, hi, bs, skipfilt, stage, lane);
                                 }
                                 if (mode == M_AND) {
@@ -564,13 +565,17 @@ __global__ void __launch_bounds__(kDocsWarps * 32) k_exec_docs(ExecParams P) {
         }
 }
 
-size_t exec_docs_smem_bytes(uint32_t exec_shift, uint32_t nslots) {
-        const size_t NW = (size_t(1) << exec_shift) >> 5;
-        return size_t(kDocsWarps) * (size_t(nslots) * NW * 4 + kDocsStageBytes);
+uint32_t exec_docs_stage_bytes(int bufs) {
+        return bufs >= 2 ? kDocsStageBytes : kDocsStageBytes1;
 }
 
-int exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots) {
-        const size_t smem = exec_docs_smem_bytes(exec_shift, nslots);
+size_t exec_docs_smem_bytes(uint32_t exec_shift, uint32_t nslots, uint32_t stageBytes) {
+        const size_t NW = (size_t(1) << exec_shift) >> 5;
+        return size_t(kDocsWarps) * (size_t(nslots) * NW * 4 + stageBytes);
+}
+
+int exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots, uint32_t stageBytes) {
+        const size_t smem = exec_docs_smem_bytes(exec_shift, nslots, stageBytes);
         if (cudaFuncSetAttribute(k_exec_docs, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
                 return 0;
         int n = 0;
@@ -588,7 +593,7 @@ cudaError_t launch_exec_docs(const ExecParams &P, int grid, cudaStream_t stream)
                         cudaMemcpyToSymbol(g_docs_lockstep, &v, sizeof(int));
                 }
         }
-        const size_t smem = exec_docs_smem_bytes(P.exec_shift, P.nslots);
+        const size_t smem = exec_docs_smem_bytes(P.exec_shift, P.nslots, P.docs_stage_bytes);
         cudaError_t  e    = cudaFuncSetAttribute(k_exec_docs, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess)
                 return e;

@@ -97,7 +97,8 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
                 return L;
         };
 
-        FlatLane cur = assign(0);
+        const bool dbuf = P.docs_stage_bytes >= 2u * kGatherBufBytes; // double-buffered staging (else: more resident warps instead)
+        FlatLane   cur  = assign(0);
         gather_issue(P.ix.index, cur.off, cur.active, stage, lane);
         __syncwarp(); // slot clears above are visible before the first reduction
         uint32_t buf = 0;
@@ -106,7 +107,7 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
                 nxt.active = false;
                 nxt.j = nxt.off = nxt.n = nxt.prev = nxt.last = 0;
                 const bool more = g + 32u < total;
-                if (more) {
+                if (more && dbuf) {
                         nxt = assign(g + 32u);
                         gather_issue(P.ix.index, nxt.off, nxt.active, stage + (buf ^ 1u) * kGatherBufBytes, lane);
                         gather_wait<1>();
@@ -120,8 +121,13 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
                         bs.flush();
                 }
                 __syncwarp();
-                cur = nxt;
-                buf ^= 1u;
+                if (dbuf) {
+                        cur = nxt;
+                        buf ^= 1u;
+                } else if (more) {
+                        cur = assign(g + 32u);
+                        gather_issue(P.ix.index, cur.off, cur.active, stage, lane);
+                }
         }
         if (isAnd) {
                 // operand i lives in slot i; the root of an all-term conjunction is slot 0
