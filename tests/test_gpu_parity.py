@@ -227,3 +227,22 @@ def test_edge_cases(ref):
 def test_no_device_fails_loudly():
     with pytest.raises(tb.TrinityError):
         tb.GpuIndexSource(device=4096)
+
+
+def test_large_batches_split_by_result_capacity_and_stay_exact(ref):
+    """a docs-only OR batch whose match upper bound exceeds the staging budget is split internally (pipelined chunks); results
+    must be identical to per-query execution, and a 64-query batch exercises the chunked host-buffer path"""
+    ndocs = 400_000
+    p = Pair(ref, tb.CODEC_GOOGLE, closed_form_lists(ndocs), ndocs)
+    qs = [f"t{1 + i % 10} OR t{1 + (i * 3 + 1) % 10}" for i in range(70)] + [f"t{1 + i % 10} AND t{1 + (i + 1) % 10}" for i in range(70)]
+    res = p.gpu.exec_batch([p.plan(q) for q in qs], tb.MODE_DOCS_ONLY)
+    sres = p.gpu.exec_batch([p.plan(q, scored=True) for q in qs], tb.MODE_SCORED_ALL)
+    cache = {}
+    for i, q in enumerate(qs):
+        if q not in cache:
+            cache[q] = (p.ref.exec(q, False, ndocs + 1)[0], p.ref.exec(q, True, ndocs + 1))
+        assert_same_docs(res.query(i)[0], cache[q][0], f"#{i} [{q}]")
+        gd, gs = sres.query(i)
+        assert_same_docs(gd, cache[q][1][0], f"#{i} [{q}] scored")
+        assert_close_scores(gs, cache[q][1][1], f"#{i} [{q}]")
+    assert int(res.offsets[-1]) == sum(len(cache[q][0]) for q in qs)

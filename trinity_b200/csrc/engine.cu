@@ -750,6 +750,18 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         }
         const uint32_t totalItems = uint32_t(items);
 
+        // ---- result staging must fit the device: a caller (trn_exec_batch) reacts to TRN_ERR_CAPACITY by splitting the batch
+        if (mode != TRN_MODE_SCORED_TOPK) {
+                const uint64_t need = segCap * (scored ? 16ull : 8ull) + uint64_t(totalItems) * 20ull;
+                const uint64_t have = c->d_seg_docids.cap + c->d_out_docids[set].cap + c->d_seg_scores.cap + c->d_out_scores[set].cap;
+                if (need > have) {
+                        size_t freeB{0}, totalB{0};
+                        CK(cudaMemGetInfo(&freeB, &totalB));
+                        if (need - have > uint64_t(double(freeB) * 0.8))
+                                return fail(c, TRN_ERR_CAPACITY, "batch needs " + std::to_string(need >> 20) + " MiB of result staging (upper bound of the matches); split it");
+                }
+        }
+
         // ---- device buffers
         CK(c->d_queries.ensure(nq * sizeof(DevQuery)));
         CK(c->d_steps.ensure(std::max<size_t>(sizeof(DevStep), steps.size() * sizeof(DevStep))));
@@ -829,6 +841,9 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 CK(cudaEventRecord(k1, c->stream));
                 c->have_kernel_events = true;
                 ++launches;
+        } else {
+                CK(cudaEventRecord(k0, c->stream)); // keep the pair fresh: readers must not see a previous batch's events
+                CK(cudaEventRecord(k1, c->stream));
         }
         if (mode != TRN_MODE_SCORED_TOPK) {
                 CK(launch_query_scan(match_counts, nq, c->d_q_offsets[set].as<uint64_t>(), c->stream));
@@ -955,7 +970,6 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                         return r;
                 return trn_fetch_results(c, out);
         }
-        nchunks = std::min<uint32_t>(nchunks, 16);
         CK(cudaSetDevice(c->device));
         const bool scored = mode == TRN_MODE_SCORED_ALL;
         CK(c->h_offsets.ensure((size_t(nq) + 1) * 8));
@@ -965,6 +979,7 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
         uint64_t *hoff = c->h_offsets.as<uint64_t>(), *hcnt = c->h_counts.as<uint64_t>();
         uint64_t  running{0}, postings{0}, bytes{0};
         uint32_t  launches{0};
+        float     ksum{0};
         struct Chunk {
                 uint32_t q0, n;
         };
@@ -1002,6 +1017,11 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                 CK(cudaMemcpyAsync(o, c->d_q_offsets[set].p, (size_t(C.n) + 1) * 8, cudaMemcpyDeviceToHost, c->copy_stream));
                 CK(cudaMemcpyAsync(m, small + 64, size_t(C.n) * 8, cudaMemcpyDeviceToHost, c->copy_stream));
                 CK(cudaStreamSynchronize(c->copy_stream));
+                {
+                        float kms{0}; // the chunk's kernels are complete: its event pair can be read (and its slot reused 16 chunks later)
+                        if (cudaEventElapsedTime(&kms, c->ev_ck0[j % 16], c->ev_ck1[j % 16]) == cudaSuccess)
+                                ksum += kms;
+                }
                 if (reinterpret_cast<uint32_t *>(hs)[4])
                         return fail(c, TRN_ERR_CAPACITY, "segment buffer overflow (internal bound violated)");
                 const uint64_t total = o[C.n];
@@ -1029,7 +1049,15 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                 if (i >= 2)
                         CK(cudaStreamWaitEvent(c->stream, c->ev_d2h[set], 0)); // the set's previous results have left the device
                 trn_result part;
-                const int  r = exec_device_impl(c, queries + ch[i].q0, ch[i].n, mode, k, &part, set, c->ev_ck0[i], c->ev_ck1[i]);
+                const int  r = exec_device_impl(c, queries + ch[i].q0, ch[i].n, mode, k, &part, set, c->ev_ck0[i % 16], c->ev_ck1[i % 16]);
+                if (r == TRN_ERR_CAPACITY && ch[i].n > 1) {
+                        // the upper bound of this chunk's matches does not fit the device: halve it and retry (nothing was launched)
+                        const Chunk a{ch[i].q0, ch[i].n / 2}, b{ch[i].q0 + ch[i].n / 2, ch[i].n - ch[i].n / 2};
+                        ch[i] = a;
+                        ch.insert(ch.begin() + i + 1, b);
+                        --i;
+                        continue;
+                }
                 if (r != TRN_OK)
                         return r;
                 CK(cudaEventRecord(c->ev_done[set], c->stream));
@@ -1062,12 +1090,9 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
         out->postings_scanned    = postings;
         out->index_bytes_touched = bytes;
         out->kernel_launches     = launches;
-        float ms{0}, ksum{0};
+        float ms{0};
         if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
                 out->device_ms = ms;
-        for (uint32_t i = 0; i < ch.size(); ++i)
-                if (cudaEventElapsedTime(&ms, c->ev_ck0[i], c->ev_ck1[i]) == cudaSuccess)
-                        ksum += ms;
         out->exec_kernel_ms = ksum;
         // the split-form API (trn_fetch_results / trn_last_topk_device) refers to a whole batch; a pipelined call leaves none behind
         c->last_mode = -1;
