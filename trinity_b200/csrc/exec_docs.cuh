@@ -194,9 +194,59 @@ __device__ __forceinline__ void google_block_docs_smem(unsigned m, const uint8_t
         google_block_docs_win(m, src, misalign, n, prev, last, lo, W, bs);
 }
 
+__device__ int g_docs_decoder = 1; // experiment switch (TRN_DOCS_DECODER): 0 = 64-bit window decoder, 1 = byte-wise decoder
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+        return v;
+}
+
+// Byte-wise decoder over the lane's gather slot.  The ncu capture of the span-staged whole-list decoder (plain byte loads,
+// profiles/r01_j_*) needs 2.0 warp-instructions per posting for deltas AND freqs at 30/32 lanes, fewer than the 64-bit-window decoder
+// spends on deltas alone: a 1-byte code costs one LDS.U8, one compare and the adds.  Codes of up to two bytes (gaps < 16384) always
+// lie inside the 80-byte slot (31 x 2 + 15 bytes of alignment slack); the first longer code switches the lane to global memory.
+template <class SINK>
+__device__ __forceinline__ void google_block_docs_bytes(const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n, uint32_t prev,
+                                                        uint32_t last, uint32_t lo, uint32_t W, SINK &bs) {
+        const uint32_t mis = off & 15u;
+        uint32_t       sp  = uint32_t(__cvta_generic_to_shared(buf + lane * kGatherBytes)) + mis; // shared address of the first delta byte
+        const uint32_t nd  = n - 1u;
+        uint32_t       doc = prev, i = 0, p = 0;
+        for (; i < nd; ++i) {
+                const uint32_t b0 = lds_u8(sp + p);
+                uint32_t       v;
+                if (b0 < 0x80u) {
+                        v = b0;
+                        p += 1u;
+                } else if (b0 < 0xc0u) {
+                        v = ((b0 & 0x3fu) << 8) | lds_u8(sp + p + 1u);
+                        p += 2u;
+                } else
+                        break; // 3..5-byte code: the section may leave the slot
+                doc += v;
+                if (doc - lo < W)
+                        bs.add(doc - lo);
+        }
+        if (i < nd) {
+                const uint8_t *g = index + off + p;
+                for (; i < nd; ++i) {
+                        doc += varbyte_get(g);
+                        if (doc - lo < W)
+                                bs.add(doc - lo);
+                }
+        }
+        if (last - lo < W)
+                bs.add(last - lo);
+}
+
 template <class SINK>
 __device__ __forceinline__ void google_block_docs_gather(unsigned m, const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n,
                                                          uint32_t prev, uint32_t last, uint32_t lo, uint32_t W, SINK &bs) {
+        if (g_docs_decoder) {
+                google_block_docs_bytes(index, off, buf, lane, n, prev, last, lo, W, bs);
+                return;
+        }
         const uint32_t A = off & ~15u, mis = off - A;
         GatherWords    src{reinterpret_cast<const uint32_t *>(buf + lane * kGatherBytes), reinterpret_cast<const uint32_t *>(index + A), mis >> 2};
         google_block_docs_win(m, src, mis & 3u, n, prev, last, lo, W, bs);
@@ -588,6 +638,10 @@ cudaError_t launch_exec_docs(const ExecParams &P, int grid, cudaStream_t stream)
         static bool once = false;
         if (!once) {
                 once = true;
+                if (const char *e = getenv("TRN_DOCS_DECODER")) {
+                        const int v = atoi(e);
+                        cudaMemcpyToSymbol(g_docs_decoder, &v, sizeof(int));
+                }
                 if (const char *e = getenv("TRN_DOCS_LOCKSTEP")) {
                         const int v = atoi(e);
                         cudaMemcpyToSymbol(g_docs_lockstep, &v, sizeof(int));
