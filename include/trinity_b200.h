@@ -80,6 +80,22 @@ int trn_synth_positions(uint32_t ndocs, uint32_t rank, uint32_t min_df, uint64_t
 int trn_directory_probe(int codec, const uint8_t *index, uint64_t nbytes, const trn_term *term, uint32_t *blk_last, uint32_t *blk_off, uint32_t cap,
                         uint32_t *nblocks, uint32_t *first_doc, char *err, size_t errcap);
 
+/* ------------------------------------------------------------------------------------------------ segment directories
+ * Host half of SegmentIndexSource (segment_index_source.cpp:5-186): opens a segment directory written by Trinity's
+ * SegmentIndexSession::commit() (indexer.cpp:241-300: `index`, `terms.data`, `id`, `updated_documents.ids`) and exposes what
+ * trn_upload_index / trn_set_masked_documents need.  Buffers stay owned by the trn_segment. */
+typedef struct trn_segment trn_segment;
+int  trn_segment_open(const char *dir, trn_segment **out, char *err, size_t errcap);
+void trn_segment_close(trn_segment *);
+/* codec + IndexSource::field_statistics (index_source.h:44-53) restored from the `id` file */
+int trn_segment_info(trn_segment *, int *codec, uint32_t *nterms, uint64_t *index_bytes, uint64_t *sum_term_hits, uint32_t *total_terms,
+                     uint64_t *sum_terms_docs, uint32_t *docs_cnt, uint64_t *nmasked);
+int trn_segment_index(trn_segment *, const uint8_t **index, uint64_t *nbytes);
+/* the terms dictionary (terms.data, terms.cpp:125-170), in dictionary order: names[i] <-> terms[i] */
+int trn_segment_terms(trn_segment *, const trn_term **terms, const char *const **names, uint32_t *nterms);
+/* docIDs recorded in updated_documents.ids: what THIS segment masks in OLDER segments (index_source.h:191-238) */
+int trn_segment_masked(trn_segment *, const uint32_t **docids, uint64_t *n);
+
 /* ------------------------------------------------------------------------------------------------ query plans
  * A query is a flat node array == the reference's compiled exec_node tree (compilation_ctx.h:8-30 ENT::*) after
  * queryexec_ctx::build_iterator's flattening (exec.cpp:253-449):
@@ -131,12 +147,14 @@ const char *trn_last_error(trn_ctx *);
 int trn_set_stream(trn_ctx *, void *cuda_stream);
 
 /* == AccessProxy(basePath, indexPtr) + Decoder::init for every term (google_codec.cpp:936-983, lucene_codec.cpp:877-932):
- * copies the raw, unmodified index bytes to HBM and builds the block directory.  max_docid = upper bound of the docID space. */
+ * copies the raw, unmodified index bytes to HBM and builds the block directory.  max_docid = upper bound of the docID space; 0 = take
+ * the largest docID found in the postings (a segment directory does not record it). */
 int trn_upload_index(trn_ctx *, int codec, const uint8_t *index, uint64_t nbytes, const trn_term *terms, uint32_t nterms, uint32_t max_docid);
 
 /* == masked_documents_registry (docidupdates.h:90-190): documents deleted/updated by newer index sources.  The reference tests every
  * match against it in the exec Handlers (exec.cpp:1108-1116, `if (!maskedDocumentsRegistry->test(id)) consider(...)`); here the docIDs are
- * kept as a device bitmap that is AND-NOTed into every tile's result before emission / top-k.  n == 0 clears the registry. */
+ * kept as a device bitmap that is AND-NOTed into every tile's result before emission / top-k.  n == 0 clears the registry; docIDs
+ * above max_docid are ignored (a newer source may mask documents this source never held). */
 int trn_set_masked_documents(trn_ctx *, const uint32_t *docids, uint64_t n);
 
 typedef struct trn_index_info {

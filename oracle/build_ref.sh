@@ -37,7 +37,7 @@ PY
 ARCH="${TRINITY_REF_MARCH:-x86-64-v3}"
 CXXF="-std=c++17 -fPIC -fno-rtti -Ofast -ffast-math -funroll-loops -march=$ARCH -fno-strict-aliasing -DLEAN_SWITCH -D_REENTRANT -w \
   -I$GEN -I$HERE/shim -I$REF -I$REF/Switch -I$REF/Switch/ext_snappy -I$REF/Switch/ext/FastPFor/headers"
-TUS="google_codec lucene_codec docset_iterators docset_iterators_scorers docset_spans exec queryexec_ctx similarity codecs utils compilation_ctx queries index_source docwordspace docidupdates terms"
+TUS="google_codec lucene_codec docset_iterators docset_iterators_scorers docset_spans exec queryexec_ctx similarity codecs utils compilation_ctx queries index_source docwordspace docidupdates terms indexer segment_index_source merge"
 pids=()
 for t in $TUS; do
   g++ $CXXF -c "$GEN/$t.cpp" -o "$OBJ/$t.o" & pids+=($!)

@@ -10,8 +10,11 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
 #include "exec.h"
 #include "google_codec.h"
+#include "indexer.h"
 #include "lucene_codec.h"
+#include "segment_index_source.h"
 #include "similarity.h"
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <queue>
@@ -58,7 +61,7 @@ namespace {
                 std::vector<term_index_ctx>           tctx;
                 std::vector<std::string>              names;
                 std::unique_ptr<Codecs::AccessProxy>  ap;
-                MemSrc *                              src{nullptr};
+                IndexSource *                         src{nullptr};
                 std::unique_ptr<IndexSourcesCollection> col;
                 uint64_t                              sumHits{0};
 
@@ -71,17 +74,18 @@ namespace {
                                 ap.reset(new Codecs::Google::AccessProxy("/tmp", index.data()));
                         else
                                 ap.reset(new Codecs::Lucene::AccessProxy("/tmp", index.data(), hits.empty() ? (const uint8_t *)"" : hits.data()));
-                        src     = new MemSrc();
-                        src->ap = ap.get();
+                        auto ms = new MemSrc();
+                        src     = ms;
+                        ms->ap  = ap.get();
                         uint64_t sumDocs{0};
                         for (size_t i = 0; i < names.size(); ++i) {
-                                src->terms.emplace(names[i], tctx[i]);
+                                ms->terms.emplace(names[i], tctx[i]);
                                 sumDocs += tctx[i].documents;
                         }
-                        src->fs.docsCnt      = docsCnt;
-                        src->fs.sumTermsDocs = sumDocs;
-                        src->fs.totalTerms   = names.size();
-                        src->fs.sumTermHits  = sumHits;
+                        ms->fs.docsCnt      = docsCnt;
+                        ms->fs.sumTermsDocs = sumDocs;
+                        ms->fs.totalTerms   = names.size();
+                        ms->fs.sumTermHits  = sumHits;
                         col.reset(new IndexSourcesCollection());
                         col->insert(src); // Retain()
                         src->Release();   // collection now holds the only ref
@@ -377,6 +381,140 @@ int64_t tref_exec_masked(void *h, const char *q, int mode, const uint32_t *maske
                 n = int64_t(sink.n);
         });
         return n;
+}
+
+// ---- segments: written by the reference's own SegmentIndexSession (indexer.cpp) and opened by its SegmentIndexSource
+// doc-major input is assembled from term-major lists; documents with id < replace_below are replace()d, the others insert()ed; `dir` must end in a numeric generation (segment_index_source.cpp:18-21)
+int tref_segment_write(int codec, const char *dir, uint32_t nterms, const char *const *names, const uint32_t *counts, const uint32_t *docids, const uint32_t *freqs,
+                       const uint32_t *erased, uint32_t nerased, uint32_t replace_below) {
+        return guarded([&] {
+                struct Hit {
+                        uint32_t doc, term, freq;
+                };
+                std::vector<Hit> hits;
+                size_t           at{0};
+                for (uint32_t t = 0; t < nterms; ++t)
+                        for (uint32_t i = 0; i < counts[t]; ++i, ++at)
+                                hits.push_back({docids[at], t, freqs[at]});
+                std::sort(hits.begin(), hits.end(), [](const Hit &a, const Hit &b) { return a.doc != b.doc ? a.doc < b.doc : a.term < b.term; });
+                SegmentIndexSession sess;
+                for (size_t i = 0; i < hits.size();) {
+                        const auto doc   = hits[i].doc;
+                        auto       proxy = sess.begin(doc);
+                        tokenpos_t pos{1};
+                        for (; i < hits.size() && hits[i].doc == doc; ++i) {
+                                const str8_t term(names[hits[i].term], uint8_t(strlen(names[hits[i].term])));
+                                if (hits[i].freq == 0)
+                                        proxy.insert(term, 0); // a posting without positional hits (freq 0)
+                                for (uint32_t k = 0; k < hits[i].freq; ++k)
+                                        proxy.insert(term, pos++);
+                        }
+                        if (doc < replace_below)
+                                sess.replace(proxy); // a document an older segment already holds: recorded in updated_documents.ids
+                        else
+                                sess.insert(proxy);
+                }
+                for (uint32_t i = 0; i < nerased; ++i)
+                        sess.erase(erased[i]);
+                if (codec == 0) {
+                        Codecs::Google::IndexSession cs(dir);
+                        sess.commit(&cs);
+                } else {
+                        Codecs::Lucene::IndexSession cs(dir);
+                        sess.commit(&cs);
+                }
+        });
+}
+
+void *tref_segment_open(const char *dir) {
+        auto x = new RefIndex();
+        if (guarded([&] {
+                    auto seg = new SegmentIndexSource(dir);
+                    x->src   = seg;
+                    x->codec = -1;
+                    x->col.reset(new IndexSourcesCollection());
+                    x->col->insert(seg);
+                    seg->Release();
+                    x->col->commit();
+            })) {
+                delete x;
+                return nullptr;
+        }
+        return x;
+}
+
+// several segments as one IndexSourcesCollection (index_source.cpp:3-30: newest generation first; source i is scanned with the
+// updated_documents of every NEWER source as its masked_documents_registry) — what Trinity applications loop over per query
+void *tref_collection_open(const char *const *dirs, uint32_t n) {
+        auto x = new RefIndex();
+        if (guarded([&] {
+                    x->codec = -1;
+                    x->col.reset(new IndexSourcesCollection());
+                    for (uint32_t i = 0; i < n; ++i) {
+                            auto seg = new SegmentIndexSource(dirs[i]);
+                            x->col->insert(seg);
+                            seg->Release();
+                    }
+                    x->col->commit();
+                    x->src = x->col->sources.front();
+            })) {
+                delete x;
+                return nullptr;
+        }
+        return x;
+}
+
+// exec_query over every source of the collection; results are concatenated in collection order, seg_counts[i] = #matches of source i
+int64_t tref_collection_exec(void *h, const char *q, int mode, uint32_t *ids, double *scores, uint64_t cap, uint64_t *seg_counts) {
+        auto    x = static_cast<RefIndex *>(h);
+        int64_t n{-1};
+        guarded([&] {
+                query                                        qq(str32_t(q, strlen(q)));
+                Similarity::IndexSourcesCollectionBM25Scorer cs;
+                uint64_t                                     at{0};
+                cs.reset(x->col.get());
+                for (size_t i = 0; i < x->col->sources.size(); ++i) {
+                        auto        src = x->col->sources[i];
+                        auto        reg = x->col->scanner_registry_for(uint16_t(i));
+                        CollectSink sink;
+                        sink.cap = cap - at;
+                        if (mode == 0) {
+                                exec_query(qq, src, reg.get(), &sink, nullptr, uint32_t(ExecFlags::DocumentsOnly));
+                        } else {
+                                std::unique_ptr<Similarity::IndexSourceTermsScorer> sc(cs.new_source_scorer(src));
+                                exec_query(qq, src, reg.get(), &sink, nullptr, uint32_t(ExecFlags::AccumulatedScoreScheme), sc.get());
+                        }
+                        memcpy(ids + at, sink.ids.data(), sink.ids.size() * sizeof(uint32_t));
+                        if (mode == 1 && scores)
+                                memcpy(scores + at, sink.scores.data(), sink.scores.size() * sizeof(double));
+                        if (seg_counts)
+                                seg_counts[i] = sink.n;
+                        at += sink.ids.size();
+                }
+                n = int64_t(at);
+        });
+        return n;
+}
+
+int tref_resolve(void *h, const char *term, uint32_t *docs, uint32_t *off, uint32_t *len) {
+        auto x = static_cast<RefIndex *>(h);
+        return guarded([&] {
+                const auto t = x->src->resolve_term_ctx(str8_t(term, uint8_t(strlen(term))));
+                *docs        = t.documents;
+                *off         = t.indexChunk.offset;
+                *len         = t.indexChunk.size();
+        });
+}
+
+int tref_field_stats(void *h, uint64_t *sumTermHits, uint32_t *totalTerms, uint64_t *sumTermsDocs, uint32_t *docsCnt) {
+        auto x = static_cast<RefIndex *>(h);
+        return guarded([&] {
+                const auto fs = x->src->default_field_stats();
+                *sumTermHits  = fs.sumTermHits;
+                *totalTerms   = fs.totalTerms;
+                *sumTermsDocs = fs.sumTermsDocs;
+                *docsCnt      = fs.docsCnt;
+        });
 }
 
 // CPU baseline: run nq queries over `threads` host threads (one query per thread at a time; exec_query is re-entrant, exec.cpp:12).

@@ -52,6 +52,47 @@ class RefLib:
         L.tref_exec_batch.restype = C.c_double
         L.tref_exec_batch.argtypes = [vp, vp, u32, C.c_int, u32, C.c_int, vp, vp, vp, vp]
         L.tref_last_error.restype = C.c_char_p
+        L.tref_segment_write.argtypes = [C.c_int, C.c_char_p, u32, vp, vp, vp, vp, vp, u32, u32]
+        L.tref_segment_open.restype = vp
+        L.tref_segment_open.argtypes = [C.c_char_p]
+        L.tref_collection_open.restype = vp
+        L.tref_collection_open.argtypes = [vp, u32]
+        L.tref_collection_exec.restype = C.c_int64
+        L.tref_collection_exec.argtypes = [vp, C.c_char_p, C.c_int, vp, vp, u64, vp]
+        L.tref_resolve.argtypes = [vp, C.c_char_p, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+        L.tref_field_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u32), C.POINTER(u64), C.POINTER(u32)]
+
+    def collection_open(self, paths):
+        """IndexSourcesCollection over several segment directories (scanned newest generation first)"""
+        enc = [str(p).encode() for p in paths]
+        arr = (C.c_char_p * len(enc))(*enc)
+        h = self.L.tref_collection_open(C.cast(arr, C.c_void_p), len(enc))
+        if not h:
+            raise RuntimeError(self.err())
+        x = RefIndex(self, -1, C.c_void_p(h))
+        x.nsources = len(enc)
+        return x
+
+    def segment_write(self, codec: int, path: str, lists: dict, erased=(), replace_below: int = 0):
+        """Index `lists` ({term: (docids, freqs)}) with the reference's SegmentIndexSession and commit() the segment to `path`
+        (the last path component must be a number: the segment's generation).  Documents with id < replace_below are committed with
+        replace() — updates of documents an older segment holds — and, like `erased`, land in updated_documents.ids."""
+        names = list(lists)
+        enc = [n.encode() for n in names]
+        arr = (C.c_char_p * len(enc))(*enc)
+        counts = np.array([len(lists[n][0]) for n in names], np.uint32)
+        d = np.ascontiguousarray(np.concatenate([np.asarray(lists[n][0], np.uint32) for n in names]) if names else np.zeros(0, np.uint32))
+        f = np.ascontiguousarray(np.concatenate([np.asarray(lists[n][1], np.uint32) for n in names]) if names else np.zeros(0, np.uint32))
+        er = np.ascontiguousarray(erased, np.uint32)
+        if self.L.tref_segment_write(codec, str(path).encode(), len(enc), C.cast(arr, C.c_void_p), _p(counts), _p(d), _p(f), _p(er), len(er), replace_below) != 0:
+            raise RuntimeError(self.err())
+
+    def segment_open(self, path: str):
+        """The reference's SegmentIndexSource over `path`, wrapped for exec()"""
+        h = self.L.tref_segment_open(str(path).encode())
+        if not h:
+            raise RuntimeError(self.err())
+        return RefIndex(self, -1, C.c_void_p(h))
 
     def err(self):
         return self.L.tref_last_error().decode()
@@ -129,6 +170,33 @@ class RefIndex:
         if self.rl.L.tref_advance(self.h, term_idx, _p(t), len(t), _p(o)) != 0:
             raise RuntimeError(self.rl.err())
         return o
+
+    def collection_exec(self, q: str, scored: bool, cap: int):
+        """per-source exec_query over the collection -> [(ids, scores)] in collection order"""
+        ids = np.zeros(max(cap, 1), np.uint32)
+        sc = np.zeros(max(cap, 1), np.float64)
+        cnt = np.zeros(self.nsources, np.uint64)
+        n = self.rl.L.tref_collection_exec(self.h, q.encode(), 1 if scored else 0, _p(ids), _p(sc), cap, _p(cnt))
+        if n < 0:
+            raise RuntimeError(self.rl.err())
+        out, at = [], 0
+        for c in cnt:
+            c = int(c)
+            out.append((ids[at:at + c], sc[at:at + c] if scored else None))
+            at += c
+        return out
+
+    def resolve(self, term: str):
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        if self.rl.L.tref_resolve(self.h, term.encode(), C.byref(a), C.byref(b), C.byref(c)) != 0:
+            raise RuntimeError(self.rl.err())
+        return a.value, b.value, c.value
+
+    def field_stats(self):
+        a, b, c, d = C.c_uint64(), C.c_uint32(), C.c_uint64(), C.c_uint32()
+        if self.rl.L.tref_field_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)) != 0:
+            raise RuntimeError(self.rl.err())
+        return {"sumTermHits": a.value, "totalTerms": b.value, "sumTermsDocs": c.value, "docsCnt": d.value}
 
     def bm25(self, term_idx, freq):
         return self.rl.L.tref_bm25(self.h, term_idx, freq)

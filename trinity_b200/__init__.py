@@ -364,3 +364,47 @@ def directory_probe(codec: int, index: np.ndarray, term: tuple):
         raise TrinityError(err.value.decode())
     n = nb.value + (1 if nb.value else 0)
     return last[:n], off[:n], fd.value
+
+
+class Segment:
+    """A segment directory written by Trinity's SegmentIndexSession::commit() (indexer.cpp:241-300) — the host half of
+    SegmentIndexSource (segment_index_source.cpp:5-186)."""
+
+    def __init__(self, path: str):
+        self._L = lib()
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        if self._L.trn_segment_open(str(path).encode(), C.byref(h), err, 512) != 0:
+            raise TrinityError(f"segment {path}: {err.value.decode()}")
+        self._h = h
+        codec, nt, nm = C.c_int(), C.c_uint32(), C.c_uint64()
+        ib, sth, std_ = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        tt, dc = C.c_uint32(), C.c_uint32()
+        self._L.trn_segment_info(h, C.byref(codec), C.byref(nt), C.byref(ib), C.byref(sth), C.byref(tt), C.byref(std_), C.byref(dc), C.byref(nm))
+        self.codec = codec.value
+        self.field_statistics = {"sumTermHits": sth.value, "totalTerms": tt.value, "sumTermsDocs": std_.value, "docsCnt": dc.value}
+        p, n = C.c_void_p(), C.c_uint64()
+        self._L.trn_segment_index(h, C.byref(p), C.byref(n))
+        self.index = (np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,)) if n.value else np.zeros(0, np.uint8))
+        tp, npp, tn = C.c_void_p(), C.c_void_p(), C.c_uint32()
+        self._L.trn_segment_terms(h, C.byref(tp), C.byref(npp), C.byref(tn))
+        if tn.value:
+            self.terms = np.ctypeslib.as_array(C.cast(tp, C.POINTER(C.c_uint8)), shape=(tn.value * 12,)).view(TERM_DTYPE).copy()
+            arr = C.cast(npp, C.POINTER(C.c_char_p))
+            self.names = [arr[i].decode() for i in range(tn.value)]
+        else:
+            self.terms, self.names = np.zeros(0, TERM_DTYPE), []
+        mp, mn = C.c_void_p(), C.c_uint64()
+        self._L.trn_segment_masked(h, C.byref(mp), C.byref(mn))
+        self.masked_documents = (np.ctypeslib.as_array(C.cast(mp, C.POINTER(C.c_uint32)), shape=(mn.value,)).copy() if mn.value
+                                 else np.zeros(0, np.uint32))
+
+    def upload(self, gpu: "GpuIndexSource", max_docid: int):
+        gpu.upload(self.codec, self.index, self.terms, max_docid)
+        return TermDictionary(self.names)
+
+    def __del__(self):
+        try:
+            self._L.trn_segment_close(self._h)
+        except Exception:
+            pass

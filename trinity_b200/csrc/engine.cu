@@ -548,6 +548,10 @@ extern "C" int trn_upload_index(trn_ctx *c, int codec, const uint8_t *index, uin
         } catch (const std::exception &e) {
                 return fail(c, TRN_ERR_FORMAT, e.what());
         }
+        if (max_docid == 0) // not recorded (e.g. a segment directory): the largest docID any postings list holds
+                for (uint32_t i = 0; i < nterms; ++i)
+                        if (dir.terms[i].nblocks)
+                                max_docid = std::max(max_docid, dir.terms[i].last_doc);
         c->codec      = codec;
         c->nterms     = nterms;
         c->max_docid  = max_docid;
@@ -630,8 +634,10 @@ extern "C" int trn_set_masked_documents(trn_ctx *c, const uint32_t *docids, uint
         const uint64_t        span  = ((uint64_t(c->max_docid) >> 17) + 2) << 17;
         std::vector<uint32_t> words(span / 32, 0u);
         for (uint64_t i = 0; i < n; ++i) {
-                if (docids[i] == 0 || docids[i] > c->max_docid)
-                        return fail(c, TRN_ERR_ARG, "masked docID outside 1..max_docid");
+                if (docids[i] == 0)
+                        return fail(c, TRN_ERR_ARG, "masked docID 0 is not a document");
+                if (docids[i] > c->max_docid)
+                        continue; // a newer source may mask documents this source never held
                 words[docids[i] >> 5] |= 1u << (docids[i] & 31u);
         }
         CK(c->d_masked.ensure(words.size() * 4));
