@@ -56,7 +56,8 @@ struct DevQuery {
         uint32_t root_slot;
         uint32_t cand_base; // SCORED_TOPK: first candidate slot of this query
         uint32_t cand_cap;
-        uint32_t flat; // 0 = general step program; 1 = conjunction of terms only; 2 = disjunction of terms only (see exec_docs_flat.cuh)
+        uint32_t flat; // 0 = general step program; 1 = conjunction of terms only; 2 = disjunction of terms only (see exec_docs_flat.cuh);
+                       // 3 = conjunction of terms, candidate-driven: items are 32-block groups of the rarest term (exec_docs_cand.cuh)
 };
 
 struct ExecParams {

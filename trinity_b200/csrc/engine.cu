@@ -82,6 +82,7 @@ struct trn_ctx {
         // index
         bool                 have_index{false};
         int                  codec{0};
+        int                  cand_cost{450}; // TRN_CAND_COST: modelled warp-instructions per 32 candidates of the candidate-driven conjunction (0 = never use it)
         uint32_t             nterms{0}, max_docid{0}, tile_shift{13}, ntiles{0}; // tile_shift: directory granularity == scored tile (8192 docs, the reference's window docset_spans.h:74)
         int                  docs_bufs{1};   // gather staging buffers per warp in k_exec_docs (TRN_DOCS_BUFS): 1 = 32 resident warps/SM beats 2 = prefetch at 24 warps (measured 49 vs 53 ms)
         uint32_t             docs_shift{14}; // docID tile (log2) of the warp-per-tile DocumentsOnly kernel
@@ -473,6 +474,8 @@ extern "C" int trn_create(int device, trn_ctx **out) {
         }
         if (const char *e = getenv("TRN_DOCS_BUFS"))
                 c->docs_bufs = atoi(e) >= 2 ? 2 : 1;
+        if (const char *e = getenv("TRN_CAND_COST"))
+                c->cand_cost = std::max(0, atoi(e));
         if (const char *e = getenv("TRN_DOCS_SHIFT")) {
                 const int v = atoi(e);
                 if (v >= 13 && v <= 17)
@@ -701,6 +704,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         std::vector<DevQuery> hq(nq);
         std::vector<DevStep>  steps;
         uint32_t              maxSlots{1};
+        bool                  anyCandidate{false};
         uint64_t              items{0}, segCap{0}, candTotal{0}, postings{0}, bytes{0};
         for (uint32_t q = 0; q < nq; ++q) {
                 const auto &Q = queries[q];
@@ -733,7 +737,38 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 postings += cc.postings;
                 bytes += cc.bytes;
                 const Range r = cc.range(cc.root); // cc.root: the effective root (see apply_reference_root_filter_quirk)
-                if (r.empty()) {
+                // candidate-driven conjunction (exec_docs_cand.cuh) when the rarest operand is sparse: its cost follows the lead's
+                // postings (~candCost warp-instructions per 32 candidates and operand) instead of the docID space (~1500 per tile +
+                // ~27 per block in it, profiles/r01_l_*)
+                bool candidate{false};
+                if (dq.flat == 1u && !scored && c->codec == TRN_CODEC_GOOGLE && c->cand_cost > 0 && !r.empty()) {
+                        uint32_t lead{kEmptyTerm}, nleaf{0};
+                        double   blocks{0};
+                        bool     known{true};
+                        for (uint32_t si = dq.step_begin; si < steps.size(); ++si)
+                                if (steps[si].op == OP_LEAF) {
+                                        if (nleaf++ == 0)
+                                                lead = steps[si].term;
+                                        if (steps[si].term == kEmptyTerm)
+                                                known = false;
+                                        else
+                                                blocks += c->h_terms[steps[si].term].nblocks;
+                                }
+                        if (known && lead != kEmptyTerm && nleaf >= 2 && c->h_terms[lead].nblocks) {
+                                const double perTile = double(1ull << execShift) / (double(c->max_docid) + 1.0);
+                                const double lhs     = double(nleaf - 1) * c->h_terms[lead].nblocks * perTile * double(c->cand_cost);
+                                const double rhs     = 1500.0 + blocks * perTile * 27.0;
+                                if (lhs < rhs) {
+                                        candidate  = true;
+                                        dq.flat    = 3u;
+                                        dq.tile_lo = 0;
+                                        dq.ntiles  = (c->h_terms[lead].nblocks + 31u) / 32u;
+                                        anyCandidate = true;
+                                }
+                        }
+                }
+                if (candidate) {
+                } else if (r.empty()) {
                         dq.tile_lo = 0;
                         dq.ntiles  = 0;
                 } else {
@@ -755,6 +790,11 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 }
         }
         const uint32_t totalItems = uint32_t(items);
+        if (anyCandidate) { // the candidate array + one gather buffer must fit a warp's share of shared memory
+                const uint32_t slotBytes = (1u << execShift) / 8u, stageB = exec_docs_stage_bytes(c->docs_bufs), need = exec_docs_cand_smem_bytes();
+                if (need > stageB)
+                        maxSlots = std::max(maxSlots, (need - stageB + slotBytes - 1u) / slotBytes);
+        }
 
         // ---- result staging must fit the device: a caller (trn_exec_batch) reacts to TRN_ERR_CAPACITY by splitting the batch
         if (mode != TRN_MODE_SCORED_TOPK) {

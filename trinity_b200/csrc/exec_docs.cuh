@@ -101,6 +101,15 @@ struct BitAcc {
                 cur   = nw ? bit : (cur | bit);
                 cur_w = w;
         }
+        // same contract as add(), shorter dependency chain: the "new word" test of a posting depends only on the previous posting's
+        // word, never on the accumulator, so consecutive postings overlap (a flush of an empty accumulator ORs in 0: harmless)
+        __device__ __forceinline__ void add_nc(uint32_t rel) {
+                const uint32_t w = rel >> 5, bit = __funnelshift_l(0u, 1u, rel); // 1 << (rel & 31)
+                const bool     nw = w != cur_w;
+                red_if(nw ? 1u : 0u);
+                cur   = (nw ? 0u : cur) | bit;
+                cur_w = w;
+        }
         __device__ __forceinline__ void flush() {
                 red_if(cur);
                 cur = 0;
@@ -194,7 +203,7 @@ __device__ __forceinline__ void google_block_docs_smem(unsigned m, const uint8_t
         google_block_docs_win(m, src, misalign, n, prev, last, lo, W, bs);
 }
 
-__device__ int g_docs_decoder = 1; // experiment switch (TRN_DOCS_DECODER): 0 = 64-bit window decoder, 1 = byte-wise decoder
+__device__ int g_docs_decoder = 4; // TRN_DOCS_DECODER: 0 = 64-bit window, 1 = byte-wise, 2 = word-at-a-time; flat conjunctions: 3 = 2 + plain-store word builder, 4 = warp-voted
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
         uint32_t v;
@@ -240,9 +249,282 @@ __device__ __forceinline__ void google_block_docs_bytes(const uint8_t *__restric
                 bs.add(last - lo);
 }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+        return v;
+}
+
+// Word-at-a-time decoder over the lane's gather slot (TRN_DOCS_DECODER=2).  The lists that carry most postings are dense: their
+// doc deltas are 1-byte codes almost everywhere.  After a byte-wise prologue that brings the read position to a 4-byte boundary
+// of the slot, every iteration takes ONE aligned 32-bit shared load, ONE test for "four 1-byte codes" and ONE branch for FOUR
+// postings (the byte-wise loop pays a load, a compare chain and two branches per posting: branch-resolve and short-scoreboard
+// stalls were 35 % of all warp stall cycles, profiles/r01_k_*).  A word holding a longer code is consumed byte-wise until the
+// position is aligned again.  The tile-edge test is made once per four postings (docIDs ascend: first and last in range => all).
+__device__ __forceinline__ void google_block_docs_w4(const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n, uint32_t prev,
+                                                     uint32_t last, uint32_t lo, uint32_t W, BitAcc &bs) {
+        const uint32_t mis  = off & 15u;
+        const uint32_t base = uint32_t(__cvta_generic_to_shared(buf + lane * kGatherBytes)) + mis; // shared address of the first delta byte
+        const uint32_t nd   = n - 1u;
+        uint32_t       sp = base, doc = prev, i = 0;
+        bool           spill = false; // met a 3..5-byte code: the section may leave the slot
+        // one code, byte-wise
+        auto one = [&]() {
+                const uint32_t b0 = lds_u8(sp);
+                uint32_t       v;
+                if (b0 < 0x80u) {
+                        v = b0;
+                        sp += 1u;
+                } else if (b0 < 0xc0u) {
+                        v = ((b0 & 0x3fu) << 8) | lds_u8(sp + 1u);
+                        sp += 2u;
+                } else {
+                        spill = true;
+                        return;
+                }
+                ++i;
+                doc += v;
+                if (doc - lo < W)
+                        bs.add_nc(doc - lo);
+        };
+        while (i < nd && (sp & 3u) && !spill)
+                one();
+        while (i + 4u <= nd && !spill) {
+                const uint32_t w = lds_u32(sp);
+                if (w & 0x80808080u) {
+                        do
+                                one();
+                        while (i < nd && (sp & 3u) && !spill);
+                        continue;
+                }
+                const uint32_t d0 = doc + (w & 0xffu), d1 = d0 + __byte_perm(w, 0u, 0x4441u), d2 = d1 + __byte_perm(w, 0u, 0x4442u), d3 = d2 + (w >> 24);
+                const uint32_t r0 = d0 - lo, r1 = d1 - lo, r2 = d2 - lo, r3 = d3 - lo;
+                doc = d3;
+                sp += 4u;
+                i += 4u;
+                if (r0 < W && r3 < W) {
+                        bs.add_nc(r0);
+                        bs.add_nc(r1);
+                        bs.add_nc(r2);
+                        bs.add_nc(r3);
+                } else {
+                        if (r0 < W) bs.add_nc(r0);
+                        if (r1 < W) bs.add_nc(r1);
+                        if (r2 < W) bs.add_nc(r2);
+                        if (r3 < W) bs.add_nc(r3);
+                }
+        }
+        while (i < nd && !spill)
+                one();
+        if (i < nd) {
+                const uint8_t *g = index + off + (sp - base);
+                for (; i < nd; ++i) {
+                        doc += varbyte_get(g);
+                        if (doc - lo < W)
+                                bs.add_nc(doc - lo);
+                }
+        }
+        if (last - lo < W)
+                bs.add_nc(last - lo);
+}
+
+// Plain-store word builder for a bitmap that only ONE term writes (flat conjunctions keep one slot per operand).  The blocks of
+// a term partition the docID space, so every 32-doc word strictly between a block's first and last word belongs to that block's
+// lane alone: it is written with a predicated STS when the lane moves on — no atomic, and no branch (ptxas turns a predicated
+// red.shared into BSSY / BRA / ATOMS / BSYNC: three control instructions per posting and the branch-resolve stalls of
+// profiles/r01_k_*).  Only a block's LAST word can be shared, with the following block(s) of the term; the caller ORs it in
+// atomically AFTER those have stored (see flat_exec_google).
+struct OwnAcc {
+        uint32_t bm;           // shared-state-space address of the term's bitmap
+        uint32_t cur_w, cur_a; // word being accumulated, and where it goes when the lane leaves it
+        uint32_t cur;
+        __device__ __forceinline__ void init(uint32_t bm_saddr, uint32_t dummy_saddr) {
+                bm    = bm_saddr;
+                asm volatile("" : "+r"(bm)); // keep the base in a register (one LEA per posting instead of recomputing slot * NW)
+                cur_w = 0xffffffffu;
+                cur_a = dummy_saddr; // the first "flush" stores an empty accumulator here
+                cur   = 0;
+        }
+        __device__ __forceinline__ void add(uint32_t rel) {
+                const uint32_t w = rel >> 5, bit = __funnelshift_l(0u, 1u, rel); // 1 << (rel & 31)
+                const uint32_t nw = w != cur_w ? 1u : 0u;
+                asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u32 [%0], %1; }" ::"r"(cur_a), "r"(cur), "r"(nw) : "memory");
+                cur   = (nw ? 0u : cur) | bit;
+                cur_w = w;
+                cur_a = bm + w * 4u;
+        }
+};
+
+// Word-at-a-time decoder into an OwnAcc (see google_block_docs_w4 for the read side).  `rel` runs relative to the tile's first docID
+// (it wraps below the tile, one unsigned compare covers both edges).
+__device__ __forceinline__ void google_block_docs_own(const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n, uint32_t prev,
+                                                      uint32_t last, uint32_t lo, uint32_t W, OwnAcc &bs) {
+        const uint32_t mis  = off & 15u;
+        const uint32_t base = uint32_t(__cvta_generic_to_shared(buf + lane * kGatherBytes)) + mis; // shared address of the first delta byte
+        const uint32_t nd   = n - 1u;
+        uint32_t       sp = base, rel = prev - lo, i = 0;
+        bool           spill = false; // met a 3..5-byte code: the section may leave the slot
+        auto           one   = [&]() {
+                const uint32_t b0 = lds_u8(sp);
+                uint32_t       v;
+                if (b0 < 0x80u) {
+                        v = b0;
+                        sp += 1u;
+                } else if (b0 < 0xc0u) {
+                        v = ((b0 & 0x3fu) << 8) | lds_u8(sp + 1u);
+                        sp += 2u;
+                } else {
+                        spill = true;
+                        return;
+                }
+                ++i;
+                rel += v;
+                if (rel < W)
+                        bs.add(rel);
+        };
+        while (i < nd && (sp & 3u) && !spill)
+                one();
+        while (i + 4u <= nd && !spill) {
+                const uint32_t w = lds_u32(sp);
+                if (w & 0x80808080u) {
+                        do
+                                one();
+                        while (i < nd && (sp & 3u) && !spill);
+                        continue;
+                }
+                const uint32_t r0 = rel + (w & 0xffu), r1 = r0 + __byte_perm(w, 0u, 0x4441u), r2 = r1 + __byte_perm(w, 0u, 0x4442u), r3 = r2 + (w >> 24);
+                rel = r3;
+                sp += 4u;
+                i += 4u;
+                if (r0 < W && r3 < W) {
+                        bs.add(r0);
+                        bs.add(r1);
+                        bs.add(r2);
+                        bs.add(r3);
+                } else {
+                        if (r0 < W) bs.add(r0);
+                        if (r1 < W) bs.add(r1);
+                        if (r2 < W) bs.add(r2);
+                        if (r3 < W) bs.add(r3);
+                }
+        }
+        while (i < nd && !spill)
+                one();
+        if (i < nd) {
+                const uint8_t *g = index + off + (sp - base);
+                for (; i < nd; ++i) {
+                        rel += varbyte_get(g);
+                        if (rel < W)
+                                bs.add(rel);
+                }
+        }
+        if (last - lo < W)
+                bs.add(last - lo);
+}
+
+// OwnAcc::add under a per-lane predicate, branch-free (every lane of the warp executes the same instructions)
+__device__ __forceinline__ void own_add_if(OwnAcc &bs, bool on, uint32_t rel) {
+        const uint32_t w = rel >> 5, bit = __funnelshift_l(0u, 1u, rel);
+        const uint32_t nw = (on && w != bs.cur_w) ? 1u : 0u;
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u32 [%0], %1; }" ::"r"(bs.cur_a), "r"(bs.cur), "r"(nw) : "memory");
+        bs.cur   = (nw ? 0u : bs.cur) | (on ? bit : 0u);
+        bs.cur_w = on ? w : bs.cur_w;
+        bs.cur_a = on ? bs.bm + w * 4u : bs.cur_a;
+}
+
+// Warp-voted decoder into an OwnAcc (TRN_DOCS_DECODER=4).  google_block_docs_own lets every lane choose between the 4-wide body
+// and byte-wise excursions on its own; the ncu capture (profiles/r01_l_*) shows what that costs: 6 % of the 4-byte words hold a
+// 2-byte code, but each of them sends its warp through ~3 byte-wise iterations at 2 of 32 lanes — more instructions than the
+// 4-wide body itself.  Here every iteration reads a 32-bit window at ANY byte position (two aligned shared loads + funnel shift:
+// no alignment prologue, no re-alignment), and the warp votes: all lanes see four 1-byte codes => the 4-wide body; otherwise ALL
+// lanes run one predicated, branch-free step that consumes the leading 1-byte codes of the window plus the first 2-byte code
+// (1..4 postings).  The two bodies are never executed in the same iteration.
+__device__ __forceinline__ void google_block_docs_vote(unsigned m, const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n,
+                                                       uint32_t prev, uint32_t last, uint32_t lo, uint32_t W, OwnAcc &bs) {
+        const uint32_t mis  = off & 15u;
+        const uint32_t base = uint32_t(__cvta_generic_to_shared(buf + lane * kGatherBytes)) + mis; // shared address of the first delta byte
+        const uint32_t nd   = n - 1u;
+        uint32_t       sp = base, rel = prev - lo, i = 0;
+        bool           spill = false; // met a 3..5-byte code: the section may leave the slot
+        for (;;) {
+                const bool live = i < nd && !spill;
+                if (!__any_sync(m, live))
+                        break;
+                const uint32_t a  = sp & ~3u;
+                const uint32_t w  = __funnelshift_r(lds_u32(a), lds_u32(a + 4u), (sp & 3u) * 8u); // bytes sp .. sp+3
+                const uint32_t hb = w & 0x80808080u, rem = nd - i;
+                const uint32_t b0 = w & 0xffu, b1 = __byte_perm(w, 0u, 0x4441u), b2 = __byte_perm(w, 0u, 0x4442u), b3 = w >> 24;
+                if (__all_sync(m, !live || (hb == 0u && rem >= 4u))) {
+                        if (live) {
+                                const uint32_t r0 = rel + b0, r1 = r0 + b1, r2 = r1 + b2, r3 = r2 + b3;
+                                rel = r3;
+                                sp += 4u;
+                                i += 4u;
+                                if (r0 < W && r3 < W) {
+                                        bs.add(r0);
+                                        bs.add(r1);
+                                        bs.add(r2);
+                                        bs.add(r3);
+                                } else {
+                                        own_add_if(bs, r0 < W, r0);
+                                        own_add_if(bs, r1 < W, r1);
+                                        own_add_if(bs, r2 < W, r2);
+                                        own_add_if(bs, r3 < W, r3);
+                                }
+                        }
+                } else {
+                        // k0 leading 1-byte codes, then (if it lies inside the window) one 2-byte code
+                        const uint32_t k0  = hb ? uint32_t(__ffs(int(hb)) - 1) >> 3 : 4u;
+                        const uint32_t k   = min(k0, rem);
+                        const uint32_t x   = w >> (8u * (k & 3u));
+                        bool           dbl = live && k0 < 3u && k0 < rem;
+                        if (dbl && (x & 0xffu) >= 0xc0u) {
+                                spill = true;
+                                dbl   = false;
+                        }
+                        const uint32_t vd = ((x & 0x3fu) << 8) | ((x >> 8) & 0xffu);
+                        const uint32_t np = live ? k + (dbl ? 1u : 0u) : 0u; // postings of this step (0..4)
+                        const uint32_t r0 = rel + (np > 0u ? (k >= 1u ? b0 : vd) : 0u);
+                        const uint32_t r1 = r0 + (np > 1u ? (k >= 2u ? b1 : vd) : 0u);
+                        const uint32_t r2 = r1 + (np > 2u ? (k >= 3u ? b2 : vd) : 0u);
+                        const uint32_t r3 = r2 + (np > 3u ? b3 : 0u);
+                        own_add_if(bs, np > 0u && r0 < W, r0);
+                        own_add_if(bs, np > 1u && r1 < W, r1);
+                        own_add_if(bs, np > 2u && r2 < W, r2);
+                        own_add_if(bs, np > 3u && r3 < W, r3);
+                        rel = r3;
+                        i += np;
+                        sp += live ? k + (dbl ? 2u : 0u) : 0u;
+                }
+        }
+        if (i < nd) {
+                const uint8_t *g = index + off + (sp - base);
+                for (; i < nd; ++i) {
+                        rel += varbyte_get(g);
+                        if (rel < W)
+                                bs.add(rel);
+                }
+        }
+        if (last - lo < W)
+                bs.add(last - lo);
+}
+
+template <class SINK> struct UseW4 {
+        static constexpr bool value = false;
+};
+template <> struct UseW4<BitAcc> {
+        static constexpr bool value = true;
+};
+
 template <class SINK>
 __device__ __forceinline__ void google_block_docs_gather(unsigned m, const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n,
                                                          uint32_t prev, uint32_t last, uint32_t lo, uint32_t W, SINK &bs) {
+        if constexpr (UseW4<SINK>::value) {
+                if (g_docs_decoder == 2) {
+                        google_block_docs_w4(index, off, buf, lane, n, prev, last, lo, W, bs);
+                        return;
+                }
+        }
         if (g_docs_decoder) {
                 google_block_docs_bytes(index, off, buf, lane, n, prev, last, lo, W, bs);
                 return;
@@ -426,8 +708,10 @@ __device__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
 }
 
 #include "exec_docs_flat.cuh"
+#include "exec_docs_cand.cuh"
 
-__global__ void __launch_bounds__(kDocsWarps * 32) k_exec_docs(ExecParams P) {
+// min 7 CTAs/SM: shared memory allows 7 at the default tile; without the bound ptxas stops at 64 registers and spills
+__global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) {
         const uint32_t W  = 1u << P.exec_shift;
         const uint32_t NW = W >> 5;
         const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -458,6 +742,11 @@ __global__ void __launch_bounds__(kDocsWarps * 32) k_exec_docs(ExecParams P) {
                         }
                         curq = qlo;
                         Q    = P.queries[qlo];
+                }
+                if (Q.flat == 3u) { // candidate-driven conjunction: the work item is a 32-block group of the lead term
+                        __syncwarp();
+                        cand_exec_google(P, Q, curq, item, item - Q.item_base, slots, reinterpret_cast<uint8_t *>(slots + kCandWords), lane);
+                        continue;
                 }
                 const uint32_t tile = Q.tile_lo + (item - Q.item_base);
                 const uint32_t lo = tile << P.exec_shift, hi = lo + W;
@@ -613,6 +902,10 @@ __global__ void __launch_bounds__(kDocsWarps * 32) k_exec_docs(ExecParams P) {
                         }
                 }
         }
+}
+
+uint32_t exec_docs_cand_smem_bytes() {
+        return kCandSmem;
 }
 
 uint32_t exec_docs_stage_bytes(int bufs) {

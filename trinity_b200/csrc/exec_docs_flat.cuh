@@ -98,6 +98,13 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
         };
 
         const bool dbuf = P.docs_stage_bytes >= 2u * kGatherBufBytes; // double-buffered staging (else: more resident warps instead)
+        // conjunctions: one bitmap per operand => plain-store word builder (OwnAcc); the last word of every block is ORed in
+        // atomically one group LATER, after every block that can share it has stored its words
+        const int      decoder = g_docs_decoder;
+        const bool     own     = isAnd && decoder >= 3 && P.docs_stage_bytes >= (dbuf ? 2u : 1u) * kGatherBufBytes + 128u;
+        const uint32_t dummy   = uint32_t(__cvta_generic_to_shared(stage + (dbuf ? 2u : 1u) * kGatherBufBytes)) + uint32_t(lane) * 4u;
+        const uint32_t slots_s = uint32_t(__cvta_generic_to_shared(slots));
+        uint32_t       tail_a = dummy, tail_bits = 0;
         FlatLane   cur  = assign(0);
         gather_issue(P.ix.index, cur.off, cur.active, stage, lane);
         __syncwarp(); // slot clears above are visible before the first reduction
@@ -114,7 +121,21 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
                 } else
                         gather_wait<0>();
                 const unsigned m = __ballot_sync(0xffffffffu, cur.active);
-                if (cur.active) {
+                if (own) {
+                        OwnAcc bs;
+                        bs.init(slots_s + cur.j * NW * 4u, dummy);
+                        if (cur.active) {
+                                if (decoder == 3)
+                                        google_block_docs_own(P.ix.index, cur.off, stage + buf * kGatherBufBytes, lane, cur.n, cur.prev, cur.last, lo, W, bs);
+                                else
+                                        google_block_docs_vote(m, P.ix.index, cur.off, stage + buf * kGatherBufBytes, lane, cur.n, cur.prev, cur.last, lo, W, bs);
+                        }
+                        __syncwarp();
+                        if (tail_bits) // the previous group's last words
+                                asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(tail_a), "r"(tail_bits) : "memory");
+                        tail_a    = bs.cur_a;
+                        tail_bits = bs.cur;
+                } else if (cur.active) {
                         BitAcc bs;
                         bs.init(isAnd ? slots + size_t(cur.j) * NW : root);
                         google_block_docs_gather(m, P.ix.index, cur.off, stage + buf * kGatherBufBytes, lane, cur.n, cur.prev, cur.last, lo, W, bs);
@@ -129,6 +150,9 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
                         gather_issue(P.ix.index, cur.off, cur.active, stage, lane);
                 }
         }
+        if (own && tail_bits)
+                asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(tail_a), "r"(tail_bits) : "memory");
+        __syncwarp();
         if (isAnd) {
                 // operand i lives in slot i; the root of an all-term conjunction is slot 0
                 for (uint32_t i = lane; i < NW; i += 32) {
