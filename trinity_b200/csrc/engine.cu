@@ -82,7 +82,7 @@ struct trn_ctx {
         // index
         bool                 have_index{false};
         int                  codec{0};
-        int                  cand_cost{450}; // TRN_CAND_COST: modelled warp-instructions per 32 candidates of the candidate-driven conjunction (0 = never use it)
+        int                  cand_cost{900}; // TRN_CAND_COST: modelled warp-instructions per 32 candidates of the candidate-driven conjunction (0 = never use it)
         uint32_t             nterms{0}, max_docid{0}, tile_shift{13}, ntiles{0}; // tile_shift: directory granularity == scored tile (8192 docs, the reference's window docset_spans.h:74)
         int                  docs_bufs{1};   // gather staging buffers per warp in k_exec_docs (TRN_DOCS_BUFS): 1 = 32 resident warps/SM beats 2 = prefetch at 24 warps (measured 49 vs 53 ms)
         uint32_t             docs_shift{14}; // docID tile (log2) of the warp-per-tile DocumentsOnly kernel
@@ -738,7 +738,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 bytes += cc.bytes;
                 const Range r = cc.range(cc.root); // cc.root: the effective root (see apply_reference_root_filter_quirk)
                 // candidate-driven conjunction (exec_docs_cand.cuh) when the rarest operand is sparse: its cost follows the lead's
-                // postings (~candCost warp-instructions per 32 candidates and operand) instead of the docID space (~1500 per tile +
+                // postings (~cand_cost/2 warp-instructions per 32 candidates and operand; the crossover was tuned on the and2 workload: 900 beats 450 and 1500) instead of the docID space (~1500 per tile +
                 // ~27 per block in it, profiles/r01_l_*)
                 bool candidate{false};
                 if (dq.flat == 1u && !scored && c->codec == TRN_CODEC_GOOGLE && c->cand_cost > 0 && !r.empty()) {

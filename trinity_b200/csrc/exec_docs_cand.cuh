@@ -39,8 +39,11 @@ __device__ __forceinline__ void google_block_to_array(const uint8_t *__restrict_
                 } else if (b0 < 0xc0u) {
                         v = ((b0 & 0x3fu) << 8) | lds_u8(sp + p + 1u);
                         p += 2u;
+                } else if (b0 < 0xe0u && mis + p + 3u <= kGatherBytes) { // 3-byte code (gaps >= 16384: the sparsest leads) still inside the slot
+                        v = ((b0 & 0x1fu) << 16) | lds_u8(sp + p + 1u) | (lds_u8(sp + p + 2u) << 8);
+                        p += 3u;
                 } else
-                        break; // 3..5-byte code: the section may leave the slot
+                        break; // the section may leave the slot
                 doc += v;
                 out[i] = doc;
         }
@@ -62,20 +65,38 @@ __device__ __forceinline__ bool google_block_find(const uint8_t *__restrict__ in
         uint32_t       sp  = uint32_t(__cvta_generic_to_shared(buf + lane * kGatherBytes)) + mis;
         const uint32_t nd  = n - 1u;
         uint32_t       doc = prev, i = 0, p = 0;
-        for (; i < nd; ++i) {
-                const uint32_t b0 = lds_u8(sp + p);
-                uint32_t       v;
-                if (b0 < 0x80u) {
-                        v = b0;
-                        p += 1u;
-                } else if (b0 < 0xc0u) {
-                        v = ((b0 & 0x3fu) << 8) | lds_u8(sp + p + 1u);
-                        p += 2u;
-                } else
-                        break;
-                doc += v;
-                if (doc >= target)
-                        return doc == target;
+        bool           spill = false;
+        while (i < nd && !spill) {
+                // four 1-byte codes at a time while their sum stays below the target (one dot product instead of four decode steps)
+                while (i + 4u <= nd) {
+                        const uint32_t a = (sp + p) & ~3u;
+                        const uint32_t w = __funnelshift_r(lds_u32(a), lds_u32(a + 4u), ((sp + p) & 3u) * 8u);
+                        if (w & 0x80808080u)
+                                break;
+                        const uint32_t sum = __dp4a(w, 0x01010101u, 0u);
+                        if (doc + sum >= target)
+                                break;
+                        doc += sum;
+                        p += 4u;
+                        i += 4u;
+                }
+                for (uint32_t k = 0; k < 4u && i < nd; ++k, ++i) {
+                        const uint32_t b0 = lds_u8(sp + p);
+                        uint32_t       v;
+                        if (b0 < 0x80u) {
+                                v = b0;
+                                p += 1u;
+                        } else if (b0 < 0xc0u) {
+                                v = ((b0 & 0x3fu) << 8) | lds_u8(sp + p + 1u);
+                                p += 2u;
+                        } else {
+                                spill = true; // 3..5-byte code: the section may leave the slot
+                                break;
+                        }
+                        doc += v;
+                        if (doc >= target)
+                                return doc == target;
+                }
         }
         if (i < nd) {
                 const uint8_t *g = index + off + p;
