@@ -309,7 +309,7 @@ def main():
         "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms, "launches_per_step": nlaunch,
-                     "note": "instruction-issue bound (lane-serial varbyte chains), not HBM bound; see DESIGN.md section 4"},
+                     "note": "achieved = SURVEY 8(d) algorithmic bytes (every referenced list once per query, skipped blocks included) / kernel time; instruction-issue and latency bound, not HBM bound; see DESIGN.md section 4"},
         "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

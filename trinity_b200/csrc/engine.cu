@@ -83,6 +83,7 @@ struct trn_ctx {
         bool                 have_index{false};
         int                  codec{0};
         int                  cand_cost{900}; // TRN_CAND_COST: modelled warp-instructions per 32 candidates of the candidate-driven conjunction (0 = never use it)
+        uint32_t             min_docid{1}; // smallest docID any term holds (a docID-range shard does not start at 1)
         uint32_t             nterms{0}, max_docid{0}, tile_shift{13}, ntiles{0}; // tile_shift: directory granularity == scored tile (8192 docs, the reference's window docset_spans.h:74)
         int                  docs_bufs{1};   // gather staging buffers per warp in k_exec_docs (TRN_DOCS_BUFS): 1 = 32 resident warps/SM beats 2 = prefetch at 24 warps (measured 49 vs 53 ms)
         uint32_t             docs_shift{14}; // docID tile (log2) of the warp-per-tile DocumentsOnly kernel
@@ -561,6 +562,7 @@ extern "C" int trn_upload_index(trn_ctx *c, int codec, const uint8_t *index, uin
         const uint32_t W = 1u << c->tile_shift;
         c->ntiles     = uint32_t((uint64_t(max_docid) + 1 + W - 1) >> c->tile_shift);
         c->h_terms.resize(nterms);
+        c->min_docid      = 0xffffffffu;
         c->total_blocks   = 0;
         c->total_postings = 0;
         for (uint32_t i = 0; i < nterms; ++i) {
@@ -573,6 +575,8 @@ extern "C" int trn_upload_index(trn_ctx *c, int codec, const uint8_t *index, uin
                 d.chunk_len = terms[i].chunk_len;
                 c->total_blocks += d.nblocks;
                 c->total_postings += d.documents;
+                if (d.nblocks)
+                        c->min_docid = std::min(c->min_docid, d.first_doc);
                 if (d.nblocks && d.last_doc > max_docid)
                         return fail(c, TRN_ERR_ARG, "a term holds a docID above max_docid");
         }
@@ -755,7 +759,8 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                                                 blocks += c->h_terms[steps[si].term].nblocks;
                                 }
                         if (known && lead != kEmptyTerm && nleaf >= 2 && c->h_terms[lead].nblocks) {
-                                const double perTile = double(1ull << execShift) / (double(c->max_docid) + 1.0);
+                                const double width   = double(c->max_docid) - double(std::min(c->min_docid, c->max_docid)) + 1.0; // docID span of THIS source
+                                const double perTile = double(1ull << execShift) / width;
                                 const double lhs     = double(nleaf - 1) * c->h_terms[lead].nblocks * perTile * double(c->cand_cost);
                                 const double rhs     = 1500.0 + blocks * perTile * 27.0;
                                 if (lhs < rhs) {
