@@ -793,6 +793,36 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
                                 }
                                 const uint32_t *skipfilt = nullptr;
                                 BitSink         bs;
+                                // Google operands that are decoded in full go through the plain-store word builder into a bitmap of their
+                                // own (dst itself for SET, the scratch slot otherwise) and are combined word-wise afterwards
+                                const bool ownOk = P.ix.codec == 0 && g_docs_decoder >= 3 && P.docs_stage_bytes >= kGatherBufBytes + 128u &&
+                                                   P.docs_stage_bytes < 2u * kGatherBufBytes && haveTerm && bA <= bB;
+                                const uint32_t dummy = uint32_t(__cvta_generic_to_shared(stage + kGatherBufBytes)) + uint32_t(lane) * 4u;
+                                if (ownOk && mode != M_AND) {
+                                        uint32_t *out = mode == M_SET ? dst : tmp;
+                                        bool      full = true;
+                                        if (mode == M_ANDNOT) { // few documents left to exclude from: block skipping (below) beats a full decode
+                                                uint32_t cnt = 0;
+                                                for (uint32_t i = lane; i < NW; i += 32)
+                                                        cnt += __popc(dst[i]);
+                                                for (int d = 16; d > 0; d >>= 1)
+                                                        cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+                                                full = cnt >= 4u * (bB - bA + 1u);
+                                        }
+                                        if (full) {
+                                                for (uint32_t i = lane; i < NW; i += 32)
+                                                        out[i] = 0;
+                                                __syncwarp();
+                                                google_leaf_own(P.ix, T, bA, bB, lo, W, out, stage, dummy, lane);
+                                                if (mode == M_OR)
+                                                        for (uint32_t i = lane; i < NW; i += 32)
+                                                                dst[i] |= tmp[i];
+                                                else if (mode == M_ANDNOT)
+                                                        for (uint32_t i = lane; i < NW; i += 32)
+                                                                dst[i] &= ~tmp[i];
+                                                goto leaf_done;
+                                        }
+                                }
                                 if (mode == M_SET) {
                                         for (uint32_t i = lane; i < NW; i += 32)
                                                 dst[i] = 0;
@@ -822,6 +852,13 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
                                         if (cnt == 0) {
                                                 bA = 1;
                                                 bB = 0;
+                                        } else if (ownOk && cnt >= kSparseThreshold) {
+                                                // dense destination: full decode into the (just cleared) scratch slot, then one word-wise AND
+                                                __syncwarp();
+                                                google_leaf_own(P.ix, T, bA, bB, lo, W, tmp, stage, dummy, lane);
+                                                for (uint32_t i = lane; i < NW; i += 32)
+                                                        dst[i] &= tmp[i];
+                                                goto leaf_done;
                                         } else if (cnt < kSparseThreshold && bA <= bB) {
                                                 const uint32_t *bl = P.ix.blk_last + T.dir_begin;
                                                 const uint32_t  a  = warp_lower_bound(bl, bA, bB, lo + mn, lane);
@@ -847,6 +884,7 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
                                         for (uint32_t i = lane; i < NW; i += 32)
                                                 dst[i] = tmp[i];
                                 }
+                        leaf_done:;
                         }
                         if (st.flags & F_BREAK_IF_EMPTY) {
                                 __syncwarp();

@@ -165,3 +165,39 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
         }
         return 1;
 }
+
+// One operand of a general step program decoded with the plain-store word builder: blocks [bA, bB] of term T into `out`, a bitmap
+// that only this call writes (cleared by the caller).  Same loop as the conjunction case of flat_exec_google for a single term.
+// `dummy`: shared address of 32 scratch words (one per lane).
+__device__ void google_leaf_own(const DevIndex &ix, const DevTerm &T, uint32_t bA, uint32_t bB, uint32_t lo, uint32_t W, uint32_t *out, uint8_t *stage,
+                                uint32_t dummy, int lane) {
+        const uint32_t *bl = ix.blk_last + T.dir_begin, *bo = ix.blk_off + T.dir_begin;
+        const uint32_t  out_s = uint32_t(__cvta_generic_to_shared(out));
+        uint32_t        tail_a = dummy, tail_bits = 0;
+        for (uint32_t g = bA; g <= bB; g += 32u) {
+                const uint32_t b      = g + uint32_t(lane);
+                const bool     active = b <= bB;
+                uint32_t       off = 0, last = 0, prev = 0, n = 0;
+                if (active) {
+                        off  = bo[b];
+                        last = bl[b];
+                        prev = b ? bl[b - 1] : 0u;
+                        n    = (b + 1u == T.nblocks) ? (T.documents - 32u * (T.nblocks - 1u)) : 32u;
+                }
+                gather_issue(ix.index, off, active, stage, lane);
+                gather_wait<0>();
+                const unsigned m = __ballot_sync(0xffffffffu, active);
+                OwnAcc         bs;
+                bs.init(out_s, dummy);
+                if (active)
+                        google_block_docs_vote(m, ix.index, off, stage, lane, n, prev, last, lo, W, bs);
+                __syncwarp();
+                if (tail_bits) // the previous group's last words, after every block that can share them has stored
+                        asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(tail_a), "r"(tail_bits) : "memory");
+                tail_a    = bs.cur_a;
+                tail_bits = bs.cur;
+        }
+        if (tail_bits)
+                asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(tail_a), "r"(tail_bits) : "memory");
+        __syncwarp();
+}
