@@ -103,18 +103,21 @@ int trn_segment_masked(trn_segment *, const uint32_t **docids, uint64_t *n);
  *   OR        -> Disjunction / DisjunctionAllPLI
  *   NOT       -> Filter(req = child 0, excl = child 1)           (docset_iterators.cpp:652-677)
  *   OPTIONAL  -> Optional(main = child 0, opt = child 1)         (docset_iterators.h:174-206)
+ *   SOME      -> DisjunctionSome(children, min = term)           (docset_iterators.cpp:679-811; ast_node::Type::MatchSome): matches the
+ *                documents at least `min` children match, scores the sum of the children that match (docset_iterators_scorers.cpp:38-56)
  * children of node i are nodes[first_child .. first_child + nchildren). */
 #define TRN_NODE_TERM 0
 #define TRN_NODE_AND 1
 #define TRN_NODE_OR 2
 #define TRN_NODE_NOT 3
 #define TRN_NODE_OPTIONAL 4
+#define TRN_NODE_SOME 5
 
 typedef struct trn_qnode {
         uint8_t  kind;
         uint8_t  nchildren;
         uint16_t first_child;
-        uint32_t term;  /* TERM: index into the uploaded terms table */
+        uint32_t term;  /* TERM: index into the uploaded terms table; SOME: min-should-match (1..15) */
         double   weight; /* TERM: BM25 idf weight == ScorerWeight::idf (similarity.h:190-222); ignored in docs-only mode */
 } trn_qnode;
 

@@ -328,12 +328,44 @@ int64_t tref_exec2(void *h, const char *q, int mode, uint32_t parserFlags, uint3
 int64_t tref_exec(void *h, const char *q, int mode, uint32_t *ids, double *scores, uint64_t cap) {
         return tref_exec2(h, q, mode, 0, ids, scores, cap);
 }
+// the parser creates MatchSome groups ([a, b, c], ParseMatchSomeExpr = 16) with min = 1; applications raise match_some.min afterwards
+static void set_match_some_min(ast_node *n, uint16_t m) {
+        if (!n)
+                return;
+        switch (n->type) {
+                case ast_node::Type::BinOp:
+                        set_match_some_min(n->binop.lhs, m);
+                        set_match_some_min(n->binop.rhs, m);
+                        break;
+                case ast_node::Type::UnaryOp:
+                        set_match_some_min(n->unaryop.expr, m);
+                        break;
+                case ast_node::Type::ConstTrueExpr:
+                        set_match_some_min(n->expr, m);
+                        break;
+                case ast_node::Type::MatchSome:
+                        n->match_some.min = m;
+                        for (size_t i = 0; i < n->match_some.size; ++i)
+                                set_match_some_min(n->match_some.nodes[i], m);
+                        break;
+                default:
+                        break;
+        }
+}
+
+int64_t tref_exec3(void *h, const char *q, int mode, uint32_t parserFlags, uint32_t minMatch, uint32_t *ids, double *scores, uint64_t cap);
 // parserFlags: ast_parser::Flags (queries.h:230-240), e.g. ParseConstTrueExpr = 8 enables the <expr> syntax (-> DocsSetIterators::Optional)
 int64_t tref_exec2(void *h, const char *q, int mode, uint32_t parserFlags, uint32_t *ids, double *scores, uint64_t cap) {
+        return tref_exec3(h, q, mode, parserFlags, 0, ids, scores, cap);
+}
+// minMatch != 0: match_some.min of every MatchSome group of the parsed query
+int64_t tref_exec3(void *h, const char *q, int mode, uint32_t parserFlags, uint32_t minMatch, uint32_t *ids, double *scores, uint64_t cap) {
         auto    x = static_cast<RefIndex *>(h);
         int64_t n{-1};
         guarded([&] {
                 query       qq(str32_t(q, strlen(q)), default_token_parser_impl, parserFlags);
+                if (minMatch)
+                        set_match_some_min(qq.root, uint16_t(minMatch));
                 CollectSink sink;
                 sink.cap  = cap;
                 auto reg  = masked_documents_registry::make(nullptr, 0);

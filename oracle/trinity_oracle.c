@@ -194,7 +194,7 @@ float orc_bm25_score(double idf, uint16_t freq) {
 }
 
 /* ---- docset algebra + structural scoring ----
- * node layout == trn_qnode of include/trinity_b200.h (kind 0 TERM, 1 AND, 2 OR, 3 NOT(req, excl), 4 OPTIONAL(main, opt)).
+ * node layout == trn_qnode of include/trinity_b200.h (kind 0 TERM, 1 AND, 2 OR, 3 NOT(req, excl), 4 OPTIONAL(main, opt), 5 SOME(children, min = term)).
  * Matching: Conjuction / Disjunction / Filter / Optional next()/advance() semantics (docset_iterators.cpp:282-677,
  * docset_iterators.h:174-206).  Scoring: the IteratorScorer wrappers (docset_iterators_scorers.cpp:8-242): a conjunction sums all
  * children, a disjunction sums the children positioned on the document, a filter scores its required side only, an optional adds
@@ -250,6 +250,29 @@ static int orc_eval_node(const orc_ctx *c, uint32_t i, uint8_t *m, double *s) {
         uint8_t *cm = (uint8_t *)malloc(n);
         double * cs = c->scored ? (double *)malloc(n * sizeof(double)) : NULL;
         int      rc = 0;
+        if (X->kind == 5) {
+                /* SOME == DisjunctionSome (docset_iterators.cpp:679-811): >= X->term children match; the children that match score
+                 * (docset_iterators_scorers.cpp:38-56) */
+                uint8_t *cnt = (uint8_t *)calloc(n, 1);
+                for (uint32_t k = 0; k < X->nchildren && rc == 0; ++k) {
+                        rc = orc_eval_node(c, X->first_child + k, cm, cs);
+                        for (size_t d = 0; d < n && rc == 0; ++d)
+                                if (cm[d]) {
+                                        if (cnt[d] < 255)
+                                                ++cnt[d];
+                                        if (cs) s[d] += cs[d];
+                                }
+                }
+                for (size_t d = 0; d < n; ++d) {
+                        m[d] = cnt[d] >= X->term;
+                        if (cs && !m[d])
+                                s[d] = 0;
+                }
+                free(cnt);
+                free(cm);
+                free(cs);
+                return rc;
+        }
         for (uint32_t k = 0; k < X->nchildren && rc == 0; ++k) {
                 rc = orc_eval_node(c, X->first_child + k, cm, cs);
                 if (rc)
@@ -304,6 +327,21 @@ static uint64_t orc_cost(const orc_ctx *c, uint32_t i) {
                 return X->term == 0xffffffffu ? 0 : c->terms[X->term].documents;
         if (X->kind == 3 || X->kind == 4)
                 return orc_cost(c, X->first_child);
+        if (X->kind == 5) { /* DisjunctionSome::cost_: the (size - min + 1) cheapest children */
+                uint64_t v[256], r = 0;
+                for (uint32_t k = 0; k < X->nchildren; ++k)
+                        v[k] = orc_cost(c, X->first_child + k);
+                for (uint32_t a = 0; a < X->nchildren; ++a)
+                        for (uint32_t b = a + 1; b < X->nchildren; ++b)
+                                if (v[b] < v[a]) {
+                                        const uint64_t t = v[a];
+                                        v[a]             = v[b];
+                                        v[b]             = t;
+                                }
+                for (uint32_t k = 0; k + X->term < X->nchildren + 1u; ++k)
+                        r += v[k];
+                return r;
+        }
         uint64_t r = X->kind == 1 ? ~0ull : 0;
         for (uint32_t k = 0; k < X->nchildren; ++k) {
                 const uint64_t v = orc_cost(c, X->first_child + k);

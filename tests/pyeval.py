@@ -32,6 +32,9 @@ def evaluate(nodes, lists, ndocs, weights=None):
         elif kind == tb.NODE_NOT:
             m = kids[0][0] & ~kids[1][0]
             s = kids[0][1] * m
+        elif kind == tb.NODE_SOME:  # DisjunctionSome: >= min children match; the matching children score
+            m = sum(k[0].astype(np.int32) for k in kids) >= int(n["term"])
+            s = sum(k[1] * k[0] for k in kids)
         else:  # OPTIONAL
             m = kids[0][0]
             s = (kids[0][1] + kids[1][1] * kids[1][0]) * m
@@ -46,6 +49,8 @@ def evaluate(nodes, lists, ndocs, weights=None):
         kids = [cost(int(n["first_child"]) + c) for c in range(int(n["nchildren"]))]
         if kind in (tb.NODE_NOT, tb.NODE_OPTIONAL):
             return kids[0]
+        if kind == tb.NODE_SOME:
+            return sum(sorted(kids)[:max(0, len(kids) - int(n["term"]) + 1)])
         return min(kids) if kind == tb.NODE_AND else sum(kids)
 
     # the reference's root-Filter-over-disjunction quirk (exec.cpp:488-501 + docset_spans.cpp:98-111), see engine.cu

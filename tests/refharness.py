@@ -47,6 +47,8 @@ class RefLib:
         L.tref_exec.argtypes = [vp, C.c_char_p, C.c_int, vp, vp, u64]
         L.tref_exec2.restype = C.c_int64
         L.tref_exec2.argtypes = [vp, C.c_char_p, C.c_int, u32, vp, vp, u64]
+        L.tref_exec3.restype = C.c_int64
+        L.tref_exec3.argtypes = [vp, C.c_char_p, C.c_int, u32, u32, vp, vp, u64]
         L.tref_exec_masked.restype = C.c_int64
         L.tref_exec_masked.argtypes = [vp, C.c_char_p, C.c_int, vp, u32, vp, vp, u64]
         L.tref_exec_batch.restype = C.c_double
@@ -201,11 +203,12 @@ class RefIndex:
     def bm25(self, term_idx, freq):
         return self.rl.L.tref_bm25(self.h, term_idx, freq)
 
-    def exec(self, q: str, scored: bool, cap: int, parser_flags: int = 0):
-        """parser_flags: ast_parser::Flags; 8 = ParseConstTrueExpr (the <expr> syntax -> Optional)"""
+    def exec(self, q: str, scored: bool, cap: int, parser_flags: int = 0, min_match: int = 0):
+        """parser_flags: ast_parser::Flags; 8 = ParseConstTrueExpr (the <expr> syntax -> Optional), 16 = ParseMatchSomeExpr ([a, b, c]);
+        min_match: match_some.min of every MatchSome group (the parser leaves it at 1)"""
         ids = np.zeros(max(cap, 1), np.uint32)
         sc = np.zeros(max(cap, 1), np.float64)
-        n = self.rl.L.tref_exec2(self.h, q.encode(), 1 if scored else 0, parser_flags, _p(ids), _p(sc), cap)
+        n = self.rl.L.tref_exec3(self.h, q.encode(), 1 if scored else 0, parser_flags, min_match, _p(ids), _p(sc), cap)
         if n < 0:
             raise RuntimeError(self.rl.err())
         assert n <= cap, "reference produced more matches than the capacity given"

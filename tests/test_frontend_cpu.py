@@ -96,3 +96,29 @@ def test_optional_semantics_match_reference(small, q):
     assert np.array_equal(ids, wd)
     rel = np.abs(s[wd] - ws) / np.maximum(np.abs(ws), 1e-30)
     assert rel.max() <= 1e-5
+
+
+SOME_QUERIES = [("[t1, t2, t3]", 2), ("[t1, t2, t3, t4, t5]", 3), ("[t1, t2, t3]", 1), ("[t1, t2, t3]", 3), ("[t1, t2]", 3),
+                ("[t3, t4 AND t5, t6 OR t7, t2]", 2), ("t1 AND [t2, t3, t4]", 2), ("[t2, t3, t4] NOT t1", 2), ("[t2, t3, t4] OR t9", 2),
+                ("[t2, nosuchterm, t4, t5]", 2), ("[t1, t2, t3, t4, t5, t6, t7, t8, t9, t10]", 5), ("(t1 AND t2) OR [t3, t4, t5]", 2), ("[t3 t4, t5, t6]", 2)]
+# (a MatchSome group nested inside another one sends the reference's compiler into a runaway allocation: not tested)
+
+
+@pytest.mark.parametrize("q,m", SOME_QUERIES)
+def test_match_some_semantics_match_reference(small, q, m):
+    """[a, b, ...] with match_some.min = m -> DocsSetIterators::DisjunctionSome (docset_iterators.cpp:679-811): the documents at least m
+    children match, scored with the sum of the children that match"""
+    r, lists, tdict = small
+    nodes = tb.parse_query(q, tdict, min_match=m)
+    for x in nodes:
+        if x["kind"] == tb.NODE_TERM and x["term"] != tb.EMPTY_TERM:
+            x["weight"] = tb.bm25_idf(len(lists[int(x["term"])][0]), NDOCS)
+    mm, s = evaluate(nodes, lists, NDOCS, weights=True)
+    ids = np.flatnonzero(mm).astype(np.uint32)
+    want, _ = r.exec(q, False, NDOCS + 1, parser_flags=16, min_match=m)
+    assert np.array_equal(ids, want), (len(ids), len(want))
+    wd, ws = r.exec(q, True, NDOCS + 1, parser_flags=16, min_match=m)
+    assert np.array_equal(ids, wd)
+    if len(wd):
+        rel = np.abs(s[wd] - ws) / np.maximum(np.abs(ws), 1e-30)
+        assert rel.max() <= 1e-5

@@ -73,3 +73,14 @@ def test_restated_exec_matches_reference_exec_query(ref, orc, codec):
         assert np.array_equal(gd, wd), q
         rel = np.abs(gs - ws) / np.maximum(np.abs(ws), 1e-30)
         assert rel.max() <= 1e-5, q
+    # MatchSome groups (DisjunctionSome)
+    for q, m in (("[t1, t2, t3]", 2), ("[t3, t4 AND t5, t6 OR t7, t2]", 2), ("t1 AND [t2, t3, t4, t5]", 3), ("[t2, t3, t4] OR t9", 2)):
+        nodes = tb.parse_query(q, tdict, min_match=m)
+        for x in nodes:
+            if x["kind"] == tb.NODE_TERM and x["term"] != tb.EMPTY_TERM:
+                x["weight"] = tb.bm25_idf(int(terms["documents"][x["term"]]), NDOCS)
+        wd, ws = r.exec(q, True, NDOCS + 1, parser_flags=16, min_match=m)
+        gd, gs = oracle_c.exec_query(orc, codec, index, terms, nodes, NDOCS, True)
+        assert np.array_equal(gd, wd), q
+        rel = np.abs(gs - ws) / np.maximum(np.abs(ws), 1e-30)
+        assert rel.max() <= 1e-5, q

@@ -16,7 +16,7 @@ from ._ffi import QNODE_DTYPE, TERM_DTYPE, TrnIndexInfo, TrnQuery, TrnResult, Tr
 
 CODEC_GOOGLE, CODEC_LUCENE = 0, 1
 MODE_DOCS_ONLY, MODE_SCORED_ALL, MODE_SCORED_TOPK = 0, 1, 2  # == ExecFlags::DocumentsOnly / AccumulatedScoreScheme (+ fused top-k sink)
-NODE_TERM, NODE_AND, NODE_OR, NODE_NOT, NODE_OPTIONAL = 0, 1, 2, 3, 4
+NODE_TERM, NODE_AND, NODE_OR, NODE_NOT, NODE_OPTIONAL, NODE_SOME = 0, 1, 2, 3, 4, 5
 EMPTY_TERM = 0xFFFFFFFF
 DOC_IDS_END = 0xFFFFFFFF  # DocIDsEND, common.h:43
 
@@ -168,9 +168,11 @@ class TermDictionary:
         return len(self.names)
 
 
-def parse_query(text: str, tdict: TermDictionary) -> np.ndarray:
+def parse_query(text: str, tdict: TermDictionary, min_match: Optional[int] = None) -> np.ndarray:
     """Query string -> flat trn_qnode array (see include/trinity_b200.h).  Mirrors the reference's operator subset and
-    precedence (queries.cpp:11-27,477-520) followed by build_iterator's flattening (exec.cpp:328-400)."""
+    precedence (queries.cpp:11-27,477-520) followed by build_iterator's flattening (exec.cpp:328-400).
+    `[a, b, c]` is a MatchSome group; like the reference's parser it starts with min = 1 and the application raises it:
+    min_match sets match_some.min of every such group."""
     L = lib()
     nodes = np.zeros(256, dtype=QNODE_DTYPE)
     nn, root = C.c_uint32(), C.c_uint32()
@@ -180,7 +182,10 @@ def parse_query(text: str, tdict: TermDictionary) -> np.ndarray:
     if rc != 0:
         raise TrinityError(f"parse error: {err.value.decode()}")
     assert root.value == 0
-    return nodes[: nn.value].copy()
+    out = nodes[: nn.value].copy()
+    if min_match is not None:
+        out["term"][out["kind"] == NODE_SOME] = min_match
+    return out
 
 
 def bm25_idf(doc_freq: int, docs_cnt: int) -> float:

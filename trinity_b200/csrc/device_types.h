@@ -36,6 +36,8 @@ enum StepOp : uint8_t {
         OP_SLOT      = 1, // combine slot src into slot dst (mode)
         OP_CLEAR     = 2, // dst = 0
         OP_LEAFSCORE = 3, // second pass: decode term, accumulate BM25 where slot src (mask) has the doc's bit
+        OP_COUNT_ADD = 4, // bit-sliced saturating counter in slots dst .. dst+mode-1 (LSB first) += slot src   (DisjunctionSome)
+        OP_COUNT_GE  = 5, // dst = documents whose counter (slots src .. src+mode-1) is >= term (min-should-match)
 };
 enum StepMode : uint8_t { M_SET = 0, M_OR = 1, M_AND = 2, M_ANDNOT = 3, M_NONE = 4 };
 enum StepFlags : uint8_t { F_SCORE = 1, F_BREAK_IF_EMPTY = 2 };

@@ -296,6 +296,44 @@ struct Compiler {
                                         // (Optional::next advances opt lazily); we do not read it at all.
                                 }
                         } break;
+                        case TRN_NODE_SOME: {
+                                // DisjunctionSome (docset_iterators.cpp:679-811): every child is evaluated into a bitmap of its own and added to a
+                                // bit-sliced saturating counter (one bitmap per counter bit); the node matches where the counter reaches `min`.
+                                // A child scores only where it matches AND the node matches (Wrapper::iterator_score sums the lead list).
+                                const uint32_t m = X.term;
+                                if (m == 0 || m > 15) {
+                                        err = "SOME: min-should-match must be in 1..15";
+                                        return -1;
+                                }
+                                uint32_t k = 1;
+                                while (((1u << k) - 1u) < m)
+                                        ++k;
+                                if (next_slot + k + 1 > 14) {
+                                        err = "query needs more than 14 docset slots";
+                                        return -1;
+                                }
+                                const uint32_t p0 = next_slot;
+                                next_slot += k;
+                                const uint32_t t = next_slot++; // shared by the leaf children
+                                for (uint32_t j = 0; j < k; ++j)
+                                        push(OP_CLEAR, 0, p0 + j, 0, 0, 0, 0);
+                                for (auto c : kids) {
+                                        uint32_t src;
+                                        if (is_leaf(c)) {
+                                                leaf(c, M_SET, t, scoring, child_cond(s), 0);
+                                                src = t;
+                                        } else {
+                                                auto cc = child_cond(s);
+                                                cc.push_back(uint8_t(next_slot)); // the child's own slot
+                                                const int cs = node(c, scoring, cc);
+                                                if (cs < 0)
+                                                        return -1;
+                                                src = uint32_t(cs);
+                                        }
+                                        push(OP_COUNT_ADD, uint8_t(k), p0, src, 0, 0, 0);
+                                }
+                                push(OP_COUNT_GE, uint8_t(k), s, p0, 0, m, 0);
+                        } break;
                         default:
                                 err = "unknown node kind";
                                 return -1;
@@ -370,7 +408,7 @@ struct Compiler {
                                         err = "term id out of range";
                                         return false;
                                 }
-                        } else if (n[i].kind > TRN_NODE_OPTIONAL) {
+                        } else if (n[i].kind > TRN_NODE_SOME) {
                                 err = "unknown node kind";
                                 return false;
                         } else {
@@ -392,6 +430,17 @@ struct Compiler {
                         return df(i);
                 if (X.kind == TRN_NODE_NOT || X.kind == TRN_NODE_OPTIONAL)
                         return cost(X.first_child);
+                if (X.kind == TRN_NODE_SOME) { // DisjunctionSome::cost_: the (size - min + 1) cheapest children (docset_iterators.cpp:733-742)
+                        std::vector<uint64_t> cs;
+                        for (uint32_t k = 0; k < X.nchildren; ++k)
+                                cs.push_back(cost(X.first_child + k));
+                        std::sort(cs.begin(), cs.end());
+                        const uint32_t keep = X.nchildren >= X.term ? X.nchildren - X.term + 1u : 0u;
+                        uint64_t       c{0};
+                        for (uint32_t k = 0; k < keep && k < cs.size(); ++k)
+                                c += cs[k];
+                        return c;
+                }
                 uint64_t c = X.kind == TRN_NODE_AND ? ~0ull : 0ull;
                 for (uint32_t k = 0; k < X.nchildren; ++k) {
                         const uint64_t cc = cost(X.first_child + k);

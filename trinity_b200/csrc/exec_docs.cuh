@@ -773,6 +773,32 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
                                         else if (st.mode == M_AND) dst[i] &= s;
                                         else if (st.mode == M_ANDNOT) dst[i] &= ~s;
                                 }
+                        } else if (st.op == OP_COUNT_ADD) {
+                                // bit-sliced saturating counters: plane j of the counter lives in slot dst + j
+                                const uint32_t *src = slots + size_t(st.src) * NW;
+                                for (uint32_t i = lane; i < NW; i += 32) {
+                                        uint32_t carry = src[i];
+                                        for (uint32_t j = 0; j < st.mode && carry; ++j) {
+                                                uint32_t *     pl = slots + size_t(st.dst + j) * NW;
+                                                const uint32_t p  = pl[i];
+                                                pl[i]             = p ^ carry;
+                                                carry &= p;
+                                        }
+                                        if (carry) // overflow: stay at the maximum
+                                                for (uint32_t j = 0; j < st.mode; ++j)
+                                                        slots[size_t(st.dst + j) * NW + i] |= carry;
+                                }
+                        } else if (st.op == OP_COUNT_GE) {
+                                const uint32_t m = st.term;
+                                for (uint32_t i = lane; i < NW; i += 32) {
+                                        uint32_t gt = 0, eq = 0xffffffffu;
+                                        for (int j = int(st.mode) - 1; j >= 0; --j) {
+                                                const uint32_t p = slots[size_t(st.src + j) * NW + i];
+                                                if ((m >> j) & 1u) eq &= p;
+                                                else gt |= eq & p;
+                                        }
+                                        dst[i] = gt | eq;
+                                }
                         } else if (st.op == OP_LEAF && st.mode != M_NONE) {
                                 uint32_t *tmp      = slots + size_t(P.nslots - 1) * NW;
                                 const int mode     = st.mode;

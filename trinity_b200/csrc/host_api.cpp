@@ -450,7 +450,7 @@ struct Parser {
         Op peek(size_t *len) {
                 ws();
                 *len = 0;
-                if (p >= e || *p == ')' || *p == '>')
+                if (p >= e || *p == ')' || *p == '>' || *p == ']' || *p == ',')
                         return NONE;
                 if (keyword("AND", 3)) {
                         *len = 3;
@@ -475,7 +475,7 @@ struct Parser {
                         *len = 1;
                         return NOT;
                 }
-                if (isterm(*p) || *p == '(' || *p == '<')
+                if (isterm(*p) || *p == '(' || *p == '<' || *p == '[')
                         return AND; // juxtaposition
                 return NONE;
         }
@@ -501,6 +501,31 @@ struct Parser {
                         const int c   = add(kConstTrue);
                         nodes[c].kids = {x};
                         return c;
+                }
+                if (p < e && *p == '[') {
+                        // [e1, e2, ...] (ast_parser::Flags::ParseMatchSomeExpr, queries.cpp:424-450): ast_node::Type::MatchSome with min = 1; the
+                        // application raises match_some.min afterwards (trn_qnode.term of the TRN_NODE_SOME node)
+                        ++p;
+                        const int s = add(TRN_NODE_SOME);
+                        nodes[s].term = 1;
+                        for (;;) {
+                                const int x = subexpr(255);
+                                if (x < 0)
+                                        return -1;
+                                nodes[s].kids.push_back(x);
+                                ws();
+                                if (p < e && *p == ',') {
+                                        ++p;
+                                        continue;
+                                }
+                                if (p < e && *p == ']') {
+                                        ++p;
+                                        break;
+                                }
+                                err = "expected ',' or ']'";
+                                return -1;
+                        }
+                        return s;
                 }
                 if (p < e && *p == '(') {
                         ++p;
@@ -669,7 +694,8 @@ extern "C" int trn_parse_query(const char *text, const char *const *names, uint3
         // single-operand AND/OR and const-true wrappers that did not end up beside a conjunction operand collapse to their child
         auto collapse = [&](int x) {
                 while (ps.nodes[x].kind != TRN_NODE_TERM && ps.nodes[x].kids.size() == 1 &&
-                       (ps.nodes[x].kind == TRN_NODE_AND || ps.nodes[x].kind == TRN_NODE_OR || ps.nodes[x].kind == kConstTrue))
+                       (ps.nodes[x].kind == TRN_NODE_AND || ps.nodes[x].kind == TRN_NODE_OR || ps.nodes[x].kind == kConstTrue ||
+                        ps.nodes[x].kind == TRN_NODE_SOME)) // [x] == x: compilation_ctx.cpp:786-789 (the parser always yields min = 1)
                         x = ps.nodes[x].kids[0];
                 return x;
         };
@@ -687,6 +713,8 @@ extern "C" int trn_parse_query(const char *text, const char *const *names, uint3
                 if (A.kind == TRN_NODE_TERM)
                         q.term = A.term;
                 else {
+                        if (A.kind == TRN_NODE_SOME)
+                                q.term = A.term; // min-should-match
                         std::vector<int> kids;
                         for (int k : A.kids) {
                                 kids.push_back(collapse(k));
