@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 
 import trinity_b200 as tb
-from util import Pair, assert_same_docs
+from test_frontend_cpu import EXTRA, OPTIONAL_QUERIES, SOME_QUERIES, TEMPLATES
+from util import Pair, assert_same_docs, closed_form_lists
 
 pytestmark = pytest.mark.gpu
 NDOCS = 2_000_000
@@ -59,3 +60,17 @@ def test_candidate_conjunctions_match_reference(ref, cand_cost, cost):
     for i, q in enumerate(QUERIES):
         want, _ = p.ref.exec_masked(q, False, masked, NDOCS + 1)
         assert_same_docs(res.query(i)[0], want, f"[{q}] masked cost={cost}")
+
+
+@pytest.mark.parametrize("cost", [1, 900], ids=["forced", "default"])
+def test_candidate_driven_trees_match_reference(ref, cand_cost, cost):
+    """every tree with 2..8 distinct terms one of which all matches must hold: lead candidates + membership probes + truth table"""
+    cand_cost(cost)
+    ndocs = 300_000
+    p = Pair(ref, tb.CODEC_GOOGLE, closed_form_lists(ndocs), ndocs)
+    qs = [(q, 0, 0) for q in TEMPLATES + EXTRA] + [(q, 8, 0) for q in OPTIONAL_QUERIES] + [(q, 16, m) for q, m in SOME_QUERIES]
+    plans = [tb.parse_query(q, p.tdict, min_match=m or None) for q, _, m in qs]
+    res = p.gpu.exec_batch(plans, tb.MODE_DOCS_ONLY)
+    for i, (q, flags, m) in enumerate(qs):
+        want, _ = p.ref.exec(q, False, ndocs + 1, parser_flags=flags, min_match=m)
+        assert_same_docs(res.query(i)[0], want, f"[{q}] min={m} cost={cost}")

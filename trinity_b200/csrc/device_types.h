@@ -38,6 +38,7 @@ enum StepOp : uint8_t {
         OP_LEAFSCORE = 3, // second pass: decode term, accumulate BM25 where slot src (mask) has the doc's bit
         OP_COUNT_ADD = 4, // bit-sliced saturating counter in slots dst .. dst+mode-1 (LSB first) += slot src   (DisjunctionSome)
         OP_COUNT_GE  = 5, // dst = documents whose counter (slots src .. src+mode-1) is >= term (min-should-match)
+        OP_TABLE     = 6, // candidate-driven trees: 4 words of the query's truth table (term, pad2, idf as two words); dst = first word index
 };
 enum StepMode : uint8_t { M_SET = 0, M_OR = 1, M_AND = 2, M_ANDNOT = 3, M_NONE = 4 };
 enum StepFlags : uint8_t { F_SCORE = 1, F_BREAK_IF_EMPTY = 2 };
@@ -59,7 +60,9 @@ struct DevQuery {
         uint32_t cand_base; // SCORED_TOPK: first candidate slot of this query
         uint32_t cand_cap;
         uint32_t flat; // 0 = general step program; 1 = conjunction of terms only; 2 = disjunction of terms only (see exec_docs_flat.cuh);
-                       // 3 = conjunction of terms, candidate-driven: items are 32-block groups of the rarest term (exec_docs_cand.cuh)
+                       // 3 = candidate-driven (exec_docs_cand.cuh): items are 32-block groups of a lead term every match must hold; the
+                       //     step program is replaced by [OP_LEAF lead, OP_LEAF other terms..., OP_TABLE...]: root_slot = number of NECESSARY
+                       //     terms (they come first), the truth table decides over the membership bits of the others
 };
 
 struct ExecParams {

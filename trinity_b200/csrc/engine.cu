@@ -10,9 +10,11 @@
 #include "device_types.h"
 #include "kernels.h"
 #include <algorithm>
+#include <array>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -736,6 +738,65 @@ static DevIndex dev_index(trn_ctx *c) {
         return ix;
 }
 
+// Truth vector of a query subtree over its (<= 8) distinct terms: bit `a` (0..255) = value of the node when exactly the terms whose
+// bit is set in `a` are present (bit j of `a` = term tv[j]).  Bitwise evaluation: one 256-bit operation per node.
+struct TruthVec {
+        uint64_t w[4];
+};
+static TruthVec truth_vector(const trn_qnode *nodes, uint32_t i, const uint32_t *tv, uint32_t n) {
+        static const uint64_t kPat[6] = {0xaaaaaaaaaaaaaaaaull, 0xccccccccccccccccull, 0xf0f0f0f0f0f0f0f0ull, 0xff00ff00ff00ff00ull, 0xffff0000ffff0000ull, 0xffffffff00000000ull};
+        const auto &X = nodes[i];
+        TruthVec    v{{0, 0, 0, 0}};
+        if (X.kind == TRN_NODE_TERM) {
+                for (uint32_t j = 0; j < n; ++j)
+                        if (tv[j] == X.term) {
+                                for (int q = 0; q < 4; ++q)
+                                        v.w[q] = j < 6 ? kPat[j] : (j == 6 ? ((q & 1) ? ~0ull : 0ull) : ((q & 2) ? ~0ull : 0ull));
+                                break;
+                        }
+                return v;
+        }
+        const uint32_t f = X.first_child;
+        if (X.kind == TRN_NODE_SOME) {
+                TruthVec kids[16];
+                const uint32_t nk = std::min<uint32_t>(X.nchildren, 16);
+                for (uint32_t k = 0; k < nk; ++k)
+                        kids[k] = truth_vector(nodes, f + k, tv, n);
+                for (uint32_t a = 0; a < 256; ++a) {
+                        uint32_t cnt{0};
+                        for (uint32_t k = 0; k < nk; ++k)
+                                cnt += uint32_t((kids[k].w[a >> 6] >> (a & 63u)) & 1ull);
+                        if (cnt >= X.term)
+                                v.w[a >> 6] |= 1ull << (a & 63u);
+                }
+                return v;
+        }
+        v = truth_vector(nodes, f, tv, n);
+        for (uint32_t k = 1; k < X.nchildren; ++k) {
+                const TruthVec w = truth_vector(nodes, f + k, tv, n);
+                for (int q = 0; q < 4; ++q) {
+                        if (X.kind == TRN_NODE_AND) v.w[q] &= w.w[q];
+                        else if (X.kind == TRN_NODE_OR) v.w[q] |= w.w[q];
+                        else if (X.kind == TRN_NODE_NOT) v.w[q] &= ~w.w[q];
+                        // OPTIONAL: the optional side never changes the match set
+                }
+        }
+        return v;
+}
+
+static void push_step(std::vector<DevStep> &steps, uint8_t op, uint8_t mode, uint32_t dst, uint32_t src, uint8_t flags, uint32_t term, double idf) {
+        DevStep s;
+        std::memset(&s, 0, sizeof(s));
+        s.op    = op;
+        s.mode  = mode;
+        s.dst   = uint8_t(dst);
+        s.src   = uint8_t(src);
+        s.flags = flags;
+        s.term  = term;
+        s.idf   = idf;
+        steps.push_back(s);
+}
+
 // =================================================================================================== exec
 // small device scratch layout (d_small): [0] ticket u32, [2..3] seg_cursor u64, [4] overflow u32, then per-query arrays
 static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, int mode, uint32_t k, trn_result *out, int set, cudaEvent_t k0, cudaEvent_t k1) {
@@ -757,7 +818,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         std::vector<DevQuery> hq(nq);
         std::vector<DevStep>  steps;
         uint32_t              maxSlots{1};
-        bool                  anyCandidate{false};
+        bool                  anyCandidate{false}, anyMembership{false};
         uint64_t              items{0}, segCap{0}, candTotal{0}, postings{0}, bytes{0};
         for (uint32_t q = 0; q < nq; ++q) {
                 const auto &Q = queries[q];
@@ -790,34 +851,117 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 postings += cc.postings;
                 bytes += cc.bytes;
                 const Range r = cc.range(cc.root); // cc.root: the effective root (see apply_reference_root_filter_quirk)
-                // candidate-driven conjunction (exec_docs_cand.cuh) when the rarest operand is sparse: its cost follows the lead's
-                // postings (~cand_cost/2 warp-instructions per 32 candidates and operand; the crossover was tuned on the and2 workload: 900 beats 450 and 1500) instead of the docID space (~1500 per tile +
-                // ~27 per block in it, profiles/r01_l_*)
+                // Candidate-driven evaluation (exec_docs_cand.cuh) when some term that EVERY match must hold is sparse: cost follows that
+                // lead's postings (~cand_cost/2 warp-instructions per 32 candidates and probed term; the crossover was tuned on the and2
+                // workload: 900 beats 450 and 1500) instead of the docID space (~1500 per tile + ~27 per block in it, profiles/r01_l_*).
+                // The boolean function of the tree over its (<= 8 distinct) terms is tabulated here; the device probes every term for
+                // each candidate and looks the membership bits up.
                 bool candidate{false};
-                if (dq.flat == 1u && !scored && c->codec == TRN_CODEC_GOOGLE && c->cand_cost > 0 && !r.empty()) {
-                        uint32_t lead{kEmptyTerm}, nleaf{0};
-                        double   blocks{0};
-                        bool     known{true};
-                        for (uint32_t si = dq.step_begin; si < steps.size(); ++si)
-                                if (steps[si].op == OP_LEAF) {
-                                        if (nleaf++ == 0)
-                                                lead = steps[si].term;
-                                        if (steps[si].term == kEmptyTerm)
-                                                known = false;
+                if (!scored && c->codec == TRN_CODEC_GOOGLE && c->cand_cost > 0 && !r.empty()) {
+                        // distinct non-empty terms below the effective root (at most 8)
+                        uint32_t tv[8];
+                        uint32_t n{0};
+                        bool     small{true};
+                        {
+                                uint32_t stack[64], sp{0};
+                                stack[sp++] = cc.root;
+                                while (sp && small) {
+                                        const auto &X = Q.nodes[stack[--sp]];
+                                        if (X.kind == TRN_NODE_TERM) {
+                                                if (X.term == kEmptyTerm || !c->h_terms[X.term].nblocks)
+                                                        continue;
+                                                bool seen{false};
+                                                for (uint32_t j = 0; j < n; ++j)
+                                                        seen |= tv[j] == X.term;
+                                                if (!seen) {
+                                                        if (n == 8)
+                                                                small = false;
+                                                        else
+                                                                tv[n++] = X.term;
+                                                }
+                                        } else if (sp + X.nchildren > 64)
+                                                small = false;
                                         else
-                                                blocks += c->h_terms[steps[si].term].nblocks;
+                                                for (uint32_t k = 0; k < X.nchildren; ++k)
+                                                        stack[sp++] = X.first_child + k;
                                 }
-                        if (known && lead != kEmptyTerm && nleaf >= 2 && c->h_terms[lead].nblocks) {
-                                const double width   = double(c->max_docid) - double(std::min(c->min_docid, c->max_docid)) + 1.0; // docID span of THIS source
-                                const double perTile = double(1ull << execShift) / width;
-                                const double lhs     = double(nleaf - 1) * c->h_terms[lead].nblocks * perTile * double(c->cand_cost);
-                                const double rhs     = 1500.0 + blocks * perTile * 27.0;
-                                if (lhs < rhs) {
-                                        candidate  = true;
-                                        dq.flat    = 3u;
-                                        dq.tile_lo = 0;
-                                        dq.ntiles  = (c->h_terms[lead].nblocks + 31u) / 32u;
-                                        anyCandidate = true;
+                        }
+                        small = small && n >= 2;
+                        if (small) {
+                                // truth vectors: bit `bits` of vec(node) = value of the node under the term assignment `bits` (bit j = tv[j])
+                                uint8_t  truth[256];
+                                uint32_t necessary{(1u << n) - 1u};
+                                bool     any{false};
+                                if (dq.flat == 1u && n == Q.nodes[cc.root].nchildren) { // all-term conjunction: only the all-ones assignment matches
+                                        std::memset(truth, 0, sizeof(truth));
+                                        truth[(1u << n) - 1u] = 1;
+                                        any                   = true;
+                                } else {
+                                        const TruthVec tvec = truth_vector(Q.nodes, cc.root, tv, n);
+                                        for (uint32_t bits = 0; bits < (1u << n); ++bits) {
+                                                truth[bits] = uint8_t((tvec.w[bits >> 6] >> (bits & 63u)) & 1ull);
+                                                if (truth[bits]) {
+                                                        necessary &= bits;
+                                                        any = true;
+                                                }
+                                        }
+                                }
+                                if (any && necessary) {
+                                        // probe order: the lead (rarest necessary term), the other necessary terms rarest first (they filter),
+                                        // then the rest
+                                        uint32_t order[8], nn{0}, no{0};
+                                        for (uint32_t j = 0; j < n; ++j)
+                                                if ((necessary >> j) & 1u)
+                                                        order[no++] = j;
+                                        nn = no;
+                                        for (uint32_t j = 0; j < n; ++j)
+                                                if (!((necessary >> j) & 1u))
+                                                        order[no++] = j;
+                                        auto byBlocks = [&](uint32_t x, uint32_t y) { return c->h_terms[tv[x]].nblocks < c->h_terms[tv[y]].nblocks; };
+                                        std::sort(order, order + nn, byBlocks);
+                                        std::sort(order + nn, order + n, byBlocks);
+                                        const uint32_t lead = tv[order[0]];
+                                        double         blocks{0};
+                                        for (uint32_t j = 0; j < n; ++j)
+                                                blocks += c->h_terms[tv[j]].nblocks;
+                                        const double width   = double(c->max_docid) - double(std::min(c->min_docid, c->max_docid)) + 1.0; // docID span of THIS source
+                                        const double perTile = double(1ull << execShift) / width;
+                                        const double lhs     = double(n - 1) * c->h_terms[lead].nblocks * perTile * double(c->cand_cost);
+                                        const double rhs     = 1500.0 + (dq.flat == 1u ? 0.0 : 150.0 * n) + blocks * perTile * (dq.flat == 1u ? 27.0 : 35.0);
+                                        if (lhs < rhs) {
+                                                // replace the step program: terms in probe order, then the truth table re-indexed to probe positions
+                                                steps.resize(dq.step_begin);
+                                                for (uint32_t j = 0; j < n; ++j)
+                                                        push_step(steps, OP_LEAF, M_NONE, 0, 0, 0, tv[order[j]], 0.0);
+                                                uint32_t words[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                                                for (uint32_t pb = 0; pb < (1u << n); ++pb) { // pb: bit j = term at probe position j
+                                                        uint32_t bits{0};
+                                                        for (uint32_t j = 0; j < n; ++j)
+                                                                if ((pb >> j) & 1u)
+                                                                        bits |= 1u << order[j];
+                                                        if (truth[bits])
+                                                                words[pb >> 5] |= 1u << (pb & 31u);
+                                                }
+                                                for (uint32_t w = 0; w < 8; w += 4) {
+                                                        DevStep st;
+                                                        std::memset(&st, 0, sizeof(st));
+                                                        st.op   = OP_TABLE;
+                                                        st.dst  = uint8_t(w);
+                                                        st.term = words[w];
+                                                        st.pad2 = words[w + 1];
+                                                        uint64_t hi = uint64_t(words[w + 2]) | (uint64_t(words[w + 3]) << 32);
+                                                        std::memcpy(&st.idf, &hi, 8);
+                                                        steps.push_back(st);
+                                                }
+                                                dq.nsteps    = uint32_t(steps.size()) - dq.step_begin;
+                                                dq.root_slot = nn;
+                                                candidate    = true;
+                                                dq.flat      = 3u;
+                                                dq.tile_lo   = 0;
+                                                dq.ntiles    = (c->h_terms[lead].nblocks + 31u) / 32u;
+                                                anyCandidate = true;
+                                                anyMembership |= nn < n;
+                                        }
                                 }
                         }
                 }
@@ -845,7 +989,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         }
         const uint32_t totalItems = uint32_t(items);
         if (anyCandidate) { // the candidate array + one gather buffer must fit a warp's share of shared memory
-                const uint32_t slotBytes = (1u << execShift) / 8u, stageB = exec_docs_stage_bytes(c->docs_bufs), need = exec_docs_cand_smem_bytes();
+                const uint32_t slotBytes = (1u << execShift) / 8u, stageB = exec_docs_stage_bytes(c->docs_bufs), need = exec_docs_cand_smem_bytes(anyMembership);
                 if (need > stageB)
                         maxSlots = std::max(maxSlots, (need - stageB + slotBytes - 1u) / slotBytes);
         }

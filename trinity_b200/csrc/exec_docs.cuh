@@ -745,7 +745,7 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
                 }
                 if (Q.flat == 3u) { // candidate-driven conjunction: the work item is a 32-block group of the lead term
                         __syncwarp();
-                        cand_exec_google(P, Q, curq, item, item - Q.item_base, slots, reinterpret_cast<uint8_t *>(slots + kCandWords), lane);
+                        cand_exec_google(P, Q, curq, item, item - Q.item_base, slots, lane);
                         continue;
                 }
                 const uint32_t tile = Q.tile_lo + (item - Q.item_base);
@@ -968,8 +968,8 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
         }
 }
 
-uint32_t exec_docs_cand_smem_bytes() {
-        return kCandSmem;
+uint32_t exec_docs_cand_smem_bytes(bool with_membership) {
+        return with_membership ? kCandSmemMask : kCandSmem;
 }
 
 uint32_t exec_docs_stage_bytes(int bufs) {

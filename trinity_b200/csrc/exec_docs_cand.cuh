@@ -20,7 +20,9 @@
 static constexpr uint32_t kCandStride  = 33;
 static constexpr uint32_t kCandWords   = 32 * kCandStride;      // 1056 words
 static constexpr uint32_t kCandBytes   = kCandWords * 4;        // 4224 B (multiple of 16: the gather buffer follows)
-static constexpr uint32_t kCandSmem    = kCandBytes + kGatherBufBytes;
+static constexpr uint32_t kCandMaskBytes = kCandWords;            // one membership byte per candidate (terms that are not necessary)
+static constexpr uint32_t kCandSmem    = kCandBytes + kGatherBufBytes;                  // candidates | one gather buffer
+static constexpr uint32_t kCandSmemMask = kCandSmem + kCandMaskBytes;                   // ... | membership bytes (only queries with terms that are not necessary)
 static constexpr uint32_t kCandInvalid = 0xffffffffu;
 
 // one lane decodes the doc section of ITS staged block into out[0..n)
@@ -109,18 +111,31 @@ __device__ __forceinline__ bool google_block_find(const uint8_t *__restrict__ in
         return false;
 }
 
-// `cand`: kCandWords words, followed by one gather buffer (`stage`).  `group`: 32-block group of the lead term.
-__device__ void cand_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t curq, uint32_t item, uint32_t group, uint32_t *cand, uint8_t *stage, int lane) {
-        // lane j adopts the j-th operand (operands are ordered rarest first)
-        uint32_t nleaf = 0, myTerm = kEmptyTerm;
+// `cand`: kCandWords words, then one gather buffer, then (if the batch has such queries) kCandMaskBytes membership bytes.  `group`: 32-block group of the lead term.
+// The query's program is [OP_LEAF lead, OP_LEAF term 1, ..., OP_TABLE x2]: terms 1 .. Q.root_slot-1 are NECESSARY (a candidate without
+// them is dropped at once); the others only set their bit in the candidate's membership byte, and the truth table (bit m = value of
+// the query when exactly the terms in m are present; bit 0 of m = the lead) decides at the end.
+__device__ void cand_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t curq, uint32_t item, uint32_t group, uint32_t *cand, int lane) {
+        uint8_t *const stage = reinterpret_cast<uint8_t *>(cand + kCandWords);
+        uint8_t *const cmask = stage + kGatherBufBytes;
+        // lane j adopts the j-th term; lane w (< 8) keeps word w of the truth table
+        uint32_t nleaf = 0, myTerm = kEmptyTerm, myTable = 0;
         for (uint32_t si = 0; si < Q.nsteps; ++si) {
                 const DevStep st = P.steps[Q.step_begin + si];
                 if (st.op == OP_LEAF) {
                         if (uint32_t(lane) == nleaf)
                                 myTerm = st.term;
                         ++nleaf;
+                } else if (st.op == OP_TABLE) {
+                        const unsigned long long hi = static_cast<unsigned long long>(__double_as_longlong(st.idf));
+                        const uint32_t           w  = uint32_t(lane) - st.dst; // 0..3 for the lanes that own these words
+                        if (w == 0u) myTable = st.term;
+                        else if (w == 1u) myTable = st.pad2;
+                        else if (w == 2u) myTable = uint32_t(hi);
+                        else if (w == 3u) myTable = uint32_t(hi >> 32);
                 }
         }
+        const uint32_t nnec = Q.root_slot; // necessary terms incl. the lead
         uint32_t mydir = 0, mynb = 0, mydocs = 0;
         if (uint32_t(lane) < nleaf && myTerm != kEmptyTerm) {
                 const DevTerm T = P.ix.terms[myTerm];
@@ -149,6 +164,11 @@ __device__ void cand_exec_google(const ExecParams &P, const DevQuery &Q, uint32_
                 __syncwarp();
         }
         const uint32_t rounds = min(32u, nb0 - min(nb0, group * 32u)); // lead blocks of this group (they are the leading lanes)
+        if (nleaf > nnec) {
+                for (uint32_t i = lane; i < kCandMaskBytes / 4u; i += 32)
+                        reinterpret_cast<uint32_t *>(cmask)[i] = 0x01010101u; // bit 0: the lead holds every candidate
+                __syncwarp();
+        }
         // ---- 2. every other operand: keep the candidates it holds
         for (uint32_t t = 1; t < nleaf; ++t) {
                 const uint32_t  dirt = __shfl_sync(0xffffffffu, mydir, int(t)), nbt = __shfl_sync(0xffffffffu, mynb, int(t)), docst = __shfl_sync(0xffffffffu, mydocs, int(t));
@@ -193,9 +213,15 @@ __device__ void cand_exec_google(const ExecParams &P, const DevQuery &Q, uint32_
                                         hit = google_block_find(P.ix.index, off, stage, lane, nblk, prev, c);
                                 __syncwarp();
                         }
-                        if (valid && !hit)
-                                cand[j * kCandStride + lane] = kCandInvalid;
-                        alive |= __ballot_sync(0xffffffffu, valid && hit);
+                        if (t < nnec) {
+                                if (valid && !hit)
+                                        cand[j * kCandStride + lane] = kCandInvalid;
+                                alive |= __ballot_sync(0xffffffffu, valid && hit);
+                        } else {
+                                if (valid && hit)
+                                        cmask[j * kCandStride + lane] |= uint8_t(1u << t);
+                                alive = 1u;
+                        }
                 }
                 __syncwarp();
                 if (!alive) {
@@ -213,6 +239,11 @@ __device__ void cand_exec_google(const ExecParams &P, const DevQuery &Q, uint32_
                 const uint32_t nj = __shfl_sync(0xffffffffu, n, int(j));
                 const uint32_t c  = uint32_t(lane) < nj ? cand[j * kCandStride + lane] : kCandInvalid;
                 bool           ok = c != kCandInvalid;
+                if (nleaf > nnec) { // the membership bits of the terms that are not necessary decide (uniform shuffle: every lane takes part)
+                        const uint32_t m    = ok ? (uint32_t(cmask[j * kCandStride + lane]) | ((1u << nnec) - 1u)) : 0u;
+                        const uint32_t word = __shfl_sync(0xffffffffu, myTable, int(m >> 5));
+                        ok                  = ok && ((word >> (m & 31u)) & 1u);
+                }
                 if (ok && P.ix.masked)
                         ok = ((__ldg(P.ix.masked + (c >> 5)) >> (c & 31u)) & 1u) == 0u;
                 const uint32_t vm = __ballot_sync(0xffffffffu, ok);

@@ -9,7 +9,7 @@ size_t      exec_smem_bytes(uint32_t tile_shift, uint32_t nslots, int mode, int 
 int         exec_max_ctas_per_sm(uint32_t tile_shift, uint32_t nslots, int mode, int codec);
 cudaError_t launch_exec_tiles(const ExecParams &P, int grid, cudaStream_t stream);
 uint32_t    exec_docs_stage_bytes(int bufs);
-uint32_t    exec_docs_cand_smem_bytes(); // per-warp shared memory of the candidate-driven conjunction path
+uint32_t    exec_docs_cand_smem_bytes(bool with_membership); // per-warp shared memory of the candidate-driven path (membership bytes: trees with terms that are not necessary)
 size_t      exec_docs_smem_bytes(uint32_t exec_shift, uint32_t nslots, uint32_t stageBytes);
 int         exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots, uint32_t stageBytes);
 cudaError_t launch_exec_docs(const ExecParams &P, int grid, cudaStream_t stream);
