@@ -313,14 +313,40 @@ def main():
         "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(synth, texts, args, mode)
+        line["cpu_baseline"] = cpu_baseline(synth, texts, args, mode, check=res)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(synth, texts, args, mode, threads: int | None = None, sample: int | None = None, repeats: int = 1):
+def full_size_parity(res, mode, k, counts, sums, tid, tsc, n):
+    """the reference run of the cpu_baseline leg doubles as the full-size checker of the GPU batch `res` (same index bytes, same
+    queries): per-query match counts and docID checksums (DocumentsOnly) / counts and top-k scores (top-k mode, 1e-5 relative)"""
+    import trinity_b200 as tb
+    out = {"queries_checked": int(n), "match_counts_equal": bool(np.array_equal(np.asarray(res.match_counts[:n], np.uint64), counts[:n]))}
+    if mode == tb.MODE_DOCS_ONLY:
+        off = np.asarray(res.offsets[: n + 1], np.int64)
+        ids = np.asarray(res.docids[: off[-1]], np.uint64)
+        cs = np.concatenate([[0], np.cumsum(ids, dtype=np.uint64)])
+        got = cs[off[1:]] - cs[off[:-1]]
+        out["docid_checksums_equal"] = bool(np.array_equal(got, sums[:n]))
+    elif mode == tb.MODE_SCORED_TOPK:
+        worst = 0.0
+        for q in range(n):
+            d, s = res.query(q)
+            want = tsc[q][: len(s)]
+            if len(s) != int(min(k, counts[q])):
+                worst = float("inf")
+                break
+            if len(s):
+                worst = max(worst, float(np.max(np.abs(np.asarray(s, np.float64) - want) / np.maximum(np.abs(want), 1e-30))))
+        out["topk_scores_max_rel_err"] = worst
+        out["topk_scores_within_1e-5"] = bool(worst <= 1e-5)
+    return out
+
+
+def cpu_baseline(synth, texts, args, mode, threads: int | None = None, sample: int | None = None, repeats: int = 1, check=None):
     """the reference's own exec_query (oracle/_ref == the reference compiled in place) on the host cores"""
     sys.path.insert(0, str(ROOT / "tests"))
     from refharness import RefIndex, load_ref
@@ -332,11 +358,17 @@ def cpu_baseline(synth, texts, args, mode, threads: int | None = None, sample: i
     qs = texts[:n]
     best = None
     for _ in range(repeats):
-        el, counts, sums, _, _ = r.exec_batch(qs, mode != 0, args.k, cores)
+        el, counts, sums, tid, tsc = r.exec_batch(qs, mode != 0, args.k, cores)
         best = el if best is None else min(best, el)
-    return {"value": n / best, "unit": "queries/s", "cores": cores, "kind": "reference",
-            "sample": f"first {n} queries of the same batch, one query per host thread ({cores} threads), {best:.2f} s wall",
-            "seconds": best}
+    out = {"value": n / best, "unit": "queries/s", "cores": cores, "kind": "reference",
+           "sample": f"first {n} queries of the same batch, one query per host thread ({cores} threads), {best:.2f} s wall",
+           "seconds": best}
+    if check is not None:
+        try:
+            out["parity"] = full_size_parity(check, mode, args.k, counts, sums, tid, tsc, n)
+        except Exception as e:  # the checker must never take the bench line down
+            out["parity"] = {"error": repr(e)}
+    return out
 
 
 def reference_arm(args, rank, world, wl, K, W):

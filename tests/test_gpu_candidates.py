@@ -21,6 +21,12 @@ def make_lists(seed=11):
         n = max(3, int(NDOCS * p))
         d = np.sort(rng.choice(np.arange(1, NDOCS + 1), size=n, replace=False)).astype(np.uint32)
         lists.append((d, rng.integers(1, 5, size=n).astype(np.uint32)))
+    # blocks whose doc-delta section starts with 3-byte codes and then runs past the 80 staged bytes (10 x 3 + 21 x 2 = 72 bytes + up to
+    # 15 bytes of alignment): the lead decoder has to leave its shared-memory slot in the middle of the 2-byte codes
+    gaps = np.tile(np.array([16400] * 10 + [130] * 22, np.uint64), 11)
+    d = np.cumsum(gaps).astype(np.uint32)
+    assert d[-1] <= NDOCS
+    lists.append((d, np.ones(len(d), np.uint32)))
     # a term of exactly 32*k documents and one with a 1-document last block
     lists.append((np.arange(7, 7 + 64 * 1000, 1000, dtype=np.uint32), np.ones(64, np.uint32)))
     lists.append((np.arange(3, 3 + 33 * 5, 5, dtype=np.uint32), np.ones(33, np.uint32)))
@@ -29,7 +35,7 @@ def make_lists(seed=11):
 
 QUERIES = ["t1 AND t2", "t1 AND t5", "t2 AND t6", "t1 AND t7", "t3 AND t4", "t4 AND t5", "t5 AND t6", "t6 AND t7", "t1 AND t2 AND t3",
            "t1 AND t4 AND t6", "t2 AND t3 AND t4 AND t5", "t1 AND t8", "t2 AND t9", "t8 AND t9", "t1 AND nosuchterm", "t7 AND t1 AND t2",
-           "t5 AND t5"]
+           "t5 AND t5", "t1 AND t10", "t2 AND t10", "t10 AND t3 AND t1", "t9 AND t10"]
 
 
 @pytest.fixture

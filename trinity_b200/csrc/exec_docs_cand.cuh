@@ -33,6 +33,10 @@ __device__ __forceinline__ void google_block_to_array(const uint8_t *__restrict_
         const uint32_t nd  = n - 1u;
         uint32_t       doc = prev, i = 0, p = 0;
         for (; i < nd; ++i) {
+                // 3-byte codes (gaps >= 16384: the sparsest leads) are decoded in place too, so the 31 x 2 + 15 <= 80 bound of the other
+                // decoders does not hold here: every code (<= 3 bytes) is checked against the end of the slot
+                if (mis + p + 3u > kGatherBytes)
+                        break;
                 const uint32_t b0 = lds_u8(sp + p);
                 uint32_t       v;
                 if (b0 < 0x80u) {
@@ -41,11 +45,11 @@ __device__ __forceinline__ void google_block_to_array(const uint8_t *__restrict_
                 } else if (b0 < 0xc0u) {
                         v = ((b0 & 0x3fu) << 8) | lds_u8(sp + p + 1u);
                         p += 2u;
-                } else if (b0 < 0xe0u && mis + p + 3u <= kGatherBytes) { // 3-byte code (gaps >= 16384: the sparsest leads) still inside the slot
+                } else if (b0 < 0xe0u) {
                         v = ((b0 & 0x1fu) << 16) | lds_u8(sp + p + 1u) | (lds_u8(sp + p + 2u) << 8);
                         p += 3u;
                 } else
-                        break; // the section may leave the slot
+                        break; // 4- and 5-byte codes: continue from global memory
                 doc += v;
                 out[i] = doc;
         }
