@@ -328,7 +328,7 @@ def full_size_parity(res, mode, k, counts, sums, tid, tsc, n):
     if mode == tb.MODE_DOCS_ONLY:
         off = np.asarray(res.offsets[: n + 1], np.int64)
         ids = np.asarray(res.docids[: off[-1]], np.uint64)
-        cs = np.concatenate([[0], np.cumsum(ids, dtype=np.uint64)])
+        cs = np.concatenate([np.zeros(1, np.uint64), np.cumsum(ids, dtype=np.uint64)])  # (a Python 0 would promote the array to float64)
         got = cs[off[1:]] - cs[off[:-1]]
         out["docid_checksums_equal"] = bool(np.array_equal(got, sums[:n]))
     elif mode == tb.MODE_SCORED_TOPK:
