@@ -1,0 +1,6 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out
+T=${1:-r01_t}
+par() { tail -1 $1 | python -c "import json,sys; d=json.loads(sys.stdin.readline()); print(round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'frac', round(d['roofline']['frac'],4), d.get('cpu_baseline',{}).get('value'), d.get('cpu_baseline',{}).get('parity'))"; }
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${T}_bench_and2_1gpu.log 2>&1; echo "and2: $(par gpurun_out/${T}_bench_and2_1gpu.log)"
+timeout 900 python bench.py --workload tree8 --steps 5 --warmup 3 > gpurun_out/${T}_bench_tree8_1gpu.log 2>&1; echo "tree8: $(par gpurun_out/${T}_bench_tree8_1gpu.log)"
