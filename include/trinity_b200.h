@@ -134,6 +134,12 @@ typedef struct trn_query {
 int trn_parse_query(const char *text, const char *const *names, uint32_t nterms, trn_qnode *nodes, uint32_t cap, uint32_t *nnodes, uint32_t *root,
                     char *err, size_t errcap);
 
+/* The boolean function of a query tree over its distinct (non-empty) terms, as the planner of the candidate-driven path tabulates
+ * it (DocumentsOnly; == which term combinations DocsSetIterators::Conjuction / Disjunction / Filter / Optional / DisjunctionSome
+ * accept): terms[j] = j-th distinct term (<= 8, else TRN_ERR_ARG); bit a of table[] (256 bits) = value of the query when exactly
+ * the terms whose bit is set in a are on the document; *necessary = mask of the terms every match holds.  Host-only (tests, tooling). */
+int trn_query_truth_table(const trn_qnode *nodes, uint32_t nnodes, uint32_t root, uint32_t *terms, uint32_t *nterms, uint32_t *table, uint32_t *necessary);
+
 /* BM25 weight of one term == IndexSourcesCollectionBM25Scorer::Scorer::idf evaluated in float (similarity.h:179-181) */
 double trn_bm25_idf(uint32_t doc_freq, uint64_t docs_cnt);
 /* == Scorer::score(id, freq, weight) (similarity.h:228-235): float(idf * float(freq) / double(freq + 1.2f)) */

@@ -6,7 +6,7 @@ import numpy as np
 import trinity_b200 as tb
 
 
-def evaluate(nodes, lists, ndocs, weights=None):
+def evaluate(nodes, lists, ndocs, weights=None, quirk=True):
     """returns (match mask[ndocs+1], score[ndocs+1]) for node 0.  lists[t] = (docids, freqs)"""
 
     def rec(i):
@@ -57,6 +57,6 @@ def evaluate(nodes, lists, ndocs, weights=None):
     root, traversed = 0, False
     while int(nodes[root]["kind"]) == tb.NODE_NOT and cost(int(nodes[root]["first_child"]) + 1) <= cost(int(nodes[root]["first_child"])):
         root, traversed = int(nodes[root]["first_child"]), True
-    if not (traversed and int(nodes[root]["kind"]) == tb.NODE_OR):
+    if not (quirk and traversed and int(nodes[root]["kind"]) == tb.NODE_OR):
         root = 0
     return rec(root)

@@ -122,3 +122,37 @@ def test_match_some_semantics_match_reference(small, q, m):
     if len(wd):
         rel = np.abs(s[wd] - ws) / np.maximum(np.abs(ws), 1e-30)
         assert rel.max() <= 1e-5
+
+
+def test_truth_tables_of_the_candidate_planner_match_the_evaluator(small):
+    """the host planner of the candidate-driven path tabulates a tree's boolean function over its terms: every assignment must agree with
+    the structural evaluator (pyeval) on one-document-per-assignment posting lists, and `necessary` must be the terms all matches hold"""
+    _, _, tdict = small
+    qs = [(q, None) for q in TEMPLATES + EXTRA + OPTIONAL_QUERIES] + list(SOME_QUERIES)
+    checked = 0
+    for q, m in qs:
+        nodes = tb.parse_query(q, tdict, min_match=m)
+        try:
+            terms, table, necessary = tb.query_truth_table(nodes)
+        except tb.TrinityError:
+            continue
+        n = len(terms)
+        # document a+1 holds exactly the terms whose bit is set in assignment a
+        ndocs = 1 << n
+        lists = {t: (np.array([a + 1 for a in range(ndocs) if (a >> j) & 1], np.uint32), None) for j, t in enumerate(terms)}
+        full = [(np.zeros(0, np.uint32), np.zeros(0, np.uint32))] * len(tdict)
+        for t, (d, _) in lists.items():
+            full[t] = (d, np.ones(len(d), np.uint32))
+        # the evaluator mirrors the reference's root-filter quirk, and so does the planner (it tabulates the effective root): compare
+        # on the plain tree semantics by evaluating node 0 without the quirk
+        from pyeval import evaluate
+        mm, _ = evaluate(nodes, full, ndocs, weights=None, quirk=False)
+        want = np.array([mm[a + 1] for a in range(ndocs)], bool)
+        assert np.array_equal(table, want), q
+        nec = (1 << n) - 1
+        for a in range(ndocs):
+            if want[a]:
+                nec &= a
+        assert necessary == nec, q
+        checked += 1
+    assert checked >= 30

@@ -188,6 +188,20 @@ def parse_query(text: str, tdict: TermDictionary, min_match: Optional[int] = Non
     return out
 
 
+def query_truth_table(nodes: np.ndarray):
+    """(terms, table, necessary): the boolean function of a plan over its distinct terms as the candidate-driven planner sees it;
+    table[a] (a = bit set of present terms, bit j = terms[j]) is True where the query matches"""
+    nodes = np.ascontiguousarray(nodes, dtype=QNODE_DTYPE)
+    terms = (C.c_uint32 * 8)()
+    table = (C.c_uint32 * 8)()
+    n, nec = C.c_uint32(), C.c_uint32()
+    rc = lib().trn_query_truth_table(_ptr(nodes), len(nodes), 0, terms, C.byref(n), table, C.byref(nec))
+    if rc != 0:
+        raise TrinityError("query has more than 8 distinct terms (or a malformed tree)")
+    tb_ = np.array([(table[a >> 5] >> (a & 31)) & 1 for a in range(1 << n.value)], bool)
+    return [int(terms[j]) for j in range(n.value)], tb_, int(nec.value)
+
+
 def bm25_idf(doc_freq: int, docs_cnt: int) -> float:
     return float(lib().trn_bm25_idf(doc_freq, docs_cnt))
 

@@ -17,7 +17,7 @@ EXPORTS = [
     "trn_synth_build", "trn_synth_build_shard", "trn_synth_destroy", "trn_synth_index", "trn_synth_hits", "trn_synth_terms", "trn_synth_sum_hits",
     "trn_synth_postings", "trn_synth_positions",
     "trn_directory_probe", "trn_segment_open", "trn_segment_close", "trn_segment_info", "trn_segment_index", "trn_segment_terms",
-    "trn_segment_masked", "trn_parse_query", "trn_bm25_idf", "trn_bm25_score",
+    "trn_segment_masked", "trn_parse_query", "trn_query_truth_table", "trn_bm25_idf", "trn_bm25_score",
     "trn_create", "trn_destroy", "trn_last_error", "trn_set_stream", "trn_upload_index", "trn_set_masked_documents", "trn_index_info_get",
     "trn_exec_batch", "trn_exec_batch_device", "trn_last_topk_device", "trn_merge_topk", "trn_fetch_results",
     "trn_decode_terms",
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
     sig("trn_segment_index", i32, vp, P(vp), P(u64))
     sig("trn_segment_terms", i32, vp, P(vp), P(vp), P(u32))
     sig("trn_segment_masked", i32, vp, P(vp), P(u64))
+    sig("trn_query_truth_table", i32, vp, u32, u32, P(u32), P(u32), P(u32), P(u32))
     sig("trn_parse_query", i32, C.c_char_p, vp, u32, vp, u32, P(u32), P(u32), C.c_char_p, C.c_size_t)
     sig("trn_bm25_idf", C.c_double, u32, u64)
     sig("trn_bm25_score", C.c_float, C.c_double, C.c_uint16)

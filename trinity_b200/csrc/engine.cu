@@ -784,6 +784,45 @@ static TruthVec truth_vector(const trn_qnode *nodes, uint32_t i, const uint32_t 
         return v;
 }
 
+extern "C" int trn_query_truth_table(const trn_qnode *nodes, uint32_t nnodes, uint32_t root, uint32_t *terms, uint32_t *nterms, uint32_t *table, uint32_t *necessary) {
+        if (!nodes || !nnodes || root >= nnodes || !terms || !nterms || !table || !necessary)
+                return TRN_ERR_ARG;
+        uint32_t n{0}, stack[64], sp{0};
+        stack[sp++] = root;
+        while (sp) {
+                const auto &X = nodes[stack[--sp]];
+                if (X.kind == TRN_NODE_TERM) {
+                        if (X.term == kEmptyTerm)
+                                continue;
+                        bool seen{false};
+                        for (uint32_t j = 0; j < n; ++j)
+                                seen |= terms[j] == X.term;
+                        if (!seen) {
+                                if (n == 8)
+                                        return TRN_ERR_ARG;
+                                terms[n++] = X.term;
+                        }
+                } else {
+                        if (X.kind > TRN_NODE_SOME || X.nchildren == 0 || uint32_t(X.first_child) + X.nchildren > nnodes || sp + X.nchildren > 64)
+                                return TRN_ERR_ARG;
+                        for (uint32_t k = 0; k < X.nchildren; ++k)
+                                stack[sp++] = X.first_child + k;
+                }
+        }
+        const TruthVec v = truth_vector(nodes, root, terms, n);
+        uint32_t       nec{n ? (1u << n) - 1u : 0u};
+        for (uint32_t w = 0; w < 8; ++w)
+                table[w] = 0;
+        for (uint32_t a = 0; a < (1u << n); ++a)
+                if ((v.w[a >> 6] >> (a & 63u)) & 1ull) {
+                        table[a >> 5] |= 1u << (a & 31u);
+                        nec &= a;
+                }
+        *nterms    = n;
+        *necessary = nec;
+        return TRN_OK;
+}
+
 static void push_step(std::vector<DevStep> &steps, uint8_t op, uint8_t mode, uint32_t dst, uint32_t src, uint8_t flags, uint32_t term, double idf) {
         DevStep s;
         std::memset(&s, 0, sizeof(s));
