@@ -1,4 +1,8 @@
-// k_exec_docs — DocumentsOnly execution with one WARP per (query, docID tile) work item.  (Included by kernels.cu.)
+// k_exec_docs — DocumentsOnly execution with one WARP per work item.  (Included by kernels.cu.)
+//
+// A work item is a (query, docID tile) pair for the bitmap paths (general step programs here, all-term conjunctions / disjunctions in
+// exec_docs_flat.cuh) or a 32-block group of a lead term for the candidate-driven path (exec_docs_cand.cuh); the host picks the path
+// per query (engine.cu, exec_device_impl).
 //
 // Why a second kernel: the ncu capture of the CTA-per-tile kernel on the 2-term AND workload (profiles/r01_a_*) showed DRAM at 5 % of
 // peak, 37 % issue utilisation and 47 % of all stall samples on CTA barriers — 4 warps waiting for the slowest lane-serial block
