@@ -156,6 +156,28 @@ struct Compiler {
             : n{nodes}, nn{cnt}, terms{t}, scored{sc}, root{r}, steps{s} {
         }
 
+        // Slots: in DocumentsOnly plans a child's bitmap is dead once it has been combined into its parent, so its slot is handed out
+        // again (scored plans keep every slot: the deferred scoring pass reads branch bitmaps at the end).  Fewer live slots = less
+        // shared memory per worker = more resident warps (the 8-term trees ran at 12 warps/SM with one slot per node, profiles/r01_u_*).
+        std::vector<uint32_t> free_slots;
+        int alloc_slot() {
+                if (!scored && !free_slots.empty()) {
+                        const auto it = std::min_element(free_slots.begin(), free_slots.end());
+                        const int  v  = int(*it);
+                        free_slots.erase(it);
+                        return v;
+                }
+                if (next_slot >= 14) {
+                        err = "query needs more than 14 docset slots";
+                        return -1;
+                }
+                return int(next_slot++);
+        }
+        void release_slot(uint32_t s) {
+                if (!scored)
+                        free_slots.push_back(s);
+        }
+
         bool is_leaf(uint32_t i) const {
                 return n[i].kind == TRN_NODE_TERM;
         }
@@ -199,11 +221,10 @@ struct Compiler {
 
         // compiles internal node i into its own slot; returns the slot
         int node(uint32_t i, bool scoring, const std::vector<uint8_t> &cond) {
-                if (next_slot >= 14) {
-                        err = "query needs more than 14 docset slots";
+                const int sAlloc = alloc_slot();
+                if (sAlloc < 0)
                         return -1;
-                }
-                const uint32_t s    = next_slot++;
+                const uint32_t s    = uint32_t(sAlloc);
                 const auto &   X    = n[i];
                 const bool     isRoot = i == root;
                 if (X.nchildren == 0 || uint32_t(X.first_child) + X.nchildren > nn) {
@@ -239,6 +260,7 @@ struct Compiler {
                                                 if (cs < 0)
                                                         return -1;
                                                 push(OP_SLOT, first ? M_SET : M_AND, s, uint32_t(cs), fl, 0, 0);
+                                                release_slot(uint32_t(cs));
                                         }
                                         first = false;
                                 }
@@ -256,6 +278,7 @@ struct Compiler {
                                                 if (cs < 0)
                                                         return -1;
                                                 push(OP_SLOT, M_OR, s, uint32_t(cs), 0, 0, 0);
+                                                release_slot(uint32_t(cs));
                                         }
                                 }
                         } break;
@@ -273,6 +296,7 @@ struct Compiler {
                                         if (cs < 0)
                                                 return -1;
                                         push(OP_SLOT, M_SET, s, uint32_t(cs), fl, 0, 0);
+                                        release_slot(uint32_t(cs));
                                 }
                                 if (X.kind == TRN_NODE_NOT) {
                                         // Filter: excluded side never scores (docset_iterators_scorers.cpp Filter -> req only)
@@ -283,6 +307,7 @@ struct Compiler {
                                                 if (cs < 0)
                                                         return -1;
                                                 push(OP_SLOT, M_ANDNOT, s, uint32_t(cs), 0, 0, 0);
+                                                release_slot(uint32_t(cs));
                                         }
                                 } else if (scored && scoring) {
                                         // Optional: main drives; opt only adds its score when it is on the document
@@ -333,8 +358,13 @@ struct Compiler {
                                                 src = uint32_t(cs);
                                         }
                                         push(OP_COUNT_ADD, uint8_t(k), p0, src, 0, 0, 0);
+                                        if (src != t)
+                                                release_slot(src);
                                 }
                                 push(OP_COUNT_GE, uint8_t(k), s, p0, 0, m, 0);
+                                for (uint32_t j = 0; j < k; ++j)
+                                        release_slot(p0 + j);
+                                release_slot(t);
                         } break;
                         default:
                                 err = "unknown node kind";
