@@ -45,3 +45,32 @@ def test_directory_rejects_corrupt_chunk():
     bad[4] ^= 0x7F  # block length byte of the first block
     with pytest.raises(tb.TrinityError):
         tb.directory_probe(tb.CODEC_GOOGLE, bad, t)
+
+
+@pytest.mark.parametrize("codec", [tb.CODEC_GOOGLE, tb.CODEC_LUCENE])
+def test_directory_build_survives_corrupted_chunks(codec):
+    """index bytes come from files: a corrupted or truncated term chunk must be reported (TRN_ERR_FORMAT) or parsed into an in-bounds
+    directory — never read outside the buffer (that would kill the process)"""
+    rng = np.random.default_rng(11 + codec)
+    lists = make_lists(rng)
+    b = tb.IndexBuilder(codec)
+    for d, f in lists:
+        b.add_term(d, f, positions_for(f, rng))
+    good = b.index().copy()
+    ok = bad = 0
+    for trial in range(400):
+        idx = good.copy()
+        t = b.terms[trial % len(b.terms)]
+        off, ln = int(t[1]), int(t[2])
+        for _ in range(int(rng.integers(1, 6))):
+            idx[off + int(rng.integers(0, ln))] = int(rng.integers(0, 256))
+        term = t
+        if trial % 5 == 0:  # a chunk that claims more bytes / documents than it has
+            term = (int(t[0]) + int(rng.integers(0, 500)), off, min(ln + int(rng.integers(0, 64)), idx.size - off))
+        try:
+            last, offs, first = tb.directory_probe(codec, idx, term)
+            assert np.all(offs[:-1] >= off) and np.all(offs <= off + int(term[2]) + 8)
+            ok += 1
+        except tb.TrinityError:
+            bad += 1
+    assert ok + bad == 400

@@ -62,3 +62,39 @@ def test_segment_without_updates_and_errors(tmp_path):
     (path / "id").write_bytes(b"\x02\x06GOOGLE" + b"\0" * 24)
     with pytest.raises(tb.TrinityError):
         tb.Segment(str(path))
+
+
+def test_segment_reader_survives_truncated_and_corrupted_files(tmp_path):
+    """the reader parses files it did not write: every truncation / byte flip must end in a TrinityError or a consistent segment,
+    never in an out-of-bounds read (the process would die)"""
+    ref = load_ref()
+    src = tmp_path / "9"
+    src.mkdir()
+    ref.segment_write(0, src, make_lists(3, nterms=12, ndocs=3000), ERASED, replace_below=50)
+    good = {f: (src / f).read_bytes() for f in ("id", "index", "terms.data", "updated_documents.ids")}
+    rng = np.random.default_rng(0)
+    dst = tmp_path / "10"
+    dst.mkdir()
+    ok = bad = 0
+    for trial in range(300):
+        for f, b in good.items():
+            (dst / f).write_bytes(b)
+        f = ("id", "terms.data", "updated_documents.ids", "index")[trial % 4]
+        b = bytearray(good[f])
+        if trial % 3 == 0 and len(b):
+            b = b[: int(rng.integers(0, len(b)))]
+        else:
+            for _ in range(int(rng.integers(1, 4))):
+                if len(b):
+                    b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        (dst / f).write_bytes(bytes(b))
+        try:
+            seg = tb.Segment(str(dst))
+            # whatever was accepted must be self-consistent
+            assert len(seg.names) == len(seg.terms)
+            for t in seg.terms:
+                assert int(t["chunk_off"]) + int(t["chunk_len"]) <= seg.index.size
+            ok += 1
+        except tb.TrinityError:
+            bad += 1
+    assert ok + bad == 300 and bad > 50

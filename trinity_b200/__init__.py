@@ -161,7 +161,7 @@ class TermDictionary:
 
     def __init__(self, names: Sequence[str]):
         self.names = list(names)
-        self._enc = [s.encode() for s in self.names]
+        self._enc = [s.encode("utf-8", "surrogateescape") for s in self.names]
         self._arr = (C.c_char_p * len(self._enc))(*self._enc)
 
     def __len__(self):
@@ -394,7 +394,7 @@ class Segment:
         h = C.c_void_p()
         err = C.create_string_buffer(512)
         if self._L.trn_segment_open(str(path).encode(), C.byref(h), err, 512) != 0:
-            raise TrinityError(f"segment {path}: {err.value.decode()}")
+            raise TrinityError(f"segment {path}: {err.value.decode('utf-8', 'replace')}")
         self._h = h
         codec, nt, nm = C.c_int(), C.c_uint32(), C.c_uint64()
         ib, sth, std_ = C.c_uint64(), C.c_uint64(), C.c_uint64()
@@ -410,7 +410,7 @@ class Segment:
         if tn.value:
             self.terms = np.ctypeslib.as_array(C.cast(tp, C.POINTER(C.c_uint8)), shape=(tn.value * 12,)).view(TERM_DTYPE).copy()
             arr = C.cast(npp, C.POINTER(C.c_char_p))
-            self.names = [arr[i].decode() for i in range(tn.value)]
+            self.names = [arr[i].decode("utf-8", "surrogateescape") for i in range(tn.value)]  # term names are bytes (str8_t)
         else:
             self.terms, self.names = np.zeros(0, TERM_DTYPE), []
         mp, mn = C.c_void_p(), C.c_uint64()

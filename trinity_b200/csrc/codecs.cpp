@@ -368,6 +368,13 @@ namespace Codecs {
 
 // =========================================================================================== block directory
 namespace {
+        // varbyte read that never leaves [p, end): the directory walks bytes that come from files
+        inline uint32_t vb_checked(const uint8_t *&p, const uint8_t *end, const char *what) {
+                if (p >= end || p + varbyte_len(*p) > end)
+                        throw std::runtime_error(std::string(what) + ": varbyte code past the end of its chunk");
+                return varbyte_get(p);
+        }
+
         // host decode of one Lucene int-block (sum only is needed for the directory; full values for tests)
         const uint8_t *lucene_ints_decode(const uint8_t *p, const uint8_t *end, uint32_t *values) {
                 using Codecs::Lucene::BLOCK_SIZE;
@@ -375,14 +382,18 @@ namespace {
                         throw std::runtime_error("lucene: int-block past chunk end");
                 const uint32_t L = *p++;
                 if (L == 0) {
-                        const uint32_t v = varbyte_get(p);
+                        const uint32_t v = vb_checked(p, end, "lucene");
                         for (uint32_t i = 0; i < BLOCK_SIZE; ++i)
                                 values[i] = v;
                         return p;
                 }
                 if (p + size_t(L) * 4 > end)
                         throw std::runtime_error("lucene: PFor page past chunk end");
-                auto w = [&](uint32_t i) { return get_u32(p + size_t(i) * 4); };
+                auto w = [&](uint32_t i) {
+                        if (i >= L)
+                                throw std::runtime_error("lucene: PFor page refers to a word outside itself");
+                        return get_u32(p + size_t(i) * 4);
+                };
                 if (w(0) != BLOCK_SIZE)
                         throw std::runtime_error("lucene: PFor page length word != 128");
                 const uint32_t wheremeta = w(1);
@@ -403,15 +414,24 @@ namespace {
                 const uint32_t meta     = 1 + wheremeta;
                 const uint32_t bytesize = w(meta);
                 const uint8_t *bytes    = p + size_t(meta + 1) * 4;
+                const size_t   pageLeft = size_t(L) * 4 - size_t(meta + 1) * 4; // bytes of the page behind the bytesize word
+                if (pageLeft < 2 || bytesize > pageLeft)
+                        throw std::runtime_error("lucene: PFor byte container outside its page");
                 if (bytes[0] != b)
                         throw std::runtime_error("lucene: PFor b mismatch");
                 const uint32_t cexcept = bytes[1];
                 if (cexcept) {
+                        if (size_t(3) + cexcept > pageLeft)
+                                throw std::runtime_error("lucene: PFor exception positions outside the page");
                         const uint32_t maxbits = bytes[2];
+                        if (maxbits <= b || maxbits > 32)
+                                throw std::runtime_error("lucene: PFor exception width out of range");
                         const uint32_t k       = maxbits - b;
                         const uint32_t excw    = meta + 1 + (bytesize + 3) / 4; // bitmap word
                         for (uint32_t e = 0; e < cexcept; ++e) {
                                 const uint32_t pos = bytes[3 + e];
+                                if (pos >= BLOCK_SIZE)
+                                        throw std::runtime_error("lucene: PFor exception position >= 128");
                                 uint32_t       ev{1};
                                 if (k > 1) {
                                         const uint32_t base = excw + 2; // after bitmap + count
@@ -436,19 +456,27 @@ namespace {
                         return;
                 }
                 const uint8_t *base     = index + t.offset;
+                if (t.size < 2)
+                        throw std::runtime_error("google: chunk shorter than its header");
                 const uint32_t entries  = get_u16(base);
+                if (size_t(entries) * 8 + 2 > t.size)
+                        throw std::runtime_error("google: skiplist larger than the chunk");
                 const uint8_t *chunkEnd = base + t.size - size_t(entries) * 8;
                 const uint8_t *p        = base + 2;
                 uint32_t       prev{0}, docs{0};
                 while (p < chunkEnd) {
-                        const uint32_t delta = varbyte_get(p);
-                        const uint32_t blen  = varbyte_get(p);
+                        const uint32_t delta = vb_checked(p, chunkEnd, "google");
+                        const uint32_t blen  = vb_checked(p, chunkEnd, "google");
+                        if (p >= chunkEnd)
+                                throw std::runtime_error("google: block header past the end of its chunk");
                         const uint32_t n     = *p++;
                         if (n == 0 || n > N)
                                 throw std::runtime_error("google: bad block doc count");
+                        if (blen > size_t(chunkEnd - p))
+                                throw std::runtime_error("google: block longer than its chunk");
                         if (last.empty()) {
                                 const uint8_t *q = p;
-                                firstDoc         = n > 1 ? varbyte_get(q) : delta;
+                                firstDoc         = n > 1 ? vb_checked(q, chunkEnd, "google") : delta;
                         }
                         prev += delta;
                         last.push_back(prev);
@@ -476,7 +504,22 @@ namespace {
                 if (t.size < 14)
                         throw std::runtime_error("lucene: chunk shorter than its header");
                 const uint32_t skipn    = get_u16(base + 12);
+                if (size_t(skipn) * 22 + 14 > t.size)
+                        throw std::runtime_error("lucene: skiplist larger than the chunk");
                 const uint8_t *chunkEnd = base + t.size - size_t(skipn) * 22;
+                // length-byte hop over one int-block, bounds-checked
+                auto hop = [&](const uint8_t *&q) {
+                        if (q >= chunkEnd)
+                                throw std::runtime_error("lucene: int-block past chunk end");
+                        const uint32_t L = *q++;
+                        if (L == 0)
+                                (void)vb_checked(q, chunkEnd, "lucene");
+                        else {
+                                if (size_t(L) * 4 > size_t(chunkEnd - q))
+                                        throw std::runtime_error("lucene: PFor page past chunk end");
+                                q += size_t(L) * 4;
+                        }
+                };
                 const uint8_t *skip     = chunkEnd;
                 const uint8_t *p        = base + 14;
                 const uint32_t nfull    = t.documents / BLOCK_SIZE;
@@ -493,13 +536,8 @@ namespace {
                         }
                         if (haveNext && blk != 0) {
                                 // fast path: skip the two int-blocks by their length bytes
-                                for (int k = 0; k < 2; ++k) {
-                                        const uint32_t L = *p++;
-                                        if (L == 0)
-                                                (void)varbyte_get(p);
-                                        else
-                                                p += size_t(L) * 4;
-                                }
+                                hop(p);
+                                hop(p);
                                 prev = get_u32(skip + size_t(blk + 1) * 22 + 4);
                         } else {
                                 p = lucene_ints_decode(p, chunkEnd, vals);
@@ -509,20 +547,15 @@ namespace {
                                 for (uint32_t i = 0; i < BLOCK_SIZE; ++i)
                                         s += vals[i];
                                 prev += s;
-                                // skip freqs block
-                                const uint32_t L = *p++;
-                                if (L == 0)
-                                        (void)varbyte_get(p);
-                                else
-                                        p += size_t(L) * 4;
+                                hop(p); // the freqs block
                         }
                         last.push_back(prev);
                 }
                 if (tail) {
                         off.push_back(uint32_t(p - index));
                         for (uint32_t i = 0; i < tail; ++i) {
-                                const uint32_t d = varbyte_get(p);
-                                (void)varbyte_get(p);
+                                const uint32_t d = vb_checked(p, chunkEnd, "lucene");
+                                (void)vb_checked(p, chunkEnd, "lucene");
                                 prev += d;
                                 if (nfull == 0 && i == 0)
                                         firstDoc = d;
