@@ -156,3 +156,27 @@ def test_truth_tables_of_the_candidate_planner_match_the_evaluator(small):
         assert necessary == nec, q
         checked += 1
     assert checked >= 30
+
+
+def test_parser_rejects_hostile_input_without_crashing(small):
+    """query text comes from users: random token soup, 200000-deep nesting and million-term chains must end in a parse error (or a plan)"""
+    _, _, tdict = small
+    rng = np.random.default_rng(1)
+    toks = ["t1", "t2", "t3", "t9", "nosuch", "AND", "OR", "NOT", "(", ")", "[", "]", ",", "<", ">", "-", "|", "||", " ", "  "]
+    ok = bad = 0
+    for _ in range(5000):
+        s = "".join(str(rng.choice(toks)) + (" " if rng.random() < 0.7 else "") for _ in range(int(rng.integers(1, 25))))
+        try:
+            nodes = tb.parse_query(s, tdict)
+            assert len(nodes) >= 1
+            ok += 1
+        except tb.TrinityError:
+            bad += 1
+    assert ok > 50 and bad > 50
+    for o, c in (("(", ")"), ("[", "]"), ("<", ">")):
+        with pytest.raises(tb.TrinityError):
+            tb.parse_query(o * 200_000 + "t1" + c * 200_000, tdict)
+        assert len(tb.parse_query(o * 50 + "t1" + c * 50, tdict)) == 1
+    for op in (" AND ", " OR ", " NOT ", " "):
+        with pytest.raises(tb.TrinityError):
+            tb.parse_query(op.join(["t1", "t2", "t3"] * 100_000), tdict)

@@ -483,7 +483,18 @@ struct Parser {
                 nodes.push_back(Ast{kind});
                 return int(nodes.size()) - 1;
         }
+        int depth{0}; // nesting of ( ) [ ] < >: bounded, the parser (and the passes after it) recurse once per level
+        struct DepthGuard {
+                int &d;
+                explicit DepthGuard(int &x) : d{x} { ++d; }
+                ~DepthGuard() { --d; }
+        };
         int unary() {
+                DepthGuard guard(depth);
+                if (depth > 200) {
+                        err = "expression nested too deeply";
+                        return -1;
+                }
                 ws();
                 if (p < e && *p == '<') {
                         // const-true expression (ast_parser::Flags::ParseConstTrueExpr, queries.cpp:378-396): matches like `true`, and, next to
@@ -572,6 +583,10 @@ struct Parser {
                         const int v = subexpr(prio(op));
                         if (v < 0)
                                 return -1;
+                        if (nodes.size() > 8192) { // the passes below recurse along operator chains; the plan format ends at 65535 nodes anyway
+                                err = "query too large";
+                                return -1;
+                        }
                         const int kind = op == AND ? TRN_NODE_AND : (op == OR ? TRN_NODE_OR : TRN_NODE_NOT);
                         const int x    = add(kind);
                         nodes[x].kids  = {cur, v};
