@@ -180,3 +180,25 @@ def test_parser_rejects_hostile_input_without_crashing(small):
     for op in (" AND ", " OR ", " NOT ", " "):
         with pytest.raises(tb.TrinityError):
             tb.parse_query(op.join(["t1", "t2", "t3"] * 100_000), tdict)
+
+
+def test_truth_table_rejects_malformed_plans():
+    """plans arrive through the C ABI: cycles, children in front of their parent and 100-level chains are argument errors"""
+    from trinity_b200._ffi import QNODE_DTYPE
+    chain = np.zeros(101, QNODE_DTYPE)
+    for i in range(100):  # AND -> AND -> ... -> term
+        chain[i] = (tb.NODE_AND, 1, i + 1, 0, 0.0)
+    chain[100] = (tb.NODE_TERM, 0, 0, 3, 0.0)
+    with pytest.raises(tb.TrinityError):
+        tb.query_truth_table(chain)
+    cyc = np.zeros(2, QNODE_DTYPE)
+    cyc[0] = (tb.NODE_AND, 1, 1, 0, 0.0)
+    cyc[1] = (tb.NODE_OR, 1, 0, 0, 0.0)  # points back at its parent
+    with pytest.raises(tb.TrinityError):
+        tb.query_truth_table(cyc)
+    okp = np.zeros(3, QNODE_DTYPE)
+    okp[0] = (tb.NODE_AND, 2, 1, 0, 0.0)
+    okp[1] = (tb.NODE_TERM, 0, 0, 4, 0.0)
+    okp[2] = (tb.NODE_TERM, 0, 0, 7, 0.0)
+    terms, table, nec = tb.query_truth_table(okp)
+    assert sorted(terms) == [4, 7] and table.tolist() == [False, False, False, True] and nec == 3

@@ -134,6 +134,24 @@ struct Range {
         }
 };
 
+// children follow their parents in the node array (checked by validate()), so one forward pass yields every node's depth; the
+// compiler and the truth-table builder recurse once per level
+static bool plan_depth_ok(const trn_qnode *n, uint32_t nn) {
+        std::vector<uint8_t> depth(nn, 0);
+        for (uint32_t i = 0; i < nn; ++i) {
+                if (n[i].kind == TRN_NODE_TERM)
+                        continue;
+                if (depth[i] >= 64)
+                        return false;
+                for (uint32_t k = 0; k < n[i].nchildren; ++k) {
+                        const uint32_t c = uint32_t(n[i].first_child) + k;
+                        if (c > i && c < nn)
+                                depth[c] = uint8_t(std::max<int>(depth[c], depth[i] + 1));
+                }
+        }
+        return true;
+}
+
 struct Compiler {
         const trn_qnode *           n;
         uint32_t                    nn;
@@ -432,6 +450,10 @@ struct Compiler {
         bool validate() {
                 if (root >= nn) {
                         err = "root out of range";
+                        return false;
+                }
+                if (!plan_depth_ok(n, nn)) {
+                        err = "query tree deeper than 64 levels";
                         return false;
                 }
                 for (uint32_t i = 0; i < nn; ++i) {
@@ -816,6 +838,11 @@ static TruthVec truth_vector(const trn_qnode *nodes, uint32_t i, const uint32_t 
 
 extern "C" int trn_query_truth_table(const trn_qnode *nodes, uint32_t nnodes, uint32_t root, uint32_t *terms, uint32_t *nterms, uint32_t *table, uint32_t *necessary) {
         if (!nodes || !nnodes || root >= nnodes || !terms || !nterms || !table || !necessary)
+                return TRN_ERR_ARG;
+        for (uint32_t i = 0; i < nnodes; ++i) // same structural rules as the plan compiler: children behind their parent, bounded depth
+                if (nodes[i].kind != TRN_NODE_TERM && (nodes[i].nchildren == 0 || nodes[i].first_child <= i || uint32_t(nodes[i].first_child) + nodes[i].nchildren > nnodes))
+                        return TRN_ERR_ARG;
+        if (!plan_depth_ok(nodes, nnodes))
                 return TRN_ERR_ARG;
         uint32_t n{0}, stack[64], sp{0};
         stack[sp++] = root;
