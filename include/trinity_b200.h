@@ -23,6 +23,7 @@ extern "C" {
 #define TRN_ERR_STATE (-4)
 #define TRN_ERR_PARSE (-5)
 #define TRN_ERR_CAPACITY (-6)
+#define TRN_ERR_UNSUPPORTED (-7) /* a plan uses something this engine does not execute (yet): never a silent wrong answer */
 
 /* codec identifiers == AccessProxy::codec_identifier() "GOOGLE" / "LUCENE" (codecs.h:312, google_codec.h:101, lucene_codec.h:213) */
 #define TRN_CODEC_GOOGLE 0
@@ -105,6 +106,8 @@ int trn_segment_masked(trn_segment *, const uint32_t **docids, uint64_t *n);
  *   OPTIONAL  -> Optional(main = child 0, opt = child 1)         (docset_iterators.h:174-206)
  *   SOME      -> DisjunctionSome(children, min = term)           (docset_iterators.cpp:679-811; ast_node::Type::MatchSome): matches the
  *                documents at least `min` children match, scores the sum of the children that match (docset_iterators_scorers.cpp:38-56)
+ *   PHRASE    -> Phrase(terms in order)   (docset_iterators.cpp:66-224): children are TERM nodes in phrase order; a document
+ *                matches when some position p of the first term has term k at p+k for every k; scores score(matchCnt, Σ idf)
  * children of node i are nodes[first_child .. first_child + nchildren). */
 #define TRN_NODE_TERM 0
 #define TRN_NODE_AND 1
@@ -112,6 +115,7 @@ int trn_segment_masked(trn_segment *, const uint32_t **docids, uint64_t *n);
 #define TRN_NODE_NOT 3
 #define TRN_NODE_OPTIONAL 4
 #define TRN_NODE_SOME 5
+#define TRN_NODE_PHRASE 6 /* front-end only so far: trn_exec_batch rejects it (TRN_ERR_UNSUPPORTED) until the positions path exists */
 
 typedef struct trn_qnode {
         uint8_t  kind;

@@ -169,6 +169,7 @@ struct Compiler {
         std::vector<Deferred> deferred;
         std::string           err;
         bool                  reference_quirks{true};
+        bool                  unsupported{false};
 
         Compiler(const trn_qnode *nodes, uint32_t cnt, const std::vector<DevTerm> &t, bool sc, uint32_t r, std::vector<DevStep> &s)
             : n{nodes}, nn{cnt}, terms{t}, scored{sc}, root{r}, steps{s} {
@@ -462,6 +463,10 @@ struct Compiler {
                                         err = "term id out of range";
                                         return false;
                                 }
+                        } else if (n[i].kind == TRN_NODE_PHRASE) {
+                                err         = "phrase nodes need the positions path (materialize_hits), which this engine does not execute yet";
+                                unsupported = true;
+                                return false;
                         } else if (n[i].kind > TRN_NODE_SOME) {
                                 err = "unknown node kind";
                                 return false;
@@ -860,6 +865,8 @@ extern "C" int trn_query_truth_table(const trn_qnode *nodes, uint32_t nnodes, ui
                                 terms[n++] = X.term;
                         }
                 } else {
+                        if (X.kind == TRN_NODE_PHRASE)
+                                return TRN_ERR_UNSUPPORTED;
                         if (X.kind > TRN_NODE_SOME || X.nchildren == 0 || uint32_t(X.first_child) + X.nchildren > nnodes || sp + X.nchildren > 64)
                                 return TRN_ERR_ARG;
                         for (uint32_t k = 0; k < X.nchildren; ++k)
@@ -925,7 +932,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 dq.step_begin   = uint32_t(steps.size());
                 const int rs    = cc.run();
                 if (rs < 0)
-                        return fail(c, TRN_ERR_ARG, "query " + std::to_string(q) + ": " + cc.err);
+                        return fail(c, cc.unsupported ? TRN_ERR_UNSUPPORTED : TRN_ERR_ARG, "query " + std::to_string(q) + ": " + cc.err);
                 dq.nsteps    = uint32_t(steps.size()) - dq.step_begin;
                 dq.root_slot = uint32_t(rs);
                 dq.flat      = 0;

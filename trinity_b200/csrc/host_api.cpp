@@ -475,7 +475,7 @@ struct Parser {
                         *len = 1;
                         return NOT;
                 }
-                if (isterm(*p) || *p == '(' || *p == '<' || *p == '[')
+                if (isterm(*p) || *p == '(' || *p == '<' || *p == '[' || *p == '"')
                         return AND; // juxtaposition
                 return NONE;
         }
@@ -512,6 +512,44 @@ struct Parser {
                         const int c   = add(kConstTrue);
                         nodes[c].kids = {x};
                         return c;
+                }
+                if (p < e && *p == '"') {
+                        // "a b c" (parse_phrase_or_token, queries.cpp:70-121): a phrase keeps its terms in order and never de-duplicates them;
+                        // one term in quotes is just the term
+                        ++p;
+                        const int ph = add(TRN_NODE_PHRASE);
+                        for (;;) {
+                                ws();
+                                if (p >= e) {
+                                        err = "unterminated phrase";
+                                        return -1;
+                                }
+                                if (*p == '"') {
+                                        ++p;
+                                        break;
+                                }
+                                const char *b = p;
+                                while (p < e && isterm(*p))
+                                        ++p;
+                                if (p == b) { // the reference skips characters it cannot tokenise inside a phrase
+                                        ++p;
+                                        continue;
+                                }
+                                if (nodes[ph].kids.size() >= 16) // Limits::MaxPhraseSize: the rest is silently ignored (queries.cpp:93-98)
+                                        continue;
+                                const std::string name(b, p);
+                                const int         x  = add(TRN_NODE_TERM);
+                                const auto        it = dict.find(name);
+                                nodes[x].term        = it == dict.end() ? kEmptyTerm : it->second;
+                                nodes[ph].kids.push_back(x);
+                        }
+                        if (nodes[ph].kids.empty()) {
+                                err = "empty phrase";
+                                return -1;
+                        }
+                        if (nodes[ph].kids.size() == 1)
+                                return nodes[ph].kids[0];
+                        return ph;
                 }
                 if (p < e && *p == '[') {
                         // [e1, e2, ...] (ast_parser::Flags::ParseMatchSomeExpr, queries.cpp:424-450): ast_node::Type::MatchSome with min = 1; the
