@@ -294,6 +294,29 @@ int64_t tref_decode(void *h, uint32_t termIdx, uint32_t *docids, uint32_t *freqs
         return n;
 }
 
+// every document's positions, through the reference's own PostingsListIterator::materialize_hits (google_codec.cpp:533-594,
+// lucene_codec.cpp:767-856): positions[] receives freq(doc) entries per document, in list order.  Returns the number of positions.
+int64_t tref_positions(void *h, uint32_t termIdx, uint32_t *positions, uint64_t cap) {
+        auto    x = static_cast<RefIndex *>(h);
+        int64_t n{0};
+        if (guarded([&] {
+                    std::unique_ptr<Codecs::Decoder>              dec(x->ap->new_decoder(x->tctx[termIdx]));
+                    std::unique_ptr<Codecs::PostingsListIterator> it(dec->new_iterator());
+                    DocWordsSpace                                 dws(Limits::MaxPosition);
+                    std::vector<term_hit>                         hits(65536);
+                    for (auto id = it->next(); id != DocIDsEND; id = it->next()) {
+                            const auto freq = it->freq;
+                            dws.reset();
+                            it->materialize_hits(&dws, hits.data());
+                            for (uint32_t i = 0; i < freq; ++i, ++n)
+                                    if (uint64_t(n) < cap)
+                                            positions[n] = hits[i].pos;
+                    }
+            }))
+                return -1;
+        return n;
+}
+
 // advance() probe: for each (ascending) target returns first docID >= target (DocIDsEND = UINT32_MAX when exhausted)
 int tref_advance(void *h, uint32_t termIdx, const uint32_t *targets, uint32_t n, uint32_t *out) {
         auto x = static_cast<RefIndex *>(h);

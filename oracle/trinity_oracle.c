@@ -182,6 +182,100 @@ int64_t orc_decode_lucene(const uint8_t *chunk, uint32_t len, uint32_t documents
         return p == end ? (int64_t)n : -1;
 }
 
+/* ---- positions (restated ahead of the device path) ----
+ * GOOGLE: Decoder::materialize_hits (google_codec.cpp:533-594): the hits of a block's documents follow its freqs; per hit
+ * varbyte((posDelta << 1) | payloadSizeChanged) [u8 payloadSize] payload[payloadSize]; positions restart at 0 for every document.
+ * positions[] receives freq(doc) entries per document in list order.  Returns the number of positions or -1. */
+int64_t orc_positions_google(const uint8_t *chunk, uint32_t len, uint32_t *positions, uint64_t cap) {
+        if (len == 0)
+                return 0;
+        const uint32_t entries = rd16(chunk);
+        const uint8_t *end     = chunk + len - (size_t)entries * 8;
+        const uint8_t *p       = chunk + 2;
+        uint64_t       n       = 0;
+        uint32_t       fr[32];
+        while (p < end) {
+                (void)vb_get(&p);
+                (void)vb_get(&p);
+                const uint32_t cnt = *p++;
+                if (cnt == 0 || cnt > 32)
+                        return -1;
+                for (uint32_t i = 0; i + 1 < cnt; ++i)
+                        (void)vb_get(&p);
+                for (uint32_t i = 0; i < cnt; ++i)
+                        fr[i] = vb_get(&p);
+                for (uint32_t i = 0; i < cnt; ++i) {
+                        uint32_t pos         = 0;
+                        uint8_t  payloadSize = 0;
+                        for (uint32_t h = 0; h < fr[i]; ++h) {
+                                const uint32_t step = vb_get(&p);
+                                if (step & 1u)
+                                        payloadSize = *p++;
+                                pos += step >> 1;
+                                p += payloadSize;
+                                if (n < cap)
+                                        positions[n] = pos;
+                                ++n;
+                        }
+                }
+        }
+        return p == end ? (int64_t)n : -1;
+}
+
+/* LUCENE: the term's hits live in hits.data at the chunk header's hitsDataOffset (lucene_codec.cpp:401-513 refill_hits, :767-856
+ * materialize_hits; encoder :200-330): blocks of 128 hits = int-block(position deltas) int-block(payload sizes)
+ * varbyte(payload bytes) payloads, then the last (sumHits % 128) hits as varbyte((delta << 1) | payloadSizeChanged) [u8 size] followed
+ * by their payload bytes.  Position deltas restart at every document; document i owns the next freq(i) hits of the stream.
+ * freqs[] = the term's per-document freqs (orc_decode_lucene).  Returns the number of positions or -1. */
+int64_t orc_positions_lucene(const uint8_t *chunk, uint32_t len, const uint8_t *hits, const uint32_t *freqs, uint32_t documents, uint32_t *positions,
+                             uint64_t cap) {
+        if (len == 0)
+                return 0;
+        const uint32_t hitsOff = rd32(chunk), sumHits = rd32(chunk + 4);
+        const uint8_t *p       = hits + hitsOff;
+        uint32_t       delta[128], psize[128];
+        uint32_t       inBlock = 0, blockFill = 0; /* cursor inside the decoded block / its number of hits */
+        uint64_t       consumed = 0, n = 0;
+        int            tail = 0;
+        uint8_t        tailPayload = 0;
+        for (uint32_t d = 0; d < documents; ++d) {
+                uint32_t pos = 0;
+                for (uint32_t h = 0; h < freqs[d]; ++h) {
+                        if (inBlock == blockFill) { /* refill */
+                                const uint64_t left = (uint64_t)sumHits - consumed;
+                                if (left == 0)
+                                        return -1;
+                                if (left >= 128) {
+                                        p = orc_ints_decode(p, delta);
+                                        p = orc_ints_decode(p, psize);
+                                        const uint32_t plen = vb_get(&p);
+                                        p += plen;
+                                        blockFill = 128;
+                                        tail      = 0;
+                                } else {
+                                        blockFill = (uint32_t)left;
+                                        tail      = 1;
+                                        for (uint32_t i = 0; i < blockFill; ++i) {
+                                                const uint32_t v = vb_get(&p);
+                                                if (v & 1u)
+                                                        tailPayload = *p++;
+                                                delta[i] = v >> 1;
+                                                psize[i] = tailPayload;
+                                        }
+                                }
+                                inBlock = 0;
+                        }
+                        pos += delta[inBlock++];
+                        ++consumed;
+                        if (n < cap)
+                                positions[n] = pos;
+                        ++n;
+                }
+        }
+        (void)tail;
+        return (int64_t)n;
+}
+
 /* ---- BM25: IndexSourcesCollectionBM25Scorer::Scorer::idf (similarity.h:179-181, float arithmetic) and score (:228-235) ---- */
 double orc_bm25_idf(uint32_t docFreq, uint64_t docsCnt) {
         const float a = (float)(docsCnt - docFreq) + 0.5f;

@@ -22,6 +22,10 @@ def load():
     L.orc_bm25_idf.argtypes = [C.c_uint32, C.c_uint64]
     L.orc_bm25_score.restype = C.c_float
     L.orc_bm25_score.argtypes = [C.c_double, C.c_uint16]
+    L.orc_positions_google.restype = C.c_int64
+    L.orc_positions_google.argtypes = [vp, C.c_uint32, vp, C.c_uint64]
+    L.orc_positions_lucene.restype = C.c_int64
+    L.orc_positions_lucene.argtypes = [vp, C.c_uint32, vp, vp, C.c_uint32, vp, C.c_uint64]
     L.orc_exec.restype = C.c_int
     L.orc_exec.argtypes = [C.c_int, vp, vp, vp, C.c_uint32, C.c_int, vp, vp]
     return L
@@ -37,6 +41,23 @@ def decode(L, codec, index, term):
         n = L.orc_decode_lucene(chunk.ctypes.data, ln, docs, d.ctypes.data, f.ctypes.data, docs)
     assert n == docs, (n, docs)
     return d[:docs], f[:docs]
+
+
+def positions(L, codec, index, hits, term):
+    """flat positions (freq entries per document, list order) of one term, restated decode of the inline hits / hits.data"""
+    docs, off, ln = int(term[0]), int(term[1]), int(term[2])
+    chunk = np.ascontiguousarray(index[off:off + ln])
+    _, f = decode(L, codec, index, term)
+    cap = int(f.astype(np.uint64).sum())
+    out = np.zeros(max(cap, 1), np.uint32)
+    if codec == 0:
+        n = L.orc_positions_google(chunk.ctypes.data, ln, out.ctypes.data, cap)
+    else:
+        hits = np.ascontiguousarray(hits, np.uint8)
+        f = np.ascontiguousarray(f, np.uint32)
+        n = L.orc_positions_lucene(chunk.ctypes.data, ln, hits.ctypes.data, f.ctypes.data, docs, out.ctypes.data, cap)
+    assert n == cap, (n, cap)
+    return out[:cap]
 
 
 def exec_query(L, codec, index, terms, nodes, ndocs, scored):

@@ -41,6 +41,8 @@ class RefLib:
         L.tref_decode.restype = C.c_int64
         L.tref_decode.argtypes = [vp, u32, vp, vp, u64]
         L.tref_advance.argtypes = [vp, u32, vp, u32, vp]
+        L.tref_positions.restype = C.c_int64
+        L.tref_positions.argtypes = [vp, u32, vp, u64]
         L.tref_bm25.restype = C.c_double
         L.tref_bm25.argtypes = [vp, u32, u32]
         L.tref_exec.restype = C.c_int64
@@ -165,6 +167,14 @@ class RefIndex:
         if n < 0:
             raise RuntimeError(self.rl.err())
         return d[:n], f[:n]
+
+    def positions(self, term_idx, cap):
+        """flat positions of every document of the term (freq entries per document), via the reference's materialize_hits"""
+        p = np.zeros(max(cap, 1), np.uint32)
+        n = self.rl.L.tref_positions(self.h, term_idx, _p(p), cap)
+        if n < 0:
+            raise RuntimeError(self.rl.err())
+        return p[:n]
 
     def advance(self, term_idx, targets):
         t = np.ascontiguousarray(targets, np.uint32)

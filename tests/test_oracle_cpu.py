@@ -84,3 +84,25 @@ def test_restated_exec_matches_reference_exec_query(ref, orc, codec):
         assert np.array_equal(gd, wd), q
         rel = np.abs(gs - ws) / np.maximum(np.abs(ws), 1e-30)
         assert rel.max() <= 1e-5, q
+
+
+@pytest.mark.parametrize("codec", [tb.CODEC_GOOGLE, tb.CODEC_LUCENE])
+def test_restated_positions_match_reference_materialize_hits(ref, orc, codec):
+    """hit streams (Google inline hits, Lucene hits.data incl. 128-hit PFor blocks and the varbyte tail) restated in C == the positions the
+    reference's PostingsListIterator::materialize_hits yields, == the positions that went in"""
+    rng = np.random.default_rng(31 + codec)
+    r = RefIndex(ref, codec)
+    want = []
+    for t, (ndocs_t, maxf) in enumerate(((40, 3), (700, 9), (3000, 2), (129, 40), (1, 1), (260, 1))):
+        docs = np.sort(rng.choice(np.arange(1, 50_000), size=ndocs_t, replace=False)).astype(np.uint32)
+        freqs = rng.integers(1, maxf + 1, size=ndocs_t).astype(np.uint32)
+        pos = np.concatenate([np.cumsum(rng.integers(1, 40, size=int(f))) for f in freqs]).astype(np.uint32)
+        r.add_term(f"p{t}", docs, freqs, pos)
+        want.append(pos)
+    r.finish(50_000)
+    index, hits, terms = r.index(), r.hits(), r.terms()
+    for t, pos in enumerate(want):
+        got_ref = r.positions(t, len(pos) + 8)
+        assert np.array_equal(got_ref, pos), f"reference positions of term {t}"
+        got = oracle_c.positions(orc, codec, index, hits, terms[t])
+        assert np.array_equal(got, pos), f"restated positions of term {t}"
