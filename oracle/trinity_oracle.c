@@ -288,7 +288,7 @@ float orc_bm25_score(double idf, uint16_t freq) {
 }
 
 /* ---- docset algebra + structural scoring ----
- * node layout == trn_qnode of include/trinity_b200.h (kind 0 TERM, 1 AND, 2 OR, 3 NOT(req, excl), 4 OPTIONAL(main, opt), 5 SOME(children, min = term)).
+ * node layout == trn_qnode of include/trinity_b200.h (kind 0 TERM, 1 AND, 2 OR, 3 NOT(req, excl), 4 OPTIONAL(main, opt), 5 SOME(children, min = term), 6 PHRASE(terms in order)).
  * Matching: Conjuction / Disjunction / Filter / Optional next()/advance() semantics (docset_iterators.cpp:282-677,
  * docset_iterators.h:174-206).  Scoring: the IteratorScorer wrappers (docset_iterators_scorers.cpp:8-242): a conjunction sums all
  * children, a disjunction sums the children positioned on the document, a filter scores its required side only, an optional adds
@@ -310,6 +310,7 @@ typedef struct {
         const orc_node *nodes;
         uint32_t        ndocs;
         int             scored;
+        const uint8_t * hits; /* Lucene hits.data (phrases only); NULL otherwise */
 } orc_ctx;
 
 static int orc_eval_node(const orc_ctx *c, uint32_t i, uint8_t *m, double *s) {
@@ -339,6 +340,97 @@ static int orc_eval_node(const orc_ctx *c, uint32_t i, uint8_t *m, double *s) {
                 }
                 free(ids);
                 free(fr);
+                return 0;
+        }
+        if (X->kind == 6) {
+                /* PHRASE == Phrase::consider_phrase_match (docset_iterators.cpp:66-158) + the Phrase scorer (docset_iterators_scorers.cpp:195-228):
+                 * children are the terms in order; every non-zero position q of the first term with term j at q + j for all j is one match;
+                 * score = score(matchCnt, sum of the terms' idf).  Positions come from orc_positions_*. */
+                const uint32_t k = X->nchildren;
+                if (k < 2 || k > 16)
+                        return -1;
+                uint32_t *ids[16], *fr[16], *pos[16];
+                uint64_t *start[16]; /* start[j][i] = index of document i's first position of term j */
+                int       ok = 1;
+                double    w  = 0;
+                for (uint32_t j = 0; j < k; ++j)
+                        ids[j] = fr[j] = pos[j] = NULL, start[j] = NULL;
+                for (uint32_t j = 0; j < k && ok; ++j) {
+                        const orc_node *T = &c->nodes[X->first_child + j];
+                        if (T->kind != 0 || T->term == 0xffffffffu) {
+                                ok = 0; /* a phrase with an unknown term matches nothing */
+                                break;
+                        }
+                        w += T->weight;
+                        const orc_term *t = &c->terms[T->term];
+                        ids[j]            = (uint32_t *)malloc(((size_t)t->documents + 1) * 4);
+                        fr[j]             = (uint32_t *)malloc(((size_t)t->documents + 1) * 4);
+                        start[j]          = (uint64_t *)malloc(((size_t)t->documents + 1) * 8);
+                        const int64_t nd  = c->codec == 0 ? orc_decode_google(c->index + t->chunk_off, t->chunk_len, ids[j], fr[j], t->documents)
+                                                        : orc_decode_lucene(c->index + t->chunk_off, t->chunk_len, t->documents, ids[j], fr[j], t->documents);
+                        if (nd != (int64_t)t->documents)
+                                return -1;
+                        uint64_t tot = 0;
+                        for (uint32_t i = 0; i < t->documents; ++i) {
+                                start[j][i] = tot;
+                                tot += fr[j][i];
+                        }
+                        start[j][t->documents] = tot;
+                        pos[j]                 = (uint32_t *)malloc((size_t)(tot + 1) * 4);
+                        const int64_t np       = c->codec == 0 ? orc_positions_google(c->index + t->chunk_off, t->chunk_len, pos[j], tot)
+                                                         : orc_positions_lucene(c->index + t->chunk_off, t->chunk_len, c->hits, fr[j], t->documents, pos[j], tot);
+                        if (np != (int64_t)tot)
+                                return -1;
+                }
+                if (ok) {
+                        const orc_term *t0 = &c->terms[c->nodes[X->first_child].term];
+                        uint32_t        cur[16];
+                        for (uint32_t j = 0; j < k; ++j)
+                                cur[j] = 0;
+                        for (uint32_t i = 0; i < t0->documents; ++i) {
+                                const uint32_t d = ids[0][i];
+                                if (d > c->ndocs)
+                                        continue;
+                                uint32_t at[16];
+                                int      all = 1;
+                                at[0]        = i;
+                                for (uint32_t j = 1; j < k && all; ++j) {
+                                        const orc_term *tj = &c->terms[c->nodes[X->first_child + j].term];
+                                        while (cur[j] < tj->documents && ids[j][cur[j]] < d)
+                                                ++cur[j];
+                                        if (cur[j] >= tj->documents || ids[j][cur[j]] != d)
+                                                all = 0;
+                                        at[j] = cur[j];
+                                }
+                                if (!all)
+                                        continue;
+                                uint32_t cnt = 0;
+                                for (uint64_t a = start[0][i]; a < start[0][i + 1]; ++a) {
+                                        const uint32_t q = pos[0][a];
+                                        if (!q)
+                                                continue;
+                                        int hit = 1;
+                                        for (uint32_t j = 1; j < k && hit; ++j) {
+                                                int found = 0;
+                                                for (uint64_t b = start[j][at[j]]; b < start[j][at[j] + 1] && !found; ++b)
+                                                        found = pos[j][b] == q + j;
+                                                hit = found;
+                                        }
+                                        cnt += (uint32_t)hit;
+                                }
+                                if (cnt) {
+                                        m[d] = 1;
+                                        if (c->scored)
+                                                s[d] = (double)orc_bm25_score(w, (uint16_t)cnt);
+                                }
+                        }
+                }
+                for (uint32_t j = 0; j < k; ++j) {
+                        free(ids[j]);
+                        free(fr[j]);
+                        free(pos[j]);
+                        free(start[j]);
+                }
                 return 0;
         }
         uint8_t *cm = (uint8_t *)malloc(n);
@@ -421,6 +513,14 @@ static uint64_t orc_cost(const orc_ctx *c, uint32_t i) {
                 return X->term == 0xffffffffu ? 0 : c->terms[X->term].documents;
         if (X->kind == 3 || X->kind == 4)
                 return orc_cost(c, X->first_child);
+        if (X->kind == 6) { /* Phrase: its lead term */
+                uint64_t r = ~0ull;
+                for (uint32_t k = 0; k < X->nchildren; ++k) {
+                        const uint64_t v = orc_cost(c, X->first_child + k);
+                        r                = v < r ? v : r;
+                }
+                return r;
+        }
         if (X->kind == 5) { /* DisjunctionSome::cost_: the (size - min + 1) cheapest children */
                 uint64_t v[256], r = 0;
                 for (uint32_t k = 0; k < X->nchildren; ++k)
@@ -448,8 +548,15 @@ static uint64_t orc_cost(const orc_ctx *c, uint32_t i) {
  * match[d] = 1 for every matched docID d in 1..ndocs, score[d] = accumulated score.  Includes build_span's behaviour for a root
  * Filter over a disjunction whose excluded side is not costlier (exec.cpp:488-501 + docset_spans.cpp:98-111,681-694: the
  * disjunction spans ignore `min`, so the exclusion is not applied) — observed on the reference, see tests. */
+int orc_exec2(int codec, const uint8_t *index, const uint8_t *hits, const orc_term *terms, const orc_node *nodes, uint32_t ndocs, int scored, uint8_t *match,
+              double *score);
 int orc_exec(int codec, const uint8_t *index, const orc_term *terms, const orc_node *nodes, uint32_t ndocs, int scored, uint8_t *match, double *score) {
-        orc_ctx  c    = {codec, index, terms, nodes, ndocs, scored};
+        return orc_exec2(codec, index, NULL, terms, nodes, ndocs, scored, match, score);
+}
+/* hits: Lucene hits.data (needed by phrase nodes on the Lucene codec; Google keeps its hits inline) */
+int orc_exec2(int codec, const uint8_t *index, const uint8_t *hits, const orc_term *terms, const orc_node *nodes, uint32_t ndocs, int scored, uint8_t *match,
+              double *score) {
+        orc_ctx  c    = {codec, index, terms, nodes, ndocs, scored, hits};
         uint32_t root = 0, cur = 0;
         int      traversed = 0;
         while (nodes[cur].kind == 3 && orc_cost(&c, nodes[cur].first_child + 1u) <= orc_cost(&c, nodes[cur].first_child)) {

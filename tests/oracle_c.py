@@ -26,6 +26,8 @@ def load():
     L.orc_positions_google.argtypes = [vp, C.c_uint32, vp, C.c_uint64]
     L.orc_positions_lucene.restype = C.c_int64
     L.orc_positions_lucene.argtypes = [vp, C.c_uint32, vp, vp, C.c_uint32, vp, C.c_uint64]
+    L.orc_exec2.restype = C.c_int
+    L.orc_exec2.argtypes = [C.c_int, vp, vp, vp, vp, C.c_uint32, C.c_int, vp, vp]
     L.orc_exec.restype = C.c_int
     L.orc_exec.argtypes = [C.c_int, vp, vp, vp, C.c_uint32, C.c_int, vp, vp]
     return L
@@ -60,13 +62,15 @@ def positions(L, codec, index, hits, term):
     return out[:cap]
 
 
-def exec_query(L, codec, index, terms, nodes, ndocs, scored):
+def exec_query(L, codec, index, terms, nodes, ndocs, scored, hits=None):
     index = np.ascontiguousarray(index, np.uint8)
     terms = np.ascontiguousarray(terms)
     nodes = np.ascontiguousarray(nodes)
     m = np.zeros(ndocs + 1, np.uint8)
     s = np.zeros(ndocs + 1, np.float64)
-    rc = L.orc_exec(codec, index.ctypes.data, terms.ctypes.data, nodes.ctypes.data, ndocs, int(scored), m.ctypes.data, s.ctypes.data)
+    hits = None if hits is None or not len(hits) else np.ascontiguousarray(hits, np.uint8)
+    rc = L.orc_exec2(codec, index.ctypes.data, None if hits is None else hits.ctypes.data, terms.ctypes.data, nodes.ctypes.data, ndocs, int(scored),
+                     m.ctypes.data, s.ctypes.data)
     assert rc == 0
     ids = np.flatnonzero(m).astype(np.uint32)
     return ids, s[ids]

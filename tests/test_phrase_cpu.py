@@ -77,3 +77,24 @@ def test_phrase_node_shape_and_truth_table_rejection(corpus):
     assert len(tb.parse_query('"w5"', tdict)) == 1  # a one-term phrase is the term
     with pytest.raises(tb.TrinityError):
         tb.query_truth_table(n)  # plans with phrases are not executable yet: never a silent answer
+
+
+@pytest.mark.parametrize("codec", [tb.CODEC_GOOGLE, tb.CODEC_LUCENE], ids=["google", "lucene"])
+def test_restated_oracle_executes_phrases_like_the_reference(corpus, codec):
+    """oracle/trinity_oracle.c end to end on phrase plans: postings + hit streams decoded by the C restatement, positions matched, scored"""
+    import oracle_c
+    refs, lists, _, tdict = corpus
+    r = refs[codec]
+    orc = oracle_c.load()
+    index, hits, terms = r.index(), r.hits(), r.terms()
+    for q in QUERIES:
+        nodes = tb.parse_query(q, tdict)
+        for x in nodes:
+            if x["kind"] == tb.NODE_TERM and x["term"] != tb.EMPTY_TERM:
+                x["weight"] = tb.bm25_idf(int(terms["documents"][x["term"]]), NDOCS)
+        wd, ws = r.exec(q, True, NDOCS + 1)
+        gd, gs = oracle_c.exec_query(orc, codec, index, terms, nodes, NDOCS, True, hits=hits)
+        assert np.array_equal(gd, wd), q
+        if len(wd):
+            rel = np.abs(gs - ws) / np.maximum(np.abs(ws), 1e-30)
+            assert rel.max() <= 1e-5, q
