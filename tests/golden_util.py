@@ -17,6 +17,10 @@ def load_closed(codec):
     return np.load(GOLDEN / f"closed_form_{CODEC_NAME[codec]}.npz")
 
 
+def load_widened(codec):
+    return np.load(GOLDEN / f"widened_{CODEC_NAME[codec]}.npz")
+
+
 def check_docs_digest(z, qi, ids, what):
     ids = np.asarray(ids, np.uint32)
     assert len(ids) == int(z[f"count_{qi}"][0]), f"{what}: count {len(ids)} != golden {int(z[f'count_{qi}'][0])}"

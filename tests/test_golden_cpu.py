@@ -69,3 +69,37 @@ def test_c_oracle_exec_reproduces_golden_results(codec):
             sid, sc = oracle_c.exec_query(L, codec, b.index(), b.terms_array(), nodes, ndocs, True)
             check_docs_digest(z, qi, sid, f"[{q}] scored")
             check_scores_digest(z, qi, sid, sc, f"[{q}]")
+
+
+@pytest.mark.parametrize("codec", CODECS)
+def test_c_oracle_reproduces_widened_golden_results(codec):
+    """rows added after SURVEY 8a-e, against fixtures generated from the reference: MatchSome groups on the closed-form index and phrase
+    plans on the reference-encoded document-major corpus (index + hits.data bytes are part of the fixture)"""
+    from golden_util import load_widened
+    z = load_widened(codec)
+    L = oracle_c.load()
+    ndocs = int(z["ndocs"][0])
+    lists = closed_form_lists(ndocs)
+    b = tb.IndexBuilder(codec)
+    for d, f in lists:
+        b.add_term(d, f)
+    tdict = tb.TermDictionary([f"t{i + 1}" for i in range(len(lists))])
+    for qi, (q, m) in enumerate(zip(z["some_queries"].tolist(), z["some_min"].tolist())):
+        nodes = tb.parse_query(q, tdict, min_match=int(m))
+        for x in nodes:
+            if x["kind"] == tb.NODE_TERM and x["term"] != tb.EMPTY_TERM:
+                x["weight"] = tb.bm25_idf(len(lists[int(x["term"])][0]), ndocs)
+        sid, sc = oracle_c.exec_query(L, codec, b.index(), b.terms_array(), nodes, ndocs, True)
+        check_docs_digest(z, f"s{qi}", sid, f"[{q}] min={m}")
+        check_scores_digest(z, f"s{qi}", sid, sc, f"[{q}] min={m}")
+    pn = int(z["phrase_ndocs"][0])
+    terms = z["phrase_terms"]
+    pdict = tb.TermDictionary([f"w{t + 1}" for t in range(len(terms))])
+    for qi, q in enumerate(z["phrase_queries"].tolist()):
+        nodes = tb.parse_query(q, pdict)
+        for x in nodes:
+            if x["kind"] == tb.NODE_TERM and x["term"] != tb.EMPTY_TERM:
+                x["weight"] = tb.bm25_idf(int(terms["documents"][x["term"]]), pn)
+        sid, sc = oracle_c.exec_query(L, codec, z["phrase_index"], terms, nodes, pn, True, hits=z["phrase_hits"])
+        check_docs_digest(z, f"p{qi}", sid, f"[{q}]")
+        check_scores_digest(z, f"p{qi}", sid, sc, f"[{q}]")
