@@ -380,11 +380,17 @@ def reference_arm(args, rank, world, wl, K, W):
     synth = tb.SynthIndex(wl["codec"], args.ndocs, args.nterms, threads=os.cpu_count() or 8)
     texts, _ = gen_queries(args.workload, args.nq, args.nterms)
     cores = os.cpu_count() or 1
-    n = args.cpu_sample or len(texts)
     sys.path.insert(0, str(ROOT / "tests"))
     from refharness import RefIndex, load_ref
 
     r = RefIndex.from_bytes(load_ref(), synth.codec, np.asarray(synth.index), np.asarray(synth.hits), synth.names, np.asarray(synth.terms), args.ndocs, synth.sum_hits)
+    # bounded sample: a probe of the first queries sizes the per-step sample so that the W + K steps together stay near 150 s of host
+    # time (the whole batch at the default K/W; a prefix of it — the batch is in random order — when the driver asks for many steps)
+    n = args.cpu_sample
+    if not n:
+        probe = min(len(texts), 128)
+        el, *_ = r.exec_batch(texts[:probe], wl["mode"] != 0, args.k, cores)
+        n = max(min(32, len(texts)), min(len(texts), int(150.0 * (probe / max(el, 1e-9)) / max(1, K + W))))
     qs = texts[:n]
     for _ in range(W):
         r.exec_batch(qs, wl["mode"] != 0, args.k, cores)
