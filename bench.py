@@ -354,7 +354,11 @@ def cpu_baseline(synth, texts, args, mode, threads: int | None = None, sample: i
     ref = load_ref()
     cores = threads or (os.cpu_count() or 1)
     r = RefIndex.from_bytes(ref, synth.codec, np.asarray(synth.index), np.asarray(synth.hits), synth.names, np.asarray(synth.terms), args.ndocs, synth.sum_hits)
-    n = sample or args.cpu_sample or len(texts)
+    n = sample or args.cpu_sample
+    if not n:  # bounded sample: a probe sizes it for ~30 s of host time (the whole batch for the headline workload)
+        probe = min(len(texts), 64)
+        el, *_ = r.exec_batch(texts[:probe], mode != 0, args.k, cores)
+        n = max(min(32, len(texts)), min(len(texts), int(30.0 * probe / max(el, 1e-9))))
     qs = texts[:n]
     best = None
     for _ in range(repeats):
