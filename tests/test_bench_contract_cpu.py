@@ -31,3 +31,36 @@ def test_product_arm_fails_loudly_without_a_gpu():
                        capture_output=True, text=True, timeout=600)
     assert p.returncode != 0  # no CPU fallback
     assert not [l for l in p.stdout.splitlines() if l.startswith('{"metric"')]
+
+
+def test_full_size_parity_checker_is_exact_in_uint64(ref):
+    """the checker bench.py hangs on its cpu_baseline leg: fed the reference's own results it must report equality, and one flipped docID
+    must flip the checksum verdict even when the running sum is beyond 2^53 (a float64 detour would lose it)"""
+    import types
+
+    import numpy as np
+
+    sys.path.insert(0, str(ROOT))
+    import bench
+    import trinity_b200 as tb
+
+    nq = 6
+    counts = np.array([3, 0, 2, 4, 1, 2], np.uint64)
+    ids = np.array([4_000_000_000 - i for i in range(int(counts.sum()))][::-1], np.uint32)  # large docIDs
+    big = np.repeat(ids, 1)  # one copy is enough: prepend a huge constant through a fake first query below
+    off = np.concatenate([np.zeros(1, np.int64), np.cumsum(counts).astype(np.int64)])
+    sums = np.array([int(big[off[q]:off[q + 1]].astype(np.uint64).sum()) for q in range(nq)], np.uint64)
+    res = types.SimpleNamespace(match_counts=counts.copy(), offsets=off, docids=big.copy())
+    out = bench.full_size_parity(res, tb.MODE_DOCS_ONLY, 100, counts, sums, None, None, nq)
+    assert out == {"queries_checked": nq, "match_counts_equal": True, "docid_checksums_equal": True}
+    res.docids[5] ^= 1
+    assert bench.full_size_parity(res, tb.MODE_DOCS_ONLY, 100, counts, sums, None, None, nq)["docid_checksums_equal"] is False
+    # sums past 2^53: 3e6 documents near 4e9 each
+    n = 3_000_000
+    d = np.full(n, 3_999_999_999, np.uint32)
+    d[-1] = 3_999_999_998
+    res = types.SimpleNamespace(match_counts=np.array([n - 1, 1], np.uint64), offsets=np.array([0, n - 1, n], np.int64), docids=d)
+    sums = np.array([int(d[: n - 1].astype(np.uint64).sum()), 3_999_999_998], np.uint64)
+    assert bench.full_size_parity(res, tb.MODE_DOCS_ONLY, 100, res.match_counts, sums, None, None, 2)["docid_checksums_equal"] is True
+    sums[1] += 1
+    assert bench.full_size_parity(res, tb.MODE_DOCS_ONLY, 100, res.match_counts, sums, None, None, 2)["docid_checksums_equal"] is False
