@@ -144,6 +144,20 @@ int trn_parse_query(const char *text, const char *const *names, uint32_t nterms,
  * the terms whose bit is set in a are on the document; *necessary = mask of the terms every match holds.  Host-only (tests, tooling). */
 int trn_query_truth_table(const trn_qnode *nodes, uint32_t nnodes, uint32_t root, uint32_t *terms, uint32_t *nterms, uint32_t *table, uint32_t *necessary);
 
+/* Host-only view of the plan compiler (tests, tooling): the step program trn_exec_batch would run for one query on the bitmap paths —
+ * == the iterator tree build_iterator/build_span would have built (exec.cpp:253-505), flattened into slot operations.  op: 0 LEAF
+ * (decode term into / against slot dst with mode), 1 SLOT (combine slot src into dst), 2 CLEAR, 3 LEAFSCORE (second scoring pass of
+ * `term` where slot src has the document), 4 COUNT_ADD / 5 COUNT_GE (MatchSome counters); mode: 0 SET 1 OR 2 AND 3 ANDNOT 4 NONE;
+ * flags: 1 = the leaf scores where it matches, 2 = stop when dst becomes empty.  Needs no GPU. */
+typedef struct trn_debug_step {
+        uint8_t  op, mode, dst, src, flags, pad[3];
+        uint32_t term;
+        uint32_t pad2;
+        double   idf;
+} trn_debug_step;
+int trn_debug_compile(int codec, const uint8_t *index, uint64_t nbytes, const trn_term *terms, uint32_t nterms, const trn_qnode *nodes, uint32_t nnodes, uint32_t root,
+                      int scored, trn_debug_step *out, uint32_t cap, uint32_t *nsteps, uint32_t *root_slot, uint32_t *nslots, char *err, size_t errcap);
+
 /* BM25 weight of one term == IndexSourcesCollectionBM25Scorer::Scorer::idf evaluated in float (similarity.h:179-181) */
 double trn_bm25_idf(uint32_t doc_freq, uint64_t docs_cnt);
 /* == Scorer::score(id, freq, weight) (similarity.h:228-235): float(idf * float(freq) / double(freq + 1.2f)) */

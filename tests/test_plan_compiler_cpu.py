@@ -1,0 +1,59 @@
+"""The plan compiler (engine.cu Compiler == build_iterator + build_span flattened into slot operations) checked WITHOUT a GPU: its step
+programs, interpreted on the CPU (tests/stepsim.py), must give the documents and scores of the structural evaluator — which is itself
+pinned against the reference's exec_query (test_frontend_cpu).  Covers slot reuse (DocumentsOnly), the deferred scoring passes,
+MatchSome counters and the reference's root-filter quirk."""
+import numpy as np
+import pytest
+
+import stepsim
+import trinity_b200 as tb
+from pyeval import evaluate
+from test_frontend_cpu import EXTRA, NDOCS, OPTIONAL_QUERIES, SOME_QUERIES, TEMPLATES
+from util import closed_form_lists
+
+ALL = [(q, None) for q in TEMPLATES + EXTRA + OPTIONAL_QUERIES] + list(SOME_QUERIES)
+
+
+@pytest.fixture(scope="module")
+def built():
+    lists = closed_form_lists(NDOCS)
+    out = {}
+    for codec in (tb.CODEC_GOOGLE, tb.CODEC_LUCENE):
+        b = tb.IndexBuilder(codec)
+        for d, f in lists:
+            b.add_term(d, f)
+        out[codec] = (b.index(), b.terms_array())
+    return lists, out, tb.TermDictionary([f"t{i + 1}" for i in range(len(lists))])
+
+
+@pytest.mark.parametrize("codec", [tb.CODEC_GOOGLE, tb.CODEC_LUCENE], ids=["google", "lucene"])
+@pytest.mark.parametrize("scored", [False, True], ids=["docs", "scored"])
+def test_step_programs_match_the_structural_evaluator(built, codec, scored):
+    lists, idx, tdict = built
+    index, terms = idx[codec]
+    worst_slots = 0
+    for q, m in ALL:
+        nodes = tb.parse_query(q, tdict, min_match=m)
+        for x in nodes:
+            if x["kind"] == tb.NODE_TERM and x["term"] != tb.EMPTY_TERM:
+                x["weight"] = tb.bm25_idf(len(lists[int(x["term"])][0]), NDOCS)
+        steps, root_slot, nslots = tb.debug_compile(codec, index, terms, nodes, scored)
+        worst_slots = max(worst_slots, nslots)
+        got_m, got_s = stepsim.run(steps, root_slot, nslots, lists, NDOCS)
+        want_m, want_s = evaluate(nodes, lists, NDOCS, weights=True if scored else None)
+        assert np.array_equal(np.flatnonzero(got_m), np.flatnonzero(want_m)), (q, m)
+        if scored:
+            ids = np.flatnonzero(want_m)
+            rel = np.abs(got_s[ids] - want_s[ids]) / np.maximum(np.abs(want_s[ids]), 1e-30)
+            assert rel.size == 0 or rel.max() <= 1e-5, (q, m, rel.max())
+    assert worst_slots <= 14
+
+
+def test_docs_only_plans_reuse_slots(built):
+    lists, idx, tdict = built
+    index, terms = idx[tb.CODEC_GOOGLE]
+    q = "(t1 OR t2) AND (t3 OR t4) AND t5 NOT (t6 OR t7 OR t8)"
+    nodes = tb.parse_query(q, tdict)
+    _, _, docs_slots = tb.debug_compile(tb.CODEC_GOOGLE, index, terms, nodes, False)
+    _, _, scored_slots = tb.debug_compile(tb.CODEC_GOOGLE, index, terms, nodes, True)
+    assert docs_slots < scored_slots and docs_slots <= 4  # root, conjunction, one disjunction at a time, scratch

@@ -188,6 +188,22 @@ def parse_query(text: str, tdict: TermDictionary, min_match: Optional[int] = Non
     return out
 
 
+def debug_compile(codec: int, index: np.ndarray, terms: np.ndarray, nodes: np.ndarray, scored: bool):
+    """(steps, root_slot, nslots): the bitmap-path step program of one plan, compiled on the host (no GPU needed)"""
+    from ._ffi import STEP_DTYPE
+    index = np.ascontiguousarray(index, dtype=np.uint8)
+    terms = np.ascontiguousarray(terms, dtype=TERM_DTYPE)
+    nodes = np.ascontiguousarray(nodes, dtype=QNODE_DTYPE)
+    steps = np.zeros(512, STEP_DTYPE)
+    n, rs, ns = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    err = C.create_string_buffer(256)
+    rc = lib().trn_debug_compile(codec, _ptr(index), index.size, _ptr(terms), len(terms), _ptr(nodes), len(nodes), 0, 1 if scored else 0, _ptr(steps), len(steps),
+                                 C.byref(n), C.byref(rs), C.byref(ns), err, 256)
+    if rc != 0:
+        raise TrinityError(err.value.decode("utf-8", "replace"))
+    return steps[: n.value].copy(), int(rs.value), int(ns.value)
+
+
 def query_truth_table(nodes: np.ndarray):
     """(terms, table, necessary): the boolean function of a plan over its distinct terms as the candidate-driven planner sees it;
     table[a] (a = bit set of present terms, bit j = terms[j]) is True where the query matches"""

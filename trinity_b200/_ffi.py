@@ -17,7 +17,7 @@ EXPORTS = [
     "trn_synth_build", "trn_synth_build_shard", "trn_synth_destroy", "trn_synth_index", "trn_synth_hits", "trn_synth_terms", "trn_synth_sum_hits",
     "trn_synth_postings", "trn_synth_positions",
     "trn_directory_probe", "trn_segment_open", "trn_segment_close", "trn_segment_info", "trn_segment_index", "trn_segment_terms",
-    "trn_segment_masked", "trn_parse_query", "trn_query_truth_table", "trn_bm25_idf", "trn_bm25_score",
+    "trn_segment_masked", "trn_parse_query", "trn_query_truth_table", "trn_debug_compile", "trn_bm25_idf", "trn_bm25_score",
     "trn_create", "trn_destroy", "trn_last_error", "trn_set_stream", "trn_upload_index", "trn_set_masked_documents", "trn_index_info_get",
     "trn_exec_batch", "trn_exec_batch_device", "trn_last_topk_device", "trn_merge_topk", "trn_fetch_results",
     "trn_decode_terms",
@@ -25,7 +25,8 @@ EXPORTS = [
 
 TERM_DTYPE = np.dtype([("documents", "<u4"), ("chunk_off", "<u4"), ("chunk_len", "<u4")])
 QNODE_DTYPE = np.dtype([("kind", "u1"), ("nchildren", "u1"), ("first_child", "<u2"), ("term", "<u4"), ("weight", "<f8")])
-assert TERM_DTYPE.itemsize == 12 and QNODE_DTYPE.itemsize == 16
+STEP_DTYPE = np.dtype([("op", "u1"), ("mode", "u1"), ("dst", "u1"), ("src", "u1"), ("flags", "u1"), ("pad", "u1", (3,)), ("term", "<u4"), ("pad2", "<u4"), ("idf", "<f8")])
+assert TERM_DTYPE.itemsize == 12 and QNODE_DTYPE.itemsize == 16 and STEP_DTYPE.itemsize == 24
 
 
 class TrnTerm(C.Structure):
@@ -97,6 +98,7 @@ def lib() -> C.CDLL:
     sig("trn_segment_index", i32, vp, P(vp), P(u64))
     sig("trn_segment_terms", i32, vp, P(vp), P(vp), P(u32))
     sig("trn_segment_masked", i32, vp, P(vp), P(u64))
+    sig("trn_debug_compile", i32, i32, vp, u64, vp, u32, vp, u32, u32, i32, vp, u32, P(u32), P(u32), P(u32), C.c_char_p, C.c_size_t)
     sig("trn_query_truth_table", i32, vp, u32, u32, P(u32), P(u32), P(u32), P(u32))
     sig("trn_parse_query", i32, C.c_char_p, vp, u32, vp, u32, P(u32), P(u32), C.c_char_p, C.c_size_t)
     sig("trn_bm25_idf", C.c_double, u32, u64)

@@ -887,6 +887,54 @@ extern "C" int trn_query_truth_table(const trn_qnode *nodes, uint32_t nnodes, ui
         return TRN_OK;
 }
 
+extern "C" int trn_debug_compile(int codec, const uint8_t *index, uint64_t nbytes, const trn_term *terms, uint32_t nterms, const trn_qnode *nodes, uint32_t nnodes,
+                                 uint32_t root, int scored, trn_debug_step *out, uint32_t cap, uint32_t *nsteps, uint32_t *root_slot, uint32_t *nslots, char *err,
+                                 size_t errcap) {
+        static_assert(sizeof(trn_debug_step) == sizeof(DevStep), "trn_debug_step mirrors DevStep");
+        auto seterr = [&](const std::string &m, int rc) {
+                if (err && errcap) {
+                        std::strncpy(err, m.c_str(), errcap - 1);
+                        err[errcap - 1] = 0;
+                }
+                return rc;
+        };
+        if (!index || !terms || !nodes || !nnodes || !out || !nsteps || !root_slot || !nslots || (codec != TRN_CODEC_GOOGLE && codec != TRN_CODEC_LUCENE))
+                return seterr("bad arguments", TRN_ERR_ARG);
+        BlockDirectory dir;
+        try {
+                std::vector<term_index_ctx> t(nterms);
+                for (uint32_t i = 0; i < nterms; ++i) {
+                        t[i].documents = terms[i].documents;
+                        t[i].offset    = terms[i].chunk_off;
+                        t[i].size      = terms[i].chunk_len;
+                }
+                build_block_directory(codec == TRN_CODEC_GOOGLE ? Codec::Google : Codec::Lucene, index, nbytes, t.data(), nterms, 1, dir);
+        } catch (const std::exception &e) {
+                return seterr(e.what(), TRN_ERR_FORMAT);
+        }
+        std::vector<DevTerm> ht(nterms);
+        for (uint32_t i = 0; i < nterms; ++i) {
+                ht[i].documents = dir.terms[i].documents;
+                ht[i].dir_begin = dir.terms[i].dir_begin;
+                ht[i].nblocks   = dir.terms[i].nblocks;
+                ht[i].first_doc = dir.terms[i].first_doc;
+                ht[i].last_doc  = dir.terms[i].last_doc;
+                ht[i].chunk_len = terms[i].chunk_len;
+        }
+        std::vector<DevStep> steps;
+        Compiler             cc(nodes, nnodes, ht, scored != 0, root, steps);
+        const int            rs = cc.run();
+        if (rs < 0)
+                return seterr(cc.err, cc.unsupported ? TRN_ERR_UNSUPPORTED : TRN_ERR_ARG);
+        if (steps.size() > cap)
+                return seterr("step buffer too small", TRN_ERR_CAPACITY);
+        std::memcpy(out, steps.data(), steps.size() * sizeof(DevStep));
+        *nsteps    = uint32_t(steps.size());
+        *root_slot = uint32_t(rs);
+        *nslots    = cc.next_slot + 1; // + the scratch slot of the kernels
+        return TRN_OK;
+}
+
 static void push_step(std::vector<DevStep> &steps, uint8_t op, uint8_t mode, uint32_t dst, uint32_t src, uint8_t flags, uint32_t term, double idf) {
         DevStep s;
         std::memset(&s, 0, sizeof(s));
