@@ -81,6 +81,18 @@ int trn_synth_positions(uint32_t ndocs, uint32_t rank, uint32_t min_df, uint64_t
 int trn_directory_probe(int codec, const uint8_t *index, uint64_t nbytes, const trn_term *term, uint32_t *blk_last, uint32_t *blk_off, uint32_t cap,
                         uint32_t *nblocks, uint32_t *first_doc, char *err, size_t errcap);
 
+/* The kernels' docID -> block lookup run on the host over one term's directory (the same code, csrc/dirlookup.h): blocks[i] = first block
+ * of the term whose last docID is >= docids[i] (nblocks if none) == skiplist_search + header hops of Decoder::advance
+ * (google_codec.cpp:464-495,821-934; lucene_codec.cpp:596-656).  *tf_shift = log2 of the term's table granularity (32: no table). */
+int trn_directory_lookup(int codec, const uint8_t *index, uint64_t nbytes, const trn_term *term, const uint32_t *docids, uint32_t n, uint32_t *blocks,
+                         uint32_t *tf_shift, uint32_t *tf_entries, char *err, size_t errcap);
+
+/* Size of the whole load-time directory trn_upload_index would build (host only, no GPU): block entries (8 B per block + sentinel),
+ * the sparse docID -> block tables and the per-term records.  It is O(blocks + terms) — a term's table never has more entries than
+ * the term has blocks, and covers only the docID range the term occupies in THIS index source. */
+int trn_directory_stats(int codec, const uint8_t *index, uint64_t nbytes, const trn_term *terms, uint32_t nterms, int threads, uint64_t *directory_bytes,
+                        uint64_t *total_blocks, uint64_t *table_entries, char *err, size_t errcap);
+
 /* ------------------------------------------------------------------------------------------------ segment directories
  * Host half of SegmentIndexSource (segment_index_source.cpp:5-186): opens a segment directory written by Trinity's
  * SegmentIndexSession::commit() (indexer.cpp:241-300: `index`, `terms.data`, `id`, `updated_documents.ids`) and exposes what
@@ -137,6 +149,12 @@ typedef struct trn_query {
  * Writes at most cap nodes; *nnodes receives the count, *root the root index. */
 int trn_parse_query(const char *text, const char *const *names, uint32_t nterms, trn_qnode *nodes, uint32_t cap, uint32_t *nnodes, uint32_t *root,
                     char *err, size_t errcap);
+/* The same with an explicit terms dictionary (== IndexSource::resolve_term_ctx's lookup, index_source.h:118), built once per vocabulary
+ * and owned by the caller.  trn_parse_query above rebuilds its map on every call and caches nothing. */
+typedef struct trn_dict trn_dict;
+int  trn_dict_create(const char *const *names, uint32_t nterms, trn_dict **out);
+void trn_dict_destroy(trn_dict *);
+int  trn_parse_query_dict(const char *text, const trn_dict *dict, trn_qnode *nodes, uint32_t cap, uint32_t *nnodes, uint32_t *root, char *err, size_t errcap);
 
 /* The boolean function of a query tree over its distinct (non-empty) terms, as the planner of the candidate-driven path tabulates
  * it (DocumentsOnly; == which term combinations DocsSetIterators::Conjuction / Disjunction / Filter / Optional / DisjunctionSome
@@ -220,7 +238,7 @@ int trn_exec_batch(trn_ctx *, const trn_query *queries, uint32_t nq, int mode, u
 
 /* Split form used by bench.py / multi-GPU: run on device only, results stay in HBM ... */
 int trn_exec_batch_device(trn_ctx *, const trn_query *queries, uint32_t nq, int mode, uint32_t k, trn_result *out_counts_only);
-/* ... device pointers of the last SCORED_TOPK run: nq*k u32 docids, nq*k f32 scores (unused slots: docid 0, score -inf), nq u32 counts */
+/* ... device pointers of the last SCORED_TOPK run: nq*k u32 docids, nq*k f32 scores (unused slots: docid 0, score -1.0; real scores are >= 0), nq u32 counts */
 int trn_last_topk_device(trn_ctx *, void **docids, void **scores, void **counts);
 /* merge `nshards` gathered top-k lists (layout [shard][nq][k]) into one; the one exchange step of the multi-GPU path.
  * All pointers are device pointers; docid_base[shard] is added to the docids of that shard (0 if docIDs are already global). */

@@ -74,3 +74,81 @@ def test_directory_build_survives_corrupted_chunks(codec):
         except tb.TrinityError:
             bad += 1
     assert ok + bad == 400
+
+
+# ---------------------------------------------------------------------------------------------- sparse docID -> block tables
+def _brute_first_block_ge(last, d):
+    """first block whose last docID >= d (nblocks if none) == what skiplist_search + header hops of Decoder::advance arrive at"""
+    return np.searchsorted(last, d, side="left").astype(np.uint32)
+
+
+@pytest.mark.parametrize("codec", [tb.CODEC_GOOGLE, tb.CODEC_LUCENE])
+def test_sparse_table_lookup_equals_brute_force(codec):
+    """the kernels' own lookup code (csrc/dirlookup.h, run on the host through trn_directory_lookup) against a plain searchsorted, on
+    dense, sparse, clustered, tiny and shard-like (first docID far from 1) lists; probes sit on block ends, table boundaries, 0 and 2^32-1"""
+    rng = np.random.default_rng(11 + codec)
+    bs = 32 if codec == tb.CODEC_GOOGLE else 128
+    shapes = {
+        "dense": np.cumsum(rng.integers(1, 3, 60_000)),
+        "sparse": np.cumsum(rng.integers(1, 40_000, 3_000)),
+        "clustered": np.concatenate([np.arange(1, 5_000), 10_000_000 + np.cumsum(rng.integers(1, 9, 20_000)), [4_000_000_000, 4_000_000_123]]),
+        "shard": 75_000_000 + np.cumsum(rng.integers(1, 50, 40_000)),
+        "tiny": np.array([7]),
+        "few": np.cumsum(rng.integers(1, 100_000, 5 * bs)),
+        "huge-gaps": np.cumsum(rng.integers(1, 1 << 20, 4_000)),
+    }
+    for name, d in shapes.items():
+        d = d.astype(np.uint32)
+        b = tb.IndexBuilder(codec)
+        t = b.add_term(d, np.ones(len(d), np.uint32))
+        index = b.index()
+        last = tb.directory_probe(codec, index, t)[0][:-1]
+        nblocks = len(last)
+        probes = np.concatenate([last, last + 1, last - 1, d[:: max(1, len(d) // 500)], rng.integers(0, 1 << 32, 2000, dtype=np.uint64).astype(np.uint32),
+                                 (np.arange(0, 1 << 19) << 13).astype(np.uint32)[:: 37], [0, 1, d[0], d[0] - 1, d[-1], d[-1] + 1, 0xFFFFFFFF]]).astype(np.uint32)
+        got, shift, entries = tb.directory_lookup(codec, index, t, probes)
+        want = _brute_first_block_ge(last, probes)
+        bad = np.flatnonzero(got != want)
+        assert len(bad) == 0, f"{name}: docID {probes[bad[0]]} -> block {got[bad[0]]}, want {want[bad[0]]} (tf_shift {shift})"
+        if nblocks <= 8:
+            assert shift == 32 and entries == 0
+        else:  # never more table entries than blocks (+ the closing entry), never finer than the 8192-document window
+            assert 13 <= shift <= 31 and entries <= nblocks + 1, (name, shift, entries, nblocks)
+
+
+@pytest.mark.parametrize("codec", [tb.CODEC_GOOGLE, tb.CODEC_LUCENE])
+def test_directory_is_linear_in_blocks_and_terms_also_per_shard(codec):
+    """the whole directory stays a small fraction of the index it describes, for the full synthetic index and for every docID-range
+    shard of it (a shard's tables cover only the shard's own range) — the dense term x tile table it replaces was 24x the index here"""
+    from trinity_b200.sharded import shard_range
+    ndocs, nterms = 4_000_000, 512
+    for world in (1, 8):
+        for rank in sorted({0, world - 1}):
+            s = tb.SynthIndex(codec, ndocs, nterms, min_df=50, threads=4, doc_range=shard_range(ndocs, rank, world))
+            st = tb.directory_stats(codec, np.asarray(s.index), np.asarray(s.terms), threads=4)
+            assert st["table_entries"] <= st["total_blocks"] + nterms
+            assert st["directory_bytes"] <= 8 * (st["total_blocks"] + nterms) + 4 * st["table_entries"] + 36 * nterms
+            assert st["directory_bytes"] <= 0.15 * st["index_bytes"], (world, rank, st)
+
+
+def test_directory_of_a_million_tiny_terms_stays_small():
+    """10^6 terms of 1..3 postings each (a real vocabulary's tail): per-term cost is the 36-byte record + its two block entries,
+    no table at all — the dense table would have needed terms x tiles x 4 bytes (tens of GB at 100M documents)"""
+    nterms = 1_000_000
+    b = tb.IndexBuilder(tb.CODEC_GOOGLE)
+    rng = np.random.default_rng(2)
+    base = rng.integers(1, 90_000_000, nterms)
+    L = b._L
+    import ctypes as C
+    from trinity_b200._ffi import TrnTerm
+    t = TrnTerm()
+    terms = np.zeros(nterms, tb._ffi.TERM_DTYPE)
+    one = np.ones(3, np.uint32)
+    for i in range(nterms):
+        n = 1 + (i % 3)
+        d = (int(base[i]) + np.arange(n, dtype=np.uint32) * 1000).astype(np.uint32)
+        L.trn_builder_add_term(b._h, d.ctypes.data_as(C.c_void_p), one.ctypes.data_as(C.c_void_p), n, None, C.byref(t))
+        terms[i] = (t.documents, t.chunk_off, t.chunk_len)
+    st = tb.directory_stats(tb.CODEC_GOOGLE, b.index(), terms, threads=4)
+    assert st["total_blocks"] == nterms and st["table_entries"] == 0
+    assert st["directory_bytes"] == nterms * (36 + 2 * 8)

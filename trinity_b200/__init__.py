@@ -160,12 +160,23 @@ class TermDictionary:
     """term name -> term id; the host-side stand-in for IndexSource::resolve_term_ctx (index_source.h:118)."""
 
     def __init__(self, names: Sequence[str]):
+        self._L = lib()
         self.names = list(names)
-        self._enc = [s.encode("utf-8", "surrogateescape") for s in self.names]
-        self._arr = (C.c_char_p * len(self._enc))(*self._enc)
+        enc = [s.encode("utf-8", "surrogateescape") for s in self.names]
+        arr = (C.c_char_p * len(enc))(*enc)
+        h = C.c_void_p()
+        if self._L.trn_dict_create(C.cast(arr, C.c_void_p), len(enc), C.byref(h)) != 0:
+            raise TrinityError("trn_dict_create failed")
+        self._h = h  # an explicit dictionary handle: the names are copied, nothing is keyed on caller memory
 
     def __len__(self):
         return len(self.names)
+
+    def __del__(self):
+        try:
+            self._L.trn_dict_destroy(self._h)
+        except Exception:
+            pass
 
 
 def parse_query(text: str, tdict: TermDictionary, min_match: Optional[int] = None) -> np.ndarray:
@@ -177,8 +188,7 @@ def parse_query(text: str, tdict: TermDictionary, min_match: Optional[int] = Non
     nodes = np.zeros(256, dtype=QNODE_DTYPE)
     nn, root = C.c_uint32(), C.c_uint32()
     err = C.create_string_buffer(256)
-    rc = L.trn_parse_query(text.encode(), C.cast(tdict._arr, C.c_void_p), len(tdict), _ptr(nodes), len(nodes),
-                           C.byref(nn), C.byref(root), err, 256)
+    rc = L.trn_parse_query_dict(text.encode(), tdict._h, _ptr(nodes), len(nodes), C.byref(nn), C.byref(root), err, 256)
     if rc != 0:
         raise TrinityError(f"parse error: {err.value.decode()}")
     assert root.value == 0
@@ -399,6 +409,32 @@ def directory_probe(codec: int, index: np.ndarray, term: tuple):
         raise TrinityError(err.value.decode())
     n = nb.value + (1 if nb.value else 0)
     return last[:n], off[:n], fd.value
+
+
+def directory_lookup(codec: int, index: np.ndarray, term: tuple, docids):
+    """(blocks, tf_shift, tf_entries): first block of the term whose last docID >= docids[i], through the kernels' own lookup code on the host"""
+    index = np.ascontiguousarray(index, dtype=np.uint8)
+    t = TrnTerm(int(term[0]), int(term[1]), int(term[2]))
+    d = _u32(docids)
+    out = np.zeros(len(d), np.uint32)
+    sh, ne = C.c_uint32(), C.c_uint32()
+    err = C.create_string_buffer(256)
+    rc = lib().trn_directory_lookup(codec, _ptr(index), index.size, C.byref(t), _ptr(d), len(d), _ptr(out), C.byref(sh), C.byref(ne), err, 256)
+    if rc != 0:
+        raise TrinityError(err.value.decode("utf-8", "replace"))
+    return out, int(sh.value), int(ne.value)
+
+
+def directory_stats(codec: int, index: np.ndarray, terms: np.ndarray, threads: int = 1) -> dict:
+    """size of the load-time directory trn_upload_index would build for this index (host only)"""
+    index = np.ascontiguousarray(index, dtype=np.uint8)
+    terms = np.ascontiguousarray(terms, dtype=TERM_DTYPE)
+    db, nb, te = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    err = C.create_string_buffer(256)
+    rc = lib().trn_directory_stats(codec, _ptr(index), index.size, _ptr(terms), len(terms), threads, C.byref(db), C.byref(nb), C.byref(te), err, 256)
+    if rc != 0:
+        raise TrinityError(err.value.decode("utf-8", "replace"))
+    return {"directory_bytes": db.value, "total_blocks": nb.value, "table_entries": te.value, "index_bytes": int(index.size)}
 
 
 class Segment:

@@ -16,7 +16,7 @@ EXPORTS = [
     "trn_builder_set_google_skiplist_countdown", "trn_builder_index", "trn_builder_hits", "trn_builder_last_error",
     "trn_synth_build", "trn_synth_build_shard", "trn_synth_destroy", "trn_synth_index", "trn_synth_hits", "trn_synth_terms", "trn_synth_sum_hits",
     "trn_synth_postings", "trn_synth_positions",
-    "trn_directory_probe", "trn_segment_open", "trn_segment_close", "trn_segment_info", "trn_segment_index", "trn_segment_terms",
+    "trn_directory_probe", "trn_directory_stats", "trn_directory_lookup", "trn_dict_create", "trn_dict_destroy", "trn_parse_query_dict", "trn_segment_open", "trn_segment_close", "trn_segment_info", "trn_segment_index", "trn_segment_terms",
     "trn_segment_masked", "trn_parse_query", "trn_query_truth_table", "trn_debug_compile", "trn_bm25_idf", "trn_bm25_score",
     "trn_create", "trn_destroy", "trn_last_error", "trn_set_stream", "trn_upload_index", "trn_set_masked_documents", "trn_index_info_get",
     "trn_exec_batch", "trn_exec_batch_device", "trn_last_topk_device", "trn_merge_topk", "trn_fetch_results",
@@ -92,6 +92,11 @@ def lib() -> C.CDLL:
     sig("trn_synth_postings", i32, u32, u32, u32, u64, vp, vp, u32, P(u32))
     sig("trn_synth_positions", i32, u32, u32, u32, u64, vp, u64, P(u64))
     sig("trn_directory_probe", i32, i32, vp, u64, P(TrnTerm), vp, vp, u32, P(u32), P(u32), C.c_char_p, C.c_size_t)
+    sig("trn_directory_stats", i32, i32, vp, u64, vp, u32, i32, P(u64), P(u64), P(u64), C.c_char_p, C.c_size_t)
+    sig("trn_directory_lookup", i32, i32, vp, u64, P(TrnTerm), vp, u32, vp, P(u32), P(u32), C.c_char_p, C.c_size_t)
+    sig("trn_dict_create", i32, vp, u32, P(vp))
+    sig("trn_dict_destroy", None, vp)
+    sig("trn_parse_query_dict", i32, C.c_char_p, vp, vp, u32, P(u32), P(u32), C.c_char_p, C.c_size_t)
     sig("trn_segment_open", i32, C.c_char_p, P(vp), C.c_char_p, C.c_size_t)
     sig("trn_segment_close", None, vp)
     sig("trn_segment_info", i32, vp, P(i32), P(u32), P(u64), P(u64), P(u32), P(u64), P(u32), P(u64))

@@ -1,6 +1,8 @@
 // Host-side encoders for the GOOGLE and LUCENE(FastPFor<4>) postings layouts + the load-time block directory.
-// See codecs.h for the reference citations.  Written from the format description,
-// byte-exactness pinned against the reference encoders by tests/test_codecs_cpu.py.
+// The two encoders restate the reference write path statement by statement (google_codec.cpp:9-176, lucene_codec.cpp:163-388;
+// best_b follows fastpfor.h:143-171) onto std::vector — a byte-exact writer leaves little freedom, and the kernels must read exactly
+// these bytes.  They are index-BUILD tooling (tests, the synthetic workload), not part of the query hot path; byte-exactness is
+// pinned against the reference encoders by tests/test_codecs_cpu.py.  The block-directory half of the file is this repo's own.
 #include "codecs.h"
 #include "varbyte.h"
 #include <algorithm>
@@ -635,6 +637,54 @@ void build_block_directory(Codec codec, const uint8_t *index, uint64_t nbytes, c
                 at += p.last.size();
                 std::vector<uint32_t>().swap(p.last);
                 std::vector<uint32_t>().swap(p.off);
+        }
+        // sparse docID -> block tables (see codecs.h): sized first, then filled in parallel
+        size_t tfTotal{0};
+        for (uint32_t i = 0; i < nterms; ++i) {
+                auto &td = out.terms[i];
+                td.tf_begin = uint32_t(tfTotal);
+                td.tf_base = td.tf_n = 0;
+                td.tf_shift          = kDirNoTable;
+                if (td.nblocks <= kDirNoTableBlocks)
+                        continue;
+                uint32_t s = kDirMinShift;
+                while (s < 31 && uint64_t(td.last_doc >> s) - (td.first_doc >> s) + 1 > td.nblocks)
+                        ++s;
+                td.tf_shift = s;
+                td.tf_base  = td.first_doc >> s;
+                td.tf_n     = (td.last_doc >> s) - td.tf_base + 1;
+                tfTotal += size_t(td.tf_n) + 1;
+                if (tfTotal >= (1ull << 32))
+                        throw std::runtime_error("block directory: tile table exceeds 2^32 entries");
+        }
+        out.tile_first.resize(tfTotal);
+        {
+                std::atomic<uint32_t> nx{0};
+                auto                  fill = [&] {
+                        for (;;) {
+                                const uint32_t i = nx.fetch_add(1);
+                                if (i >= nterms)
+                                        break;
+                                const auto &td = out.terms[i];
+                                if (td.tf_shift == kDirNoTable)
+                                        continue;
+                                const uint32_t *bl = out.blk_last.data() + td.dir_begin;
+                                uint32_t *      o  = out.tile_first.data() + td.tf_begin;
+                                uint32_t        b{0};
+                                for (uint32_t j = 0; j <= td.tf_n; ++j) {
+                                        const uint64_t lo = uint64_t(td.tf_base + j) << td.tf_shift;
+                                        while (b < td.nblocks && bl[b] < lo)
+                                                ++b;
+                                        o[j] = b;
+                                }
+                        }
+                };
+                std::vector<std::thread> fths;
+                for (int i = 1; i < threads; ++i)
+                        fths.emplace_back(fill);
+                fill();
+                for (auto &t : fths)
+                        t.join();
         }
 }
 

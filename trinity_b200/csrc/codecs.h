@@ -126,16 +126,31 @@ namespace Codecs {
 //   byte (Google: first doc-delta varbyte, after the n byte; Lucene: the u8 L of the deltas int-block / the first
 //   varbyte of the tail).  Each term owns nblocks+1 consecutive entries; the sentinel entry holds
 //   {last = UINT32_MAX, off = end of the term's block area}.
+//
+// Sparse docID -> block index on top of it (the O(1) part of skiplist_search, google_codec.cpp:464-495 / lucene_codec.cpp:596-656):
+// a term with more than kDirNoTableBlocks blocks owns tf_n + 1 entries of `tile_first`, entry j = first block whose last docID is
+// >= (tf_base + j) << tf_shift.  The entries cover only [first_doc, last_doc] of the term (inside THIS index source: a docID-range
+// shard indexes its own range), and tf_shift is the smallest granularity >= kDirMinShift that keeps the table at or below one entry
+// per block — so the whole directory is O(blocks + terms), never terms x tiles.  A lookup reads two neighbouring entries and finishes
+// with a binary search over the blk_last entries between them; smaller terms (tf_shift == kDirNoTable) search all of blk_last.
+static constexpr uint32_t kDirMinShift      = 13; // == the 8192-document window of the scored spans (docset_spans.h:74)
+static constexpr uint32_t kDirNoTable       = 32; // tf_shift value of a term without table
+static constexpr uint32_t kDirNoTableBlocks = 8;
+
 struct TermDir {
         uint32_t documents;
         uint32_t dir_begin; // index of the term's first entry in blk_last/blk_off
         uint32_t nblocks;   // excluding sentinel
         uint32_t first_doc, last_doc;
+        uint32_t tf_begin{0}, tf_base{0}, tf_shift{kDirNoTable}, tf_n{0};
 };
 
 struct BlockDirectory {
-        std::vector<uint32_t> blk_last, blk_off;
+        std::vector<uint32_t> blk_last, blk_off, tile_first;
         std::vector<TermDir>  terms;
+        uint64_t              bytes() const { // what the device copy occupies (DevTerm = 36 B per term)
+                return (blk_last.size() + blk_off.size() + tile_first.size()) * 4ull + terms.size() * 36ull;
+        }
 };
 
 // throws std::runtime_error on malformed chunks

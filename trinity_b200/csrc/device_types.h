@@ -6,7 +6,7 @@ namespace trn {
 
 static constexpr uint32_t kEmptyTerm = 0xffffffffu;
 
-// one per dictionary term (16 B + 8)
+// one per dictionary term (36 B)
 struct DevTerm {
         uint32_t documents;
         uint32_t dir_begin; // first entry in blk_last / blk_off (nblocks + 1 entries incl. sentinel)
@@ -14,7 +14,13 @@ struct DevTerm {
         uint32_t first_doc;
         uint32_t last_doc;
         uint32_t chunk_len;
+        // sparse docID -> block table (codecs.h): tile_first[tf_begin + j] = first block whose last docID >= (tf_base + j) << tf_shift,
+        // j = 0 .. (last_doc >> tf_shift) - tf_base + 1; tf_shift == 32: the term has no table (few blocks: search blk_last directly)
+        uint32_t tf_begin;
+        uint32_t tf_base;
+        uint32_t tf_shift;
 };
+static_assert(sizeof(DevTerm) == 36, "DevTerm layout (BlockDirectory::bytes counts 36 B per term)");
 
 struct DevIndex {
         const uint8_t * index;    // raw reference-format bytes (google index / lucene index), 256B aligned, 64B tail padding
@@ -22,10 +28,10 @@ struct DevIndex {
         const uint32_t *blk_off;  // payload byte offset per block (+ sentinel = end of block area)
         const DevTerm * terms;
         const uint32_t *masked;     // optional docID bitmap of masked (deleted/updated) documents, word i = docIDs [32i, 32i+32)
-        const uint32_t *tile_first; // [nterms][ntiles + 1]: first block whose last docID >= tile * tile_docs
+        const uint32_t *tile_first; // per-term sparse docID -> block tables (DevTerm::tf_*)
         uint32_t        nterms;
-        uint32_t        ntiles;
-        uint32_t        tile_shift; // tile_docs = 1 << tile_shift
+        uint32_t        ntiles;     // number of 2^tile_shift-document tiles of the docID space
+        uint32_t        tile_shift; // tile of the scored kernel (8192 documents: the reference's window, docset_spans.h:74)
         uint32_t        max_docid;
         int             codec;
 };
@@ -74,7 +80,7 @@ struct ExecParams {
         uint32_t        nslots; // bitmap slots per worker (CTA for k_exec_tiles, warp for k_exec_docs)
         uint32_t        stage_bytes; // per-warp staging bytes of k_exec_tiles (codec dependent)
         uint32_t        docs_stage_bytes; // per-warp staging bytes of k_exec_docs (1 or 2 gather buffers)
-        uint32_t        exec_shift; // log2 of the docID tile of THIS launch (>= ix.tile_shift; tile_first is indexed at ix.tile_shift granularity)
+        uint32_t        exec_shift; // log2 of the docID tile of THIS launch
         int             mode;   // TRN_MODE_*
         uint32_t        k;
         uint32_t *      ticket; // work-item dispenser

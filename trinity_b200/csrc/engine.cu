@@ -134,6 +134,25 @@ struct Range {
         }
 };
 
+// every node has at most one parent: a plan is a TREE (a node shared by several parents would make the recursive passes — cost, range,
+// bound, truth tables — revisit it once per path, exponentially often in a hostile plan)
+static bool plan_is_tree(const trn_qnode *n, uint32_t nn, uint32_t root) {
+        std::vector<uint8_t> seen(nn, 0);
+        if (root < nn)
+                seen[root] = 1;
+        for (uint32_t i = 0; i < nn; ++i) {
+                if (n[i].kind == TRN_NODE_TERM)
+                        continue;
+                for (uint32_t k = 0; k < n[i].nchildren; ++k) {
+                        const uint32_t c = uint32_t(n[i].first_child) + k;
+                        if (c >= nn || seen[c])
+                                return false;
+                        seen[c] = 1;
+                }
+        }
+        return true;
+}
+
 // children follow their parents in the node array (checked by validate()), so one forward pass yields every node's depth; the
 // compiler and the truth-table builder recurse once per level
 static bool plan_depth_ok(const trn_qnode *n, uint32_t nn) {
@@ -478,6 +497,10 @@ struct Compiler {
                                 }
                         }
                 }
+                if (!plan_is_tree(n, nn, root)) {
+                        err = "a node is referenced by more than one parent (a plan is a tree)";
+                        return false;
+                }
                 return true;
         }
 
@@ -622,10 +645,17 @@ extern "C" void trn_destroy(trn_ctx *c) {
                 b->release();
         for (PinBuf *b : {&c->h_offsets, &c->h_docids, &c->h_scores, &c->h_counts, &c->h_small, &c->h_chunk})
                 b->release();
-        if (c->ev0)
-                cudaEventDestroy(c->ev0);
-        if (c->ev1)
-                cudaEventDestroy(c->ev1);
+        for (cudaEvent_t e : {c->ev0, c->ev1, c->evk0, c->evk1, c->ev_done[0], c->ev_done[1], c->ev_d2h[0], c->ev_d2h[1]})
+                if (e)
+                        cudaEventDestroy(e);
+        for (int i = 0; i < 16; ++i) {
+                if (c->ev_ck0[i])
+                        cudaEventDestroy(c->ev_ck0[i]);
+                if (c->ev_ck1[i])
+                        cudaEventDestroy(c->ev_ck1[i]);
+        }
+        if (c->copy_stream)
+                cudaStreamDestroy(c->copy_stream);
         delete c;
 }
 
@@ -657,6 +687,8 @@ extern "C" int trn_upload_index(trn_ctx *c, int codec, const uint8_t *index, uin
                 }
                 const int threads = int(std::max(1u, std::min(64u, std::thread::hardware_concurrency())));
                 build_block_directory(codec == TRN_CODEC_GOOGLE ? Codec::Google : Codec::Lucene, index, nbytes, t.data(), nterms, threads, dir);
+        } catch (const std::bad_alloc &) {
+                return fail(c, TRN_ERR_CAPACITY, "trn_upload_index: out of host memory while building the block directory");
         } catch (const std::exception &e) {
                 return fail(c, TRN_ERR_FORMAT, e.what());
         }
@@ -669,7 +701,12 @@ extern "C" int trn_upload_index(trn_ctx *c, int codec, const uint8_t *index, uin
         c->max_docid  = max_docid;
         const uint32_t W = 1u << c->tile_shift;
         c->ntiles     = uint32_t((uint64_t(max_docid) + 1 + W - 1) >> c->tile_shift);
-        c->h_terms.resize(nterms);
+        try {
+                c->h_terms.resize(nterms);
+        } catch (const std::bad_alloc &) {
+                return fail(c, TRN_ERR_CAPACITY, "trn_upload_index: out of host memory");
+        }
+        c->have_index     = false; // until the new index is completely in place
         c->min_docid      = 0xffffffffu;
         c->total_blocks   = 0;
         c->total_postings = 0;
@@ -681,38 +718,15 @@ extern "C" int trn_upload_index(trn_ctx *c, int codec, const uint8_t *index, uin
                 d.first_doc = dir.terms[i].first_doc;
                 d.last_doc  = dir.terms[i].last_doc;
                 d.chunk_len = terms[i].chunk_len;
+                d.tf_begin  = dir.terms[i].tf_begin;
+                d.tf_base   = dir.terms[i].tf_base;
+                d.tf_shift  = dir.terms[i].tf_shift;
                 c->total_blocks += d.nblocks;
                 c->total_postings += d.documents;
                 if (d.nblocks)
                         c->min_docid = std::min(c->min_docid, d.first_doc);
                 if (d.nblocks && d.last_doc > max_docid)
                         return fail(c, TRN_ERR_ARG, "a term holds a docID above max_docid");
-        }
-        // tile directory: first block of every term whose last docID reaches the tile (O(1) replacement for skiplist_search,
-        // google_codec.cpp:464-495 / lucene_codec.cpp:596-656)
-        std::vector<uint32_t> tf(size_t(nterms) * (c->ntiles + 1));
-        {
-                const uint32_t nthreads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-                auto           work     = [&](uint32_t tid) {
-                        for (uint32_t t = tid; t < nterms; t += nthreads) {
-                                const auto &    d  = c->h_terms[t];
-                                const uint32_t *bl = dir.blk_last.data() + d.dir_begin;
-                                uint32_t *      o  = tf.data() + size_t(t) * (c->ntiles + 1);
-                                uint32_t        b  = 0;
-                                for (uint32_t j = 0; j <= c->ntiles; ++j) {
-                                        const uint64_t lo = uint64_t(j) << c->tile_shift;
-                                        while (b < d.nblocks && bl[b] < lo)
-                                                ++b;
-                                        o[j] = b;
-                                }
-                        }
-                };
-                std::vector<std::thread> ths;
-                for (uint32_t i = 1; i < nthreads; ++i)
-                        ths.emplace_back(work, i);
-                work(0);
-                for (auto &t : ths)
-                        t.join();
         }
         CK(c->d_index.ensure(nbytes + 256));
         CK(cudaMemsetAsync(c->d_index.p, 0, nbytes + 256, c->stream));
@@ -724,12 +738,16 @@ extern "C" int trn_upload_index(trn_ctx *c, int codec, const uint8_t *index, uin
         CK(cudaMemcpyAsync(c->d_blk_off.p, dir.blk_off.data(), nent * 4, cudaMemcpyHostToDevice, c->stream));
         CK(c->d_terms.ensure(std::max<size_t>(4, nterms * sizeof(DevTerm))));
         CK(cudaMemcpyAsync(c->d_terms.p, c->h_terms.data(), nterms * sizeof(DevTerm), cudaMemcpyHostToDevice, c->stream));
-        CK(c->d_tile_first.ensure(std::max<size_t>(4, tf.size() * 4)));
-        CK(cudaMemcpyAsync(c->d_tile_first.p, tf.data(), tf.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(c->d_tile_first.ensure(std::max<size_t>(4, dir.tile_first.size() * 4)));
+        if (!dir.tile_first.empty())
+                CK(cudaMemcpyAsync(c->d_tile_first.p, dir.tile_first.data(), dir.tile_first.size() * 4, cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         c->index_bytes = nbytes;
-        c->dir_bytes   = nent * 8 + tf.size() * 4 + nterms * sizeof(DevTerm);
+        c->dir_bytes   = dir.bytes();
         c->have_index  = true;
+        // the masked-documents bitmap belongs to the index it was set for (its size follows that index's max_docid): a new upload
+        // starts with an empty registry, callers set it again (trn_set_masked_documents)
+        c->have_masked = false;
         return TRN_OK;
 }
 
@@ -815,8 +833,8 @@ static TruthVec truth_vector(const trn_qnode *nodes, uint32_t i, const uint32_t 
         }
         const uint32_t f = X.first_child;
         if (X.kind == TRN_NODE_SOME) {
-                TruthVec kids[16];
-                const uint32_t nk = std::min<uint32_t>(X.nchildren, 16);
+                const uint32_t        nk = X.nchildren; // all of them (<= 255)
+                std::vector<TruthVec> kids(nk);
                 for (uint32_t k = 0; k < nk; ++k)
                         kids[k] = truth_vector(nodes, f + k, tv, n);
                 for (uint32_t a = 0; a < 256; ++a) {
@@ -847,7 +865,7 @@ extern "C" int trn_query_truth_table(const trn_qnode *nodes, uint32_t nnodes, ui
         for (uint32_t i = 0; i < nnodes; ++i) // same structural rules as the plan compiler: children behind their parent, bounded depth
                 if (nodes[i].kind != TRN_NODE_TERM && (nodes[i].nchildren == 0 || nodes[i].first_child <= i || uint32_t(nodes[i].first_child) + nodes[i].nchildren > nnodes))
                         return TRN_ERR_ARG;
-        if (!plan_depth_ok(nodes, nnodes))
+        if (!plan_depth_ok(nodes, nnodes) || !plan_is_tree(nodes, nnodes, root))
                 return TRN_ERR_ARG;
         uint32_t n{0}, stack[64], sp{0};
         stack[sp++] = root;
@@ -920,6 +938,9 @@ extern "C" int trn_debug_compile(int codec, const uint8_t *index, uint64_t nbyte
                 ht[i].first_doc = dir.terms[i].first_doc;
                 ht[i].last_doc  = dir.terms[i].last_doc;
                 ht[i].chunk_len = terms[i].chunk_len;
+                ht[i].tf_begin  = dir.terms[i].tf_begin;
+                ht[i].tf_base   = dir.terms[i].tf_base;
+                ht[i].tf_shift  = dir.terms[i].tf_shift;
         }
         std::vector<DevStep> steps;
         Compiler             cc(nodes, nnodes, ht, scored != 0, root, steps);
@@ -962,7 +983,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         CK(cudaSetDevice(c->device));
         const bool scored = mode != TRN_MODE_DOCS_ONLY;
         // docID tile of this launch: set queries run one warp per tile (k_exec_docs) on larger tiles; scored queries keep a CTA-wide
-        // fp32 score tile (k_exec_tiles).  Both index the same tile_first table (granularity 2^tile_shift).
+        // fp32 score tile (k_exec_tiles).
         uint32_t execShift = scored ? c->tile_shift : c->docs_shift;
         execShift          = std::max(execShift, c->tile_shift);
 

@@ -723,7 +723,6 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
         uint32_t *     slots = reinterpret_cast<uint32_t *>(dyn_smem + perWarp * warp);
         uint8_t *      stage = reinterpret_cast<uint8_t *>(slots + size_t(P.nslots) * NW);
         const uint32_t wpl   = NW >> 5; // bitmap words per lane (contiguous ownership: lane l owns words [l*wpl, (l+1)*wpl))
-        const uint32_t fs    = P.exec_shift - P.ix.tile_shift;
 
         uint32_t curq = 0xffffffffu;
         DevQuery Q;
@@ -757,7 +756,7 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
                 bool           dead = false;
                 int            handled = 0;
                 if (Q.flat && P.ix.codec == 0)
-                        handled = flat_exec_google(P, Q, tile, lo, W, NW, fs, slots, stage, lane);
+                        handled = flat_exec_google(P, Q, lo, W, NW, slots, stage, lane);
                 if (handled == 2)
                         dead = true;
 
@@ -811,15 +810,7 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
                                 uint32_t   bA = 1, bB = 0;
                                 if (haveTerm) {
                                         T = P.ix.terms[st.term];
-                                        if (T.nblocks) {
-                                                const uint32_t *tf = P.ix.tile_first + size_t(st.term) * (P.ix.ntiles + 1);
-                                                bA                 = tf[min(tile << fs, P.ix.ntiles)];
-                                                bB                 = min(tf[min((tile + 1u) << fs, P.ix.ntiles)], T.nblocks - 1u);
-                                                if (bA >= T.nblocks) {
-                                                        bA = 1;
-                                                        bB = 0;
-                                                }
-                                        }
+                                        tile_block_range(P.ix, T, lo, W, bA, bB);
                                 }
                                 const uint32_t *skipfilt = nullptr;
                                 BitSink         bs;

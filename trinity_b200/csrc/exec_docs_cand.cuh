@@ -10,7 +10,7 @@
 //   1. lane = block: the 32 blocks are decoded into a candidate array in shared memory (row stride 33 words: conflict-free for
 //      the lane-per-block writes and for the lane-per-candidate reads below);
 //   2. for every other operand, for each lead block (32 candidates, lane = candidate): the lane finds the one block of the operand
-//      that can hold its candidate — tile_first bounds the block directory to the candidate's tile, a short binary search over
+//      that can hold its candidate — the term's sparse docID -> block table bounds the block directory, a short binary search over
 //      blk_last finishes it (== skiplist_search + the header hops of Decoder::advance, google_codec.cpp:821-934, in O(log) loads) —
 //      stages that block's head with cp.async and decodes it only as far as the candidate;
 //   3. the survivors (minus masked documents) are compacted and emitted in order.
@@ -140,12 +140,17 @@ __device__ void cand_exec_google(const ExecParams &P, const DevQuery &Q, uint32_
                 }
         }
         const uint32_t nnec = Q.root_slot; // necessary terms incl. the lead
-        uint32_t mydir = 0, mynb = 0, mydocs = 0;
+        uint32_t mydir = 0, mynb = 0, mydocs = 0, myfirst = 0, mylast = 0, mytfb = 0, mytfbase = 0, mytfs = 32;
         if (uint32_t(lane) < nleaf && myTerm != kEmptyTerm) {
                 const DevTerm T = P.ix.terms[myTerm];
                 mydir           = T.dir_begin;
                 mynb            = T.nblocks;
                 mydocs          = T.documents;
+                myfirst         = T.first_doc;
+                mylast          = T.last_doc;
+                mytfb           = T.tf_begin;
+                mytfbase        = T.tf_base;
+                mytfs           = T.tf_shift;
         }
         // ---- 1. the lead's blocks -> candidates
         const uint32_t dir0 = __shfl_sync(0xffffffffu, mydir, 0), nb0 = __shfl_sync(0xffffffffu, mynb, 0), docs0 = __shfl_sync(0xffffffffu, mydocs, 0);
@@ -176,9 +181,9 @@ __device__ void cand_exec_google(const ExecParams &P, const DevQuery &Q, uint32_
         // ---- 2. every other operand: keep the candidates it holds
         for (uint32_t t = 1; t < nleaf; ++t) {
                 const uint32_t  dirt = __shfl_sync(0xffffffffu, mydir, int(t)), nbt = __shfl_sync(0xffffffffu, mynb, int(t)), docst = __shfl_sync(0xffffffffu, mydocs, int(t));
-                const uint32_t  term = __shfl_sync(0xffffffffu, myTerm, int(t));
+                const uint32_t  firstt = __shfl_sync(0xffffffffu, myfirst, int(t)), lastt = __shfl_sync(0xffffffffu, mylast, int(t));
+                const uint32_t  tfbt = __shfl_sync(0xffffffffu, mytfb, int(t)), tfbaset = __shfl_sync(0xffffffffu, mytfbase, int(t)), tfst = __shfl_sync(0xffffffffu, mytfs, int(t));
                 const uint32_t *bl = P.ix.blk_last + dirt, *bo = P.ix.blk_off + dirt;
-                const uint32_t *tf = P.ix.tile_first + size_t(term == kEmptyTerm ? 0u : term) * (P.ix.ntiles + 1);
                 uint32_t        alive = 0;
                 for (uint32_t j = 0; j < rounds; ++j) {
                         const uint32_t nj = __shfl_sync(0xffffffffu, n, int(j));
@@ -189,14 +194,8 @@ __device__ void cand_exec_google(const ExecParams &P, const DevQuery &Q, uint32_
                         bool     hit = false, need = false;
                         uint32_t off = 0, prev = 0, nblk = 0;
                         if (valid && nbt) {
-                                // the one block that can hold c: first block whose last document is >= c, inside c's directory tile
-                                const uint32_t tj = min(c >> P.ix.tile_shift, P.ix.ntiles);
-                                uint32_t       lo = tf[tj], hi = min(tf[min(tj + 1u, P.ix.ntiles)], nbt);
-                                while (lo < hi) {
-                                        const uint32_t mid = (lo + hi) >> 1;
-                                        if (__ldg(bl + mid) < c) lo = mid + 1u;
-                                        else hi = mid;
-                                }
+                                // the one block that can hold c: first block whose last document is >= c
+                                const uint32_t lo = first_block_ge(P.ix, dirt, nbt, firstt, lastt, tfbt, tfbaset, tfst, c);
                                 if (lo < nbt) {
                                         const uint32_t lastv = __ldg(bl + lo);
                                         if (lastv >= c) {

@@ -22,8 +22,7 @@ struct FlatLane { // per-lane description of one (term, block) work unit
 };
 
 // returns 0 = not applicable (use the step program), 1 = handled (root docset in slot Q.root_slot), 2 = handled, result empty
-__device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t tile, uint32_t lo, uint32_t W, uint32_t NW, uint32_t fs, uint32_t *slots,
-                                uint8_t *stage, int lane) {
+__device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t lo, uint32_t W, uint32_t NW, uint32_t *slots, uint8_t *stage, int lane) {
         const bool isAnd = Q.flat == 1u;
         // lane j adopts the j-th leaf of the plan
         uint32_t nleaf = 0, myTerm = kEmptyTerm;
@@ -43,14 +42,11 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
                 mydir           = T.dir_begin;
                 mynb            = T.nblocks;
                 mydocs          = T.documents;
-                if (T.nblocks) {
-                        const uint32_t *tf = P.ix.tile_first + size_t(myTerm) * (P.ix.ntiles + 1);
-                        const uint32_t  a  = tf[min(tile << fs, P.ix.ntiles)];
-                        const uint32_t  b  = min(tf[min((tile + 1u) << fs, P.ix.ntiles)], T.nblocks - 1u);
-                        if (a < T.nblocks && a <= b) {
-                                mybA  = a;
-                                mycnt = b - a + 1u;
-                        }
+                uint32_t a, b;
+                tile_block_range(P.ix, T, lo, W, a, b);
+                if (a <= b) {
+                        mybA  = a;
+                        mycnt = b - a + 1u;
                 }
         }
         const uint32_t incl  = warp_incl_scan(uint32_t(lane) < nleaf ? mycnt : 0u, lane);

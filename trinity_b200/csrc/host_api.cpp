@@ -2,6 +2,7 @@
 // (The device half lives in engine.cu.)  No reference code is linked here; formats are pinned by tests against oracle/_ref.
 #include "../../include/trinity_b200.h"
 #include "codecs.h"
+#include "dirlookup.h"
 #include "varbyte.h"
 #include <algorithm>
 #include <atomic>
@@ -140,6 +141,68 @@ extern "C" int trn_directory_probe(int codec, const uint8_t *index, uint64_t nby
                         if (blk_off)
                                 blk_off[i] = d.blk_off[i];
                 }
+                return TRN_OK;
+        } catch (const std::exception &e) {
+                if (err && errcap) {
+                        std::strncpy(err, e.what(), errcap - 1);
+                        err[errcap - 1] = 0;
+                }
+                return TRN_ERR_FORMAT;
+        }
+}
+
+extern "C" int trn_directory_lookup(int codec, const uint8_t *index, uint64_t nbytes, const trn_term *term, const uint32_t *docids, uint32_t n, uint32_t *blocks,
+                                    uint32_t *tf_shift, uint32_t *tf_entries, char *err, size_t errcap) {
+        if (!index || !term || (n && (!docids || !blocks)) || (codec != TRN_CODEC_GOOGLE && codec != TRN_CODEC_LUCENE))
+                return TRN_ERR_ARG;
+        try {
+                term_index_ctx t;
+                t.documents = term->documents;
+                t.offset    = term->chunk_off;
+                t.size      = term->chunk_len;
+                BlockDirectory d;
+                build_block_directory(codec == TRN_CODEC_GOOGLE ? Codec::Google : Codec::Lucene, index, nbytes, &t, 1, 1, d);
+                const auto &T = d.terms[0];
+                if (tf_shift)
+                        *tf_shift = T.tf_shift;
+                if (tf_entries)
+                        *tf_entries = uint32_t(d.tile_first.size());
+                for (uint32_t i = 0; i < n; ++i)
+                        blocks[i] = T.nblocks ? dir_first_block_ge(d.blk_last.data() + T.dir_begin, d.tile_first.data() + T.tf_begin, T.nblocks, T.first_doc, T.last_doc,
+                                                                   T.tf_base, T.tf_shift, docids[i])
+                                              : 0u;
+                return TRN_OK;
+        } catch (const std::exception &e) {
+                if (err && errcap) {
+                        std::strncpy(err, e.what(), errcap - 1);
+                        err[errcap - 1] = 0;
+                }
+                return TRN_ERR_FORMAT;
+        }
+}
+
+extern "C" int trn_directory_stats(int codec, const uint8_t *index, uint64_t nbytes, const trn_term *terms, uint32_t nterms, int threads, uint64_t *directory_bytes,
+                                   uint64_t *total_blocks, uint64_t *table_entries, char *err, size_t errcap) {
+        if (!index || !terms || (codec != TRN_CODEC_GOOGLE && codec != TRN_CODEC_LUCENE))
+                return TRN_ERR_ARG;
+        try {
+                std::vector<term_index_ctx> t(nterms);
+                for (uint32_t i = 0; i < nterms; ++i) {
+                        t[i].documents = terms[i].documents;
+                        t[i].offset    = terms[i].chunk_off;
+                        t[i].size      = terms[i].chunk_len;
+                }
+                BlockDirectory d;
+                build_block_directory(codec == TRN_CODEC_GOOGLE ? Codec::Google : Codec::Lucene, index, nbytes, t.data(), nterms, std::max(1, threads), d);
+                uint64_t blocks{0};
+                for (const auto &x : d.terms)
+                        blocks += x.nblocks;
+                if (directory_bytes)
+                        *directory_bytes = d.bytes();
+                if (total_blocks)
+                        *total_blocks = blocks;
+                if (table_entries)
+                        *table_entries = d.tile_first.size();
                 return TRN_OK;
         } catch (const std::exception &e) {
                 if (err && errcap) {
@@ -712,8 +775,63 @@ void flatten(std::vector<Ast> &n, int i) {
 }
 } // namespace
 
+// == the terms dictionary an IndexSource resolves query tokens through (IndexSource::resolve_term_ctx, index_source.h:118):
+// name -> term id, built ONCE and owned by the caller as an explicit handle.
+struct trn_dict {
+        std::unordered_map<std::string, uint32_t> map;
+};
+
+extern "C" int trn_dict_create(const char *const *names, uint32_t nterms, trn_dict **out) {
+        if (!out || (nterms && !names))
+                return TRN_ERR_ARG;
+        try {
+                auto d = std::make_unique<trn_dict>();
+                d->map.reserve(size_t(nterms) * 2);
+                for (uint32_t i = 0; i < nterms; ++i) {
+                        if (!names[i])
+                                return TRN_ERR_ARG;
+                        d->map.emplace(names[i], i); // first occurrence wins, like a dictionary lookup would
+                }
+                *out = d.release();
+                return TRN_OK;
+        } catch (...) {
+                return TRN_ERR_CAPACITY;
+        }
+}
+extern "C" void trn_dict_destroy(trn_dict *d) {
+        delete d;
+}
+
+static int parse_query_impl(const char *text, const std::unordered_map<std::string, uint32_t> &dict, trn_qnode *nodes, uint32_t cap, uint32_t *nnodes, uint32_t *root,
+                            char *err, size_t errcap);
+
+extern "C" int trn_parse_query_dict(const char *text, const trn_dict *dict, trn_qnode *nodes, uint32_t cap, uint32_t *nnodes, uint32_t *root, char *err,
+                                    size_t errcap) {
+        if (!text || !dict || !nodes || !nnodes || !root)
+                return TRN_ERR_ARG;
+        return parse_query_impl(text, dict->map, nodes, cap, nnodes, root, err, errcap);
+}
+
+// convenience form: resolves through a names array; the map is rebuilt on every call (nothing is cached across calls — a caller that
+// parses many queries against one vocabulary creates a trn_dict once)
 extern "C" int trn_parse_query(const char *text, const char *const *names, uint32_t nterms, trn_qnode *nodes, uint32_t cap, uint32_t *nnodes, uint32_t *root,
                                char *err, size_t errcap) {
+        if (!text || !nodes || !nnodes || !root || (nterms && !names))
+                return TRN_ERR_ARG;
+        std::unordered_map<std::string, uint32_t> dict;
+        try {
+                dict.reserve(size_t(nterms) * 2);
+                for (uint32_t i = 0; i < nterms; ++i)
+                        if (names[i])
+                                dict.emplace(names[i], i);
+        } catch (...) {
+                return TRN_ERR_CAPACITY;
+        }
+        return parse_query_impl(text, dict, nodes, cap, nnodes, root, err, errcap);
+}
+
+static int parse_query_impl(const char *text, const std::unordered_map<std::string, uint32_t> &dict, trn_qnode *nodes, uint32_t cap, uint32_t *nnodes, uint32_t *root,
+                            char *err, size_t errcap) {
         auto seterr = [&](const std::string &m) {
                 if (err && errcap) {
                         std::strncpy(err, m.c_str(), errcap - 1);
@@ -721,20 +839,6 @@ extern "C" int trn_parse_query(const char *text, const char *const *names, uint3
                 }
                 return TRN_ERR_PARSE;
         };
-        if (!text || !nodes || !nnodes || !root)
-                return TRN_ERR_ARG;
-        // the dictionary is rebuilt per call only for small inputs; callers with big vocabularies use trn_dict_* below
-        static thread_local const char *const *                   cachedNames{nullptr};
-        static thread_local uint32_t                              cachedN{0};
-        static thread_local std::unordered_map<std::string, uint32_t> dict;
-        if (cachedNames != names || cachedN != nterms) {
-                dict.clear();
-                dict.reserve(nterms * 2);
-                for (uint32_t i = 0; i < nterms; ++i)
-                        dict.emplace(names[i], i);
-                cachedNames = names;
-                cachedN     = nterms;
-        }
         Parser ps{text, text + std::strlen(text), dict, {}, {}};
         const int r = ps.subexpr(255);
         if (r < 0)

@@ -14,6 +14,7 @@
 //   k_topk_merge   merge of per-shard top-k lists after the all-gather (multi-GPU exchange step).
 //   k_decode_terms whole-list decode (microbench + parity probe) == PostingsListIterator::next() over a list.
 #include "device_types.h"
+#include "dirlookup.h"
 #include "kernels.h"
 #include "varbyte.h"
 #include <cstdlib>
@@ -61,6 +62,27 @@ __device__ __forceinline__ uint32_t stage_copy(const uint8_t *__restrict__ index
         for (uint32_t i = lane * 16u; i < total; i += 512u)
                 *reinterpret_cast<uint4 *>(stage + i) = ld_stream_v4(index + abase + i);
         return off - abase;
+}
+
+// docID -> block lookup (dirlookup.h) over the device copy of the directory
+__device__ __forceinline__ uint32_t first_block_ge(const DevIndex &ix, uint32_t dir_begin, uint32_t nblocks, uint32_t first_doc, uint32_t last_doc, uint32_t tf_begin,
+                                                   uint32_t tf_base, uint32_t tf_shift, uint32_t d) {
+        return dir_first_block_ge(ix.blk_last + dir_begin, ix.tile_first + tf_begin, nblocks, first_doc, last_doc, tf_base, tf_shift, d);
+}
+__device__ __forceinline__ uint32_t first_block_ge(const DevIndex &ix, const DevTerm &T, uint32_t d) {
+        return first_block_ge(ix, T.dir_begin, T.nblocks, T.first_doc, T.last_doc, T.tf_begin, T.tf_base, T.tf_shift, d);
+}
+// blocks [bA, bB] of term T that can hold a document of [lo, lo + W): bA > bB when there is none
+__device__ __forceinline__ void tile_block_range(const DevIndex &ix, const DevTerm &T, uint32_t lo, uint32_t W, uint32_t &bA, uint32_t &bB) {
+        bA = 1u;
+        bB = 0u;
+        if (!T.nblocks || lo > T.last_doc || lo + (W - 1u) < T.first_doc)
+                return;
+        const uint32_t a = first_block_ge(ix, T, lo);
+        if (a >= T.nblocks)
+                return;
+        bA = a;
+        bB = min(first_block_ge(ix, T, lo + (W - 1u)), T.nblocks - 1u);
 }
 
 // BM25 per-posting score == IndexSourcesCollectionBM25Scorer::Scorer::score (similarity.h:228-235)
@@ -525,16 +547,7 @@ __global__ void __launch_bounds__(kThreads) k_exec_tiles(ExecParams P) {
                                 uint32_t       bA = 1, bB = 0;
                                 if (haveTerm) {
                                         T = P.ix.terms[st.term];
-                                        if (T.nblocks) {
-                                                const uint32_t *tf = P.ix.tile_first + size_t(st.term) * (P.ix.ntiles + 1);
-                                                const uint32_t  fs = P.exec_shift - P.ix.tile_shift; // exec tile = 2^fs directory tiles
-                                                bA                 = tf[min(tile << fs, P.ix.ntiles)];
-                                                bB                 = min(tf[min((tile + 1u) << fs, P.ix.ntiles)], T.nblocks - 1u);
-                                                if (bA >= T.nblocks) {
-                                                        bA = 1;
-                                                        bB = 0;
-                                                }
-                                        }
+                                        tile_block_range(P.ix, T, lo, W, bA, bB);
                                 }
                                 // prepare destination
                                 if (mode == M_SET) {

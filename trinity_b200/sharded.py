@@ -59,3 +59,17 @@ def concat_docs_only(dist, local_docids: np.ndarray) -> np.ndarray:
     parts = [torch.zeros(mx, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(parts, buf)
     return np.concatenate([p[: int(s)].numpy() for p, s in zip(parts, sizes)]).astype(np.uint32)
+
+
+def device_view(ptr: int, n: int, dtype):
+    """a torch tensor aliasing `n` 4-byte elements of device memory at `ptr` (no copy): how the engine's own device result buffers
+    (trn_last_topk_device) enter torch.distributed collectives without a host round trip"""
+    import torch
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4" if dtype == torch.int32 else "<f4", "data": (int(ptr), False), "version": 3,
+                                  "strides": None}
+    return torch.as_tensor(h, device="cuda")
