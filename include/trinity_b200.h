@@ -236,6 +236,18 @@ typedef struct trn_result {
  * batched (gpu_exec_queries).  H2D of the plans and D2H of the results are part of the call. */
 int trn_exec_batch(trn_ctx *, const trn_query *queries, uint32_t nq, int mode, uint32_t k, trn_result *out);
 
+/* Host-side wall-clock breakdown of the last trn_exec_batch / trn_exec_batch_device call of this ctx (milliseconds): where a rank's
+ * end-to-end time goes when several ranks share one host (bench.py prints it per rank). */
+typedef struct trn_timings {
+        float host_compile_ms; /* plan compilation (== build_iterator + build_span per query, exec.cpp:253-505) */
+        float enqueue_ms;      /* buffer sizing, plan H2D and kernel launches (asynchronous enqueue) */
+        float chunk_wait_ms;   /* pipelined call: blocked until a chunk's kernels finished (its counts are needed to size the result copy) */
+        float final_wait_ms;   /* blocked at the end: last kernels + result D2H */
+        float kernel_ms;       /* CUDA-event time of the fused exec kernels (device) */
+        float total_ms;        /* the whole call */
+} trn_timings;
+int trn_last_timings(trn_ctx *, trn_timings *out);
+
 /* Split form used by bench.py / multi-GPU: run on device only, results stay in HBM ... */
 int trn_exec_batch_device(trn_ctx *, const trn_query *queries, uint32_t nq, int mode, uint32_t k, trn_result *out_counts_only);
 /* ... device pointers of the last SCORED_TOPK run: nq*k u32 docids, nq*k f32 scores (unused slots: docid 0, score -1.0; real scores are >= 0), nq u32 counts */

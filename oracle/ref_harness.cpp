@@ -17,6 +17,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
 #include <queue>
 #include <string>
 #include <thread>
@@ -653,4 +656,164 @@ double tref_exec_batch(void *h, const char *const *qs, uint32_t nq, int mode, ui
         }
         return el;
 }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// The BASELINE.md synthetic Zipfian index authored by the REFERENCE's own Encoders, so that bench.py's --impl reference
+// arm never maps the product library: V terms, df_r = max(min_df, floor(0.5 * N / r)), geometric docID gaps from splitmix64(seed ^ r),
+// freq = 1 + min(7, Geom(1/2)), positions cumulative 2..17 — the same workload generator as trn_synth_build (restated here; the two are
+// held byte-equal by tests/test_codecs_cpu.py).  Terms are encoded in parallel, one reference IndexSession per term; the one piece of
+// encoder state that survives end_term() — the Google skiplist countdown (google_codec.h:57) — is reproduced through the public API by
+// encoding a throw-away term with (blocks committed so far mod 8) blocks first.
+namespace {
+        inline uint64_t sm64(uint64_t &s) {
+                uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+                z          = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                z          = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+                return z ^ (z >> 31);
+        }
+        inline uint32_t synth_df(uint32_t ndocs, uint32_t rank, uint32_t min_df) {
+                const uint64_t z = uint64_t(ndocs) / (2ull * rank);
+                return uint32_t(std::min<uint64_t>(ndocs, std::max<uint64_t>(min_df, z)));
+        }
+        template <class F>
+        void synth_term(uint32_t ndocs, uint32_t rank, uint32_t min_df, uint64_t seed, F &&f) {
+                const uint32_t df = synth_df(ndocs, rank, min_df);
+                uint64_t       s  = seed ^ uint64_t(rank);
+                uint64_t       s2 = (seed ^ uint64_t(rank)) * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull;
+                const double   p  = double(df) / double(ndocs);
+                const double   il = p < 1.0 ? 1.0 / std::log1p(-p) : 0.0;
+                uint64_t       doc{0};
+                for (uint32_t i = 0; i < df; ++i) {
+                        const uint64_t x = sm64(s);
+                        uint64_t       gap{1};
+                        if (p < 1.0) {
+                                const double u = double((x >> 11) + 1) * (1.0 / 9007199254740992.0);
+                                const double g = std::floor(std::log(u) * il);
+                                gap            = 1 + uint64_t(std::min(g, 4.0e9));
+                        }
+                        const uint64_t maxdoc = uint64_t(ndocs) - (df - 1 - i);
+                        doc                   = std::min(doc + gap, maxdoc);
+                        const uint32_t geo    = uint32_t(__builtin_ctzll((x & 0x7ffull) | 0x800ull));
+                        f(uint32_t(doc), 1 + std::min<uint32_t>(7, geo), sm64(s2));
+                }
+        }
+} // namespace
+
+extern "C" void *tref_synth_build(int codec, uint32_t ndocs, uint32_t nterms, uint32_t min_df, uint64_t seed, int with_hits, int threads) {
+        struct Part {
+                std::vector<uint8_t> index, hits;
+                uint32_t             documents{0};
+                uint64_t             hitsCnt{0};
+        };
+        std::vector<Part>     parts(nterms);
+        std::vector<uint32_t> warm(nterms, 0); // Google: blocks the throw-away term must commit first
+        if (codec == 0) {
+                uint64_t blocks{0};
+                for (uint32_t r = 1; r <= nterms; ++r) {
+                        warm[r - 1] = uint32_t(blocks % Codecs::Google::SKIPLIST_STEP);
+                        blocks += (synth_df(ndocs, r, min_df) + Codecs::Google::N - 1) / Codecs::Google::N;
+                }
+        }
+        std::atomic<uint32_t> next{0};
+        std::atomic<int>      failed{0};
+        auto                  worker = [&] {
+                try {
+                        for (;;) {
+                                const uint32_t i = next.fetch_add(1);
+                                if (i >= nterms || failed.load())
+                                        break;
+                                std::unique_ptr<Codecs::IndexSession> sess;
+                                if (codec == 0)
+                                        sess.reset(new Codecs::Google::IndexSession("/tmp"));
+                                else
+                                        sess.reset(new Codecs::Lucene::IndexSession("/tmp"));
+                                sess->begin();
+                                std::unique_ptr<Codecs::Encoder> enc(sess->new_encoder());
+                                term_index_ctx                   t;
+                                if (warm[i]) { // full blocks except the last, which end_term() commits with a single document
+                                        enc->begin_term();
+                                        const uint32_t ndummy = uint32_t(Codecs::Google::N) * (warm[i] - 1) + 1;
+                                        for (uint32_t d = 1; d <= ndummy; ++d) {
+                                                enc->begin_document(d);
+                                                enc->new_hit(1, {});
+                                                enc->end_document();
+                                        }
+                                        enc->end_term(&t);
+                                }
+                                auto &P = parts[i];
+                                enc->begin_term();
+                                synth_term(ndocs, i + 1, min_df, seed, [&](uint32_t doc, uint32_t freq, uint64_t y) {
+                                        enc->begin_document(doc);
+                                        uint32_t pos{0};
+                                        for (uint32_t h = 0; h < freq; ++h) {
+                                                pos = with_hits ? pos + 2u + uint32_t((y >> (4u * h)) & 15u) : h + 1;
+                                                enc->new_hit(pos, {});
+                                        }
+                                        P.hitsCnt += freq;
+                                        enc->end_document();
+                                });
+                                enc->end_term(&t);
+                                const auto *ib = reinterpret_cast<const uint8_t *>(sess->indexOut.data());
+                                P.index.assign(ib + t.indexChunk.offset, ib + t.indexChunk.offset + t.indexChunk.size());
+                                P.documents = t.documents;
+                                if (codec == 1) {
+                                        auto ls = static_cast<Codecs::Lucene::IndexSession *>(sess.get());
+                                        P.hits.assign(reinterpret_cast<const uint8_t *>(ls->positionsOut.data()),
+                                                      reinterpret_cast<const uint8_t *>(ls->positionsOut.data()) + ls->positionsOut.size());
+                                }
+                        }
+                } catch (...) {
+                        failed.store(1);
+                }
+        };
+        std::vector<std::thread> ths;
+        for (int i = 1; i < std::max(1, threads); ++i)
+                ths.emplace_back(worker);
+        worker();
+        for (auto &t : ths)
+                t.join();
+        if (failed.load()) {
+                g_err = "tref_synth_build: a reference encoder failed";
+                return nullptr;
+        }
+        uint64_t ib{0}, hb{0};
+        for (auto &p : parts) {
+                ib += p.index.size();
+                hb += p.hits.size();
+        }
+        if (ib >= (1ull << 32) || hb >= (1ull << 32)) {
+                g_err = "tref_synth_build: index larger than range32_t";
+                return nullptr;
+        }
+        auto x   = new RefIndex();
+        x->codec = codec;
+        x->index.resize(ib);
+        x->hits.resize(hb);
+        uint64_t io{0}, ho{0};
+        char     name[16];
+        for (uint32_t i = 0; i < nterms; ++i) {
+                auto &p = parts[i];
+                std::memcpy(x->index.data() + io, p.index.data(), p.index.size());
+                if (codec == 1) { // the chunk header's first u32 is the term's absolute offset into hits.data (lucene_codec.cpp:178)
+                        const uint32_t v = uint32_t(ho);
+                        std::memcpy(x->index.data() + io, &v, 4);
+                        if (!p.hits.empty())
+                                std::memcpy(x->hits.data() + ho, p.hits.data(), p.hits.size());
+                }
+                snprintf(name, sizeof(name), "t%04u", i + 1);
+                x->names.emplace_back(name);
+                x->tctx.emplace_back(p.documents, range32_t{uint32_t(io), uint32_t(p.index.size())});
+                x->sumHits += p.hitsCnt;
+                io += p.index.size();
+                ho += p.hits.size();
+                std::vector<uint8_t>().swap(p.index);
+                std::vector<uint8_t>().swap(p.hits);
+        }
+        if (guarded([&] { x->open(ndocs); })) {
+                delete x;
+                return nullptr;
+        }
+        return x;
 }

@@ -55,6 +55,8 @@ class RefLib:
         L.tref_exec_masked.argtypes = [vp, C.c_char_p, C.c_int, vp, u32, vp, vp, u64]
         L.tref_exec_batch.restype = C.c_double
         L.tref_exec_batch.argtypes = [vp, vp, u32, C.c_int, u32, C.c_int, vp, vp, vp, vp]
+        L.tref_synth_build.restype = vp
+        L.tref_synth_build.argtypes = [C.c_int, u32, u32, u32, u64, C.c_int, C.c_int]
         L.tref_last_error.restype = C.c_char_p
         L.tref_segment_write.argtypes = [C.c_int, C.c_char_p, u32, vp, vp, vp, vp, vp, u32, u32]
         L.tref_segment_open.restype = vp
@@ -125,6 +127,16 @@ class RefIndex:
             raise RuntimeError(rl.err())
         x = cls(rl, codec, C.c_void_p(h))
         x.names = list(names)
+        return x
+
+    @classmethod
+    def synth_build(cls, rl, codec, ndocs, nterms, min_df=1000, seed=0x5EED, with_hits=True, threads=1):
+        """the BASELINE.md synthetic index authored by the reference's own Encoders (no product code involved)"""
+        h = rl.L.tref_synth_build(codec, ndocs, nterms, min_df, seed, int(with_hits), threads)
+        if not h:
+            raise RuntimeError(rl.err())
+        x = cls(rl, codec, C.c_void_p(h))
+        x.names = [f"t{r:04d}" for r in range(1, nterms + 1)]
         return x
 
     def add_term(self, name, docids, freqs, positions=None):

@@ -143,3 +143,29 @@ def test_synth_docid_shards_partition_the_index(ref, codec):
         assert np.all(mine[diff] == 0) and (codec == tb.CODEC_LUCENE or diff.size == 0)
     for rank in range(1, nterms + 1):
         assert counts[rank - 1] == max(min_df, ndocs // (2 * rank))
+
+
+def test_reference_authored_synthetic_index_is_the_same_workload(ref):
+    """bench.py's --impl reference arm authors its index with the reference's own Encoders (tref_synth_build: one IndexSession per term,
+    in parallel) so that it never loads the product library.  GOOGLE: byte-identical to the product builder's index (term tuples too).
+    LUCENE: identical term tuples (sizes, offsets) and identical decoded postings; the bytes may differ in don't-care padding bits of the
+    FastPFor pages (a fresh reference Encoder packs from uninitialised scratch buffers)."""
+    from refharness import RefIndex
+    ndocs, nterms, min_df = 300_000, 48, 70
+    for codec in (tb.CODEC_GOOGLE, tb.CODEC_LUCENE):
+        r = RefIndex.synth_build(ref, codec, ndocs, nterms, min_df=min_df, threads=3)
+        s = tb.SynthIndex(codec, ndocs, nterms, min_df=min_df, threads=2)
+        assert np.array_equal(r.terms(), np.asarray(s.terms))
+        if codec == tb.CODEC_GOOGLE:
+            assert np.array_equal(r.index(), np.asarray(s.index))
+        assert len(r.hits()) == len(np.asarray(s.hits))
+        for ti in (0, 1, 7, nterms - 1):
+            d, f = tb.SynthIndex.postings(ndocs, ti + 1, min_df)
+            rd, rf = r.decode(ti, len(d) + 4)
+            assert np.array_equal(rd, d) and np.array_equal(rf, f)
+        # and it executes: the reference's exec_query over its own index == over the product builder's bytes
+        r2 = RefIndex.from_bytes(ref, codec, np.asarray(s.index), np.asarray(s.hits), s.names, np.asarray(s.terms), ndocs, s.sum_hits)
+        for q in ("t0001 AND t0002", "t0003 OR t0040 OR t0011"):
+            a, _ = r.exec(q, False, ndocs + 1)
+            b, _ = r2.exec(q, False, ndocs + 1)
+            assert np.array_equal(a, b)

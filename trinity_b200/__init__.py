@@ -12,7 +12,7 @@ from typing import Iterable, List, Optional, Sequence
 
 import numpy as np
 
-from ._ffi import QNODE_DTYPE, TERM_DTYPE, TrnIndexInfo, TrnQuery, TrnResult, TrnTerm, lib
+from ._ffi import QNODE_DTYPE, TERM_DTYPE, TrnIndexInfo, TrnQuery, TrnResult, TrnTerm, TrnTimings, lib
 
 CODEC_GOOGLE, CODEC_LUCENE = 0, 1
 MODE_DOCS_ONLY, MODE_SCORED_ALL, MODE_SCORED_TOPK = 0, 1, 2  # == ExecFlags::DocumentsOnly / AccumulatedScoreScheme (+ fused top-k sink)
@@ -361,6 +361,12 @@ class GpuIndexSource:
         self._ck(self._L.trn_exec_batch(self._h, C.cast(arr, C.c_void_p), len(queries), mode, k, C.byref(r)))
         self._last = (mode, k, len(queries))
         return self._wrap(r, mode, k, copy)
+
+    def last_timings(self) -> dict:
+        """host-side breakdown (ms) of the last exec_batch / exec_batch_device call"""
+        t = TrnTimings()
+        self._ck(self._L.trn_last_timings(self._h, C.byref(t)))
+        return {n: float(getattr(t, n)) for n, _ in TrnTimings._fields_}
 
     def last_topk_device(self):
         d, s, c = C.c_void_p(), C.c_void_p(), C.c_void_p()

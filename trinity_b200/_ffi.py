@@ -19,7 +19,7 @@ EXPORTS = [
     "trn_directory_probe", "trn_directory_stats", "trn_directory_lookup", "trn_dict_create", "trn_dict_destroy", "trn_parse_query_dict", "trn_segment_open", "trn_segment_close", "trn_segment_info", "trn_segment_index", "trn_segment_terms",
     "trn_segment_masked", "trn_parse_query", "trn_query_truth_table", "trn_debug_compile", "trn_bm25_idf", "trn_bm25_score",
     "trn_create", "trn_destroy", "trn_last_error", "trn_set_stream", "trn_upload_index", "trn_set_masked_documents", "trn_index_info_get",
-    "trn_exec_batch", "trn_exec_batch_device", "trn_last_topk_device", "trn_merge_topk", "trn_fetch_results",
+    "trn_exec_batch", "trn_exec_batch_device", "trn_last_topk_device", "trn_merge_topk", "trn_fetch_results", "trn_last_timings",
     "trn_decode_terms",
 ]
 
@@ -48,6 +48,10 @@ class TrnResult(C.Structure):
                 ("docids", C.POINTER(C.c_uint32)), ("scores", C.POINTER(C.c_float)),
                 ("match_counts", C.POINTER(C.c_uint64)), ("postings_scanned", C.c_uint64),
                 ("index_bytes_touched", C.c_uint64), ("kernel_launches", C.c_uint32), ("device_ms", C.c_float), ("exec_kernel_ms", C.c_float)]
+
+
+class TrnTimings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("host_compile_ms", "enqueue_ms", "chunk_wait_ms", "final_wait_ms", "kernel_ms", "total_ms")]
 
 
 _lib = None
@@ -120,6 +124,7 @@ def lib() -> C.CDLL:
     sig("trn_last_topk_device", i32, vp, P(vp), P(vp), P(vp))
     sig("trn_merge_topk", i32, vp, vp, vp, u32, u32, u32, vp, vp)
     sig("trn_fetch_results", i32, vp, P(TrnResult))
+    sig("trn_last_timings", i32, vp, P(TrnTimings))
     sig("trn_decode_terms", i32, vp, vp, u32, i32, vp, vp, vp, P(C.c_float))
     _lib = L
     return L

@@ -65,10 +65,49 @@ struct DevQuery {
         uint32_t root_slot;
         uint32_t cand_base; // SCORED_TOPK: first candidate slot of this query
         uint32_t cand_cap;
+        uint32_t gen_base; // k_exec_tiles: the query's first item in that kernel's own ticket space (queries run by k_score_flat own none)
         uint32_t flat; // 0 = general step program; 1 = conjunction of terms only; 2 = disjunction of terms only (see exec_docs_flat.cuh);
                        // 3 = candidate-driven (exec_docs_cand.cuh): items are 32-block groups of a lead term every match must hold; the
                        //     step program is replaced by [OP_LEAF lead, OP_LEAF other terms..., OP_TABLE...]: root_slot = number of NECESSARY
                        //     terms (they come first), the truth table decides over the membership bits of the others
+};
+
+// ---- flat scored disjunctions (k_score_flat, score_flat.cuh)
+struct FlatLeaf {
+        uint32_t term; // kEmptyTerm: the query names a term this index source does not hold
+        uint32_t pad;
+        double   idf;
+};
+static_assert(sizeof(FlatLeaf) == 16, "FlatLeaf layout");
+struct FlatQuery {
+        uint32_t qid; // position in the batch: match_counts / theta / cand_cursor index
+        uint32_t leaf_begin, nleaf;
+        uint32_t tile_lo, ntiles;
+        uint32_t nruns;      // top-k: ceil(ntiles / run_tiles) work items
+        uint32_t cand_base, cand_cap;
+        uint32_t item_base;  // scored-all: the query's first (query, tile) item in the batch-wide segment arrays
+        uint32_t local_base; // scored-all: the query's first item in this kernel's own ticket space
+};
+struct ScoreParams {
+        DevIndex         ix;
+        const FlatQuery *fq;
+        const FlatLeaf * leaves;
+        const float *    luts; // [leaf][64]
+        uint32_t         nflat, total_items, run_tiles, tile_shift;
+        int              mode; // TRN_MODE_SCORED_ALL / TRN_MODE_SCORED_TOPK
+        uint32_t         k;
+        uint32_t *       ticket;
+        unsigned long long *match_counts;
+        uint32_t *          theta;
+        uint32_t *          cand_cursor;
+        uint2 *             cand;
+        unsigned long long *seg_cursor;
+        uint64_t            seg_capacity;
+        uint32_t *          seg_docids;
+        float *             seg_scores;
+        uint64_t *          item_off;
+        uint32_t *          item_cnt;
+        uint32_t *          overflow;
 };
 
 struct ExecParams {
@@ -77,6 +116,7 @@ struct ExecParams {
         const DevStep * steps;
         uint32_t        nq;
         uint32_t        total_items;
+        uint32_t        gen_items; // k_exec_tiles: number of tickets (items of the queries it runs)
         uint32_t        nslots; // bitmap slots per worker (CTA for k_exec_tiles, warp for k_exec_docs)
         uint32_t        stage_bytes; // per-warp staging bytes of k_exec_tiles (codec dependent)
         uint32_t        docs_stage_bytes; // per-warp staging bytes of k_exec_docs (1 or 2 gather buffers)

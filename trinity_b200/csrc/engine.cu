@@ -11,6 +11,8 @@
 #include "kernels.h"
 #include <algorithm>
 #include <array>
+#include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -89,13 +91,15 @@ struct trn_ctx {
         uint32_t             nterms{0}, max_docid{0}, tile_shift{13}, ntiles{0}; // tile_shift: directory granularity == scored tile (8192 docs, the reference's window docset_spans.h:74)
         int                  docs_bufs{1};   // gather staging buffers per warp in k_exec_docs (TRN_DOCS_BUFS): 1 = 32 resident warps/SM beats 2 = prefetch at 24 warps (measured 49 vs 53 ms)
         uint32_t             docs_shift{14}; // docID tile (log2) of the warp-per-tile DocumentsOnly kernel
+        uint32_t             run_tiles{32};  // TRN_RUN_TILES: consecutive tiles per work item of the flat scored kernel (top-k state lives across a run)
+        int                  flat_scored{1}; // TRN_FLAT_SCORED=0: every scored query through the general step-program kernel (A/B switch)
         uint64_t             index_bytes{0}, dir_bytes{0}, total_blocks{0}, total_postings{0};
         DevBuf               d_index, d_blk_last, d_blk_off, d_terms, d_tile_first, d_masked;
         bool                 have_masked{false};
         std::vector<DevTerm> h_terms;
         // batch scratch (grow-only)
         DevBuf d_queries, d_steps, d_small[2], d_item_off, d_item_cnt, d_item_dst, d_seg_docids, d_seg_scores, d_out_docids[2], d_out_scores[2], d_q_offsets[2], d_cand,
-            d_topk_docids, d_topk_scores, d_topk_counts, d_dec_a, d_dec_b, d_dec_c, d_dec_docids, d_dec_freqs, d_dec_sums, d_merge_docids, d_merge_scores;
+            d_topk_docids, d_topk_scores, d_topk_counts, d_fq, d_leaves, d_luts, d_dec_a, d_dec_b, d_dec_c, d_dec_docids, d_dec_freqs, d_dec_sums, d_merge_docids, d_merge_scores;
         PinBuf h_offsets, h_docids, h_scores, h_counts, h_small, h_chunk;
         cudaEvent_t ev0{nullptr}, ev1{nullptr}, evk0{nullptr}, evk1{nullptr};
         bool        have_kernel_events{false};
@@ -104,6 +108,8 @@ struct trn_ctx {
         cudaEvent_t  ev_done[2]{nullptr, nullptr}, ev_d2h[2]{nullptr, nullptr}, ev_ck0[16]{}, ev_ck1[16]{};
         uint32_t     pipeline_chunks{4};
         uint64_t     last_total_hint{0};
+        // host-side breakdown of the last trn_exec_batch / trn_exec_batch_device call (trn_last_timings)
+        trn_timings tm{};
         // last batch
         int      last_mode{-1};
         uint32_t last_nq{0}, last_k{0}, last_launches{0};
@@ -119,6 +125,10 @@ struct trn_ctx {
                         return TRN_ERR_CUDA;                                                                                                                   \
                 }                                                                                                                                              \
         } while (0)
+
+static inline double now_ms() {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 static int fail(trn_ctx *c, int code, const std::string &m) {
         c->err = m;
@@ -613,6 +623,13 @@ extern "C" int trn_create(int device, trn_ctx **out) {
                 if (v >= 13 && v <= 17)
                         c->docs_shift = uint32_t(v);
         }
+        if (const char *e = getenv("TRN_RUN_TILES")) {
+                const int v = atoi(e);
+                if (v >= 1 && v <= 4096)
+                        c->run_tiles = uint32_t(v);
+        }
+        if (const char *e = getenv("TRN_FLAT_SCORED"))
+                c->flat_scored = atoi(e) != 0;
         if (const char *e = getenv("TRN_PIPELINE_CHUNKS")) {
                 const int v = atoi(e);
                 if (v >= 1 && v <= 16)
@@ -640,7 +657,7 @@ extern "C" void trn_destroy(trn_ctx *c) {
         cudaSetDevice(c->device);
         for (DevBuf *b : {&c->d_index, &c->d_blk_last, &c->d_blk_off, &c->d_terms, &c->d_tile_first, &c->d_masked, &c->d_queries, &c->d_steps, &c->d_small[0], &c->d_small[1], &c->d_item_off,
                           &c->d_item_cnt, &c->d_item_dst, &c->d_seg_docids, &c->d_seg_scores, &c->d_out_docids[0], &c->d_out_docids[1], &c->d_out_scores[0], &c->d_out_scores[1], &c->d_q_offsets[0], &c->d_q_offsets[1], &c->d_cand,
-                          &c->d_topk_docids, &c->d_topk_scores, &c->d_topk_counts, &c->d_dec_a, &c->d_dec_b, &c->d_dec_c, &c->d_dec_docids, &c->d_dec_freqs,
+                          &c->d_topk_docids, &c->d_topk_scores, &c->d_topk_counts, &c->d_fq, &c->d_leaves, &c->d_luts, &c->d_dec_a, &c->d_dec_b, &c->d_dec_c, &c->d_dec_docids, &c->d_dec_freqs,
                           &c->d_dec_sums, &c->d_merge_docids, &c->d_merge_scores})
                 b->release();
         for (PinBuf *b : {&c->h_offsets, &c->h_docids, &c->h_scores, &c->h_counts, &c->h_small, &c->h_chunk})
@@ -987,8 +1004,13 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         uint32_t execShift = scored ? c->tile_shift : c->docs_shift;
         execShift          = std::max(execShift, c->tile_shift);
 
-        std::vector<DevQuery> hq(nq);
-        std::vector<DevStep>  steps;
+        const double           tCompile0 = now_ms();
+        std::vector<DevQuery>  hq(nq);
+        std::vector<DevStep>   steps;
+        std::vector<FlatQuery> fqs;    // queries k_score_flat runs
+        std::vector<FlatLeaf>  leaves;
+        uint64_t               genItems{0}, flatItems{0};
+        uint32_t               maxRuns{0};
         uint32_t              maxSlots{1};
         bool                  anyCandidate{false}, anyMembership{false};
         uint64_t              items{0}, segCap{0}, candTotal{0}, postings{0}, bytes{0};
@@ -1019,10 +1041,49 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                                 }
                         }
                 }
-                maxSlots     = std::max(maxSlots, cc.next_slot + 1); // + scratch slot
                 postings += cc.postings;
                 bytes += cc.bytes;
                 const Range r = cc.range(cc.root); // cc.root: the effective root (see apply_reference_root_filter_quirk)
+                // Flat scored disjunction (a k-term OR / a single term, every leaf scoring with a weight >= +0.0) on the LUCENE codec:
+                // k_score_flat (score_flat.cuh) instead of the step program
+                bool flatScored{false};
+                if (scored && c->flat_scored && c->codec == TRN_CODEC_LUCENE && execShift >= 13) {
+                        const auto &R = Q.nodes[cc.root];
+                        uint32_t    f0{cc.root}, nl{1};
+                        bool        ok = R.kind == TRN_NODE_TERM;
+                        if (R.kind == TRN_NODE_OR && R.nchildren <= score_flat_max_leaves()) {
+                                ok = true;
+                                f0 = R.first_child;
+                                nl = R.nchildren;
+                                for (uint32_t ch = 0; ch < nl; ++ch)
+                                        ok &= Q.nodes[f0 + ch].kind == TRN_NODE_TERM;
+                        }
+                        for (uint32_t ch = 0; ok && ch < nl; ++ch) {
+                                const double w = Q.nodes[f0 + ch].weight;
+                                ok             = std::isfinite(w) && !std::signbit(w); // the -0.0f "untouched" sentinel of the score tile needs contributions >= +0.0
+                        }
+                        if (ok) {
+                                flatScored = true;
+                                steps.resize(dq.step_begin); // no step program
+                                dq.nsteps = 0;
+                                dq.flat   = 4u;
+                                FlatQuery fq;
+                                std::memset(&fq, 0, sizeof(fq));
+                                fq.qid        = q;
+                                fq.leaf_begin = uint32_t(leaves.size());
+                                fq.nleaf      = nl;
+                                for (uint32_t ch = 0; ch < nl; ++ch) {
+                                        FlatLeaf L;
+                                        L.term = Q.nodes[f0 + ch].term;
+                                        L.pad  = 0;
+                                        L.idf  = Q.nodes[f0 + ch].weight;
+                                        leaves.push_back(L);
+                                }
+                                fqs.push_back(fq);
+                        }
+                }
+                if (!flatScored)
+                        maxSlots = std::max(maxSlots, cc.next_slot + 1); // + scratch slot
                 // Candidate-driven evaluation (exec_docs_cand.cuh) when some term that EVERY match must hold is sparse: cost follows that
                 // lead's postings (~cand_cost/2 warp-instructions per 32 candidates and probed term; the crossover was tuned on the and2
                 // workload: 900 beats 450 and 1500) instead of the docID space (~1500 per tile + ~27 per block in it, profiles/r01_l_*).
@@ -1146,19 +1207,37 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                         dq.ntiles  = (r.hi >> execShift) - dq.tile_lo + 1;
                 }
                 dq.item_base = uint32_t(items);
+                dq.gen_base  = uint32_t(genItems);
                 items += dq.ntiles;
+                if (!flatScored)
+                        genItems += dq.ntiles;
                 if (items >= (1ull << 32))
                         return fail(c, TRN_ERR_CAPACITY, "batch has more than 2^32 (query, tile) work items; split it");
                 const uint64_t width = r.empty() ? 0 : uint64_t(r.hi) - r.lo + 1;
                 segCap += std::min(cc.bound(cc.root), width);
                 dq.cand_base = uint32_t(candTotal);
                 dq.cand_cap  = uint32_t(std::min<uint64_t>(uint64_t(dq.ntiles) * k, 0xffffffffull));
+                if (flatScored) {
+                        auto &fq      = fqs.back();
+                        fq.tile_lo    = dq.tile_lo;
+                        fq.ntiles     = dq.ntiles;
+                        fq.nruns      = (dq.ntiles + c->run_tiles - 1u) / c->run_tiles;
+                        fq.item_base  = dq.item_base;
+                        fq.local_base = uint32_t(flatItems);
+                        flatItems += dq.ntiles;
+                        maxRuns     = std::max(maxRuns, fq.nruns);
+                        dq.cand_cap = uint32_t(std::min<uint64_t>(uint64_t(fq.nruns) * k, 0xffffffffull));
+                        fq.cand_base = dq.cand_base;
+                        fq.cand_cap  = dq.cand_cap;
+                }
                 if (mode == TRN_MODE_SCORED_TOPK) {
                         candTotal += dq.cand_cap;
                         if (candTotal >= (1ull << 32))
                                 return fail(c, TRN_ERR_CAPACITY, "top-k candidate space exceeds 2^32 entries; split the batch");
                 }
         }
+        c->tm.host_compile_ms += float(now_ms() - tCompile0);
+        const double   tEnqueue0  = now_ms();
         const uint32_t totalItems = uint32_t(items);
         if (anyCandidate) { // the candidate array + one gather buffer must fit a warp's share of shared memory
                 const uint32_t slotBytes = (1u << execShift) / 8u, stageB = exec_docs_stage_bytes(c->docs_bufs), need = exec_docs_cand_smem_bytes(anyMembership);
@@ -1200,6 +1279,14 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 CK(c->d_topk_scores.ensure(size_t(nq) * k * 4));
                 CK(c->d_topk_counts.ensure(size_t(nq) * 4));
         }
+        const uint32_t nflat = uint32_t(fqs.size());
+        if (nflat) {
+                CK(c->d_fq.ensure(fqs.size() * sizeof(FlatQuery)));
+                CK(c->d_leaves.ensure(leaves.size() * sizeof(FlatLeaf)));
+                CK(c->d_luts.ensure(leaves.size() * 64 * sizeof(float)));
+                CK(cudaMemcpyAsync(c->d_fq.p, fqs.data(), fqs.size() * sizeof(FlatQuery), cudaMemcpyHostToDevice, c->stream));
+                CK(cudaMemcpyAsync(c->d_leaves.p, leaves.data(), leaves.size() * sizeof(FlatLeaf), cudaMemcpyHostToDevice, c->stream));
+        }
         uint8_t *small        = c->d_small[set].as<uint8_t>();
         auto *   ticket       = reinterpret_cast<uint32_t *>(small);
         auto *   seg_cursor   = reinterpret_cast<unsigned long long *>(small + 8);
@@ -1222,6 +1309,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         P.steps        = c->d_steps.as<DevStep>();
         P.nq           = nq;
         P.total_items  = totalItems;
+        P.gen_items    = uint32_t(genItems);
         P.nslots       = maxSlots;
         P.exec_shift   = execShift;
         P.stage_bytes  = exec_stage_bytes(c->codec);
@@ -1243,20 +1331,55 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
 
         uint32_t launches{0};
         if (totalItems) {
-                const bool warpKernel = !scored;
-                const int  perSM      = warpKernel ? exec_docs_max_ctas_per_sm(execShift, maxSlots, exec_docs_stage_bytes(c->docs_bufs)) : exec_max_ctas_per_sm(execShift, maxSlots, mode, c->codec);
-                if (perSM <= 0)
-                        return fail(c, TRN_ERR_CUDA, "the exec kernel does not fit on an SM with this many docset slots");
-                const uint64_t workers = warpKernel ? (uint64_t(totalItems) + 3) / 4 : totalItems; // 4 warp-workers per CTA
-                const int      grid    = int(std::min<uint64_t>(uint64_t(c->num_sms) * perSM, std::max<uint64_t>(1, workers)));
+                const bool     warpKernel = !scored;
+                const uint64_t ownItems   = warpKernel ? totalItems : genItems; // (query, tile) items of the step-program kernel
                 CK(cudaEventRecord(k0, c->stream));
-                if (warpKernel)
-                        CK(launch_exec_docs(P, grid, c->stream));
-                else
-                        CK(launch_exec_tiles(P, grid, c->stream));
+                if (nflat && flatItems) {
+                        // flat scored disjunctions: per-leaf BM25 tables once per batch, then k_score_flat
+                        ScoreParams S;
+                        std::memset(&S, 0, sizeof(S));
+                        S.ix           = P.ix;
+                        S.fq           = c->d_fq.as<FlatQuery>();
+                        S.leaves       = c->d_leaves.as<FlatLeaf>();
+                        S.luts         = c->d_luts.as<float>();
+                        S.nflat        = nflat;
+                        S.run_tiles    = c->run_tiles;
+                        S.total_items  = mode == TRN_MODE_SCORED_TOPK ? uint32_t(std::min<uint64_t>(uint64_t(maxRuns) * nflat, 0xffffffffull)) : uint32_t(flatItems);
+                        S.tile_shift   = execShift;
+                        S.mode         = mode;
+                        S.k            = k;
+                        S.ticket       = reinterpret_cast<uint32_t *>(small + 4);
+                        S.match_counts = match_counts;
+                        S.theta        = theta;
+                        S.cand_cursor  = cand_cursor;
+                        S.cand         = P.cand;
+                        S.seg_cursor   = seg_cursor;
+                        S.seg_capacity = segCap;
+                        S.seg_docids   = P.seg_docids;
+                        S.seg_scores   = P.seg_scores;
+                        S.item_off     = P.item_off;
+                        S.item_cnt     = P.item_cnt;
+                        S.overflow     = overflow;
+                        if (uint64_t(maxRuns) * nflat >= (1ull << 32))
+                                return fail(c, TRN_ERR_CAPACITY, "batch has more than 2^32 (run, query) work items; split it");
+                        CK(launch_build_luts(S.leaves, uint32_t(leaves.size()), c->d_luts.as<float>(), c->stream));
+                        CK(launch_score_flat(S, c->num_sms, c->stream));
+                        launches += 2;
+                }
+                if (ownItems) {
+                        const int perSM = warpKernel ? exec_docs_max_ctas_per_sm(execShift, maxSlots, exec_docs_stage_bytes(c->docs_bufs)) : exec_max_ctas_per_sm(execShift, maxSlots, mode, c->codec);
+                        if (perSM <= 0)
+                                return fail(c, TRN_ERR_CUDA, "the exec kernel does not fit on an SM with this many docset slots");
+                        const uint64_t workers = warpKernel ? (ownItems + 3) / 4 : ownItems; // 4 warp-workers per CTA
+                        const int      grid    = int(std::min<uint64_t>(uint64_t(c->num_sms) * perSM, std::max<uint64_t>(1, workers)));
+                        if (warpKernel)
+                                CK(launch_exec_docs(P, grid, c->stream));
+                        else
+                                CK(launch_exec_tiles(P, grid, c->stream));
+                        ++launches;
+                }
                 CK(cudaEventRecord(k1, c->stream));
                 c->have_kernel_events = true;
-                ++launches;
         } else {
                 CK(cudaEventRecord(k0, c->stream)); // keep the pair fresh: readers must not see a previous batch's events
                 CK(cudaEventRecord(k1, c->stream));
@@ -1275,6 +1398,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                                       c->d_topk_counts.as<uint32_t>(), c->stream));
                 ++launches;
         }
+        c->tm.enqueue_ms += float(now_ms() - tEnqueue0);
         c->last_mode     = mode;
         c->last_nq       = nq;
         c->last_k        = k;
@@ -1296,8 +1420,11 @@ extern "C" int trn_exec_batch_device(trn_ctx *c, const trn_query *queries, uint3
                 return TRN_ERR_ARG;
         CK(cudaSetDevice(c->device));
         c->have_kernel_events = false;
+        c->tm                 = trn_timings{};
+        const double t0       = now_ms();
         CK(cudaEventRecord(c->ev0, c->stream));
         const int r = exec_device_impl(c, queries, nq, mode, k, out, 0, c->evk0, c->evk1);
+        c->tm.total_ms = float(now_ms() - t0);
         if (r != TRN_OK)
                 return r;
         CK(cudaEventRecord(c->ev1, c->stream));
@@ -1381,12 +1508,21 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                 return TRN_ERR_ARG;
         uint32_t nchunks = c->pipeline_chunks;
         if (mode == TRN_MODE_SCORED_TOPK || nq < 8 * nchunks || nchunks <= 1) {
-                const int r = trn_exec_batch_device(c, queries, nq, mode, k, nullptr);
+                const double t0 = now_ms();
+                const int    r  = trn_exec_batch_device(c, queries, nq, mode, k, nullptr);
                 if (r != TRN_OK)
                         return r;
-                return trn_fetch_results(c, out);
+                const double tw = now_ms();
+                const int    fr = trn_fetch_results(c, out);
+                c->tm.final_wait_ms = float(now_ms() - tw);
+                c->tm.total_ms      = float(now_ms() - t0);
+                if (fr == TRN_OK)
+                        c->tm.kernel_ms = out->exec_kernel_ms;
+                return fr;
         }
         CK(cudaSetDevice(c->device));
+        c->tm            = trn_timings{};
+        const double tB0 = now_ms();
         const bool scored = mode == TRN_MODE_SCORED_ALL;
         CK(c->h_offsets.ensure((size_t(nq) + 1) * 8));
         CK(c->h_counts.ensure(size_t(nq) * 8));
@@ -1432,7 +1568,11 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                 CK(cudaMemcpyAsync(hs, small, 64, cudaMemcpyDeviceToHost, c->copy_stream));
                 CK(cudaMemcpyAsync(o, c->d_q_offsets[set].p, (size_t(C.n) + 1) * 8, cudaMemcpyDeviceToHost, c->copy_stream));
                 CK(cudaMemcpyAsync(m, small + 64, size_t(C.n) * 8, cudaMemcpyDeviceToHost, c->copy_stream));
-                CK(cudaStreamSynchronize(c->copy_stream));
+                {
+                        const double tw = now_ms(); // waits for the chunk's kernels (and the previous chunk's result copy on the same stream)
+                        CK(cudaStreamSynchronize(c->copy_stream));
+                        c->tm.chunk_wait_ms += float(now_ms() - tw);
+                }
                 {
                         float kms{0}; // the chunk's kernels are complete: its event pair can be read (and its slot reused 16 chunks later)
                         if (cudaEventElapsedTime(&kms, c->ev_ck0[j % 16], c->ev_ck1[j % 16]) == cudaSuccess)
@@ -1492,8 +1632,14 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                 if (fr != TRN_OK)
                         return fr;
         }
-        CK(cudaStreamSynchronize(c->copy_stream));
-        CK(cudaStreamSynchronize(c->stream));
+        {
+                const double tw = now_ms();
+                CK(cudaStreamSynchronize(c->copy_stream));
+                CK(cudaStreamSynchronize(c->stream));
+                c->tm.final_wait_ms = float(now_ms() - tw);
+        }
+        c->tm.total_ms     = float(now_ms() - tB0);
+        c->tm.kernel_ms    = ksum;
         hoff[nq]           = running;
         c->last_total_hint = running + running / 16;
         std::memset(out, 0, sizeof(*out));
@@ -1512,6 +1658,13 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
         out->exec_kernel_ms = ksum;
         // the split-form API (trn_fetch_results / trn_last_topk_device) refers to a whole batch; a pipelined call leaves none behind
         c->last_mode = -1;
+        return TRN_OK;
+}
+
+extern "C" int trn_last_timings(trn_ctx *c, trn_timings *out) {
+        if (!c || !out)
+                return TRN_ERR_ARG;
+        *out = c->tm;
         return TRN_OK;
 }
 

@@ -17,6 +17,7 @@
 #include "dirlookup.h"
 #include "kernels.h"
 #include "varbyte.h"
+#include <algorithm>
 #include <cstdlib>
 #include <cuda_runtime.h>
 
@@ -471,20 +472,21 @@ __global__ void __launch_bounds__(kThreads) k_exec_tiles(ExecParams P) {
                 if (tid == 0)
                         s_item = atomicAdd(P.ticket, 1u);
                 __syncthreads();
-                const uint32_t item = s_item;
-                if (item >= P.total_items)
+                const uint32_t gitem = s_item; // ticket: the kernel's own item space (queries taken by k_score_flat own no tickets)
+                if (gitem >= P.gen_items)
                         break;
-                // locate the query: last q with item_base <= item
+                // locate the query: last q with gen_base <= gitem
                 uint32_t qlo = 0, qhi = P.nq;
                 while (qhi - qlo > 1) {
                         const uint32_t mid = (qlo + qhi) >> 1;
-                        if (P.queries[mid].item_base <= item)
+                        if (P.queries[mid].gen_base <= gitem)
                                 qlo = mid;
                         else
                                 qhi = mid;
                 }
                 const uint32_t q    = qlo;
                 const DevQuery Q    = P.queries[q];
+                const uint32_t item = Q.item_base + (gitem - Q.gen_base); // batch-wide (query, tile) item: index of the segment arrays
                 const uint32_t tile = Q.tile_lo + (item - Q.item_base);
                 const uint32_t lo = tile << P.exec_shift, hi = lo + W;
 
@@ -783,6 +785,7 @@ __global__ void __launch_bounds__(kThreads) k_exec_tiles(ExecParams P) {
         }
 }
 
+#include "score_flat.cuh"
 #include "exec_docs.cuh"
 
 // ------------------------------------------------------------------------------------------------ segment ordering
