@@ -325,9 +325,9 @@ __global__ void __launch_bounds__(kThreads) k_decode_stream_lucene(DevIndex ix, 
                         uint32_t *     od   = MAT ? docids + trow + size_t(bj) * 128u : nullptr;
                         uint32_t *     of   = MAT ? freqs + trow + size_t(bj) * 128u : nullptr;
                         if (bj < nfull) {
-                                uint32_t d[4], fr[4];
-                                const uint32_t o2 = lucene_intblock_v(s, skew, lane, d, scratch);
-                                (void)lucene_intblock_v(s, o2, lane, fr, scratch);
+                                uint32_t d[4], fr[4], dbits, fbits;
+                                const uint32_t o2 = lucene_intblock_v(s, skew, lane, d, scratch, dbits);
+                                (void)lucene_intblock_v(s, o2, lane, fr, scratch, fbits);
                                 uint32_t base = pj;
 #pragma unroll
                                 for (int g = 0; g < 4; ++g) {

@@ -33,6 +33,7 @@ struct DevIndex {
         uint32_t        ntiles;     // number of 2^tile_shift-document tiles of the docID space
         uint32_t        tile_shift; // tile of the scored kernel (8192 documents: the reference's window, docset_spans.h:74)
         uint32_t        max_docid;
+        uint32_t        block_docs; // documents per full block (GOOGLE: google_codec.h:18 N = 32 — other values only for the decode sweep; LUCENE: 128)
         int             codec;
 };
 

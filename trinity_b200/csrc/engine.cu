@@ -87,11 +87,14 @@ struct trn_ctx {
         bool                 have_index{false};
         int                  codec{0};
         int                  cand_cost{900}; // TRN_CAND_COST: modelled warp-instructions per 32 candidates of the candidate-driven conjunction (0 = never use it)
+        uint32_t             block_docs{32}; // documents per full block of the uploaded index (GOOGLE 32 unless built for the decode sweep; LUCENE 128)
         uint32_t             min_docid{1}; // smallest docID any term holds (a docID-range shard does not start at 1)
         uint32_t             nterms{0}, max_docid{0}, tile_shift{13}, ntiles{0}; // tile_shift: directory granularity == scored tile (8192 docs, the reference's window docset_spans.h:74)
         int                  docs_bufs{1};   // gather staging buffers per warp in k_exec_docs (TRN_DOCS_BUFS): 1 = 32 resident warps/SM beats 2 = prefetch at 24 warps (measured 49 vs 53 ms)
         uint32_t             docs_shift{14}; // docID tile (log2) of the warp-per-tile DocumentsOnly kernel
         uint32_t             run_tiles{32};  // TRN_RUN_TILES: consecutive tiles per work item of the flat scored kernel (top-k state lives across a run)
+        int                  flat_threads{256}; // TRN_SF_THREADS: CTA size of k_score_flat (256/320/384: two CTAs per SM; 512/640: one)
+        uint32_t             scored_shift{13};  // TRN_SCORED_SHIFT: log2 of k_score_flat's tile (13 = the reference's window, 14)
         int                  flat_scored{1}; // TRN_FLAT_SCORED=0: every scored query through the general step-program kernel (A/B switch)
         uint64_t             index_bytes{0}, dir_bytes{0}, total_blocks{0}, total_postings{0};
         DevBuf               d_index, d_blk_last, d_blk_off, d_terms, d_tile_first, d_masked;
@@ -630,6 +633,13 @@ extern "C" int trn_create(int device, trn_ctx **out) {
         }
         if (const char *e = getenv("TRN_FLAT_SCORED"))
                 c->flat_scored = atoi(e) != 0;
+        if (const char *e = getenv("TRN_SF_THREADS"))
+                c->flat_threads = atoi(e);
+        if (const char *e = getenv("TRN_SCORED_SHIFT")) {
+                const int v = atoi(e);
+                if (v == 13 || v == 14)
+                        c->scored_shift = uint32_t(v);
+        }
         if (const char *e = getenv("TRN_PIPELINE_CHUNKS")) {
                 const int v = atoi(e);
                 if (v >= 1 && v <= 16)
@@ -714,6 +724,7 @@ extern "C" int trn_upload_index(trn_ctx *c, int codec, const uint8_t *index, uin
                         if (dir.terms[i].nblocks)
                                 max_docid = std::max(max_docid, dir.terms[i].last_doc);
         c->codec      = codec;
+        c->block_docs = codec == TRN_CODEC_GOOGLE ? 32u : 128u;
         c->nterms     = nterms;
         c->max_docid  = max_docid;
         const uint32_t W = 1u << c->tile_shift;
@@ -826,6 +837,7 @@ static DevIndex dev_index(trn_ctx *c) {
         ix.ntiles     = c->ntiles;
         ix.tile_shift = c->tile_shift;
         ix.max_docid  = c->max_docid;
+        ix.block_docs = c->block_docs;
         ix.codec      = c->codec;
         return ix;
 }
@@ -1203,8 +1215,9 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                         dq.tile_lo = 0;
                         dq.ntiles  = 0;
                 } else {
-                        dq.tile_lo = r.lo >> execShift;
-                        dq.ntiles  = (r.hi >> execShift) - dq.tile_lo + 1;
+                        const uint32_t qshift = flatScored ? c->scored_shift : execShift; // k_score_flat may run on a larger tile
+                        dq.tile_lo            = r.lo >> qshift;
+                        dq.ntiles             = (r.hi >> qshift) - dq.tile_lo + 1;
                 }
                 dq.item_base = uint32_t(items);
                 dq.gen_base  = uint32_t(genItems);
@@ -1345,7 +1358,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                         S.nflat        = nflat;
                         S.run_tiles    = c->run_tiles;
                         S.total_items  = mode == TRN_MODE_SCORED_TOPK ? uint32_t(std::min<uint64_t>(uint64_t(maxRuns) * nflat, 0xffffffffull)) : uint32_t(flatItems);
-                        S.tile_shift   = execShift;
+                        S.tile_shift   = c->scored_shift;
                         S.mode         = mode;
                         S.k            = k;
                         S.ticket       = reinterpret_cast<uint32_t *>(small + 4);
@@ -1363,7 +1376,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                         if (uint64_t(maxRuns) * nflat >= (1ull << 32))
                                 return fail(c, TRN_ERR_CAPACITY, "batch has more than 2^32 (run, query) work items; split it");
                         CK(launch_build_luts(S.leaves, uint32_t(leaves.size()), c->d_luts.as<float>(), c->stream));
-                        CK(launch_score_flat(S, c->num_sms, c->stream));
+                        CK(launch_score_flat(S, c->flat_threads, c->num_sms, c->stream));
                         launches += 2;
                 }
                 if (ownItems) {
@@ -1701,6 +1714,10 @@ extern "C" int trn_decode_terms(trn_ctx *c, const uint32_t *term_ids, uint32_t n
         if (!term_ids || !nterms || (materialise && (!docids || !freqs)))
                 return fail(c, TRN_ERR_ARG, "trn_decode_terms: bad arguments");
         CK(cudaSetDevice(c->device));
+        // TRN_DECODE_KERNEL=legacy | single-pass: the round-1 kernels (register-staged span copy / cp.async lane gather), kept for A/B runs;
+        // default: the bulk-copy streaming kernels of decode_stream.cuh
+        static const std::string decodeKernel = getenv("TRN_DECODE_KERNEL") ? getenv("TRN_DECODE_KERNEL") : "";
+        const bool               legacyDecode = (decodeKernel == "legacy" || decodeKernel == "single-pass") && c->block_docs == (c->codec == TRN_CODEC_GOOGLE ? 32u : 128u);
         std::vector<uint32_t> unit_base(nterms + 1);
         std::vector<uint64_t> out_base(nterms + 1), host_base(nterms + 1);
         uint64_t              units{0}, posts{0}, padded{0};
@@ -1711,7 +1728,7 @@ extern "C" int trn_decode_terms(trn_ctx *c, const uint32_t *term_ids, uint32_t n
                 unit_base[i]  = uint32_t(units);
                 out_base[i]   = padded; // device rows start on a 128-entry boundary (16-byte vector stores)
                 host_base[i]  = posts;
-                units += c->codec == TRN_CODEC_GOOGLE ? (t.nblocks + 31) / 32 : t.nblocks;
+                units += (legacyDecode && c->codec == TRN_CODEC_LUCENE) ? t.nblocks : (t.nblocks + 31) / 32;
                 posts += t.documents;
                 padded += (uint64_t(t.documents) + 127) / 128 * 128;
                 if (units >= (1ull << 32))
@@ -1737,8 +1754,12 @@ extern "C" int trn_decode_terms(trn_ctx *c, const uint32_t *term_ids, uint32_t n
                 const int grid = int(std::min<uint64_t>(uint64_t(c->num_sms) * 8, (units + 3) / 4));
                 // GOOGLE: the materialising variant uses the single-pass kernel with 16-byte vector stores (k_decode_google); the fused
                 // checksum-only variant is faster with the span-staged kernel (measured, profiles/r01_g_microbench_decode.txt)
-                static const bool forceNew = getenv("TRN_DECODE_KERNEL") && std::string(getenv("TRN_DECODE_KERNEL")) == "single-pass";
-                if (c->codec == TRN_CODEC_GOOGLE && (materialise || forceNew))
+                const bool forceNew = decodeKernel == "single-pass";
+                if (!legacyDecode)
+                        CK(launch_decode_stream(dev_index(c), c->d_dec_a.as<uint32_t>(), c->d_dec_b.as<uint32_t>(), c->d_dec_c.as<uint64_t>(), nterms, uint32_t(units),
+                                                materialise ? c->d_dec_docids.as<uint32_t>() : nullptr, materialise ? c->d_dec_freqs.as<uint32_t>() : nullptr,
+                                                c->d_dec_sums.as<unsigned long long>(), c->num_sms, c->stream));
+                else if (c->codec == TRN_CODEC_GOOGLE && (materialise || forceNew))
                         CK(launch_decode_google(dev_index(c), c->d_dec_a.as<uint32_t>(), c->d_dec_b.as<uint32_t>(), c->d_dec_c.as<uint64_t>(), nterms,
                                                 uint32_t(units), materialise ? c->d_dec_docids.as<uint32_t>() : nullptr,
                                                 materialise ? c->d_dec_freqs.as<uint32_t>() : nullptr, c->d_dec_sums.as<unsigned long long>(), grid, c->stream));

@@ -18,15 +18,14 @@
 //   * the score tile starts at -0.0f: BM25 contributions are >= +0.0, x + (-0.0) == x, and a document matched iff its word is no
 //     longer the sentinel — a flat disjunction needs no docset bitmap at all;
 //   * the per-term 64-entry BM25 table is computed once per batch (k_build_luts), not once per (tile, term);
+//   * a block that straddles a tile boundary (every block of a sparse term does) is decoded ONCE per run: its documents and scores stay in a
+//     per-leaf shared-memory cache and the following tiles just apply them;
 //   * top-k: a work item is a RUN of consecutive tiles of one query whose candidate list and threshold live in shared memory across the
 //     run; items are handed out run-major (every query's first run, then every query's second run, ...), so when a query's later runs
 //     start its first run has already published a threshold — only ~1 in nruns tiles sees the expensive "everything passes" start.
 #pragma once
 
-static constexpr int      kSfThreads   = 256;
-static constexpr int      kSfWarps     = kSfThreads / 32;
 static constexpr uint32_t kSfMaxLeaves = 16;
-static constexpr uint32_t kSfListCap   = 2048;  // candidate keys kept per run (>= kMaxK + 4 * kSfThreads)
 static constexpr uint32_t kSfStage     = 2080;  // one Lucene block: two int-blocks of at most 1 + 4*255 bytes, + 15 bytes of skew, 16 B multiple
 static constexpr uint32_t kSfScratch   = 512;   // 128 words: exception patches of one int-block
 static constexpr uint32_t kSfWarpBytes = 2 * kSfStage + kSfScratch;
@@ -59,12 +58,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // One int-block (lucene_codec.cpp:69-100 + FastPFor<4> page, fastpfor.h:222-270) decoded by one warp, lane l
 // receiving values l, l+32, l+64, l+96 (v[g] = value l + 32 g).  `s` = 16 B-aligned shared staging, `o` = byte offset of the u8 L.
 // Returns the byte offset just past the int-block.
-__device__ __forceinline__ uint32_t lucene_intblock_v(const uint8_t *s, uint32_t o, int lane, uint32_t v[4], uint32_t *scratch /*128 words, warp-private*/) {
+// `bits`: an upper bound of the values' width (b, or maxbits when the page holds exceptions).
+__device__ __forceinline__ uint32_t lucene_intblock_v(const uint8_t *s, uint32_t o, int lane, uint32_t v[4], uint32_t *scratch /*128 words, warp-private*/, uint32_t &bits) {
         const uint32_t L = s[o];
         if (L == 0) { // all 128 values equal
                 const uint8_t *p = s + o + 1;
                 const uint32_t x = varbyte_get(p);
                 v[0] = v[1] = v[2] = v[3] = x;
+                bits                      = 32u - uint32_t(__clz(int(x)));
                 return uint32_t(p - s);
         }
         const uint32_t pw        = o + 1; // byte offset of page word 0 (unaligned)
@@ -89,7 +90,9 @@ __device__ __forceinline__ uint32_t lucene_intblock_v(const uint8_t *s, uint32_t
         const uint32_t bytesize = lds_u32_unaligned(s, meta);
         const uint8_t *bytes    = s + meta + 4;
         const uint32_t cexcept  = bytes[1];
+        bits                    = b;
         if (cexcept) {
+                bits = bytes[2];
                 // out[pos] |= exc << b (fastpfor.h:248-266); exception e belongs to lane e, the patches travel through the scratch
                 const uint32_t maxbits = bytes[2];
                 const uint32_t k       = maxbits - b;
@@ -128,11 +131,15 @@ __global__ void __launch_bounds__(256) k_build_luts(const FlatLeaf *leaves, uint
 
 // descending prune of the run's candidate list to its k best (list sorted afterwards); returns the new score-bits threshold.
 // Called by ALL threads; *s_n is read after a barrier the caller has passed.
-__device__ __forceinline__ uint32_t sf_prune(unsigned long long *list, uint32_t *s_n, uint32_t k) {
-        const uint32_t n  = min(*s_n, kSfListCap);
+// candidate keys kept per run: a power of two (the prune sorts in place) >= kMaxK + 4 * threads (a scan round adds at most 4 keys per thread)
+template <int NT> struct SfCap {
+        static constexpr uint32_t value = NT <= 384 ? 2048u : 4096u;
+};
+template <int NT> __device__ __forceinline__ uint32_t sf_prune(unsigned long long *list, uint32_t *s_n, uint32_t k) {
+        const uint32_t n  = min(*s_n, SfCap<NT>::value);
         const uint32_t n2 = next_pow2(max(n, 2u));
         __syncthreads();
-        for (uint32_t i = n + threadIdx.x; i < n2; i += kSfThreads)
+        for (uint32_t i = n + threadIdx.x; i < n2; i += NT)
                 list[i] = 0ull;
         __syncthreads();
         cta_bitonic_desc(list, n2);
@@ -145,16 +152,27 @@ __device__ __forceinline__ uint32_t sf_prune(unsigned long long *list, uint32_t 
         return thr;
 }
 
-__global__ void __launch_bounds__(kSfThreads, 2) k_score_flat(ScoreParams S) {
-        const uint32_t W = 1u << S.tile_shift, W4 = W >> 2, NW = W >> 5;
-        float *             acc  = reinterpret_cast<float *>(dyn_smem);
-        unsigned long long *list = reinterpret_cast<unsigned long long *>(dyn_smem + size_t(W) * 4);                 // top-k: candidate keys
-        uint32_t *          bmap = reinterpret_cast<uint32_t *>(list);                                             // scored-all: match bitmap (NW words)
-        float *             lut  = reinterpret_cast<float *>(dyn_smem + size_t(W) * 4 + size_t(kSfListCap) * 8);   // kSfMaxLeaves x 64
-        uint8_t *           wst  = dyn_smem + size_t(W) * 4 + size_t(kSfListCap) * 8 + size_t(kSfMaxLeaves) * 256; // kSfWarps x kSfWarpBytes
+static constexpr uint32_t kSfCacheLeaves = 12;                        // leaves that own a cache slot (the others always decode)
+static constexpr uint32_t kSfCacheBytes  = kSfCacheLeaves * 128 * 8;  // per leaf: 128 docIDs + 128 scores of its cached (tile-straddling) block
 
-        __shared__ __align__(8) unsigned long long s_bar[kSfWarps * 2];
-        __shared__ uint32_t           s_item, s_n, s_theta, s_warp[kSfWarps + 1];
+template <int NT>
+__global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParams S) {
+        constexpr int      NWARPS       = NT / 32;
+        constexpr uint32_t kSfListCap   = SfCap<NT>::value;
+        constexpr uint32_t kSfListBytes = kSfListCap * 8;
+        static_assert(kSfListCap >= kMaxK + 4 * NT, "a scan round must fit behind the k best");
+        const uint32_t W = 1u << S.tile_shift, W4 = W >> 2, NW = W >> 5;
+        float *             acc   = reinterpret_cast<float *>(dyn_smem);
+        unsigned long long *list  = reinterpret_cast<unsigned long long *>(dyn_smem + size_t(W) * 4);               // top-k: candidate keys
+        uint32_t *          bmap  = reinterpret_cast<uint32_t *>(list);                                           // scored-all: match bitmap (NW words)
+        float *             lut   = reinterpret_cast<float *>(dyn_smem + size_t(W) * 4 + kSfListBytes);            // kSfMaxLeaves x 64
+        uint32_t *          cdoc  = reinterpret_cast<uint32_t *>(dyn_smem + size_t(W) * 4 + kSfListBytes + size_t(kSfMaxLeaves) * 256); // [leaf][128]
+        float *             csc   = reinterpret_cast<float *>(cdoc + kSfCacheLeaves * 128);                        // [leaf][128]
+        uint8_t *           wst   = reinterpret_cast<uint8_t *>(csc + kSfCacheLeaves * 128);                       // NWARPS x kSfWarpBytes
+
+        __shared__ __align__(8) unsigned long long s_bar[NWARPS * 2];
+        __shared__ uint32_t           s_item, s_n, s_theta, s_warp[NWARPS + 1];
+        __shared__ uint32_t           s_fill_blk[2][kSfMaxLeaves], s_fill_tile[2][kSfMaxLeaves]; // block cached for a leaf during tile T: slot T & 1
         __shared__ unsigned long long s_base;
 
         const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -223,21 +241,28 @@ __global__ void __launch_bounds__(kSfThreads, 2) k_score_flat(ScoreParams S) {
                                 mytfs           = T.tf_shift;
                         }
                 }
-                for (uint32_t i = tid; i < nleaf * 64u; i += kSfThreads)
+                for (uint32_t i = tid; i < nleaf * 64u; i += NT)
                         lut[i] = S.luts[size_t(FQ.leaf_begin) * 64u + i];
-                for (uint32_t i = tid; i < W4; i += kSfThreads)
+                for (uint32_t i = tid; i < W4; i += NT)
                         reinterpret_cast<float4 *>(acc)[i] = sent4;
+                if (tid < 2 * int(kSfMaxLeaves))
+                        (&s_fill_tile[0][0])[tid] = 0xffffffffu;
                 if (tid == 0)
                         s_n = 0;
                 uint32_t thr_local = 0, nmatch = 0, n_list = 0; // n_list: s_n as of the last point where nobody was pushing (same in every thread)
+                uint32_t mycb = 0xffffffffu;                    // lane t: the block of leaf t whose documents + scores sit in the cache (same in every warp)
                 // first block of every leaf that can reach the run's first document; afterwards each tile's end lookup is the next tile's start
                 uint32_t nextA = mynb ? first_block_ge(S.ix, mydir, mynb, myfirst, mylast, mytfb, mytfbase, mytfs, t0 << S.tile_shift) : 0u;
                 __syncthreads();
 
                 for (uint32_t tile = t0; tile < t1; ++tile) {
                         const uint32_t lo = tile << S.tile_shift, hi = lo + W; // hi wraps to 0 for the last tile of a 2^32 docID space
+                        const uint32_t par = tile & 1u;
                         if (S.mode == 2 && tid == 0)
                                 s_theta = *reinterpret_cast<volatile uint32_t *>(&S.theta[q]);
+                        // a block cached during the previous tile (by whichever warp decoded it) becomes this leaf's cached block
+                        if (uint32_t(lane) < nleaf && tile != t0 && s_fill_tile[par ^ 1u][lane] == tile - 1u)
+                                mycb = s_fill_blk[par ^ 1u][lane];
                         // ---- the tile's blocks of every leaf
                         uint32_t bA = nextA, cnt = 0;
                         if (mynb && bA < mynb) {
@@ -249,11 +274,14 @@ __global__ void __launch_bounds__(kSfThreads, 2) k_score_flat(ScoreParams S) {
                                 if (lo > mylast)
                                         cnt = 0;
                         }
+                        const bool usesCache = cnt && bA == mycb; // the leaf's first block of this tile is the cached one: applied, not decoded
+                        if (!usesCache && !(cnt && nextA == mycb))
+                                mycb = 0xffffffffu;                  // the cached block ends before the next tile: forget it
                         const uint32_t incl  = warp_incl_scan(cnt, lane);
                         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                        // ---- this warp's (term, block) pairs: p = warp + kSfWarps * j
+                        // ---- this warp's (term, block) pairs: p = warp + NWARPS * j
                         for (uint32_t jb = 0;; jb += 32u) {
-                                const uint32_t p    = uint32_t(warp) + kSfWarps * (jb + uint32_t(lane));
+                                const uint32_t p    = uint32_t(warp) + NWARPS * (jb + uint32_t(lane));
                                 const bool     have = p < total;
                                 const uint32_t hm   = __ballot_sync(0xffffffffu, have);
                                 if (!hm)
@@ -264,17 +292,30 @@ __global__ void __launch_bounds__(kSfThreads, 2) k_score_flat(ScoreParams S) {
                                 if (!have)
                                         t = 0;
                                 const uint32_t tincl = __shfl_sync(0xffffffffu, incl, int(t)), tcnt = __shfl_sync(0xffffffffu, cnt, int(t));
-                                const uint32_t b     = __shfl_sync(0xffffffffu, bA, int(t)) + (p - (tincl - tcnt));
+                                const uint32_t tbA   = __shfl_sync(0xffffffffu, bA, int(t));
+                                const uint32_t b     = tbA + (p - (tincl - tcnt));
                                 const uint32_t dir   = __shfl_sync(0xffffffffu, mydir, int(t));
                                 const uint32_t docs  = __shfl_sync(0xffffffffu, mydocs, int(t));
-                                uint32_t       off = 0, offn = 0, prev = 0;
+                                const bool     tuse  = __shfl_sync(0xffffffffu, usesCache ? 1 : 0, int(t)) != 0;
+                                // kind: 0 = decode, 1 = apply the leaf's cached block, 2 = decode and cache (the leaf's last block of the tile, if the leaf
+                                // does not read its cache in this tile: a straddling block will be this leaf's first block of the next tile)
+                                uint32_t kind = 0;
                                 if (have) {
+                                        if (tuse && b == tbA)
+                                                kind = 1;
+                                        else if (!tuse && b == tbA + tcnt - 1u && b < (docs >> 7) && t < kSfCacheLeaves)
+                                                kind = 2;
+                                }
+                                uint32_t off = 0, offn = 0, prev = 0;
+                                if (have && kind != 1u) {
                                         off  = __ldg(S.ix.blk_off + dir + b);
                                         offn = __ldg(S.ix.blk_off + dir + b + 1u);
                                         prev = b ? __ldg(S.ix.blk_last + dir + b - 1u) : 0u;
                                 }
                                 const uint32_t npairs = __popc(hm);
-                                auto issue = [&](uint32_t j) {
+                                auto issue = [&](uint32_t j) { // bulk copy of pair j's block (cached pairs need no bytes)
+                                        if (__shfl_sync(0xffffffffu, kind, int(j)) == 1u)
+                                                return;
                                         const uint32_t o = __shfl_sync(0xffffffffu, off, int(j)), on = __shfl_sync(0xffffffffu, offn, int(j));
                                         const uint32_t abase = o & ~15u, bytes = min(((on + 15u) & ~15u) - abase, kSfStage);
                                         if (lane == 0) {
@@ -288,40 +329,92 @@ __global__ void __launch_bounds__(kSfThreads, 2) k_score_flat(ScoreParams S) {
                                 for (uint32_t j = 0; j < npairs; ++j) {
                                         if (j + 1u < npairs)
                                                 issue(j + 1u);
+                                        const uint32_t kj = __shfl_sync(0xffffffffu, kind, int(j));
+                                        const uint32_t tj = __shfl_sync(0xffffffffu, t, int(j));
+                                        const float *  lt = lut + tj * 64u;
+                                        if (kj == 1u) {
+                                                // ---- cached block: its documents and scores were left behind by an earlier tile of this run
+#pragma unroll
+                                                for (int g = 0; g < 4; ++g) {
+                                                        const uint32_t rel = cdoc[tj * 128u + lane + 32 * g] - lo;
+                                                        if (rel < W)
+                                                                atomicAdd(&acc[rel], csc[tj * 128u + lane + 32 * g]);
+                                                }
+                                                continue;
+                                        }
                                         const uint32_t bsel = seq_wait & 1u;
                                         mbar_wait(bar_s + bsel * 8u, (seq_wait >> 1) & 1u);
                                         ++seq_wait;
                                         const uint8_t *s    = stage + bsel * kSfStage;
                                         const uint32_t oj   = __shfl_sync(0xffffffffu, off, int(j));
-                                        const uint32_t tj   = __shfl_sync(0xffffffffu, t, int(j));
                                         const uint32_t bj   = __shfl_sync(0xffffffffu, b, int(j));
                                         const uint32_t pj   = __shfl_sync(0xffffffffu, prev, int(j));
                                         const uint32_t dj   = __shfl_sync(0xffffffffu, docs, int(j));
                                         const uint32_t skew = oj & 15u;
-                                        const float *  lt   = lut + tj * 64u;
                                         if (bj < (dj >> 7)) {
-                                                uint32_t d[4], fr[4];
-                                                const uint32_t o2 = lucene_intblock_v(s, skew, lane, d, scratch);
-                                                (void)lucene_intblock_v(s, o2, lane, fr, scratch);
+                                                uint32_t d[4], fr[4], dbits, fbits;
+                                                const uint32_t o2 = lucene_intblock_v(s, skew, lane, d, scratch, dbits);
+                                                (void)lucene_intblock_v(s, o2, lane, fr, scratch, fbits);
                                                 // docIDs = prev + inclusive prefix sum over the block (lucene_codec.cpp:568-594 update_curdoc), group by group
-                                                uint32_t base = pj;
+                                                uint32_t last;
+                                                if (dbits <= 11u) { // 32 values below 2048 sum to less than 65536: two groups share one scan
+                                                        const uint32_t sa = warp_incl_scan(d[0] | (d[1] << 16), lane), sb = warp_incl_scan(d[2] | (d[3] << 16), lane);
+                                                        const uint32_t ta = __shfl_sync(0xffffffffu, sa, 31), tb = __shfl_sync(0xffffffffu, sb, 31);
+                                                        const uint32_t b1 = pj + (ta & 0xffffu), b2 = b1 + (ta >> 16), b3 = b2 + (tb & 0xffffu);
+                                                        d[0] = pj + (sa & 0xffffu);
+                                                        d[1] = b1 + (sa >> 16);
+                                                        d[2] = b2 + (sb & 0xffffu);
+                                                        d[3] = b3 + (sb >> 16);
+                                                        last = b3 + (tb >> 16);
+                                                } else {
+                                                        uint32_t base = pj;
 #pragma unroll
-                                                for (int g = 0; g < 4; ++g) {
-                                                        const uint32_t sc = warp_incl_scan(d[g], lane);
-                                                        d[g]              = base + sc;
-                                                        base += __shfl_sync(0xffffffffu, sc, 31);
+                                                        for (int g = 0; g < 4; ++g) {
+                                                                const uint32_t sc = warp_incl_scan(d[g], lane);
+                                                                d[g]              = base + sc;
+                                                                base += __shfl_sync(0xffffffffu, sc, 31);
+                                                        }
+                                                        last = base;
                                                 }
-                                                const bool big = __any_sync(0xffffffffu, ((fr[0] | fr[1] | fr[2] | fr[3]) & 0xffffu) >= 64u);
+                                                const bool big = fbits > 6u; // some freq may be >= 64: outside the table
                                                 double     idfj = 0.0;
                                                 if (big)
                                                         idfj = __shfl_sync(0xffffffffu, myidf, int(tj));
+                                                const uint32_t first = __shfl_sync(0xffffffffu, d[0], 0);
+                                                if (kj == 2u) {
+                                                        // every posting's score is needed (the block is cached for the following tiles)
+                                                        float sc[4];
 #pragma unroll
-                                                for (int g = 0; g < 4; ++g) {
-                                                        const uint32_t rel = d[g] - lo;
-                                                        if (rel < W) {
+                                                        for (int g = 0; g < 4; ++g) {
                                                                 const uint32_t f16 = fr[g] & 0xffffu; // freq is uint16_t in the reference (codecs.h:217)
-                                                                const float    sc  = f16 < 64u ? lt[f16] : bm25_score(idfj, f16);
-                                                                atomicAdd(&acc[rel], sc);
+                                                                sc[g]              = (!big || f16 < 64u) ? lt[f16 & 63u] : bm25_score(idfj, f16);
+                                                                const uint32_t rel = d[g] - lo;
+                                                                if (rel < W)
+                                                                        atomicAdd(&acc[rel], sc[g]);
+                                                                cdoc[tj * 128u + lane + 32 * g] = d[g];
+                                                                csc[tj * 128u + lane + 32 * g]  = sc[g];
+                                                        }
+                                                        if (lane == 0 && (hi != 0u && last >= hi)) { // it does reach into the next tile
+                                                                s_fill_blk[par][tj]  = bj;
+                                                                s_fill_tile[par][tj] = tile;
+                                                        }
+                                                } else if (first - lo < W && last - lo < W) {
+                                                        // block completely inside the tile: no range checks
+#pragma unroll
+                                                        for (int g = 0; g < 4; ++g) {
+                                                                const uint32_t f16 = fr[g] & 0xffffu;
+                                                                const float    sc  = (!big || f16 < 64u) ? lt[f16 & 63u] : bm25_score(idfj, f16);
+                                                                atomicAdd(&acc[d[g] - lo], sc);
+                                                        }
+                                                } else {
+#pragma unroll
+                                                        for (int g = 0; g < 4; ++g) {
+                                                                const uint32_t rel = d[g] - lo;
+                                                                if (rel < W) {
+                                                                        const uint32_t f16 = fr[g] & 0xffffu;
+                                                                        const float    sc  = (!big || f16 < 64u) ? lt[f16 & 63u] : bm25_score(idfj, f16);
+                                                                        atomicAdd(&acc[rel], sc);
+                                                                }
                                                         }
                                                 }
                                         } else {
@@ -350,7 +443,7 @@ __global__ void __launch_bounds__(kSfThreads, 2) k_score_flat(ScoreParams S) {
                                 // ---- threshold scan: as signed integers the sentinel is INT_MIN and scores (>= +0.0) order like their bits
                                 const int      thr      = int(max(thr_local, s_theta));
                                 const uint32_t n_before = n_list;
-                                for (uint32_t i4 = tid; i4 < W4; i4 += kSfThreads) {
+                                for (uint32_t i4 = tid; i4 < W4; i4 += NT) {
                                         float4   v  = reinterpret_cast<const float4 *>(acc)[i4];
                                         uint32_t b0 = __float_as_uint(v.x), b1 = __float_as_uint(v.y), b2 = __float_as_uint(v.z), b3 = __float_as_uint(v.w);
                                         if (mk) { // masked documents (masked_documents_registry::test, exec.cpp:1108-1116) never reach the sink
@@ -375,64 +468,70 @@ __global__ void __launch_bounds__(kSfThreads, 2) k_score_flat(ScoreParams S) {
                                 __syncthreads();
                                 if (s_n > kSfListCap) {
                                         // more candidates than the list holds (only while the threshold is still ~0): redo the tile in rounds of
-                                        // kSfThreads * 4 documents, pruning to the k best whenever the next round might not fit
+                                        // NT * 4 documents, pruning to the k best whenever the next round might not fit
                                         __syncthreads();
                                         if (tid == 0)
                                                 s_n = n_before;
                                         __syncthreads();
-                                        for (uint32_t i4 = tid; i4 < W4; i4 += kSfThreads) {
+                                        for (uint32_t r4 = 0; r4 < W4; r4 += NT) {
                                                 __syncthreads();
                                                 const uint32_t cur = s_n; // read between two barriers: nobody is pushing
                                                 __syncthreads();
-                                                if (cur + 4u * kSfThreads > kSfListCap)
-                                                        thr_local = max(thr_local, sf_prune(list, &s_n, k));
-                                                const int thr2 = int(max(thr_local, uint32_t(thr)));
-                                                float4    v    = reinterpret_cast<const float4 *>(acc)[i4];
-                                                uint32_t  bb[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
-                                                if (mk) {
-                                                        const uint32_t m = (__ldg(mk + (i4 >> 3)) >> ((i4 & 7u) * 4u)) & 0xfu;
+                                                if (cur + 4u * NT > kSfListCap)
+                                                        thr_local = max(thr_local, sf_prune<NT>(list, &s_n, k));
+                                                const uint32_t i4 = r4 + tid;
+                                                if (i4 < W4) {
+                                                        const int thr2 = int(max(thr_local, uint32_t(thr)));
+                                                        float4    v    = reinterpret_cast<const float4 *>(acc)[i4];
+                                                        uint32_t  bb[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+                                                        if (mk) {
+                                                                const uint32_t m = (__ldg(mk + (i4 >> 3)) >> ((i4 & 7u) * 4u)) & 0xfu;
+#pragma unroll
+                                                                for (int c = 0; c < 4; ++c)
+                                                                        if ((m >> c) & 1u)
+                                                                                bb[c] = kSfSentinel;
+                                                        }
 #pragma unroll
                                                         for (int c = 0; c < 4; ++c)
-                                                                if ((m >> c) & 1u)
-                                                                        bb[c] = kSfSentinel;
+                                                                if (int(bb[c]) >= thr2) {
+                                                                        const uint32_t idx = atomicAdd(&s_n, 1u);
+                                                                        list[idx] = (static_cast<unsigned long long>(bb[c]) << 32) | static_cast<unsigned long long>(~(lo + i4 * 4u + c));
+                                                                }
                                                 }
-#pragma unroll
-                                                for (int c = 0; c < 4; ++c)
-                                                        if (int(bb[c]) >= thr2) {
-                                                                const uint32_t idx = atomicAdd(&s_n, 1u);
-                                                                list[idx] = (static_cast<unsigned long long>(bb[c]) << 32) | static_cast<unsigned long long>(~(lo + i4 * 4u + c));
-                                                        }
                                         }
                                         __syncthreads();
                                 }
                                 if (s_n > kSfListCap / 2u)
-                                        thr_local = max(thr_local, sf_prune(list, &s_n, k));
+                                        thr_local = max(thr_local, sf_prune<NT>(list, &s_n, k));
                         } else {
                                 // ---- scored-all: match bitmap out of the score tile, then the ordered compaction of k_exec_tiles
-                                for (uint32_t i4 = tid; i4 < W4; i4 += kSfThreads) {
-                                        const float4   v   = reinterpret_cast<const float4 *>(acc)[i4];
+                                for (uint32_t r4 = 0; r4 < W4; r4 += NT) { // (every lane of a warp takes part in the shuffles: W4 is a multiple of 32)
+                                        const uint32_t i4  = r4 + tid;
+                                        const bool     on  = i4 < W4;
+                                        const float4   v   = on ? reinterpret_cast<const float4 *>(acc)[i4] : sent4;
                                         uint32_t       nib = ((~__float_as_uint(v.x)) >> 31) | (((~__float_as_uint(v.y)) >> 31) << 1) | (((~__float_as_uint(v.z)) >> 31) << 2) |
                                                        (((~__float_as_uint(v.w)) >> 31) << 3);
                                         nib <<= (i4 & 7u) * 4u;
                                         nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
                                         nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
                                         nib |= __shfl_xor_sync(0xffffffffu, nib, 4);
-                                        if ((i4 & 7u) == 0u)
+                                        if (on && (i4 & 7u) == 0u)
                                                 bmap[i4 >> 3] = mk ? (nib & ~__ldg(mk + (i4 >> 3))) : nib;
                                 }
                                 __syncthreads();
-                                const uint32_t wpt = NW / kSfThreads; // >= 1: the host launches this kernel with tiles of >= 8192 documents
+                                const uint32_t wpt = (NW + NT - 1u) / NT; // bitmap words per thread (contiguous: thread order == docID order)
                                 uint32_t       c   = 0;
                                 for (uint32_t i = 0; i < wpt; ++i)
-                                        c += __popc(bmap[tid * wpt + i]);
-                                // CTA exclusive scan (8 warps)
+                                        if (tid * wpt + i < NW)
+                                                c += __popc(bmap[tid * wpt + i]);
+                                // CTA exclusive scan
                                 const uint32_t inclc = warp_incl_scan(c, lane);
                                 if (lane == 31)
                                         s_warp[warp] = inclc;
                                 __syncthreads();
                                 uint32_t wbase = 0, tot = 0;
 #pragma unroll
-                                for (int w8 = 0; w8 < kSfWarps; ++w8) {
+                                for (int w8 = 0; w8 < NWARPS; ++w8) {
                                         const uint32_t x = s_warp[w8];
                                         if (w8 < warp)
                                                 wbase += x;
@@ -459,7 +558,7 @@ __global__ void __launch_bounds__(kSfThreads, 2) k_score_flat(ScoreParams S) {
                                         unsigned long long pos = base + wbase + (inclc - c);
                                         for (uint32_t i = 0; i < wpt; ++i) {
                                                 const uint32_t wi = tid * wpt + i;
-                                                uint32_t       w  = bmap[wi];
+                                                uint32_t       w  = wi < NW ? bmap[wi] : 0u;
                                                 while (w) {
                                                         const uint32_t bit = uint32_t(__ffs(int(w)) - 1);
                                                         w &= w - 1;
@@ -473,7 +572,7 @@ __global__ void __launch_bounds__(kSfThreads, 2) k_score_flat(ScoreParams S) {
                         }
                         __syncthreads();
                         n_list = s_n;
-                        for (uint32_t i = tid; i < W4; i += kSfThreads) // the next tile starts from an untouched score tile
+                        for (uint32_t i = tid; i < W4; i += NT) // the next tile starts from an untouched score tile
                                 reinterpret_cast<float4 *>(acc)[i] = sent4;
                         __syncthreads();
                 }
@@ -481,10 +580,10 @@ __global__ void __launch_bounds__(kSfThreads, 2) k_score_flat(ScoreParams S) {
                 if (S.mode == 2) {
                         // ---- end of the run: its k best (those that can still matter) join the query's candidates; its k-th best bounds the query's
                         if (s_n >= k || s_n > kSfListCap / 2u)
-                                thr_local = max(thr_local, sf_prune(list, &s_n, k));
+                                thr_local = max(thr_local, sf_prune<NT>(list, &s_n, k));
                         const uint32_t n      = s_n;
                         const uint32_t theta0 = *reinterpret_cast<volatile uint32_t *>(&S.theta[q]);
-                        for (uint32_t i = tid; i < n; i += kSfThreads) {
+                        for (uint32_t i = tid; i < n; i += NT) {
                                 const unsigned long long key = list[i];
                                 if (uint32_t(key >> 32) >= theta0) {
                                         const uint32_t pos = atomicAdd(&S.cand_cursor[q], 1u);
@@ -502,8 +601,9 @@ __global__ void __launch_bounds__(kSfThreads, 2) k_score_flat(ScoreParams S) {
         }
 }
 
-size_t score_flat_smem_bytes(uint32_t tile_shift) {
-        return (size_t(1) << tile_shift) * 4 + size_t(kSfListCap) * 8 + size_t(kSfMaxLeaves) * 256 + size_t(kSfWarps) * kSfWarpBytes;
+size_t score_flat_smem_bytes(uint32_t tile_shift, int threads) {
+        const size_t listBytes = (threads <= 384 ? 2048u : 4096u) * 8u;
+        return (size_t(1) << tile_shift) * 4 + listBytes + size_t(kSfMaxLeaves) * 256 + kSfCacheBytes + size_t(threads / 32) * kSfWarpBytes;
 }
 
 uint32_t score_flat_max_leaves() {
@@ -517,18 +617,23 @@ cudaError_t launch_build_luts(const FlatLeaf *leaves, uint32_t nleaves, float *l
         return cudaGetLastError();
 }
 
-cudaError_t launch_score_flat(const ScoreParams &S, int num_sms, cudaStream_t stream) {
-        const size_t smem = score_flat_smem_bytes(S.tile_shift);
-        cudaError_t  e    = cudaFuncSetAttribute(k_score_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+// threads: CTA size (256 / 320: two CTAs per SM on 2^13-document tiles; 512 / 640: one CTA per SM, for 2^14-document tiles)
+cudaError_t launch_score_flat(const ScoreParams &S, int threads, int num_sms, cudaStream_t stream) {
+        const void *fn = threads == 320 ? (const void *)k_score_flat<320> : threads == 512 ? (const void *)k_score_flat<512>
+                                                                         : threads == 640 ? (const void *)k_score_flat<640> : (const void *)k_score_flat<256>;
+        if (threads != 320 && threads != 512 && threads != 640)
+                threads = 256;
+        const size_t smem = score_flat_smem_bytes(S.tile_shift, threads);
+        cudaError_t  e    = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess)
                 return e;
         int per = 0;
-        e       = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_score_flat, kSfThreads, smem);
+        e       = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, threads, smem);
         if (e != cudaSuccess)
                 return e;
         if (per <= 0)
                 return cudaErrorLaunchOutOfResources;
         const int grid = int(std::min<uint64_t>(uint64_t(num_sms) * per, std::max<uint32_t>(1u, S.total_items)));
-        k_score_flat<<<grid, kSfThreads, smem, stream>>>(S);
-        return cudaGetLastError();
+        void *    args[] = {(void *)&S};
+        return cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, stream);
 }
