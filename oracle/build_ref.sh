@@ -17,7 +17,7 @@ if [ ! -d "$REF" ]; then
   echo "FATAL: reference tree $REF not found and no prebuilt oracle/_ref/libtrinity_ref.so" >&2; exit 1
 fi
 GEN="$OUT/gen"; OBJ="$OUT/obj"
-rm -rf "$GEN"; mkdir -p "$GEN" "$OBJ"
+rm -rf "$GEN" "$OBJ"; mkdir -p "$GEN" "$OBJ"
 # symlink farm so that quote-includes resolve to the patched header first
 for f in "$REF"/*.cpp "$REF"/*.h; do ln -s "$f" "$GEN/$(basename "$f")"; done
 rm -f "$GEN/queryexec_ctx.h"
@@ -50,5 +50,41 @@ done
 g++ $CXXF -c "$HERE/ref_harness.cpp" -o "$OBJ/ref_harness.o" & pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 g++ -shared -o "$OUT/libtrinity_ref.so" "$OBJ"/*.o -lpthread -lz
-rm -rf "$GEN" "$OBJ"   # keep only the binary under oracle/_ref/
 echo "built $OUT/libtrinity_ref.so"
+
+# ---- second library: the SAME reference objects, except that exec_query() builds its span through the reference-side binding of
+# libtrinity_b200.so (integration/gpu_exec.{h,cpp}) when the IndexSource has a device-resident twin.  The one call site
+# (exec.cpp:1083-1086: build_iterator + build_span) is patched in a GENERATED copy of exec.cpp; nothing else of the reference changes.
+B200LIB="$HERE/../trinity_b200/libtrinity_b200.so"
+if [ -f "$B200LIB" ]; then
+  python3 - "$REF" "$GEN" <<'PY'
+import re, sys
+ref, gen = sys.argv[1], sys.argv[2]
+src = open(f"{ref}/exec.cpp").read()
+pat = re.compile(r"auto \*const sit = rctx\.build_iterator\(rootExecNode, execFlags\);(.*?)auto\s+span\s+= build_span\(sit, &rctx\);", re.S)
+def repl(m):
+    return ("std::unique_ptr<DocsSetSpan> span = Trinity::b200_gpu_span(rctx, rootExecNode, execFlags, idxsrc, scorer);\n"
+            "                        DocsSetIterators::Iterator *sit{nullptr};\n"
+            "                        if (!span)\n"
+            "                                sit = rctx.build_iterator(rootExecNode, execFlags);" + m.group(1) +
+            "if (!span)\n                                span = build_span(sit, &rctx);")
+new, n = pat.subn(repl, src)
+assert n == 1, "exec_query span-site patch did not apply exactly once"
+new = new.replace('#include "exec.h"', '#include "exec.h"\n#include "gpu_exec.h"', 1)
+assert "gpu_exec.h" in new
+open(f"{gen}/exec_gpu.cpp", "w").write(new)
+PY
+  INTEG="$HERE/../integration"
+  gp=()
+  g++ $CXXF -I"$INTEG" -c "$GEN/exec_gpu.cpp" -o "$OBJ/exec_gpu.o" & gp+=($!)
+  g++ $CXXF -I"$INTEG" -c "$INTEG/gpu_exec.cpp" -o "$OBJ/gpu_exec.o" & gp+=($!)
+  g++ $CXXF -I"$INTEG" -DTRINITY_B200_GPU_SPAN -c "$HERE/ref_harness.cpp" -o "$OBJ/ref_harness_gpu.o" & gp+=($!)
+  for p in "${gp[@]}"; do wait "$p"; done
+  objs=""
+  for o in "$OBJ"/*.o; do
+    case "$(basename "$o")" in exec.o|ref_harness.o) ;; *) objs="$objs $o";; esac
+  done
+  g++ -shared -o "$OUT/libtrinity_ref_gpu.so" $objs -L"$HERE/../trinity_b200" -ltrinity_b200 -Wl,-rpath,'$ORIGIN/../../trinity_b200' -lpthread -lz
+  echo "built $OUT/libtrinity_ref_gpu.so"
+fi
+rm -rf "$GEN" "$OBJ"   # keep only the binaries under oracle/_ref/

@@ -817,3 +817,35 @@ extern "C" void *tref_synth_build(int codec, uint32_t ndocs, uint32_t nterms, ui
         }
         return x;
 }
+
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Only in oracle/_ref/libtrinity_ref_gpu.so (built with -DTRINITY_B200_GPU_SPAN): attach a device-resident twin (integration/gpu_exec.h,
+// the reference-side binding of libtrinity_b200.so) to the index source, so that the library's exec_query() — the reference's own, with
+// its one span-building call site going through b200_gpu_span() — executes on the GPU and replays into the same Handlers / consider().
+#ifdef TRINITY_B200_GPU_SPAN
+#include "gpu_exec.h"
+namespace {
+        std::unordered_map<void *, std::unique_ptr<Trinity::GpuAccessProxy>> g_gaps;
+}
+extern "C" int tref_gpu_attach(void *h, int device, uint64_t maxDocID) {
+        auto x = static_cast<RefIndex *>(h);
+        return guarded([&] {
+                std::vector<std::pair<std::string, term_index_ctx>> terms;
+                for (size_t i = 0; i < x->names.size(); ++i)
+                        terms.emplace_back(x->names[i], x->tctx[i]);
+                auto gap = std::make_unique<Trinity::GpuAccessProxy>(device, x->ap.get(), x->index.size(), terms, isrc_docid_t(maxDocID));
+                Trinity::gpu_proxy_register(x->src, gap.get());
+                g_gaps[h] = std::move(gap);
+        });
+}
+extern "C" void tref_gpu_detach(void *h) {
+        auto x = static_cast<RefIndex *>(h);
+        Trinity::gpu_proxy_register(x->src, nullptr);
+        g_gaps.erase(h);
+}
+extern "C" uint64_t tref_gpu_spans_executed(void *h) {
+        const auto it = g_gaps.find(h);
+        return it == g_gaps.end() ? 0 : it->second->spansExecuted;
+}
+#endif

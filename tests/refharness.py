@@ -10,6 +10,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
 REF_SO = ROOT / "oracle" / "_ref" / "libtrinity_ref.so"
+REF_GPU_SO = ROOT / "oracle" / "_ref" / "libtrinity_ref_gpu.so"  # the same reference objects + the reference-side binding of libtrinity_b200.so
 
 
 def _p(a):
@@ -267,6 +268,22 @@ class RefIndex:
 
 
 _ref = None
+_ref_gpu = None
+
+
+def load_ref_gpu() -> RefLib:
+    """the reference compiled with its exec_query() span site going through integration/gpu_exec.cpp (needs a CUDA device at run time)"""
+    global _ref_gpu
+    if _ref_gpu is None:
+        if not REF_GPU_SO.exists():
+            subprocess.check_call(["bash", str(ROOT / "oracle" / "build_ref.sh")])
+        rl = RefLib(C.CDLL(str(REF_GPU_SO)))
+        rl.L.tref_gpu_attach.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+        rl.L.tref_gpu_detach.argtypes = [C.c_void_p]
+        rl.L.tref_gpu_spans_executed.restype = C.c_uint64
+        rl.L.tref_gpu_spans_executed.argtypes = [C.c_void_p]
+        _ref_gpu = rl
+    return _ref_gpu
 
 
 def load_ref() -> RefLib:

@@ -64,3 +64,26 @@ def test_full_size_parity_checker_is_exact_in_uint64(ref):
     assert bench.full_size_parity(res, tb.MODE_DOCS_ONLY, 100, res.match_counts, sums, None, None, 2)["docid_checksums_equal"] is True
     sums[1] += 1
     assert bench.full_size_parity(res, tb.MODE_DOCS_ONLY, 100, res.match_counts, sums, None, None, 2)["docid_checksums_equal"] is False
+
+
+def test_reference_side_binding_fails_loudly_without_a_gpu(ref):
+    """oracle/_ref/libtrinity_ref_gpu.so = the reference + integration/gpu_exec.cpp: attaching the device twin of an index source needs
+    a CUDA device; without one it reports the engine's error (no silent CPU detour), and the library's exec_query() keeps using the
+    reference's own span for sources that have no twin"""
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, str(ROOT / "tests"))
+    from refharness import RefIndex, load_ref_gpu
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    refg = load_ref_gpu()
+    r = RefIndex(refg, 0)
+    r.add_term("a", np.arange(2, 2000, 2, dtype=np.uint32), np.ones(999, np.uint32))
+    r.add_term("b", np.arange(3, 2000, 3, dtype=np.uint32), np.ones(666, np.uint32))
+    r.finish(2000)
+    assert refg.L.tref_gpu_attach(r.h, 0, 2000) != 0
+    assert "CUDA" in refg.err()
+    ids, _ = r.exec("a AND b", False, 4000)  # no twin registered: the stock CPU span
+    assert np.array_equal(ids, np.arange(6, 2000, 6, dtype=np.uint32))

@@ -1,0 +1,65 @@
+"""The drop-in boundary, EXECUTED: oracle/_ref/libtrinity_ref_gpu.so is the reference itself (same objects as the oracle) with the one
+span-building call site of exec_query() (exec.cpp:1083-1086) going through the reference-side binding of libtrinity_b200.so
+(integration/gpu_exec.{h,cpp}: GpuAccessProxy / PlanBuilder / GpuDocsSetSpan).  The reference's own query -> compile_query -> exec_node
+tree is turned into a plan by PlanBuilder (not by this repo's parser), runs through trn_exec_batch, and is replayed through
+MatchesProxy::process -> the stock exec Handlers -> MatchedIndexDocumentsFilter::consider().  The stream consider() sees must equal the
+stock library's, for every golden query shape, both ExecFlags modes, both codecs, with and without masked documents."""
+import numpy as np
+import pytest
+
+import trinity_b200 as tb
+from refharness import RefIndex, load_ref_gpu
+from test_frontend_cpu import EXTRA, OPTIONAL_QUERIES, SOME_QUERIES
+from test_gpu_parity import TEMPLATES
+from util import assert_close_scores, assert_same_docs, closed_form_lists
+
+pytestmark = pytest.mark.gpu
+NDOCS = 400_000
+
+
+def _twin(rl, codec, lists, names):
+    r = RefIndex(rl, codec)
+    for n, (d, f) in zip(names, lists):
+        r.add_term(n, d, f)
+    r.finish(NDOCS)
+    return r
+
+
+@pytest.mark.parametrize("codec", [tb.CODEC_GOOGLE, tb.CODEC_LUCENE], ids=["google", "lucene"])
+def test_exec_query_through_the_gpu_span_equals_stock_exec_query(ref, codec):
+    refg = load_ref_gpu()
+    lists = closed_form_lists(NDOCS)
+    names = [f"t{i + 1}" for i in range(len(lists))]
+    stock = _twin(ref, codec, lists, names)
+    gpu = _twin(refg, codec, lists, names)
+    assert refg.L.tref_gpu_attach(gpu.h, 0, NDOCS) == 0, refg.err()
+    try:
+        shapes = [(q, 0, 0) for q in TEMPLATES + EXTRA] + [(q, 8, 0) for q in OPTIONAL_QUERIES] + [(q, 16, m) for q, m in SOME_QUERIES]
+        before = refg.L.tref_gpu_spans_executed(gpu.h)
+        ran = 0
+        for q, pflags, mm in shapes:
+            for scored in (False, True):
+                if scored and "nosuchterm" in q:
+                    continue
+                wd, ws = stock.exec(q, scored, NDOCS + 1, parser_flags=pflags, min_match=mm)
+                gd, gs = gpu.exec(q, scored, NDOCS + 1, parser_flags=pflags, min_match=mm)
+                assert_same_docs(gd, wd, f"[{q}] scored={scored}")
+                if scored:
+                    assert_close_scores(gs, ws, f"[{q}]")
+                ran += 1
+        executed = refg.L.tref_gpu_spans_executed(gpu.h) - before
+        # single-term DocumentsOnly queries take exec_query's own specialisation (exec.cpp:894-1080) before any span is built, and a query
+        # whose tree collapses to nothing never reaches the span site; everything else must have gone through the GPU span
+        assert executed >= ran - 8, (executed, ran)
+        # masked documents: the Handler's registry test stays where it is (exec.cpp:1108-1116) and filters the replayed stream
+        rng = np.random.default_rng(5)
+        masked = np.unique(rng.integers(1, NDOCS + 1, 9000)).astype(np.uint32)
+        for q in ("t1 AND t2", "t3 OR t7 OR t9", "t1 AND (t2 OR t3) NOT t5"):
+            for scored in (False, True):
+                wd, ws = stock.exec_masked(q, scored, masked, NDOCS + 1)
+                gd, gs = gpu.exec_masked(q, scored, masked, NDOCS + 1)
+                assert_same_docs(gd, wd, f"[{q}] masked scored={scored}")
+                if scored:
+                    assert_close_scores(gs, ws, f"[{q}] masked")
+    finally:
+        refg.L.tref_gpu_detach(gpu.h)
