@@ -90,7 +90,6 @@ struct trn_ctx {
         uint32_t             block_docs{32}; // documents per full block of the uploaded index (GOOGLE 32 unless built for the decode sweep; LUCENE 128)
         uint32_t             min_docid{1}; // smallest docID any term holds (a docID-range shard does not start at 1)
         uint32_t             nterms{0}, max_docid{0}, tile_shift{13}, ntiles{0}; // tile_shift: directory granularity == scored tile (8192 docs, the reference's window docset_spans.h:74)
-        int                  docs_bufs{1};   // gather staging buffers per warp in k_exec_docs (TRN_DOCS_BUFS): 1 = 32 resident warps/SM beats 2 = prefetch at 24 warps (measured 49 vs 53 ms)
         uint32_t             docs_shift{14}; // docID tile (log2) of the warp-per-tile DocumentsOnly kernel
         uint32_t             run_tiles{32};  // TRN_RUN_TILES: consecutive tiles per work item of the flat scored kernel (top-k state lives across a run)
         int                  flat_threads{256}; // TRN_SF_THREADS: CTA size of k_score_flat (256/320/384: two CTAs per SM; 512/640: one)
@@ -617,8 +616,6 @@ extern "C" int trn_create(int device, trn_ctx **out) {
                 if (v >= 12 && v <= 14)
                         c->tile_shift = uint32_t(v);
         }
-        if (const char *e = getenv("TRN_DOCS_BUFS"))
-                c->docs_bufs = atoi(e) >= 2 ? 2 : 1;
         if (const char *e = getenv("TRN_CAND_COST"))
                 c->cand_cost = std::max(0, atoi(e));
         if (const char *e = getenv("TRN_DOCS_SHIFT")) {
@@ -1253,7 +1250,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         const double   tEnqueue0  = now_ms();
         const uint32_t totalItems = uint32_t(items);
         if (anyCandidate) { // the candidate array + one gather buffer must fit a warp's share of shared memory
-                const uint32_t slotBytes = (1u << execShift) / 8u, stageB = exec_docs_stage_bytes(c->docs_bufs), need = exec_docs_cand_smem_bytes(anyMembership);
+                const uint32_t slotBytes = (1u << execShift) / 8u, stageB = exec_docs_stage_bytes(), need = exec_docs_cand_smem_bytes(anyMembership);
                 if (need > stageB)
                         maxSlots = std::max(maxSlots, (need - stageB + slotBytes - 1u) / slotBytes);
         }
@@ -1326,7 +1323,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         P.nslots       = maxSlots;
         P.exec_shift   = execShift;
         P.stage_bytes  = exec_stage_bytes(c->codec);
-        P.docs_stage_bytes = exec_docs_stage_bytes(c->docs_bufs);
+        P.docs_stage_bytes = exec_docs_stage_bytes();
         P.mode         = mode;
         P.k            = k;
         P.ticket       = ticket;
@@ -1380,7 +1377,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                         launches += 2;
                 }
                 if (ownItems) {
-                        const int perSM = warpKernel ? exec_docs_max_ctas_per_sm(execShift, maxSlots, exec_docs_stage_bytes(c->docs_bufs)) : exec_max_ctas_per_sm(execShift, maxSlots, mode, c->codec);
+                        const int perSM = warpKernel ? exec_docs_max_ctas_per_sm(execShift, maxSlots, exec_docs_stage_bytes()) : exec_max_ctas_per_sm(execShift, maxSlots, mode, c->codec);
                         if (perSM <= 0)
                                 return fail(c, TRN_ERR_CUDA, "the exec kernel does not fit on an SM with this many docset slots");
                         const uint64_t workers = warpKernel ? (ownItems + 3) / 4 : ownItems; // 4 warp-workers per CTA

@@ -16,10 +16,11 @@
 static constexpr int      kDocsWarps       = 4;   // warps per CTA (independent workers)
 static constexpr uint32_t kSparseThreshold = 192; // candidates per tile below which AND switches to advance()-style skipping
 static constexpr uint32_t kGatherBytes     = 80;  // bytes of a block's head each lane stages (5 x 16 B; >= 64 payload bytes after alignment)
-static constexpr uint32_t kGatherWords     = kGatherBytes / 4;
 static constexpr uint32_t kGatherBufBytes  = 32 * kGatherBytes;  // one group
-static constexpr uint32_t kDocsStageBytes  = 2 * kGatherBufBytes; // double-buffered staging (also hosts one Lucene block: <= 2042 B + 512 B scratch)
-static constexpr uint32_t kDocsStageBytes1 = kGatherBufBytes + 512; // single-buffered variant: one group + 128-entry need-list / Lucene scratch
+// per-warp staging: ONE gather buffer + a 128-word area (need-list of the block-skipping path / scratch words of the word builders / Lucene
+// exception patches).  A second, prefetching buffer was measured and dropped: it costs a quarter of the resident warps (24 instead of 32
+// per SM) and lost 49 vs 53 ms on the headline batch (profiles/r01_e, r01_l).
+static constexpr uint32_t kDocsStageBytes1 = kGatherBufBytes + 512;
 
 // ---- lane-gather staging with cp.async (LDGSTS): no registers, no L1 allocation, completion tracked per group
 __device__ __forceinline__ void gather_issue(const uint8_t *__restrict__ index, uint32_t off, bool need, uint8_t *buf, int lane) {
@@ -36,23 +37,6 @@ template <int N> __device__ __forceinline__ void gather_wait() {
         asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
         __syncwarp();
 }
-
-// word sources for the windowed decoder
-struct SmemWords { // contiguous staged bytes
-        const uint32_t *wp;
-        __device__ __forceinline__ uint32_t next() {
-                return *wp++;
-        }
-};
-struct GatherWords { // the lane's kGatherBytes slot, continued from global memory for the rare longer doc-delta section
-        const uint32_t *slot, *g32;
-        uint32_t        k;
-        __device__ __forceinline__ uint32_t next() {
-                const uint32_t w = k < kGatherWords ? slot[k] : __ldg(g32 + k);
-                ++k;
-                return w;
-        }
-};
 
 // lower_bound over bl[a..b] (ascending) for the first index with bl[idx] >= v; returns b+1 if none.  Warp-cooperative 32-ary search.
 __device__ __forceinline__ uint32_t warp_lower_bound(const uint32_t *__restrict__ bl, uint32_t a, uint32_t b, uint32_t v, int lane) {
@@ -80,10 +64,6 @@ struct DocSink {
         }
 };
 
-// One lane decodes the doc-delta section of one Google block from SHARED memory; INTERIOR = block lies completely inside the tile
-// (no range checks).  The bytes are consumed through a 64-bit register window that is refilled from aligned 32-bit shared loads issued
-// one step ahead (the load is off the dependency chain), and runs of 1-byte deltas — the common case for the dense lists that carry
-// most postings — are consumed four at a time.
 // lean word-register bit builder (or-in only, no filter): one shared-memory reduction per touched 32-doc word.
 // The flush is a single PREDICATED red.shared.or (no branch): with a branch, the two or three lanes of a warp that cross a word
 // boundary at any given posting made the whole warp execute the flush body at ~2/32 lane occupancy on almost every posting.
@@ -105,109 +85,11 @@ struct BitAcc {
                 cur   = nw ? bit : (cur | bit);
                 cur_w = w;
         }
-        // same contract as add(), shorter dependency chain: the "new word" test of a posting depends only on the previous posting's
-        // word, never on the accumulator, so consecutive postings overlap (a flush of an empty accumulator ORs in 0: harmless)
-        __device__ __forceinline__ void add_nc(uint32_t rel) {
-                const uint32_t w = rel >> 5, bit = __funnelshift_l(0u, 1u, rel); // 1 << (rel & 31)
-                const bool     nw = w != cur_w;
-                red_if(nw ? 1u : 0u);
-                cur   = (nw ? 0u : cur) | bit;
-                cur_w = w;
-        }
         __device__ __forceinline__ void flush() {
                 red_if(cur);
                 cur = 0;
         }
 };
-
-// One lane decodes the doc-delta section of one Google block from SHARED memory, all participating lanes in LOCKSTEP.
-//  * bytes are consumed through a 64-bit register window refilled from aligned 32-bit shared loads issued one step ahead;
-//  * one unsigned compare covers both tile edges: (doc - lo) < W;
-//  * runs of 1-byte deltas are consumed four at a time, but only when EVERY lane of the warp can do so (warp vote), so the warp never
-//    executes the 4-wide and the 1-wide bodies in the same iteration (the per-lane version of this branch cost half the lanes:
-//    16.7 of 32 threads active per instruction, profiles/r01_c_*).
-// Must be called by all lanes in `m` (the lanes that decode a block in this group).
-__device__ int g_docs_lockstep = 1; // experiment switch (TRN_DOCS_LOCKSTEP): warp-voted vs per-lane choice of the 4-wide path
-
-template <class SINK, class WORDS>
-__device__ __forceinline__ void google_block_docs_win(unsigned m, WORDS &src, uint32_t misalign, uint32_t n, uint32_t prev, uint32_t last, uint32_t lo, uint32_t W,
-                                                      SINK &bs) {
-        const uint32_t     w0  = src.next(), w1 = src.next();
-        unsigned long long win = (static_cast<unsigned long long>(w1) << 32 | w0) >> (misalign * 8u);
-        uint32_t        avail    = 8u - misalign; // valid bytes in win
-        uint32_t        nxt      = src.next();    // prefetched next word
-        uint32_t doc = prev, i = 0;
-        const uint32_t nd = n - 1u; // deltas in the block (the last doc comes from the directory)
-        const bool     lockstep = g_docs_lockstep != 0;
-        for (;;) {
-                const bool live = i < nd;
-                if (lockstep ? !__any_sync(m, live) : !live)
-                        break;
-                if (live && avail < 4u) {
-                        win |= static_cast<unsigned long long>(nxt) << (avail * 8u);
-                        avail += 4u;
-                        nxt = src.next();
-                }
-                const uint32_t b = uint32_t(win);
-                const bool fast4 = (b & 0x80808080u) == 0u && i + 4u <= nd;
-                if (lockstep ? __all_sync(m, !live || fast4) : fast4) {
-                        if (live) {
-                                // four 1-byte deltas
-                                const uint32_t d0 = doc + (b & 0xffu), d1 = d0 + ((b >> 8) & 0xffu), d2 = d1 + ((b >> 16) & 0xffu), d3 = d2 + (b >> 24);
-                                win >>= 32;
-                                avail -= 4u;
-                                i += 4u;
-                                doc = d3;
-                                if (d0 - lo < W) bs.add(d0 - lo);
-                                if (d1 - lo < W) bs.add(d1 - lo);
-                                if (d2 - lo < W) bs.add(d2 - lo);
-                                if (d3 - lo < W) bs.add(d3 - lo);
-                        }
-                } else if (live) {
-                        uint32_t       v, len;
-                        const uint32_t b0 = b & 0xffu;
-                        if (b0 < 0x80u) {
-                                v   = b0;
-                                len = 1u;
-                        } else if (b0 < 0xc0u) {
-                                v   = ((b0 & 0x3fu) << 8) | ((b >> 8) & 0xffu);
-                                len = 2u;
-                        } else if (b0 < 0xe0u) {
-                                v   = ((b0 & 0x1fu) << 16) | ((b >> 8) & 0xffffu);
-                                len = 3u;
-                        } else if (b0 < 0xf0u) {
-                                v   = ((b0 & 0x0fu) << 24) | (((b >> 8) & 0xffu) << 16) | (((b >> 16) & 0xffu) << 8) | (b >> 24);
-                                len = 4u;
-                        } else {
-                                // 5-byte code: u32le in bytes 1..4 (needs one more byte than the 4 guaranteed)
-                                if (avail < 5u) {
-                                        win |= static_cast<unsigned long long>(nxt) << (avail * 8u);
-                                        avail += 4u;
-                                        nxt = src.next();
-                                }
-                                v   = uint32_t(win >> 8);
-                                len = 5u;
-                        }
-                        win >>= len * 8u;
-                        avail -= len;
-                        ++i;
-                        doc += v;
-                        if (doc - lo < W)
-                                bs.add(doc - lo);
-                }
-        }
-        if (last - lo < W)
-                bs.add(last - lo);
-}
-
-template <class SINK>
-__device__ __forceinline__ void google_block_docs_smem(unsigned m, const uint8_t *p, uint32_t n, uint32_t prev, uint32_t last, uint32_t lo, uint32_t W, SINK &bs) {
-        const uint32_t misalign = uint32_t(reinterpret_cast<uintptr_t>(p) & 3u);
-        SmemWords      src{reinterpret_cast<const uint32_t *>(p - misalign)};
-        google_block_docs_win(m, src, misalign, n, prev, last, lo, W, bs);
-}
-
-__device__ int g_docs_decoder = 4; // TRN_DOCS_DECODER: 0 = 64-bit window, 1 = byte-wise, 2 = word-at-a-time; flat conjunctions: 3 = 2 + plain-store word builder, 4 = warp-voted
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
         uint32_t v;
@@ -259,79 +141,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
         return v;
 }
 
-// Word-at-a-time decoder over the lane's gather slot (TRN_DOCS_DECODER=2).  The lists that carry most postings are dense: their
-// doc deltas are 1-byte codes almost everywhere.  After a byte-wise prologue that brings the read position to a 4-byte boundary
-// of the slot, every iteration takes ONE aligned 32-bit shared load, ONE test for "four 1-byte codes" and ONE branch for FOUR
-// postings (the byte-wise loop pays a load, a compare chain and two branches per posting: branch-resolve and short-scoreboard
-// stalls were 35 % of all warp stall cycles, profiles/r01_k_*).  A word holding a longer code is consumed byte-wise until the
-// position is aligned again.  The tile-edge test is made once per four postings (docIDs ascend: first and last in range => all).
-__device__ __forceinline__ void google_block_docs_w4(const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n, uint32_t prev,
-                                                     uint32_t last, uint32_t lo, uint32_t W, BitAcc &bs) {
-        const uint32_t mis  = off & 15u;
-        const uint32_t base = uint32_t(__cvta_generic_to_shared(buf + lane * kGatherBytes)) + mis; // shared address of the first delta byte
-        const uint32_t nd   = n - 1u;
-        uint32_t       sp = base, doc = prev, i = 0;
-        bool           spill = false; // met a 3..5-byte code: the section may leave the slot
-        // one code, byte-wise
-        auto one = [&]() {
-                const uint32_t b0 = lds_u8(sp);
-                uint32_t       v;
-                if (b0 < 0x80u) {
-                        v = b0;
-                        sp += 1u;
-                } else if (b0 < 0xc0u) {
-                        v = ((b0 & 0x3fu) << 8) | lds_u8(sp + 1u);
-                        sp += 2u;
-                } else {
-                        spill = true;
-                        return;
-                }
-                ++i;
-                doc += v;
-                if (doc - lo < W)
-                        bs.add_nc(doc - lo);
-        };
-        while (i < nd && (sp & 3u) && !spill)
-                one();
-        while (i + 4u <= nd && !spill) {
-                const uint32_t w = lds_u32(sp);
-                if (w & 0x80808080u) {
-                        do
-                                one();
-                        while (i < nd && (sp & 3u) && !spill);
-                        continue;
-                }
-                const uint32_t d0 = doc + (w & 0xffu), d1 = d0 + __byte_perm(w, 0u, 0x4441u), d2 = d1 + __byte_perm(w, 0u, 0x4442u), d3 = d2 + (w >> 24);
-                const uint32_t r0 = d0 - lo, r1 = d1 - lo, r2 = d2 - lo, r3 = d3 - lo;
-                doc = d3;
-                sp += 4u;
-                i += 4u;
-                if (r0 < W && r3 < W) {
-                        bs.add_nc(r0);
-                        bs.add_nc(r1);
-                        bs.add_nc(r2);
-                        bs.add_nc(r3);
-                } else {
-                        if (r0 < W) bs.add_nc(r0);
-                        if (r1 < W) bs.add_nc(r1);
-                        if (r2 < W) bs.add_nc(r2);
-                        if (r3 < W) bs.add_nc(r3);
-                }
-        }
-        while (i < nd && !spill)
-                one();
-        if (i < nd) {
-                const uint8_t *g = index + off + (sp - base);
-                for (; i < nd; ++i) {
-                        doc += varbyte_get(g);
-                        if (doc - lo < W)
-                                bs.add_nc(doc - lo);
-                }
-        }
-        if (last - lo < W)
-                bs.add_nc(last - lo);
-}
-
 // Plain-store word builder for a bitmap that only ONE term writes (flat conjunctions keep one slot per operand).  The blocks of
 // a term partition the docID space, so every 32-doc word strictly between a block's first and last word belongs to that block's
 // lane alone: it is written with a predicated STS when the lane moves on — no atomic, and no branch (ptxas turns a predicated
@@ -359,73 +168,6 @@ struct OwnAcc {
         }
 };
 
-// Word-at-a-time decoder into an OwnAcc (see google_block_docs_w4 for the read side).  `rel` runs relative to the tile's first docID
-// (it wraps below the tile, one unsigned compare covers both edges).
-__device__ __forceinline__ void google_block_docs_own(const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n, uint32_t prev,
-                                                      uint32_t last, uint32_t lo, uint32_t W, OwnAcc &bs) {
-        const uint32_t mis  = off & 15u;
-        const uint32_t base = uint32_t(__cvta_generic_to_shared(buf + lane * kGatherBytes)) + mis; // shared address of the first delta byte
-        const uint32_t nd   = n - 1u;
-        uint32_t       sp = base, rel = prev - lo, i = 0;
-        bool           spill = false; // met a 3..5-byte code: the section may leave the slot
-        auto           one   = [&]() {
-                const uint32_t b0 = lds_u8(sp);
-                uint32_t       v;
-                if (b0 < 0x80u) {
-                        v = b0;
-                        sp += 1u;
-                } else if (b0 < 0xc0u) {
-                        v = ((b0 & 0x3fu) << 8) | lds_u8(sp + 1u);
-                        sp += 2u;
-                } else {
-                        spill = true;
-                        return;
-                }
-                ++i;
-                rel += v;
-                if (rel < W)
-                        bs.add(rel);
-        };
-        while (i < nd && (sp & 3u) && !spill)
-                one();
-        while (i + 4u <= nd && !spill) {
-                const uint32_t w = lds_u32(sp);
-                if (w & 0x80808080u) {
-                        do
-                                one();
-                        while (i < nd && (sp & 3u) && !spill);
-                        continue;
-                }
-                const uint32_t r0 = rel + (w & 0xffu), r1 = r0 + __byte_perm(w, 0u, 0x4441u), r2 = r1 + __byte_perm(w, 0u, 0x4442u), r3 = r2 + (w >> 24);
-                rel = r3;
-                sp += 4u;
-                i += 4u;
-                if (r0 < W && r3 < W) {
-                        bs.add(r0);
-                        bs.add(r1);
-                        bs.add(r2);
-                        bs.add(r3);
-                } else {
-                        if (r0 < W) bs.add(r0);
-                        if (r1 < W) bs.add(r1);
-                        if (r2 < W) bs.add(r2);
-                        if (r3 < W) bs.add(r3);
-                }
-        }
-        while (i < nd && !spill)
-                one();
-        if (i < nd) {
-                const uint8_t *g = index + off + (sp - base);
-                for (; i < nd; ++i) {
-                        rel += varbyte_get(g);
-                        if (rel < W)
-                                bs.add(rel);
-                }
-        }
-        if (last - lo < W)
-                bs.add(last - lo);
-}
-
 // OwnAcc::add under a per-lane predicate, branch-free (every lane of the warp executes the same instructions)
 __device__ __forceinline__ void own_add_if(OwnAcc &bs, bool on, uint32_t rel) {
         const uint32_t w = rel >> 5, bit = __funnelshift_l(0u, 1u, rel);
@@ -436,10 +178,9 @@ __device__ __forceinline__ void own_add_if(OwnAcc &bs, bool on, uint32_t rel) {
         bs.cur_a = on ? bs.bm + w * 4u : bs.cur_a;
 }
 
-// Warp-voted decoder into an OwnAcc (TRN_DOCS_DECODER=4).  google_block_docs_own lets every lane choose between the 4-wide body
-// and byte-wise excursions on its own; the ncu capture (profiles/r01_l_*) shows what that costs: 6 % of the 4-byte words hold a
-// 2-byte code, but each of them sends its warp through ~3 byte-wise iterations at 2 of 32 lanes — more instructions than the
-// 4-wide body itself.  Here every iteration reads a 32-bit window at ANY byte position (two aligned shared loads + funnel shift:
+// Warp-voted decoder into an OwnAcc.  Its predecessor let every lane choose between a 4-wide body and byte-wise excursions on its
+// own; the ncu capture (profiles/r01_l_*) shows what that cost: 6 % of the 4-byte words hold a 2-byte code, but each of them sent its
+// warp through ~3 byte-wise iterations at 2 of 32 lanes — more instructions than the 4-wide body itself.  Here every iteration reads a 32-bit window at ANY byte position (two aligned shared loads + funnel shift:
 // no alignment prologue, no re-alignment), and the warp votes: all lanes see four 1-byte codes => the 4-wide body; otherwise ALL
 // lanes run one predicated, branch-free step that consumes the leading 1-byte codes of the window plus the first 2-byte code
 // (1..4 postings).  The two bodies are never executed in the same iteration.
@@ -513,29 +254,11 @@ __device__ __forceinline__ void google_block_docs_vote(unsigned m, const uint8_t
                 bs.add(last - lo);
 }
 
-template <class SINK> struct UseW4 {
-        static constexpr bool value = false;
-};
-template <> struct UseW4<BitAcc> {
-        static constexpr bool value = true;
-};
-
+// generic sinks (BitSink of the step programs, BitAcc of flat disjunctions): the byte-wise decoder over the lane's gather slot
 template <class SINK>
-__device__ __forceinline__ void google_block_docs_gather(unsigned m, const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n,
+__device__ __forceinline__ void google_block_docs_gather(unsigned, const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n,
                                                          uint32_t prev, uint32_t last, uint32_t lo, uint32_t W, SINK &bs) {
-        if constexpr (UseW4<SINK>::value) {
-                if (g_docs_decoder == 2) {
-                        google_block_docs_w4(index, off, buf, lane, n, prev, last, lo, W, bs);
-                        return;
-                }
-        }
-        if (g_docs_decoder) {
-                google_block_docs_bytes(index, off, buf, lane, n, prev, last, lo, W, bs);
-                return;
-        }
-        const uint32_t A = off & ~15u, mis = off - A;
-        GatherWords    src{reinterpret_cast<const uint32_t *>(buf + lane * kGatherBytes), reinterpret_cast<const uint32_t *>(index + A), mis >> 2};
-        google_block_docs_win(m, src, mis & 3u, n, prev, last, lo, W, bs);
+        google_block_docs_bytes(index, off, buf, lane, n, prev, last, lo, W, bs);
 }
 
 // generic-pointer fallback (blocks that do not fit the staging area are read straight from global memory)
@@ -816,8 +539,7 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
                                 BitSink         bs;
                                 // Google operands that are decoded in full go through the plain-store word builder into a bitmap of their
                                 // own (dst itself for SET, the scratch slot otherwise) and are combined word-wise afterwards
-                                const bool ownOk = P.ix.codec == 0 && g_docs_decoder >= 3 && P.docs_stage_bytes >= kGatherBufBytes + 128u &&
-                                                   P.docs_stage_bytes < 2u * kGatherBufBytes && haveTerm && bA <= bB;
+                                const bool ownOk = P.ix.codec == 0 && haveTerm && bA <= bB;
                                 const uint32_t dummy = uint32_t(__cvta_generic_to_shared(stage + kGatherBufBytes)) + uint32_t(lane) * 4u;
                                 if (ownOk && mode != M_AND) {
                                         uint32_t *out = mode == M_SET ? dst : tmp;
@@ -967,8 +689,8 @@ uint32_t exec_docs_cand_smem_bytes(bool with_membership) {
         return with_membership ? kCandSmemMask : kCandSmem;
 }
 
-uint32_t exec_docs_stage_bytes(int bufs) {
-        return bufs >= 2 ? kDocsStageBytes : kDocsStageBytes1;
+uint32_t exec_docs_stage_bytes() {
+        return kDocsStageBytes1;
 }
 
 size_t exec_docs_smem_bytes(uint32_t exec_shift, uint32_t nslots, uint32_t stageBytes) {
@@ -987,18 +709,6 @@ int exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots, uint32_t sta
 }
 
 cudaError_t launch_exec_docs(const ExecParams &P, int grid, cudaStream_t stream) {
-        static bool once = false;
-        if (!once) {
-                once = true;
-                if (const char *e = getenv("TRN_DOCS_DECODER")) {
-                        const int v = atoi(e);
-                        cudaMemcpyToSymbol(g_docs_decoder, &v, sizeof(int));
-                }
-                if (const char *e = getenv("TRN_DOCS_LOCKSTEP")) {
-                        const int v = atoi(e);
-                        cudaMemcpyToSymbol(g_docs_lockstep, &v, sizeof(int));
-                }
-        }
         const size_t smem = exec_docs_smem_bytes(P.exec_shift, P.nslots, P.docs_stage_bytes);
         cudaError_t  e    = cudaFuncSetAttribute(k_exec_docs, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess)

@@ -9,9 +9,8 @@
 //
 // Staging: every lane copies only the head of ITS block (kGatherBytes from the 16B-aligned address below the first doc-delta byte)
 // with cp.async (LDGSTS) into its own slot — the doc-delta section of a 32-doc block is at most 31 x 2 bytes for gaps < 16384, and
-// the inline hits behind it (half of the index bytes) never enter the SM.  Groups are double-buffered: the copies of group g+1 are
-// in flight while group g is decoded.  (The span-copy version kept 6 KB per warp for one group, capped the SM at 20 resident warps
-// and exposed every group's global-load latency: 14 % of all stall samples, profiles/r01_c_*.)
+// the inline hits behind it (half of the index bytes) never enter the SM.  (The span-copy version kept 6 KB per warp for one group,
+// capped the SM at 20 resident warps and exposed every group's global-load latency: 14 % of all stall samples, profiles/r01_c_*.)
 #pragma once
 
 static constexpr uint32_t kFlatMaxLeaves = 16;
@@ -93,39 +92,24 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
                 return L;
         };
 
-        const bool dbuf = P.docs_stage_bytes >= 2u * kGatherBufBytes; // double-buffered staging (else: more resident warps instead)
         // conjunctions: one bitmap per operand => plain-store word builder (OwnAcc); the last word of every block is ORed in
         // atomically one group LATER, after every block that can share it has stored its words
-        const int      decoder = g_docs_decoder;
-        const bool     own     = isAnd && decoder >= 3 && P.docs_stage_bytes >= (dbuf ? 2u : 1u) * kGatherBufBytes + 128u;
-        const uint32_t dummy   = uint32_t(__cvta_generic_to_shared(stage + (dbuf ? 2u : 1u) * kGatherBufBytes)) + uint32_t(lane) * 4u;
+        const bool     own     = isAnd;
+        const uint32_t dummy   = uint32_t(__cvta_generic_to_shared(stage + kGatherBufBytes)) + uint32_t(lane) * 4u;
         const uint32_t slots_s = uint32_t(__cvta_generic_to_shared(slots));
         uint32_t       tail_a = dummy, tail_bits = 0;
         FlatLane   cur  = assign(0);
         gather_issue(P.ix.index, cur.off, cur.active, stage, lane);
         __syncwarp(); // slot clears above are visible before the first reduction
-        uint32_t buf = 0;
         for (uint32_t g = 0; g < total; g += 32u) {
-                FlatLane nxt;
-                nxt.active = false;
-                nxt.j = nxt.off = nxt.n = nxt.prev = nxt.last = 0;
                 const bool more = g + 32u < total;
-                if (more && dbuf) {
-                        nxt = assign(g + 32u);
-                        gather_issue(P.ix.index, nxt.off, nxt.active, stage + (buf ^ 1u) * kGatherBufBytes, lane);
-                        gather_wait<1>();
-                } else
-                        gather_wait<0>();
+                gather_wait<0>();
                 const unsigned m = __ballot_sync(0xffffffffu, cur.active);
                 if (own) {
                         OwnAcc bs;
                         bs.init(slots_s + cur.j * NW * 4u, dummy);
-                        if (cur.active) {
-                                if (decoder == 3)
-                                        google_block_docs_own(P.ix.index, cur.off, stage + buf * kGatherBufBytes, lane, cur.n, cur.prev, cur.last, lo, W, bs);
-                                else
-                                        google_block_docs_vote(m, P.ix.index, cur.off, stage + buf * kGatherBufBytes, lane, cur.n, cur.prev, cur.last, lo, W, bs);
-                        }
+                        if (cur.active)
+                                google_block_docs_vote(m, P.ix.index, cur.off, stage, lane, cur.n, cur.prev, cur.last, lo, W, bs);
                         __syncwarp();
                         if (tail_bits) // the previous group's last words
                                 asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(tail_a), "r"(tail_bits) : "memory");
@@ -133,15 +117,12 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
                         tail_bits = bs.cur;
                 } else if (cur.active) {
                         BitAcc bs;
-                        bs.init(isAnd ? slots + size_t(cur.j) * NW : root);
-                        google_block_docs_gather(m, P.ix.index, cur.off, stage + buf * kGatherBufBytes, lane, cur.n, cur.prev, cur.last, lo, W, bs);
+                        bs.init(root);
+                        google_block_docs_gather(m, P.ix.index, cur.off, stage, lane, cur.n, cur.prev, cur.last, lo, W, bs);
                         bs.flush();
                 }
                 __syncwarp();
-                if (dbuf) {
-                        cur = nxt;
-                        buf ^= 1u;
-                } else if (more) {
+                if (more) {
                         cur = assign(g + 32u);
                         gather_issue(P.ix.index, cur.off, cur.active, stage, lane);
                 }

@@ -8,7 +8,7 @@ uint32_t    exec_stage_bytes(int codec);
 size_t      exec_smem_bytes(uint32_t tile_shift, uint32_t nslots, int mode, int codec);
 int         exec_max_ctas_per_sm(uint32_t tile_shift, uint32_t nslots, int mode, int codec);
 cudaError_t launch_exec_tiles(const ExecParams &P, int grid, cudaStream_t stream);
-uint32_t    exec_docs_stage_bytes(int bufs);
+uint32_t    exec_docs_stage_bytes();
 uint32_t    exec_docs_cand_smem_bytes(bool with_membership); // per-warp shared memory of the candidate-driven path (membership bytes: trees with terms that are not necessary)
 size_t      exec_docs_smem_bytes(uint32_t exec_shift, uint32_t nslots, uint32_t stageBytes);
 int         exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots, uint32_t stageBytes);
