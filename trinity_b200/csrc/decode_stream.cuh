@@ -160,10 +160,105 @@ __device__ __forceinline__ void ds_google_block_global(const uint8_t *p, uint32_
         }
 }
 
-// unit = 32 consecutive blocks of one term, one warp per unit, units handed out with a fixed stride
+// SPARSE lists (average gap >= 48: most doc deltas are 2-byte codes, so the warp-voted 4-wide step above would fail on almost every
+// window): every lane walks ITS block on its own — no votes — taking up to TWO codes of 1-2 bytes out of each 32-bit window (two such
+// codes always fit), a rare side path for 3-5-byte codes; the freq section (1-byte codes) goes four at a time.
 template <bool MAT>
-__global__ void __launch_bounds__(kThreads) k_decode_stream_google(DevIndex ix, const uint32_t *term_ids, const uint32_t *unit_base /*nterms+1*/, const uint64_t *out_base,
-                                                                  uint32_t nterms, uint32_t total_units, uint32_t *docids, uint32_t *freqs, unsigned long long *sums) {
+__device__ __forceinline__ void ds_google_block_sparse(uint32_t sp, uint32_t n, uint32_t prev, uint32_t last, uint32_t *outd, uint32_t *outf, unsigned long long &sumd,
+                                                       unsigned long long &sumf) {
+        const uint32_t nd  = n - 1u;
+        uint32_t       doc = prev, i = 0;
+        while (i < nd) {
+                const uint32_t a  = sp & ~3u;
+                const uint32_t w  = __funnelshift_r(lds_u32(a), lds_u32(a + 4u), (sp & 3u) * 8u); // bytes sp .. sp+3
+                const uint32_t b0 = w & 0xffu;
+                if (b0 >= 0xc0u) { // 3..5-byte code
+                        uint32_t v, len;
+                        if (b0 < 0xe0u) {
+                                v   = ((b0 & 0x1fu) << 16) | ((w >> 8) & 0xffffu);
+                                len = 3u;
+                        } else if (b0 < 0xf0u) {
+                                v   = ((b0 & 0x0fu) << 24) | (((w >> 8) & 0xffu) << 16) | (((w >> 16) & 0xffu) << 8) | (w >> 24);
+                                len = 4u;
+                        } else {
+                                const uint32_t a1 = (sp + 1u) & ~3u;
+                                v   = __funnelshift_r(lds_u32(a1), lds_u32(a1 + 4u), ((sp + 1u) & 3u) * 8u);
+                                len = 5u;
+                        }
+                        doc += v;
+                        sumd += doc;
+                        if (MAT)
+                                outd[i] = doc;
+                        sp += len;
+                        ++i;
+                        continue;
+                }
+                const uint32_t two = b0 >> 7;
+                uint32_t       len = 1u + two;
+                doc += two ? (((b0 & 0x3fu) << 8) | __byte_perm(w, 0u, 0x4441u)) : b0;
+                sumd += doc;
+                if (MAT)
+                        outd[i] = doc;
+                ++i;
+                // the second code of the window
+                const uint32_t w2 = w >> (8u * len), c0 = w2 & 0xffu;
+                if (i < nd && c0 < 0xc0u) {
+                        const uint32_t two2 = c0 >> 7;
+                        doc += two2 ? (((c0 & 0x3fu) << 8) | ((w2 >> 8) & 0xffu)) : c0;
+                        sumd += doc;
+                        if (MAT)
+                                outd[i] = doc;
+                        ++i;
+                        len += 1u + two2;
+                }
+                sp += len;
+        }
+        sumd += last;
+        if (MAT)
+                outd[nd] = last;
+        i = 0;
+        while (i < n) {
+                const uint32_t a = sp & ~3u;
+                const uint32_t w = __funnelshift_r(lds_u32(a), lds_u32(a + 4u), (sp & 3u) * 8u);
+                if ((w & 0x80808080u) == 0u && i + 4u <= n && (!MAT || (i & 3u) == 0u)) {
+                        sumf += __dp4a(w, 0x01010101u, 0u);
+                        if (MAT)
+                                *reinterpret_cast<uint4 *>(outf + i) = make_uint4(w & 0xffu, __byte_perm(w, 0u, 0x4441u), __byte_perm(w, 0u, 0x4442u), w >> 24);
+                        sp += 4u;
+                        i += 4u;
+                } else {
+                        const uint32_t b0 = w & 0xffu;
+                        uint32_t       v, len;
+                        if (b0 < 0xc0u) {
+                                const uint32_t two = b0 >> 7;
+                                v   = two ? (((b0 & 0x3fu) << 8) | __byte_perm(w, 0u, 0x4441u)) : b0;
+                                len = 1u + two;
+                        } else if (b0 < 0xe0u) {
+                                v   = ((b0 & 0x1fu) << 16) | ((w >> 8) & 0xffffu);
+                                len = 3u;
+                        } else if (b0 < 0xf0u) {
+                                v   = ((b0 & 0x0fu) << 24) | (((w >> 8) & 0xffu) << 16) | (((w >> 16) & 0xffu) << 8) | (w >> 24);
+                                len = 4u;
+                        } else {
+                                const uint32_t a1 = (sp + 1u) & ~3u;
+                                v   = __funnelshift_r(lds_u32(a1), lds_u32(a1 + 4u), ((sp + 1u) & 3u) * 8u);
+                                len = 5u;
+                        }
+                        sumf += v;
+                        if (MAT)
+                                outf[i] = v;
+                        sp += len;
+                        ++i;
+                }
+        }
+}
+
+// unit = 32 consecutive blocks of one term, one warp per unit, units handed out with a fixed stride.  The host lays the units out
+// (DecUnit); the kernel is a three-stage software pipeline per warp: unit descriptor (u+3) -> directory entries (u+2) -> bulk copy of
+// the span (u+1) -> decode (u), so no load sits on the critical path of a decode.
+template <bool MAT>
+__global__ void __launch_bounds__(kThreads) k_decode_stream_google(DevIndex ix, const DecUnit *units, const uint64_t *out_base, uint32_t total_units, uint32_t *docids,
+                                                                  uint32_t *freqs, unsigned long long *sums) {
         __shared__ __align__(8) unsigned long long s_bar[kWarps * 2];
         const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         uint8_t *      stage   = dyn_smem + size_t(warp) * kDsWarpBytes;
@@ -178,43 +273,52 @@ __global__ void __launch_bounds__(kThreads) k_decode_stream_google(DevIndex ix, 
         const uint32_t stride = gridDim.x * kWarps;
         const uint32_t bd     = ix.block_docs;
 
-        struct Unit {
-                uint32_t ti, off, n, prev, last, b, first_off, span;
-                bool     active;
+        struct Dir { // this lane's block of a unit
+                uint32_t off, offn, last, prev, n, cnt, ti, g0;
         };
-        uint32_t tcur = 0; // units are visited in ascending order: the term index only moves forward
-        auto locate = [&](uint32_t unit) {
-                Unit U;
-                U.active = false;
-                U.ti = U.off = U.n = U.prev = U.last = U.b = U.first_off = U.span = 0;
-                if (unit >= total_units)
-                        return U;
-                while (tcur + 1u < nterms && __ldg(unit_base + tcur + 1u) <= unit)
-                        ++tcur;
-                const DevTerm  T  = ix.terms[__ldg(term_ids + tcur)];
-                const uint32_t g0 = (unit - __ldg(unit_base + tcur)) * 32u, b = g0 + uint32_t(lane);
-                U.ti              = tcur;
-                U.b               = b;
-                uint32_t offn     = 0;
-                if (b < T.nblocks) {
-                        const uint32_t *bl = ix.blk_last + T.dir_begin, *bo = ix.blk_off + T.dir_begin;
-                        U.active = true;
-                        U.off    = __ldg(bo + b);
-                        offn     = __ldg(bo + b + 1u);
-                        U.last   = __ldg(bl + b);
-                        U.prev   = b ? __ldg(bl + b - 1u) : 0u;
-                        U.n      = (b + 1u == T.nblocks) ? (T.documents - bd * (T.nblocks - 1u)) : bd;
+        auto load_desc = [&](uint32_t u) {
+                DecUnit D;
+                D.first_entry = D.cnt = D.term_start = D.last_n = D.ti = D.g0 = D.pad0 = D.pad1 = 0;
+                if (u < total_units) {
+                        const uint4 x = __ldg(reinterpret_cast<const uint4 *>(units + u));
+                        const uint2 y = __ldg(reinterpret_cast<const uint2 *>(units + u) + 2);
+                        D.first_entry = x.x;
+                        D.cnt         = x.y;
+                        D.term_start  = x.z;
+                        D.last_n      = x.w;
+                        D.ti          = y.x;
+                        D.g0          = y.y;
                 }
-                const uint32_t cnt = min(32u, T.nblocks - min(T.nblocks, g0));
-                U.first_off        = __shfl_sync(0xffffffffu, U.off, 0);
-                const uint32_t end = __shfl_sync(0xffffffffu, offn, int(max(cnt, 1u)) - 1);
-                U.span             = cnt ? end - U.first_off : 0u;
-                return U;
+                return D;
+        };
+        auto load_dir = [&](const DecUnit &D) {
+                Dir R;
+                R.off = R.offn = R.last = R.prev = R.n = 0;
+                R.cnt = D.cnt;
+                R.ti  = D.ti;
+                R.g0  = D.g0;
+                if (uint32_t(lane) < D.cnt) {
+                        const uint32_t e = D.first_entry + uint32_t(lane);
+                        R.off  = __ldg(ix.blk_off + e);
+                        R.offn = __ldg(ix.blk_off + e + 1u);
+                        R.last = __ldg(ix.blk_last + e);
+                        R.prev = (D.term_start && lane == 0) ? 0u : __ldg(ix.blk_last + e - 1u);
+                        R.n    = (D.last_n && uint32_t(lane) + 1u == D.cnt) ? D.last_n : bd;
+                }
+                return R;
         };
         uint32_t seq_issue = 0, seq_wait = 0;
-        auto     issue     = [&](const Unit &U) { // one bulk copy of the unit's span (only when it fits: otherwise the lanes read global memory)
-                const uint32_t abase = U.first_off & ~15u, bytes = ((U.first_off + U.span + 15u) & ~15u) - abase;
-                if (U.span && bytes <= kDsStage) {
+        // the span of a unit: [first_off, end) with a 16-byte aligned window around it; `fits`: it goes through the staging buffer
+        auto span_of = [&](const Dir &R, uint32_t &abase, uint32_t &bytes) {
+                const uint32_t first_off = __shfl_sync(0xffffffffu, R.off, 0);
+                const uint32_t end       = __shfl_sync(0xffffffffu, R.offn, int(max(R.cnt, 1u)) - 1);
+                abase                    = first_off & ~15u;
+                bytes                    = ((end + 15u) & ~15u) - abase;
+                return R.cnt != 0u && bytes <= kDsStage;
+        };
+        auto issue = [&](const Dir &R) {
+                uint32_t abase, bytes;
+                if (span_of(R, abase, bytes)) {
                         if (lane == 0) {
                                 const uint32_t bsel = seq_issue & 1u;
                                 mbar_expect_tx(bar_s + bsel * 8u, bytes);
@@ -225,51 +329,59 @@ __global__ void __launch_bounds__(kThreads) k_decode_stream_google(DevIndex ix, 
         };
 
         uint32_t unit = blockIdx.x * kWarps + warp;
-        Unit     cur  = locate(unit);
-        Unit     nxt  = locate(unit + stride);
+        Dir      cur  = load_dir(load_desc(unit));
+        Dir      nxt  = load_dir(load_desc(unit + stride));
+        DecUnit  d2   = load_desc(unit + 2u * stride);
         issue(cur);
         for (; unit < total_units; unit += stride) {
                 issue(nxt);
-                const Unit nn = locate(unit + 2u * stride); // its directory loads are in flight while this unit is decoded
-                const uint32_t abase = cur.first_off & ~15u, bytes = ((cur.first_off + cur.span + 15u) & ~15u) - abase;
-                const bool     staged = cur.span && bytes <= kDsStage;
+                const Dir     nn = load_dir(d2);                    // directory loads of u+2: in flight while u is decoded
+                const DecUnit d3 = load_desc(unit + 3u * stride);
+                uint32_t       abase, bytes;
+                const bool     staged = span_of(cur, abase, bytes);
                 uint32_t       bsel   = 0;
                 if (staged) {
                         bsel = seq_wait & 1u;
                         mbar_wait(bar_s + bsel * 8u, (seq_wait >> 1) & 1u);
                         ++seq_wait;
                 }
-                const unsigned     m    = __ballot_sync(0xffffffffu, cur.active);
+                const bool         active = uint32_t(lane) < cur.cnt;
+                const unsigned     m      = __ballot_sync(0xffffffffu, active);
                 unsigned long long sumd = 0, sumf = 0;
-                if (cur.active) {
-                        const size_t row = MAT ? size_t(out_base[cur.ti]) + size_t(cur.b) * bd : 0;
+                // dense or sparse walk: decided per unit from its docID span (uniform across the warp)
+                const uint32_t lastDoc = __shfl_sync(0xffffffffu, cur.last, int(max(cur.cnt, 1u)) - 1), firstPrev = __shfl_sync(0xffffffffu, cur.prev, 0);
+                const bool     dense   = (lastDoc - firstPrev) < 48u * cur.cnt * bd;
+                if (active) {
+                        const size_t row = MAT ? size_t(out_base[cur.ti]) + (size_t(cur.g0) + size_t(lane)) * bd : 0;
                         uint32_t *   od  = MAT ? docids + row : nullptr;
                         uint32_t *   of  = MAT ? freqs + row : nullptr;
-                        if (staged)
+                        if (!staged)
+                                ds_google_block_global<MAT>(ix.index + cur.off, cur.n, cur.prev, cur.last, od, of, sumd, sumf);
+                        else if (dense)
                                 ds_google_block<MAT>(m, stage_s + bsel * kDsStage + (cur.off - abase), cur.n, cur.prev, cur.last, od, of, sumd, sumf);
                         else
-                                ds_google_block_global<MAT>(ix.index + cur.off, cur.n, cur.prev, cur.last, od, of, sumd, sumf);
+                                ds_google_block_sparse<MAT>(stage_s + bsel * kDsStage + (cur.off - abase), cur.n, cur.prev, cur.last, od, of, sumd, sumf);
                 }
                 // per-term checksums (a unit never spans two terms)
                 for (int d = 16; d > 0; d >>= 1) {
                         sumd += __shfl_xor_sync(0xffffffffu, sumd, d);
                         sumf += __shfl_xor_sync(0xffffffffu, sumf, d);
                 }
-                const uint32_t ti = __shfl_sync(0xffffffffu, cur.ti, 0);
                 if (lane == 0 && sums && m) {
-                        atomicAdd(&sums[2 * ti], sumd);
-                        atomicAdd(&sums[2 * ti + 1], sumf);
+                        atomicAdd(&sums[2 * cur.ti], sumd);
+                        atomicAdd(&sums[2 * cur.ti + 1], sumf);
                 }
                 __syncwarp();
                 cur = nxt;
                 nxt = nn;
+                d2  = d3;
         }
 }
 
 // unit = 32 consecutive blocks of one term (lane j loads the directory entries of block j), the warp decodes them one after the other
 template <bool MAT>
-__global__ void __launch_bounds__(kThreads) k_decode_stream_lucene(DevIndex ix, const uint32_t *term_ids, const uint32_t *unit_base /*nterms+1*/, const uint64_t *out_base,
-                                                                  uint32_t nterms, uint32_t total_units, uint32_t *docids, uint32_t *freqs, unsigned long long *sums) {
+__global__ void __launch_bounds__(kThreads) k_decode_stream_lucene(DevIndex ix, const DecUnit *units, const uint64_t *out_base, uint32_t total_units, uint32_t *docids,
+                                                                  uint32_t *freqs, unsigned long long *sums) {
         __shared__ __align__(8) unsigned long long s_bar[kWarps * 2];
         const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         uint8_t *      stage   = dyn_smem + size_t(warp) * kDlWarpBytes;
@@ -282,19 +394,18 @@ __global__ void __launch_bounds__(kThreads) k_decode_stream_lucene(DevIndex ix, 
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        uint32_t seq_issue = 0, seq_wait = 0, tcur = 0;
+        uint32_t seq_issue = 0, seq_wait = 0;
         for (uint32_t unit = blockIdx.x * kWarps + warp; unit < total_units; unit += gridDim.x * kWarps) {
-                while (tcur + 1u < nterms && __ldg(unit_base + tcur + 1u) <= unit)
-                        ++tcur;
-                const DevTerm  T     = ix.terms[__ldg(term_ids + tcur)];
-                const uint32_t g0    = (unit - __ldg(unit_base + tcur)) * 32u, b = g0 + uint32_t(lane);
-                const uint32_t nfull = T.documents >> 7;
-                const bool     have  = b < T.nblocks;
+                const uint4    dx   = __ldg(reinterpret_cast<const uint4 *>(units + unit));
+                const uint2    dy   = __ldg(reinterpret_cast<const uint2 *>(units + unit) + 2);
+                const uint32_t tcur = dy.x, g0 = dy.y, ucnt = dx.y, tailDocs = dx.w; // tailDocs: documents of the unit's last block if that is the term's tail block
+                const bool     have = uint32_t(lane) < ucnt;
                 uint32_t       off = 0, offn = 0, prev = 0;
                 if (have) {
-                        off  = __ldg(ix.blk_off + T.dir_begin + b);
-                        offn = __ldg(ix.blk_off + T.dir_begin + b + 1u);
-                        prev = b ? __ldg(ix.blk_last + T.dir_begin + b - 1u) : 0u;
+                        const uint32_t e = dx.x + uint32_t(lane);
+                        off  = __ldg(ix.blk_off + e);
+                        offn = __ldg(ix.blk_off + e + 1u);
+                        prev = (dx.z && lane == 0) ? 0u : __ldg(ix.blk_last + e - 1u);
                 }
                 const uint32_t nblk = __popc(__ballot_sync(0xffffffffu, have));
                 auto           issue = [&](uint32_t j) {
@@ -324,7 +435,7 @@ __global__ void __launch_bounds__(kThreads) k_decode_stream_lucene(DevIndex ix, 
                         const uint32_t skew = oj & 15u;
                         uint32_t *     od   = MAT ? docids + trow + size_t(bj) * 128u : nullptr;
                         uint32_t *     of   = MAT ? freqs + trow + size_t(bj) * 128u : nullptr;
-                        if (bj < nfull) {
+                        if (!(tailDocs && j + 1u == nblk)) {
                                 uint32_t d[4], fr[4], dbits, fbits;
                                 const uint32_t o2 = lucene_intblock_v(s, skew, lane, d, scratch, dbits);
                                 (void)lucene_intblock_v(s, o2, lane, fr, scratch, fbits);
@@ -343,9 +454,8 @@ __global__ void __launch_bounds__(kThreads) k_decode_stream_lucene(DevIndex ix, 
                                 }
                         } else if (lane == 0) { // tail block: (varbyte delta, varbyte freq) pairs (lucene_codec.cpp:527-550)
                                 const uint8_t *pp   = s + skew;
-                                const uint32_t tail = T.documents & 127u;
                                 uint32_t       doc  = pj;
-                                for (uint32_t i = 0; i < tail; ++i) {
+                                for (uint32_t i = 0; i < tailDocs; ++i) {
                                         doc += varbyte_get(pp);
                                         const uint32_t f = varbyte_get(pp);
                                         sumd += doc;
@@ -370,8 +480,8 @@ __global__ void __launch_bounds__(kThreads) k_decode_stream_lucene(DevIndex ix, 
         }
 }
 
-cudaError_t launch_decode_stream(const DevIndex &ix, const uint32_t *term_ids, const uint32_t *unit_base, const uint64_t *out_base, uint32_t nterms,
-                                 uint32_t total_units, uint32_t *docids, uint32_t *freqs, unsigned long long *sums, int num_sms, cudaStream_t stream) {
+cudaError_t launch_decode_stream(const DevIndex &ix, const DecUnit *units, const uint64_t *out_base, uint32_t total_units, uint32_t *docids, uint32_t *freqs,
+                                 unsigned long long *sums, int num_sms, cudaStream_t stream) {
         const bool   mat  = docids != nullptr;
         const size_t smem = size_t(kWarps) * (ix.codec == 0 ? kDsWarpBytes : kDlWarpBytes);
         const void * fn   = ix.codec == 0 ? (mat ? (const void *)k_decode_stream_google<true> : (const void *)k_decode_stream_google<false>)
@@ -384,6 +494,6 @@ cudaError_t launch_decode_stream(const DevIndex &ix, const uint32_t *term_ids, c
         if (e != cudaSuccess)
                 return e;
         const int grid = int(std::min<uint64_t>(uint64_t(num_sms) * std::max(per, 1), (uint64_t(total_units) + kWarps - 1) / kWarps));
-        void *args[] = {(void *)&ix, (void *)&term_ids, (void *)&unit_base, (void *)&out_base, (void *)&nterms, (void *)&total_units, (void *)&docids, (void *)&freqs, (void *)&sums};
+        void *args[] = {(void *)&ix, (void *)&units, (void *)&out_base, (void *)&total_units, (void *)&docids, (void *)&freqs, (void *)&sums};
         return cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream);
 }

@@ -111,6 +111,18 @@ struct ScoreParams {
         uint32_t *          overflow;
 };
 
+// one unit of the whole-list decode kernels (decode_stream.cuh): 32 consecutive blocks of one term, laid out by the host
+struct DecUnit {
+        uint32_t first_entry; // index of the unit's first block in blk_last / blk_off
+        uint32_t cnt;         // blocks in the unit (1..32)
+        uint32_t term_start;  // 1: the unit starts the term (its first block's previous docID is 0)
+        uint32_t last_n;      // documents of the unit's last block when that is the term's last (possibly short) block, else 0
+        uint32_t ti;          // position of the term in the caller's term list (checksum / output row index)
+        uint32_t g0;          // index of the unit's first block within its term
+        uint32_t pad0, pad1;
+};
+static_assert(sizeof(DecUnit) == 32, "DecUnit layout");
+
 struct ExecParams {
         DevIndex        ix;
         const DevQuery *queries;

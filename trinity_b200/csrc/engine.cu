@@ -101,7 +101,7 @@ struct trn_ctx {
         std::vector<DevTerm> h_terms;
         // batch scratch (grow-only)
         DevBuf d_queries, d_steps, d_small[2], d_item_off, d_item_cnt, d_item_dst, d_seg_docids, d_seg_scores, d_out_docids[2], d_out_scores[2], d_q_offsets[2], d_cand,
-            d_topk_docids, d_topk_scores, d_topk_counts, d_fq, d_leaves, d_luts, d_dec_a, d_dec_b, d_dec_c, d_dec_docids, d_dec_freqs, d_dec_sums, d_merge_docids, d_merge_scores;
+            d_topk_docids, d_topk_scores, d_topk_counts, d_fq, d_leaves, d_luts, d_dec_units, d_dec_a, d_dec_b, d_dec_c, d_dec_docids, d_dec_freqs, d_dec_sums, d_merge_docids, d_merge_scores;
         PinBuf h_offsets, h_docids, h_scores, h_counts, h_small, h_chunk;
         cudaEvent_t ev0{nullptr}, ev1{nullptr}, evk0{nullptr}, evk1{nullptr};
         bool        have_kernel_events{false};
@@ -664,7 +664,7 @@ extern "C" void trn_destroy(trn_ctx *c) {
         cudaSetDevice(c->device);
         for (DevBuf *b : {&c->d_index, &c->d_blk_last, &c->d_blk_off, &c->d_terms, &c->d_tile_first, &c->d_masked, &c->d_queries, &c->d_steps, &c->d_small[0], &c->d_small[1], &c->d_item_off,
                           &c->d_item_cnt, &c->d_item_dst, &c->d_seg_docids, &c->d_seg_scores, &c->d_out_docids[0], &c->d_out_docids[1], &c->d_out_scores[0], &c->d_out_scores[1], &c->d_q_offsets[0], &c->d_q_offsets[1], &c->d_cand,
-                          &c->d_topk_docids, &c->d_topk_scores, &c->d_topk_counts, &c->d_fq, &c->d_leaves, &c->d_luts, &c->d_dec_a, &c->d_dec_b, &c->d_dec_c, &c->d_dec_docids, &c->d_dec_freqs,
+                          &c->d_topk_docids, &c->d_topk_scores, &c->d_topk_counts, &c->d_fq, &c->d_leaves, &c->d_luts, &c->d_dec_units, &c->d_dec_a, &c->d_dec_b, &c->d_dec_c, &c->d_dec_docids, &c->d_dec_freqs,
                           &c->d_dec_sums, &c->d_merge_docids, &c->d_merge_scores})
                 b->release();
         for (PinBuf *b : {&c->h_offsets, &c->h_docids, &c->h_scores, &c->h_counts, &c->h_small, &c->h_chunk})
@@ -1734,6 +1734,30 @@ extern "C" int trn_decode_terms(trn_ctx *c, const uint32_t *term_ids, uint32_t n
         unit_base[nterms] = uint32_t(units);
         out_base[nterms]  = padded;
         host_base[nterms] = posts;
+        if (!legacyDecode) { // unit descriptors of the streaming kernels
+                std::vector<DecUnit> du(units);
+                const uint32_t       bd = c->block_docs;
+                for (uint32_t i = 0; i < nterms; ++i) {
+                        const auto &t = c->h_terms[term_ids[i]];
+                        for (uint32_t g0 = 0, u = unit_base[i]; g0 < t.nblocks; g0 += 32, ++u) {
+                                DecUnit &D    = du[u];
+                                D.first_entry = t.dir_begin + g0;
+                                D.cnt         = std::min(32u, t.nblocks - g0);
+                                D.term_start  = g0 == 0;
+                                const uint32_t lastN = t.documents - bd * (t.nblocks - 1u); // documents of the term's last block
+                                D.last_n      = (g0 + D.cnt == t.nblocks && (c->codec == TRN_CODEC_GOOGLE ? true : lastN != bd)) ? lastN : 0u;
+                                if (c->codec == TRN_CODEC_LUCENE && (t.documents & 127u) == 0u)
+                                        D.last_n = 0;
+                                D.ti   = i;
+                                D.g0   = g0;
+                                D.pad0 = D.pad1 = 0;
+                        }
+                }
+                CK(c->d_dec_units.ensure(std::max<size_t>(32, du.size() * sizeof(DecUnit))));
+                if (!du.empty())
+                        CK(cudaMemcpyAsync(c->d_dec_units.p, du.data(), du.size() * sizeof(DecUnit), cudaMemcpyHostToDevice, c->stream));
+                CK(cudaStreamSynchronize(c->stream)); // `du` leaves scope
+        }
         CK(c->d_dec_a.ensure(nterms * 4));
         CK(c->d_dec_b.ensure((nterms + 1) * 4));
         CK(c->d_dec_c.ensure((nterms + 1) * 8));
@@ -1753,7 +1777,7 @@ extern "C" int trn_decode_terms(trn_ctx *c, const uint32_t *term_ids, uint32_t n
                 // checksum-only variant is faster with the span-staged kernel (measured, profiles/r01_g_microbench_decode.txt)
                 const bool forceNew = decodeKernel == "single-pass";
                 if (!legacyDecode)
-                        CK(launch_decode_stream(dev_index(c), c->d_dec_a.as<uint32_t>(), c->d_dec_b.as<uint32_t>(), c->d_dec_c.as<uint64_t>(), nterms, uint32_t(units),
+                        CK(launch_decode_stream(dev_index(c), c->d_dec_units.as<DecUnit>(), c->d_dec_c.as<uint64_t>(), uint32_t(units),
                                                 materialise ? c->d_dec_docids.as<uint32_t>() : nullptr, materialise ? c->d_dec_freqs.as<uint32_t>() : nullptr,
                                                 c->d_dec_sums.as<unsigned long long>(), c->num_sms, c->stream));
                 else if (c->codec == TRN_CODEC_GOOGLE && (materialise || forceNew))

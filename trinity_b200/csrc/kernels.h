@@ -29,7 +29,7 @@ size_t      score_flat_smem_bytes(uint32_t tile_shift, int threads);
 uint32_t    score_flat_max_leaves();
 cudaError_t launch_build_luts(const FlatLeaf *leaves, uint32_t nleaves, float *luts, cudaStream_t stream);
 cudaError_t launch_score_flat(const ScoreParams &S, int threads, int num_sms, cudaStream_t stream);
-cudaError_t launch_decode_stream(const DevIndex &ix, const uint32_t *term_ids, const uint32_t *unit_base, const uint64_t *out_base, uint32_t nterms,
-                                 uint32_t total_units, uint32_t *docids, uint32_t *freqs, unsigned long long *sums, int num_sms, cudaStream_t stream);
+cudaError_t launch_decode_stream(const DevIndex &ix, const DecUnit *units, const uint64_t *out_base, uint32_t total_units, uint32_t *docids, uint32_t *freqs,
+                                 unsigned long long *sums, int num_sms, cudaStream_t stream);
 uint32_t    kernel_max_k();
 } // namespace trn

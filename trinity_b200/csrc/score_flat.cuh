@@ -122,6 +122,29 @@ __device__ __forceinline__ uint32_t lucene_intblock_v(const uint8_t *s, uint32_t
         return pw + L * 4u;
 }
 
+// acc[rel[g]] += sc[g] for the postings selected by `on` (bit g), atomically (another warp may be adding another term's score to the
+// same document).  Shared memory has no native fp32 add: atomicAdd compiles to a load / add / compare-and-swap loop per posting, and four
+// of them in a row are four serialised ~100-cycle chains.  Here the four loads, adds and CAS attempts are issued side by side; a CAS that
+// lost a race (rare) retries on its own.
+__device__ __forceinline__ void sf_add4(float *acc, const uint32_t rel[4], const float sc[4], uint32_t on) {
+        uint32_t *a = reinterpret_cast<uint32_t *>(acc);
+        uint32_t  old[4], seen[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+                old[g] = ((on >> g) & 1u) ? a[rel[g]] : 0u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+                seen[g] = ((on >> g) & 1u) ? atomicCAS(&a[rel[g]], old[g], __float_as_uint(__uint_as_float(old[g]) + sc[g])) : old[g];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+                uint32_t o = old[g], r = seen[g];
+                while (r != o) { // lost a race: retry from the value the CAS saw
+                        o = r;
+                        r = atomicCAS(&a[rel[g]], o, __float_as_uint(__uint_as_float(o) + sc[g]));
+                }
+        }
+}
+
 // per-term BM25 table: lut[leaf][f] = Scorer::score(f) for f < 64 (similarity.h:228-235), once per batch
 __global__ void __launch_bounds__(256) k_build_luts(const FlatLeaf *leaves, uint32_t nleaves, float *luts) {
         const uint32_t i = blockIdx.x * 256u + threadIdx.x;
@@ -334,12 +357,15 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
                                         const float *  lt = lut + tj * 64u;
                                         if (kj == 1u) {
                                                 // ---- cached block: its documents and scores were left behind by an earlier tile of this run
+                                                uint32_t rel[4], on = 0;
+                                                float    sc[4];
 #pragma unroll
                                                 for (int g = 0; g < 4; ++g) {
-                                                        const uint32_t rel = cdoc[tj * 128u + lane + 32 * g] - lo;
-                                                        if (rel < W)
-                                                                atomicAdd(&acc[rel], csc[tj * 128u + lane + 32 * g]);
+                                                        rel[g] = cdoc[tj * 128u + lane + 32 * g] - lo;
+                                                        sc[g]  = csc[tj * 128u + lane + 32 * g];
+                                                        on |= (rel[g] < W ? 1u : 0u) << g;
                                                 }
+                                                sf_add4(acc, rel, sc, on);
                                                 continue;
                                         }
                                         const uint32_t bsel = seq_wait & 1u;
@@ -381,40 +407,32 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
                                                 if (big)
                                                         idfj = __shfl_sync(0xffffffffu, myidf, int(tj));
                                                 const uint32_t first = __shfl_sync(0xffffffffu, d[0], 0);
-                                                if (kj == 2u) {
-                                                        // every posting's score is needed (the block is cached for the following tiles)
-                                                        float sc[4];
+                                                // the four scores (table look-ups side by side) and tile-relative documents of this lane
+                                                float    sc[4];
+                                                uint32_t rel[4], on = 0;
+#pragma unroll
+                                                for (int g = 0; g < 4; ++g) {
+                                                        const uint32_t f16 = fr[g] & 0xffffu; // freq is uint16_t in the reference (codecs.h:217)
+                                                        sc[g]              = (!big || f16 < 64u) ? lt[f16 & 63u] : bm25_score(idfj, f16);
+                                                        rel[g]             = d[g] - lo;
+                                                }
+                                                if (first - lo < W && last - lo < W)
+                                                        on = 0xfu; // block completely inside the tile: no range checks
+                                                else {
+#pragma unroll
+                                                        for (int g = 0; g < 4; ++g)
+                                                                on |= (rel[g] < W ? 1u : 0u) << g;
+                                                }
+                                                sf_add4(acc, rel, sc, on);
+                                                if (kj == 2u) { // the leaf's last block of the tile: keep it for the following tiles of the run
 #pragma unroll
                                                         for (int g = 0; g < 4; ++g) {
-                                                                const uint32_t f16 = fr[g] & 0xffffu; // freq is uint16_t in the reference (codecs.h:217)
-                                                                sc[g]              = (!big || f16 < 64u) ? lt[f16 & 63u] : bm25_score(idfj, f16);
-                                                                const uint32_t rel = d[g] - lo;
-                                                                if (rel < W)
-                                                                        atomicAdd(&acc[rel], sc[g]);
                                                                 cdoc[tj * 128u + lane + 32 * g] = d[g];
                                                                 csc[tj * 128u + lane + 32 * g]  = sc[g];
                                                         }
                                                         if (lane == 0 && (hi != 0u && last >= hi)) { // it does reach into the next tile
                                                                 s_fill_blk[par][tj]  = bj;
                                                                 s_fill_tile[par][tj] = tile;
-                                                        }
-                                                } else if (first - lo < W && last - lo < W) {
-                                                        // block completely inside the tile: no range checks
-#pragma unroll
-                                                        for (int g = 0; g < 4; ++g) {
-                                                                const uint32_t f16 = fr[g] & 0xffffu;
-                                                                const float    sc  = (!big || f16 < 64u) ? lt[f16 & 63u] : bm25_score(idfj, f16);
-                                                                atomicAdd(&acc[d[g] - lo], sc);
-                                                        }
-                                                } else {
-#pragma unroll
-                                                        for (int g = 0; g < 4; ++g) {
-                                                                const uint32_t rel = d[g] - lo;
-                                                                if (rel < W) {
-                                                                        const uint32_t f16 = fr[g] & 0xffffu;
-                                                                        const float    sc  = (!big || f16 < 64u) ? lt[f16 & 63u] : bm25_score(idfj, f16);
-                                                                        atomicAdd(&acc[rel], sc);
-                                                                }
                                                         }
                                                 }
                                         } else {
