@@ -9,8 +9,9 @@ M_SET, M_OR, M_AND, M_ANDNOT, M_NONE = 0, 1, 2, 3, 4
 F_SCORE, F_BREAK_IF_EMPTY = 1, 2
 
 
-def run(steps, root_slot, nslots, lists, ndocs):
-    """returns (match[ndocs+1], score[ndocs+1]); lists[t] = (docids, freqs)"""
+def run(steps, root_slot, nslots, lists, ndocs, tree=False):
+    """returns (match[ndocs+1], score[ndocs+1]); lists[t] = (docids, freqs).  tree: a flat-tree program — its leading
+    [LEAF, mode NONE, dst] markers name bitmaps that one flat decode pass fills before the slot operations run"""
     slots = [np.zeros(ndocs + 1, bool) for _ in range(nslots)]
     acc = np.zeros(ndocs + 1, np.float32)  # the kernels accumulate fp32 scores in step order
     dead = False
@@ -38,6 +39,7 @@ def run(steps, root_slot, nslots, lists, ndocs):
         elif op in (OP_LEAF, OP_LEAFSCORE):
             m, s = leaf(int(st["term"]))
             if op == OP_LEAF:
+                if tree and mode == M_NONE: slots[dst] = m.copy()
                 if mode == M_SET: slots[dst] = m.copy()
                 elif mode == M_OR: slots[dst] |= m
                 elif mode == M_AND: slots[dst] &= m

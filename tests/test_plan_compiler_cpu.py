@@ -57,3 +57,22 @@ def test_docs_only_plans_reuse_slots(built):
     _, _, docs_slots = tb.debug_compile(tb.CODEC_GOOGLE, index, terms, nodes, False)
     _, _, scored_slots = tb.debug_compile(tb.CODEC_GOOGLE, index, terms, nodes, True)
     assert docs_slots < scored_slots and docs_slots <= 4  # root, conjunction, one disjunction at a time, scratch
+
+
+def test_flat_tree_programs_match_the_structural_evaluator(built):
+    """the DocumentsOnly program in the form the flat-tree launch of k_exec_docs runs (leaf bitmaps first, slot operations after)"""
+    lists, idx, tdict = built
+    index, terms = idx[tb.CODEC_GOOGLE]
+    transformed = 0
+    for q, m in ALL:
+        nodes = tb.parse_query(q, tdict, min_match=m)
+        steps, root_slot, nslots = tb.debug_compile(tb.CODEC_GOOGLE, index, terms, nodes, 2)
+        markers = [s for s in steps if int(s["op"]) == stepsim.OP_LEAF and int(s["mode"]) == stepsim.M_NONE]
+        if markers:  # transformed: markers come first and name slots 0 .. nl-1; no decoding leaf remains
+            transformed += 1
+            assert [int(s["dst"]) for s in steps[: len(markers)]] == list(range(len(markers)))
+            assert not any(int(s["op"]) == stepsim.OP_LEAF and int(s["mode"]) != stepsim.M_NONE for s in steps)
+        got_m, _ = stepsim.run(steps, root_slot, nslots, lists, NDOCS, tree=True)
+        want_m, _ = evaluate(nodes, lists, NDOCS, weights=None)
+        assert np.array_equal(np.flatnonzero(got_m), np.flatnonzero(want_m)), (q, m)
+    assert transformed >= 20

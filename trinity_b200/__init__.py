@@ -198,8 +198,9 @@ def parse_query(text: str, tdict: TermDictionary, min_match: Optional[int] = Non
     return out
 
 
-def debug_compile(codec: int, index: np.ndarray, terms: np.ndarray, nodes: np.ndarray, scored: bool):
-    """(steps, root_slot, nslots): the bitmap-path step program of one plan, compiled on the host (no GPU needed)"""
+def debug_compile(codec: int, index: np.ndarray, terms: np.ndarray, nodes: np.ndarray, scored):
+    """(steps, root_slot, nslots): the bitmap-path step program of one plan, compiled on the host (no GPU needed).
+    scored: False / True, or 2 = the DocumentsOnly program in its flat-tree form"""
     from ._ffi import STEP_DTYPE
     index = np.ascontiguousarray(index, dtype=np.uint8)
     terms = np.ascontiguousarray(terms, dtype=TERM_DTYPE)
@@ -207,7 +208,7 @@ def debug_compile(codec: int, index: np.ndarray, terms: np.ndarray, nodes: np.nd
     steps = np.zeros(512, STEP_DTYPE)
     n, rs, ns = C.c_uint32(), C.c_uint32(), C.c_uint32()
     err = C.create_string_buffer(256)
-    rc = lib().trn_debug_compile(codec, _ptr(index), index.size, _ptr(terms), len(terms), _ptr(nodes), len(nodes), 0, 1 if scored else 0, _ptr(steps), len(steps),
+    rc = lib().trn_debug_compile(codec, _ptr(index), index.size, _ptr(terms), len(terms), _ptr(nodes), len(nodes), 0, int(scored), _ptr(steps), len(steps),
                                  C.byref(n), C.byref(rs), C.byref(ns), err, 256)
     if rc != 0:
         raise TrinityError(err.value.decode("utf-8", "replace"))

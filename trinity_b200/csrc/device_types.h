@@ -66,11 +66,15 @@ struct DevQuery {
         uint32_t root_slot;
         uint32_t cand_base; // SCORED_TOPK: first candidate slot of this query
         uint32_t cand_cap;
-        uint32_t gen_base; // k_exec_tiles: the query's first item in that kernel's own ticket space (queries run by k_score_flat own none)
+        uint32_t gen_base;  // the query's first ticket in the step-program launch (k_exec_tiles / k_exec_docs); queries other kernels / launches run own none
+        uint32_t gen_base2; // k_exec_docs, second launch (flat-tree plans on a smaller tile): the query's first ticket there
         uint32_t flat; // 0 = general step program; 1 = conjunction of terms only; 2 = disjunction of terms only (see exec_docs_flat.cuh);
                        // 3 = candidate-driven (exec_docs_cand.cuh): items are 32-block groups of a lead term every match must hold; the
                        //     step program is replaced by [OP_LEAF lead, OP_LEAF other terms..., OP_TABLE...]: root_slot = number of NECESSARY
                        //     terms (they come first), the truth table decides over the membership bits of the others
+                       // 4 = scored flat disjunction run by k_score_flat; 5 = flat-tree (exec_docs_flat.cuh): the program starts with one
+                       //     [OP_LEAF M_NONE dst = leaf slot] per leaf — all leaves of the tile are decoded in ONE flat (leaf, block) pass into
+                       //     bitmaps of their own — followed by slot operations only
 };
 
 // ---- flat scored disjunctions (k_score_flat, score_flat.cuh)
@@ -129,7 +133,8 @@ struct ExecParams {
         const DevStep * steps;
         uint32_t        nq;
         uint32_t        total_items;
-        uint32_t        gen_items; // k_exec_tiles: number of tickets (items of the queries it runs)
+        uint32_t        gen_items; // number of tickets of this launch (items of the queries it runs)
+        uint32_t        gen_sel;   // k_exec_docs: 0 = tickets follow DevQuery::gen_base, 1 = gen_base2
         uint32_t        nslots; // bitmap slots per worker (CTA for k_exec_tiles, warp for k_exec_docs)
         uint32_t        stage_bytes; // per-warp staging bytes of k_exec_tiles (codec dependent)
         uint32_t        docs_stage_bytes; // per-warp staging bytes of k_exec_docs (1 or 2 gather buffers)

@@ -91,6 +91,7 @@ struct trn_ctx {
         uint32_t             min_docid{1}; // smallest docID any term holds (a docID-range shard does not start at 1)
         uint32_t             nterms{0}, max_docid{0}, tile_shift{13}, ntiles{0}; // tile_shift: directory granularity == scored tile (8192 docs, the reference's window docset_spans.h:74)
         uint32_t             docs_shift{14}; // docID tile (log2) of the warp-per-tile DocumentsOnly kernel
+        uint32_t             tree_shift{12}; // TRN_TREE_SHIFT: docID tile (log2) of the flat-tree launch of k_exec_docs (0 = flat-tree path off)
         uint32_t             run_tiles{32};  // TRN_RUN_TILES: consecutive tiles per work item of the flat scored kernel (top-k state lives across a run)
         int                  flat_threads{256}; // TRN_SF_THREADS: CTA size of k_score_flat (256/320/384: two CTAs per SM; 512/640: one)
         uint32_t             scored_shift{13};  // TRN_SCORED_SHIFT: log2 of k_score_flat's tile (13 = the reference's window, 14)
@@ -623,6 +624,11 @@ extern "C" int trn_create(int device, trn_ctx **out) {
                 if (v >= 13 && v <= 17)
                         c->docs_shift = uint32_t(v);
         }
+        if (const char *e = getenv("TRN_TREE_SHIFT")) {
+                const int v = atoi(e);
+                if (v == 0 || (v >= 10 && v <= 14))
+                        c->tree_shift = uint32_t(v);
+        }
         if (const char *e = getenv("TRN_RUN_TILES")) {
                 const int v = atoi(e);
                 if (v >= 1 && v <= 4096)
@@ -931,6 +937,51 @@ extern "C" int trn_query_truth_table(const trn_qnode *nodes, uint32_t nnodes, ui
         return TRN_OK;
 }
 
+// Flat-tree form of a DocumentsOnly step program (k_exec_docs, exec_docs_flat.cuh): every leaf gets a bitmap of its own (slots 0 .. nl-1,
+// announced by one [OP_LEAF M_NONE dst = leaf slot] marker each, at the front of the program) that ONE flat (leaf, block) pass over the tile
+// fills; the rest of the program becomes slot operations on them, the compiler's own slots moved behind the leaf bitmaps.
+// Returns the number of leaves (0: the program stays as it is).
+static uint32_t flat_tree_transform(std::vector<DevStep> &steps, size_t begin, uint32_t next_slot) {
+        uint32_t nl{0};
+        for (size_t i = begin; i < steps.size(); ++i)
+                nl += steps[i].op == OP_LEAF && steps[i].mode != M_NONE;
+        if (nl < 2 || nl > 16 || nl + next_slot > 30)
+                return 0;
+        const std::vector<DevStep> prog(steps.begin() + begin, steps.end());
+        steps.resize(begin);
+        uint32_t li{0};
+        for (const auto &st : prog)
+                if (st.op == OP_LEAF && st.mode != M_NONE) { // decode marker: term -> leaf bitmap li
+                        DevStep L = st;
+                        L.mode    = M_NONE;
+                        L.dst     = uint8_t(li++);
+                        L.src     = 0;
+                        L.flags   = 0;
+                        steps.push_back(L);
+                }
+        li = 0;
+        for (auto st : prog) {
+                if (st.op == OP_LEAF) {
+                        if (st.mode == M_NONE)
+                                continue; // nothing to do in DocumentsOnly mode
+                        DevStep S;
+                        std::memset(&S, 0, sizeof(S));
+                        S.op    = OP_SLOT;
+                        S.mode  = st.mode;
+                        S.dst   = uint8_t(st.dst + nl);
+                        S.src   = uint8_t(li++);
+                        S.flags = st.flags;
+                        steps.push_back(S);
+                        continue;
+                }
+                st.dst = uint8_t(st.dst + nl); // compiler slots live behind the leaf bitmaps
+                if (st.op == OP_SLOT || st.op == OP_COUNT_ADD || st.op == OP_COUNT_GE)
+                        st.src = uint8_t(st.src + nl);
+                steps.push_back(st);
+        }
+        return nl;
+}
+
 extern "C" int trn_debug_compile(int codec, const uint8_t *index, uint64_t nbytes, const trn_term *terms, uint32_t nterms, const trn_qnode *nodes, uint32_t nnodes,
                                  uint32_t root, int scored, trn_debug_step *out, uint32_t cap, uint32_t *nsteps, uint32_t *root_slot, uint32_t *nslots, char *err,
                                  size_t errcap) {
@@ -969,16 +1020,21 @@ extern "C" int trn_debug_compile(int codec, const uint8_t *index, uint64_t nbyte
                 ht[i].tf_shift  = dir.terms[i].tf_shift;
         }
         std::vector<DevStep> steps;
-        Compiler             cc(nodes, nnodes, ht, scored != 0, root, steps);
-        const int            rs = cc.run();
+        Compiler             cc(nodes, nnodes, ht, scored == 1, root, steps);
+        int                  rs = cc.run();
         if (rs < 0)
                 return seterr(cc.err, cc.unsupported ? TRN_ERR_UNSUPPORTED : TRN_ERR_ARG);
+        uint32_t treeLeaves{0};
+        if (scored == 2) { // DocumentsOnly program in its flat-tree form (what the second k_exec_docs launch runs)
+                treeLeaves = flat_tree_transform(steps, 0, cc.next_slot);
+                rs += int(treeLeaves);
+        }
         if (steps.size() > cap)
                 return seterr("step buffer too small", TRN_ERR_CAPACITY);
         std::memcpy(out, steps.data(), steps.size() * sizeof(DevStep));
         *nsteps    = uint32_t(steps.size());
         *root_slot = uint32_t(rs);
-        *nslots    = cc.next_slot + 1; // + the scratch slot of the kernels
+        *nslots    = cc.next_slot + 1 + treeLeaves; // + the scratch slot of the kernels
         return TRN_OK;
 }
 
@@ -1018,7 +1074,8 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         std::vector<DevStep>   steps;
         std::vector<FlatQuery> fqs;    // queries k_score_flat runs
         std::vector<FlatLeaf>  leaves;
-        uint64_t               genItems{0}, flatItems{0};
+        uint64_t               genItems{0}, genItems2{0}, flatItems{0};
+        uint32_t               treeSlots{1};
         uint32_t               maxRuns{0};
         uint32_t              maxSlots{1};
         bool                  anyCandidate{false}, anyMembership{false};
@@ -1091,8 +1148,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                                 fqs.push_back(fq);
                         }
                 }
-                if (!flatScored)
-                        maxSlots = std::max(maxSlots, cc.next_slot + 1); // + scratch slot
+                const uint32_t planSlots = cc.next_slot + 1; // + scratch slot (applied below, once the path of the query is known)
                 // Candidate-driven evaluation (exec_docs_cand.cuh) when some term that EVERY match must hold is sparse: cost follows that
                 // lead's postings (~cand_cost/2 warp-instructions per 32 candidates and probed term; the crossover was tuned on the and2
                 // workload: 900 beats 450 and 1500) instead of the docID space (~1500 per tile + ~27 per block in it, profiles/r01_l_*).
@@ -1207,19 +1263,39 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                                 }
                         }
                 }
+                // Flat-tree path (exec_docs_flat.cuh): a DocumentsOnly tree that is neither an all-term run nor candidate-driven decodes ALL its
+                // leaves of a tile in one flat (leaf, block) pass — each leaf into a bitmap of its own — and then runs slot operations only.
+                // The per-leaf groups of the step-program path ran at 10 of 32 lanes with up to 8 live bitmaps per warp (profiles/r01_u); here
+                // the lanes are packed across leaves, and a smaller tile pays for the extra bitmaps.
+                bool treeFlat{false};
+                if (!scored && !candidate && dq.flat == 0u && c->codec == TRN_CODEC_GOOGLE && c->tree_shift && !r.empty()) {
+                        const uint32_t nl = flat_tree_transform(steps, dq.step_begin, cc.next_slot);
+                        if (nl) {
+                                dq.nsteps = uint32_t(steps.size()) - dq.step_begin;
+                                dq.root_slot += nl;
+                                dq.flat   = 5u;
+                                treeSlots = std::max(treeSlots, nl + cc.next_slot);
+                                treeFlat  = true;
+                        }
+                }
+                if (!flatScored && !treeFlat)
+                        maxSlots = std::max(maxSlots, planSlots);
                 if (candidate) {
                 } else if (r.empty()) {
                         dq.tile_lo = 0;
                         dq.ntiles  = 0;
                 } else {
-                        const uint32_t qshift = flatScored ? c->scored_shift : execShift; // k_score_flat may run on a larger tile
+                        const uint32_t qshift = flatScored ? c->scored_shift : (treeFlat ? c->tree_shift : execShift); // per-path tile
                         dq.tile_lo            = r.lo >> qshift;
                         dq.ntiles             = (r.hi >> qshift) - dq.tile_lo + 1;
                 }
                 dq.item_base = uint32_t(items);
                 dq.gen_base  = uint32_t(genItems);
+                dq.gen_base2 = uint32_t(genItems2);
                 items += dq.ntiles;
-                if (!flatScored)
+                if (treeFlat)
+                        genItems2 += dq.ntiles;
+                else if (!flatScored)
                         genItems += dq.ntiles;
                 if (items >= (1ull << 32))
                         return fail(c, TRN_ERR_CAPACITY, "batch has more than 2^32 (query, tile) work items; split it");
@@ -1342,7 +1418,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         uint32_t launches{0};
         if (totalItems) {
                 const bool     warpKernel = !scored;
-                const uint64_t ownItems   = warpKernel ? totalItems : genItems; // (query, tile) items of the step-program kernel
+                const uint64_t ownItems   = genItems; // tickets of the step-program launch
                 CK(cudaEventRecord(k0, c->stream));
                 if (nflat && flatItems) {
                         // flat scored disjunctions: per-leaf BM25 tables once per batch, then k_score_flat
@@ -1386,6 +1462,20 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                                 CK(launch_exec_docs(P, grid, c->stream));
                         else
                                 CK(launch_exec_tiles(P, grid, c->stream));
+                        ++launches;
+                }
+                if (warpKernel && genItems2) { // flat-tree plans: same kernel, own tile size / slot count / ticket space
+                        ExecParams P2 = P;
+                        P2.exec_shift = c->tree_shift;
+                        P2.nslots     = treeSlots;
+                        P2.gen_items  = uint32_t(genItems2);
+                        P2.gen_sel    = 1;
+                        P2.ticket     = reinterpret_cast<uint32_t *>(small + 4);
+                        const int perSM = exec_docs_max_ctas_per_sm(P2.exec_shift, P2.nslots, exec_docs_stage_bytes());
+                        if (perSM <= 0)
+                                return fail(c, TRN_ERR_CUDA, "the flat-tree launch does not fit on an SM with this many docset slots");
+                        const int grid = int(std::min<uint64_t>(uint64_t(c->num_sms) * perSM, std::max<uint64_t>(1, (genItems2 + 3) / 4)));
+                        CK(launch_exec_docs(P2, grid, c->stream));
                         ++launches;
                 }
                 CK(cudaEventRecord(k1, c->stream));

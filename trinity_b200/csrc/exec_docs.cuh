@@ -447,28 +447,32 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
         uint8_t *      stage = reinterpret_cast<uint8_t *>(slots + size_t(P.nslots) * NW);
         const uint32_t wpl   = NW >> 5; // bitmap words per lane (contiguous ownership: lane l owns words [l*wpl, (l+1)*wpl))
 
-        uint32_t curq = 0xffffffffu;
+        uint32_t curq = 0xffffffffu, qgen = 0; // qgen: the current query's first ticket
         DevQuery Q;
         Q.item_base = 0;
         Q.ntiles    = 0;
 
         for (;;) {
-                uint32_t item = 0;
+                // tickets run over THIS launch's queries only (a batch can take two launches: trees on the flat-tree path use a smaller tile)
+                uint32_t gitem = 0;
                 if (lane == 0)
-                        item = atomicAdd(P.ticket, 1u);
-                item = __shfl_sync(0xffffffffu, item, 0);
-                if (item >= P.total_items)
+                        gitem = atomicAdd(P.ticket, 1u);
+                gitem = __shfl_sync(0xffffffffu, gitem, 0);
+                if (gitem >= P.gen_items)
                         break;
-                if (curq == 0xffffffffu || item < Q.item_base || item - Q.item_base >= Q.ntiles) {
+                if (curq == 0xffffffffu || gitem < qgen || gitem - qgen >= Q.ntiles) {
                         uint32_t qlo = 0, qhi = P.nq;
                         while (qhi - qlo > 1) {
                                 const uint32_t mid = (qlo + qhi) >> 1;
-                                if (P.queries[mid].item_base <= item) qlo = mid;
+                                const uint32_t gb  = P.gen_sel ? P.queries[mid].gen_base2 : P.queries[mid].gen_base;
+                                if (gb <= gitem) qlo = mid;
                                 else qhi = mid;
                         }
                         curq = qlo;
                         Q    = P.queries[qlo];
+                        qgen = P.gen_sel ? Q.gen_base2 : Q.gen_base;
                 }
+                const uint32_t item = Q.item_base + (gitem - qgen); // batch-wide (query, tile) item: index of the segment arrays
                 if (Q.flat == 3u) { // candidate-driven conjunction: the work item is a 32-block group of the lead term
                         __syncwarp();
                         cand_exec_google(P, Q, curq, item, item - Q.item_base, slots, lane);
@@ -479,7 +483,7 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
                 bool           dead = false;
                 int            handled = 0;
                 if (Q.flat && P.ix.codec == 0)
-                        handled = flat_exec_google(P, Q, lo, W, NW, slots, stage, lane);
+                        handled = flat_exec_google(P, Q, lo, W, NW, slots, stage, lane); // flat-tree plans (5): leaves decoded, "not handled" => the slot program runs
                 if (handled == 2)
                         dead = true;
 

@@ -22,14 +22,17 @@ struct FlatLane { // per-lane description of one (term, block) work unit
 
 // returns 0 = not applicable (use the step program), 1 = handled (root docset in slot Q.root_slot), 2 = handled, result empty
 __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t lo, uint32_t W, uint32_t NW, uint32_t *slots, uint8_t *stage, int lane) {
-        const bool isAnd = Q.flat == 1u;
+        const bool isTree = Q.flat == 5u; // flat-tree: every leaf owns the bitmap its OP_LEAF step names; the slot program follows in the caller
+        const bool isAnd  = Q.flat == 1u || isTree;
         // lane j adopts the j-th leaf of the plan
-        uint32_t nleaf = 0, myTerm = kEmptyTerm;
+        uint32_t nleaf = 0, myTerm = kEmptyTerm, mySlot = 0;
         for (uint32_t si = 0; si < Q.nsteps; ++si) {
                 const DevStep st = P.steps[Q.step_begin + si];
                 if (st.op == OP_LEAF) {
-                        if (uint32_t(lane) == nleaf)
+                        if (uint32_t(lane) == nleaf) {
                                 myTerm = st.term;
+                                mySlot = isTree ? st.dst : nleaf;
+                        }
                         ++nleaf;
                 }
         }
@@ -50,7 +53,9 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
         }
         const uint32_t incl  = warp_incl_scan(uint32_t(lane) < nleaf ? mycnt : 0u, lane);
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (isAnd) {
+        if (isTree) {
+                // nothing to decide here: every leaf is decoded, the slot program does the rest
+        } else if (isAnd) {
                 if (__ballot_sync(0xffffffffu, uint32_t(lane) < nleaf && mycnt == 0u))
                         return 2; // an operand has no posting in this tile
                 // rarest term (operands are sorted by df) sparse in this tile => skipping beats packing
@@ -61,7 +66,7 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
                 return 2;
 
         uint32_t *     root   = slots + size_t(Q.root_slot) * NW;
-        const uint32_t nclear = isAnd ? nleaf : 1u;
+        const uint32_t nclear = isAnd ? nleaf : 1u; // (flat-tree plans keep their leaves in slots 0 .. nleaf-1)
         for (uint32_t i = lane; i < nclear * NW; i += 32)
                 (isAnd ? slots : root)[i] = 0;
 
@@ -80,7 +85,7 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
                 const uint32_t dir   = __shfl_sync(0xffffffffu, mydir, int(j));
                 const uint32_t nb    = __shfl_sync(0xffffffffu, mynb, int(j));
                 const uint32_t docs  = __shfl_sync(0xffffffffu, mydocs, int(j));
-                L.j                  = j;
+                L.j                  = __shfl_sync(0xffffffffu, mySlot, int(j)); // the bitmap this block goes into
                 L.off = L.n = L.prev = L.last = 0;
                 if (L.active) {
                         const uint32_t *bl = P.ix.blk_last + dir, *bo = P.ix.blk_off + dir;
@@ -130,6 +135,8 @@ __device__ int flat_exec_google(const ExecParams &P, const DevQuery &Q, uint32_t
         if (own && tail_bits)
                 asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(tail_a), "r"(tail_bits) : "memory");
         __syncwarp();
+        if (isTree)
+                return 0; // leaves are in place: the caller runs the slot operations of the plan
         if (isAnd) {
                 // operand i lives in slot i; the root of an all-term conjunction is slot 0
                 for (uint32_t i = lane; i < NW; i += 32) {
