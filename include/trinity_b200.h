@@ -52,6 +52,8 @@ int trn_builder_end_term(trn_builder *, trn_term *out);
 int trn_builder_add_term(trn_builder *, const uint32_t *docids, const uint32_t *freqs, uint32_t n, const uint32_t *positions, trn_term *out);
 /* Google only: the encoder's skiplist countdown is session state that survives end_term (google_codec.h:57) */
 int trn_builder_set_google_skiplist_countdown(trn_builder *, uint32_t countdown);
+/* Google only, decode sweep only: documents per block / blocks per skiplist entry (the reference format is 32 / 8) */
+int trn_builder_set_google_block(trn_builder *, uint32_t block_docs, uint32_t skiplist_step);
 /* buffers stay owned by the builder */
 int trn_builder_index(trn_builder *, const uint8_t **index, uint64_t *nbytes);
 int trn_builder_hits(trn_builder *, const uint8_t **hits, uint64_t *nbytes); /* Lucene hits.data; 0 bytes for Google */
@@ -66,6 +68,11 @@ int  trn_synth_build(int codec, uint32_t ndocs, uint32_t nterms, uint32_t min_df
 /* docID-range shard [doc_lo, doc_hi] of the same index (global docIDs kept): one IndexSource of a docID-partitioned collection */
 int  trn_synth_build_shard(int codec, uint32_t ndocs, uint32_t nterms, uint32_t min_df, uint64_t seed, int with_hits, int threads, uint32_t doc_lo,
                            uint32_t doc_hi, trn_synth **out);
+/* the same with the two compile-time constants of the GOOGLE format (google_codec.h:17-20: N = 32, SKIPLIST_STEP = 8) as parameters —
+ * ONLY for the decode sweep of BASELINE.json configs[4]: other values are not the reference's on-disk format, trn_upload_index detects the
+ * block size and the exec entry points refuse such an index (TRN_ERR_UNSUPPORTED); trn_decode_terms handles 1..128 documents per block */
+int  trn_synth_build_ex(int codec, uint32_t ndocs, uint32_t nterms, uint32_t min_df, uint64_t seed, int with_hits, int threads, uint32_t doc_lo,
+                        uint32_t doc_hi, uint32_t google_block_docs, uint32_t google_skiplist_step, trn_synth **out);
 void trn_synth_destroy(trn_synth *);
 int  trn_synth_index(trn_synth *, const uint8_t **index, uint64_t *nbytes);
 int  trn_synth_hits(trn_synth *, const uint8_t **hits, uint64_t *nbytes);
@@ -206,7 +213,7 @@ int trn_set_masked_documents(trn_ctx *, const uint32_t *docids, uint64_t n);
 
 typedef struct trn_index_info {
         int      codec;
-        uint32_t nterms, max_docid, tile_docs, ntiles;
+        uint32_t nterms, max_docid, tile_docs, ntiles, block_docs;
         uint64_t index_bytes, directory_bytes, total_blocks, total_postings;
 } trn_index_info;
 int trn_index_info_get(trn_ctx *, trn_index_info *out);

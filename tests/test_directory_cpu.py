@@ -152,3 +152,19 @@ def test_directory_of_a_million_tiny_terms_stays_small():
     st = tb.directory_stats(tb.CODEC_GOOGLE, b.index(), terms, threads=4)
     assert st["total_blocks"] == nterms and st["table_entries"] == 0
     assert st["directory_bytes"] == nterms * (36 + 2 * 8)
+
+
+@pytest.mark.parametrize("block_docs,step", [(8, 8), (16, 1), (64, 4), (128, 64)])
+def test_directory_follows_the_block_size_of_sweep_indexes(block_docs, step):
+    """GOOGLE-layout indexes built with other block sizes / skiplist steps (the decode sweep of BASELINE.json configs[4]): the directory
+    finds the block size in the bytes; the reference format's (32, 8) stays the default"""
+    rng = np.random.default_rng(block_docs)
+    d = np.cumsum(rng.integers(1, 300, block_docs * 11 + 5)).astype(np.uint32)
+    b = tb.IndexBuilder(tb.CODEC_GOOGLE)
+    b.set_google_block(block_docs, step)
+    t = b.add_term(d, np.ones(len(d), np.uint32))
+    last, off, first = tb.directory_probe(tb.CODEC_GOOGLE, b.index(), t)
+    assert len(last) == 12 + 1 and first == d[0]
+    assert np.array_equal(last[:11], d[block_docs - 1::block_docs][:11]) and last[11] == d[-1]
+    entries = int(np.frombuffer(b.index()[t[1]:t[1] + 2].tobytes(), "<u2")[0])
+    assert entries == 12 // step  # one skiplist entry per `step` committed blocks

@@ -246,3 +246,32 @@ def test_large_batches_split_by_result_capacity_and_stay_exact(ref):
         assert_same_docs(gd, cache[q][1][0], f"#{i} [{q}] scored")
         assert_close_scores(gs, cache[q][1][1], f"#{i} [{q}]")
     assert int(res.offsets[-1]) == sum(len(cache[q][0]) for q in qs)
+
+
+@pytest.mark.parametrize("block_docs,step", [(8, 8), (16, 1), (64, 8), (128, 64)])
+def test_decode_other_google_block_sizes(ref, block_docs, step):
+    """the decode sweep of BASELINE.json configs[4]: GOOGLE-layout indexes built with other block sizes / skiplist steps than the
+    reference's 32 / 8 (google_codec.h:17-20) decode to the same postings; the exec entry points refuse them"""
+    rng = np.random.default_rng(block_docs)
+    lists = make_lists(rng)
+    nd = int(max(int(d[-1]) for d, _ in lists))
+    b = tb.IndexBuilder(tb.CODEC_GOOGLE)
+    b.set_google_block(block_docs, step)
+    for d, f in lists:
+        b.add_term(d, f)
+    g = tb.GpuIndexSource(0)
+    g.upload(tb.CODEC_GOOGLE, b.index(), b.terms_array(), nd)
+    assert g.info()["block_docs"] in (block_docs, 32)  # 32 only if no list is long enough to show the block size
+    d, f, sums, _ = g.decode_terms(list(range(len(lists))), materialise=True)
+    at = 0
+    for i, (dd, ff) in enumerate(lists):
+        assert_same_docs(d[at:at + len(dd)], dd, f"block {block_docs} term {i} docids")
+        assert np.array_equal(f[at:at + len(dd)], ff), f"block {block_docs} term {i} freqs"
+        assert int(sums[i, 0]) == int(dd.astype(np.uint64).sum()) and int(sums[i, 1]) == int(ff.astype(np.uint64).sum())
+        at += len(dd)
+    _, _, sums2, _ = g.decode_terms(list(range(len(lists))), materialise=False)
+    assert np.array_equal(sums, sums2)
+    if g.info()["block_docs"] != 32:
+        with pytest.raises(tb.TrinityError):
+            g.exec_batch([tb.parse_query("t1", tb.TermDictionary([f"t{i + 1}" for i in range(len(lists))]))], tb.MODE_DOCS_ONLY)
+    g.close()

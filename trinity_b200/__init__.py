@@ -50,6 +50,10 @@ class IndexBuilder:
         if rc != 0:
             raise TrinityError(self._L.trn_builder_last_error(self._h).decode())
 
+    def set_google_block(self, block_docs: int, skiplist_step: int = 8):
+        """decode sweep only: documents per block / blocks per skiplist entry of the GOOGLE format (reference: 32 / 8)"""
+        self._ck(self._L.trn_builder_set_google_block(self._h, block_docs, skiplist_step))
+
     def set_google_skiplist_countdown(self, n: int):
         self._ck(self._L.trn_builder_set_google_skiplist_countdown(self._h, n))
 
@@ -107,13 +111,14 @@ class SynthIndex:
     """The BASELINE.md synthetic Zipfian index, built multi-threaded through the host encoders."""
 
     def __init__(self, codec: int, ndocs: int, nterms: int = 4096, min_df: int = 1000, seed: int = 0x5EED,
-                 with_hits: bool = True, threads: int = 0, doc_range: Optional[tuple] = None):
+                 with_hits: bool = True, threads: int = 0, doc_range: Optional[tuple] = None, google_block_docs: int = 32,
+                 google_skiplist_step: int = 8):
         self._L = lib()
         self.codec, self.ndocs, self.nterms, self.min_df, self.seed = codec, ndocs, nterms, min_df, seed
         self.doc_range = doc_range or (1, ndocs)
         h = C.c_void_p()
-        rc = self._L.trn_synth_build_shard(codec, ndocs, nterms, min_df, seed, int(with_hits), threads,
-                                           self.doc_range[0], self.doc_range[1], C.byref(h))
+        rc = self._L.trn_synth_build_ex(codec, ndocs, nterms, min_df, seed, int(with_hits), threads, self.doc_range[0], self.doc_range[1],
+                                        google_block_docs, google_skiplist_step, C.byref(h))  # (32, 8) == the reference format
         if rc != 0:
             raise TrinityError(f"trn_synth_build failed rc={rc}")
         self._h = h
@@ -409,7 +414,7 @@ def directory_probe(codec: int, index: np.ndarray, term: tuple):
     t = TrnTerm(int(term[0]), int(term[1]), int(term[2]))
     nb, fd = C.c_uint32(), C.c_uint32()
     err = C.create_string_buffer(256)
-    cap = int(term[0]) // 32 + 4
+    cap = int(term[0]) + 4  # (block sizes below 32 exist in sweep indexes)
     last, off = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
     rc = L.trn_directory_probe(codec, _ptr(index), index.size, C.byref(t), _ptr(last), _ptr(off), cap, C.byref(nb), C.byref(fd), err, 256)
     if rc != 0:

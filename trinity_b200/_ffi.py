@@ -14,7 +14,7 @@ EXPORTS = [
     "trn_builder_create", "trn_builder_destroy", "trn_builder_begin_term", "trn_builder_begin_document",
     "trn_builder_new_hit", "trn_builder_end_document", "trn_builder_end_term", "trn_builder_add_term",
     "trn_builder_set_google_skiplist_countdown", "trn_builder_index", "trn_builder_hits", "trn_builder_last_error",
-    "trn_synth_build", "trn_synth_build_shard", "trn_synth_destroy", "trn_synth_index", "trn_synth_hits", "trn_synth_terms", "trn_synth_sum_hits",
+    "trn_synth_build", "trn_synth_build_shard", "trn_synth_build_ex", "trn_builder_set_google_block", "trn_synth_destroy", "trn_synth_index", "trn_synth_hits", "trn_synth_terms", "trn_synth_sum_hits",
     "trn_synth_postings", "trn_synth_positions",
     "trn_directory_probe", "trn_directory_stats", "trn_directory_lookup", "trn_dict_create", "trn_dict_destroy", "trn_parse_query_dict", "trn_segment_open", "trn_segment_close", "trn_segment_info", "trn_segment_index", "trn_segment_terms",
     "trn_segment_masked", "trn_parse_query", "trn_query_truth_table", "trn_debug_compile", "trn_bm25_idf", "trn_bm25_score",
@@ -39,7 +39,7 @@ class TrnQuery(C.Structure):
 
 class TrnIndexInfo(C.Structure):
     _fields_ = [("codec", C.c_int), ("nterms", C.c_uint32), ("max_docid", C.c_uint32), ("tile_docs", C.c_uint32),
-                ("ntiles", C.c_uint32), ("index_bytes", C.c_uint64), ("directory_bytes", C.c_uint64),
+                ("ntiles", C.c_uint32), ("block_docs", C.c_uint32), ("index_bytes", C.c_uint64), ("directory_bytes", C.c_uint64),
                 ("total_blocks", C.c_uint64), ("total_postings", C.c_uint64)]
 
 
@@ -88,6 +88,8 @@ def lib() -> C.CDLL:
     sig("trn_builder_last_error", C.c_char_p, vp)
     sig("trn_synth_build", i32, i32, u32, u32, u32, u64, i32, i32, P(vp))
     sig("trn_synth_build_shard", i32, i32, u32, u32, u32, u64, i32, i32, u32, u32, P(vp))
+    sig("trn_synth_build_ex", i32, i32, u32, u32, u32, u64, i32, i32, u32, u32, u32, u32, P(vp))
+    sig("trn_builder_set_google_block", i32, vp, u32, u32)
     sig("trn_synth_destroy", None, vp)
     sig("trn_synth_index", i32, vp, P(vp), P(u64))
     sig("trn_synth_hits", i32, vp, P(vp), P(u64))

@@ -59,7 +59,7 @@ namespace Codecs {
 
                 void Encoder::end_document() {
                         docDeltas[curBlockSize++] = curDocID - lastCommitedDocID;
-                        if (curBlockSize == N)
+                        if (curBlockSize == blockDocs)
                                 commit_block();
                         lastCommitedDocID = curDocID;
                         ++termDocuments;
@@ -82,7 +82,7 @@ namespace Codecs {
                                         put_u32(skipListData, prevBlockLastDocumentID);
                                         put_u32(skipListData, uint32_t(out.size()) - curTermOffset);
                                 }
-                                skiplistEntryCountdown = SKIPLIST_STEP;
+                                skiplistEntryCountdown = skiplistStep;
                         }
 
                         varbyte_put(out, delta);
@@ -449,9 +449,11 @@ namespace {
                 return p + size_t(L) * 4;
         }
 
-        void dir_google_term(const uint8_t *index, const term_index_ctx &t, std::vector<uint32_t> &last, std::vector<uint32_t> &off, uint32_t &firstDoc) {
-                using Codecs::Google::N;
+        // blockN: documents per full block of this term (0 when the term has a single block: it cannot tell)
+        void dir_google_term(const uint8_t *index, const term_index_ctx &t, std::vector<uint32_t> &last, std::vector<uint32_t> &off, uint32_t &firstDoc, uint32_t &blockN) {
+                const uint32_t N = Codecs::Google::MAX_N;
                 firstDoc = 0;
+                blockN   = 0;
                 if (!t.size) {
                         if (t.documents)
                                 throw std::runtime_error("google: term with documents but empty chunk");
@@ -484,8 +486,13 @@ namespace {
                         last.push_back(prev);
                         off.push_back(uint32_t(p - index));
                         docs += n;
-                        if (n != N && docs != t.documents)
-                                throw std::runtime_error("google: non-final block is not full (unsupported by the GPU directory)");
+                        if (docs != t.documents) { // not the term's last block: all of these must have the same size
+                                if (!blockN)
+                                        blockN = n;
+                                else if (n != blockN)
+                                        throw std::runtime_error("google: non-final block is not full (unsupported by the GPU directory)");
+                        } else if (blockN && n > blockN)
+                                throw std::runtime_error("google: final block larger than the term's block size");
                         p += blen;
                 }
                 if (p != chunkEnd || docs != t.documents)
@@ -579,7 +586,7 @@ const uint8_t *lucene_ints_decode_host(const uint8_t *p, const uint8_t *end, uin
 void build_block_directory(Codec codec, const uint8_t *index, uint64_t nbytes, const term_index_ctx *terms, uint32_t nterms, int threads, BlockDirectory &out) {
         struct PerTerm {
                 std::vector<uint32_t> last, off;
-                uint32_t              firstDoc{0};
+                uint32_t              firstDoc{0}, blockN{0};
         };
         std::vector<PerTerm>  per(nterms);
         std::atomic<uint32_t> next{0};
@@ -594,7 +601,7 @@ void build_block_directory(Codec codec, const uint8_t *index, uint64_t nbytes, c
                                 if (uint64_t(terms[i].offset) + terms[i].size > nbytes)
                                         throw std::runtime_error("term chunk exceeds index size");
                                 if (codec == Codec::Google)
-                                        dir_google_term(index, terms[i], per[i].last, per[i].off, per[i].firstDoc);
+                                        dir_google_term(index, terms[i], per[i].last, per[i].off, per[i].firstDoc, per[i].blockN);
                                 else
                                         dir_lucene_term(index, terms[i], per[i].last, per[i].off, per[i].firstDoc);
                         } catch (const std::exception &e) {
@@ -615,6 +622,18 @@ void build_block_directory(Codec codec, const uint8_t *index, uint64_t nbytes, c
         if (failed.load())
                 throw std::runtime_error("build_block_directory: " + err);
 
+        // one block size per index (GOOGLE: google_codec.h:18 says 32; a multi-block term shows it)
+        out.block_docs = codec == Codec::Lucene ? Codecs::Lucene::BLOCK_SIZE : 0u;
+        if (codec == Codec::Google) {
+                for (auto &p : per)
+                        if (p.blockN) {
+                                if (out.block_docs && out.block_docs != p.blockN)
+                                        throw std::runtime_error("build_block_directory: terms disagree on the block size");
+                                out.block_docs = p.blockN;
+                        }
+                if (!out.block_docs)
+                        out.block_docs = Codecs::Google::N;
+        }
         size_t total{0};
         for (auto &p : per)
                 total += p.last.size();

@@ -52,6 +52,7 @@ namespace Codecs {
 
         namespace Google {
                 static constexpr uint32_t N{32};                  // docs per block (google_codec.h:18)
+                static constexpr uint32_t MAX_N{128};             // largest block size the decode sweep (BASELINE configs[4]) builds
                 static constexpr uint32_t SKIPLIST_STEP{256 / N}; // one skiplist entry every 8 blocks (google_codec.h:19)
 
                 class Encoder final : public Codecs::Encoder {
@@ -60,8 +61,8 @@ namespace Codecs {
                         uint32_t             curBlockSize{0};
                         uint8_t              curPayloadSize{0};
                         uint32_t             lastPos{0};
-                        uint32_t             docDeltas[N];
-                        uint32_t             blockFreqs[N];
+                        uint32_t             docDeltas[MAX_N];
+                        uint32_t             blockFreqs[MAX_N];
                         uint32_t             curTermOffset{0};
                         uint32_t             termDocuments{0};
                         void                 commit_block();
@@ -70,6 +71,9 @@ namespace Codecs {
                         // NOT reset per term in the reference (google_codec.h:57, google_codec.cpp:9-23): the phase of the
                         // first skiplist entry of a term depends on how many blocks earlier terms committed.
                         uint32_t skiplistEntryCountdown{SKIPLIST_STEP};
+                        // the two compile-time constants of google_codec.h:17-20 as run-time values — ONLY for the decode sweep
+                        // (BASELINE.json configs[4]: block size / skiplist step vs HBM GB/s); the reference format is {32, 8}
+                        uint32_t blockDocs{N}, skiplistStep{SKIPLIST_STEP};
 
                         explicit Encoder(IndexSession *s)
                             : Codecs::Encoder{s} {
@@ -148,6 +152,7 @@ struct TermDir {
 struct BlockDirectory {
         std::vector<uint32_t> blk_last, blk_off, tile_first;
         std::vector<TermDir>  terms;
+        uint32_t              block_docs{0}; // documents per full block: GOOGLE 32 (what the terms' blocks say; other values come from the decode sweep), LUCENE 128
         uint64_t              bytes() const { // what the device copy occupies (DevTerm = 36 B per term)
                 return (blk_last.size() + blk_off.size() + tile_first.size()) * 4ull + terms.size() * 36ull;
         }

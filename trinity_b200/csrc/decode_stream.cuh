@@ -16,8 +16,8 @@
 // Every docID and freq is produced in a register (the checksum variant adds them up, the materialising variant stores them).
 #pragma once
 
-static constexpr uint32_t kDsStage      = 6144; // bytes of one staging buffer (GOOGLE: the span of 32 blocks; larger spans read global memory)
-static constexpr uint32_t kDsWarpBytes  = 2 * kDsStage;
+// GOOGLE staging buffer = the span of 32 blocks (a template parameter of the kernel: 6 KB for the reference format's 32-document blocks,
+// scaled with the block size for the decode sweep; a span that does not fit is read from global memory)
 static constexpr uint32_t kDlWarpBytes  = 2 * kSfStage + kSfScratch; // LUCENE: two block buffers + exception scratch
 
 // 64-bit accumulate of a 32-bit value (two instructions; the sums of docIDs exceed 32 bits)
@@ -231,12 +231,12 @@ __device__ __forceinline__ void ds_google_block_dense(uint32_t sp, uint32_t n, u
 // (DecUnit); the kernel is a three-stage software pipeline per warp: unit descriptor (u+3) -> directory entries (u+2) -> bulk copy of
 // the span (u+1) -> decode (u).  Loaded values stay RAW in registers until the stage that needs them (no select behind a load: a select
 // right after its load is a stall on that load), so no load sits on the critical path of a decode.
-template <bool MAT>
+template <bool MAT, uint32_t kDsStage>
 __global__ void __launch_bounds__(kThreads) k_decode_stream_google(DevIndex ix, const DecUnit *units, const uint64_t *out_base, uint32_t total_units, uint32_t *docids,
                                                                   uint32_t *freqs, unsigned long long *sums) {
         __shared__ __align__(8) unsigned long long s_bar[kWarps * 2];
         const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        uint8_t *      stage   = dyn_smem + size_t(warp) * kDsWarpBytes;
+        uint8_t *      stage   = dyn_smem + size_t(warp) * (2 * kDsStage);
         const uint32_t stage_s = uint32_t(__cvta_generic_to_shared(stage));
         const uint32_t bar_s   = uint32_t(__cvta_generic_to_shared(&s_bar[warp * 2]));
         if (lane == 0) {
@@ -463,12 +463,34 @@ __global__ void __launch_bounds__(kThreads) k_decode_stream_lucene(DevIndex ix, 
         }
 }
 
+template <uint32_t STAGE> static const void *decode_google_fn(bool mat) {
+        return mat ? (const void *)k_decode_stream_google<true, STAGE> : (const void *)k_decode_stream_google<false, STAGE>;
+}
+
 cudaError_t launch_decode_stream(const DevIndex &ix, const DecUnit *units, const uint64_t *out_base, uint32_t total_units, uint32_t *docids, uint32_t *freqs,
                                  unsigned long long *sums, int num_sms, cudaStream_t stream) {
-        const bool   mat  = docids != nullptr;
-        const size_t smem = size_t(kWarps) * (ix.codec == 0 ? kDsWarpBytes : kDlWarpBytes);
-        const void * fn   = ix.codec == 0 ? (mat ? (const void *)k_decode_stream_google<true> : (const void *)k_decode_stream_google<false>)
-                                          : (mat ? (const void *)k_decode_stream_lucene<true> : (const void *)k_decode_stream_lucene<false>);
+        const bool  mat = docids != nullptr;
+        size_t      smem;
+        const void *fn;
+        if (ix.codec == 0) { // staging sized for the span of 32 blocks of block_docs documents (~4.6 bytes per posting with positions)
+                const uint32_t bd = ix.block_docs;
+                if (bd <= 16) {
+                        fn   = decode_google_fn<3072>(mat);
+                        smem = size_t(kWarps) * 2 * 3072;
+                } else if (bd <= 32) {
+                        fn   = decode_google_fn<6144>(mat);
+                        smem = size_t(kWarps) * 2 * 6144;
+                } else if (bd <= 64) {
+                        fn   = decode_google_fn<12288>(mat);
+                        smem = size_t(kWarps) * 2 * 12288;
+                } else {
+                        fn   = decode_google_fn<24576>(mat);
+                        smem = size_t(kWarps) * 2 * 24576;
+                }
+        } else {
+                fn   = mat ? (const void *)k_decode_stream_lucene<true> : (const void *)k_decode_stream_lucene<false>;
+                smem = size_t(kWarps) * kDlWarpBytes;
+        }
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess)
                 return e;

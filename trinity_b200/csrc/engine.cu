@@ -727,7 +727,7 @@ extern "C" int trn_upload_index(trn_ctx *c, int codec, const uint8_t *index, uin
                         if (dir.terms[i].nblocks)
                                 max_docid = std::max(max_docid, dir.terms[i].last_doc);
         c->codec      = codec;
-        c->block_docs = codec == TRN_CODEC_GOOGLE ? 32u : 128u;
+        c->block_docs = dir.block_docs;
         c->nterms     = nterms;
         c->max_docid  = max_docid;
         const uint32_t W = 1u << c->tile_shift;
@@ -821,6 +821,7 @@ extern "C" int trn_index_info_get(trn_ctx *c, trn_index_info *o) {
         o->max_docid       = c->max_docid;
         o->tile_docs       = 1u << c->tile_shift;
         o->ntiles          = c->ntiles;
+        o->block_docs      = c->block_docs;
         o->index_bytes     = c->index_bytes;
         o->directory_bytes = c->dir_bytes;
         o->total_blocks    = c->total_blocks;
@@ -1060,6 +1061,8 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 return fail(c, TRN_ERR_STATE, "no index uploaded");
         if (!queries || !nq || mode < 0 || mode > 2)
                 return fail(c, TRN_ERR_ARG, "trn_exec_batch: bad arguments");
+        if (c->block_docs != (c->codec == TRN_CODEC_GOOGLE ? 32u : 128u))
+                return fail(c, TRN_ERR_UNSUPPORTED, "the uploaded index was built with a block size other than the reference format's (decode sweep only)");
         if (mode == TRN_MODE_SCORED_TOPK && (k == 0 || k > kernel_max_k()))
                 return fail(c, TRN_ERR_ARG, "top-k: k must be in [1, 512]");
         CK(cudaSetDevice(c->device));

@@ -106,6 +106,15 @@ extern "C" int trn_builder_set_google_skiplist_countdown(trn_builder *b, uint32_
                 static_cast<Codecs::Google::Encoder *>(b->enc.get())->skiplistEntryCountdown = countdown;
         });
 }
+extern "C" int trn_builder_set_google_block(trn_builder *b, uint32_t block_docs, uint32_t skiplist_step) {
+        return guarded(b, [&] {
+                if (b->sess.codec != Codec::Google || block_docs == 0 || block_docs > Codecs::Google::MAX_N || skiplist_step == 0)
+                        throw std::invalid_argument("google block size must be in 1..128 and the skiplist step >= 1 (GOOGLE codec only)");
+                auto *e = static_cast<Codecs::Google::Encoder *>(b->enc.get());
+                e->blockDocs = block_docs;
+                e->skiplistStep = e->skiplistEntryCountdown = skiplist_step;
+        });
+}
 extern "C" int trn_builder_index(trn_builder *b, const uint8_t **index, uint64_t *nbytes) {
         if (!b || !index || !nbytes)
                 return TRN_ERR_ARG;
@@ -272,8 +281,17 @@ extern "C" int trn_synth_build(int codec, uint32_t ndocs, uint32_t nterms, uint3
 // an IndexSourcesCollection partitioned by docID, index_source.h:191-238).  docIDs stay global.
 extern "C" int trn_synth_build_shard(int codec, uint32_t ndocs, uint32_t nterms, uint32_t min_df, uint64_t seed, int with_hits, int threads, uint32_t doc_lo,
                                      uint32_t doc_hi, trn_synth **out) {
-        if (!out || !ndocs || !nterms || (codec != TRN_CODEC_GOOGLE && codec != TRN_CODEC_LUCENE) || doc_lo == 0 || doc_lo > doc_hi)
+        return trn_synth_build_ex(codec, ndocs, nterms, min_df, seed, with_hits, threads, doc_lo, doc_hi, Codecs::Google::N, Codecs::Google::SKIPLIST_STEP, out);
+}
+
+// the same with the two compile-time constants of the GOOGLE format (google_codec.h:17-20: N, SKIPLIST_STEP) as parameters: the decode
+// sweep of BASELINE.json configs[4] (other values are not the reference's on-disk format; the exec kernels refuse such an index)
+extern "C" int trn_synth_build_ex(int codec, uint32_t ndocs, uint32_t nterms, uint32_t min_df, uint64_t seed, int with_hits, int threads, uint32_t doc_lo,
+                                  uint32_t doc_hi, uint32_t google_block_docs, uint32_t google_skiplist_step, trn_synth **out) {
+        if (!out || !ndocs || !nterms || (codec != TRN_CODEC_GOOGLE && codec != TRN_CODEC_LUCENE) || doc_lo == 0 || doc_lo > doc_hi || google_block_docs == 0 ||
+            google_block_docs > Codecs::Google::MAX_N || google_skiplist_step == 0)
                 return TRN_ERR_ARG;
+        const uint32_t GN = google_block_docs, GS = google_skiplist_step;
         const Codec cd = codec == TRN_CODEC_GOOGLE ? Codec::Google : Codec::Lucene;
         const bool  whole = doc_lo <= 1 && doc_hi >= ndocs;
         if (threads < 1)
@@ -309,12 +327,12 @@ extern "C" int trn_synth_build_shard(int codec, uint32_t ndocs, uint32_t nterms,
         };
         std::vector<Part> parts(nterms);
         // Google: the skiplist countdown carries over between terms (google_codec.h:57): phase = committed blocks so far mod 8
-        std::vector<uint32_t> countdown(nterms, Codecs::Google::SKIPLIST_STEP);
+        std::vector<uint32_t> countdown(nterms, GS);
         {
                 uint64_t blocks{0};
                 for (uint32_t r = 1; r <= nterms; ++r) {
-                        countdown[r - 1] = Codecs::Google::SKIPLIST_STEP - uint32_t(blocks % Codecs::Google::SKIPLIST_STEP);
-                        blocks += (dfIn[r - 1] + Codecs::Google::N - 1) / Codecs::Google::N;
+                        countdown[r - 1] = GS - uint32_t(blocks % GS);
+                        blocks += (dfIn[r - 1] + GN - 1) / GN;
                 }
         }
         std::atomic<uint32_t> next{0};
@@ -327,8 +345,12 @@ extern "C" int trn_synth_build_shard(int codec, uint32_t ndocs, uint32_t nterms,
                         try {
                                 Codecs::IndexSession             sess(cd);
                                 std::unique_ptr<Codecs::Encoder> enc(Codecs::new_encoder(&sess));
-                                if (cd == Codec::Google)
-                                        static_cast<Codecs::Google::Encoder *>(enc.get())->skiplistEntryCountdown = countdown[i];
+                                if (cd == Codec::Google) {
+                                        auto *ge                   = static_cast<Codecs::Google::Encoder *>(enc.get());
+                                        ge->blockDocs              = GN;
+                                        ge->skiplistStep           = GS;
+                                        ge->skiplistEntryCountdown = countdown[i];
+                                }
                                 auto &P = parts[i];
                                 enc->begin_term();
                                 synth_term(ndocs, i + 1, min_df, seed, [&](uint32_t doc, uint32_t freq, uint64_t y) {
