@@ -278,22 +278,28 @@ __global__ void __launch_bounds__(kThreads) k_decode_stream_google(DevIndex ix, 
                 return R;
         };
         uint32_t seq_issue = 0, seq_wait = 0;
-        // the span of a unit: [first_off, end) with a 16-byte aligned window around it; returns whether it goes through the staging buffer
-        auto span_of = [&](const Dir &R, uint32_t &abase, uint32_t &bytes) {
+        // the span of a unit: [first_off, end) with a 16-byte aligned window around it.  Computed (two shuffles of loaded directory words)
+        // at the END of an iteration for the unit after the next one — a whole decode after its loads were issued — and carried in registers.
+        struct Span {
+                uint32_t abase, bytes;
+                bool     staged; // it goes through the staging buffer (else the lanes read global memory)
+        };
+        auto span_of = [&](const Dir &R) {
+                Span           S;
                 const uint32_t cnt       = R.d.x.y;
                 const uint32_t first_off = __shfl_sync(0xffffffffu, R.off, 0);
                 const uint32_t end       = __shfl_sync(0xffffffffu, R.offn, int(cnt) - 1);
-                abase                    = first_off & ~15u;
-                bytes                    = ((end + 15u) & ~15u) - abase;
-                return R.d.valid && bytes <= kDsStage;
+                S.abase                  = first_off & ~15u;
+                S.bytes                  = ((end + 15u) & ~15u) - S.abase;
+                S.staged                 = R.d.valid && S.bytes <= kDsStage;
+                return S;
         };
-        auto issue = [&](const Dir &R) {
-                uint32_t abase, bytes;
-                if (span_of(R, abase, bytes)) {
+        auto issue = [&](const Span &S) {
+                if (S.staged) {
                         if (lane == 0) {
                                 const uint32_t bsel = seq_issue & 1u;
-                                mbar_expect_tx(bar_s + bsel * 8u, bytes);
-                                bulk_g2s(stage_s + bsel * kDsStage, ix.index + abase, bytes, bar_s + bsel * 8u);
+                                mbar_expect_tx(bar_s + bsel * 8u, S.bytes);
+                                bulk_g2s(stage_s + bsel * kDsStage, ix.index + S.abase, S.bytes, bar_s + bsel * 8u);
                         }
                         ++seq_issue;
                 }
@@ -303,7 +309,8 @@ __global__ void __launch_bounds__(kThreads) k_decode_stream_google(DevIndex ix, 
         Dir      cur  = load_dir(load_desc(unit));
         Dir      nxt  = load_dir(load_desc(unit + stride));
         Desc     d2   = load_desc(unit + 2u * stride);
-        issue(cur);
+        Span     scur = span_of(cur), snxt = span_of(nxt);
+        issue(scur);
         // checksums are kept per warp across the units of one term (units of a term are mostly handled in a row by the same warps) and
         // flushed when the term changes
         unsigned long long accd = 0, accf = 0;
@@ -320,12 +327,12 @@ __global__ void __launch_bounds__(kThreads) k_decode_stream_google(DevIndex ix, 
                 accd = accf = 0;
         };
         for (; unit < total_units; unit += stride) {
-                issue(nxt);
+                issue(snxt);
                 const Dir  nn = load_dir(d2);                    // directory loads of u+2: in flight while u is decoded
                 const Desc d3 = load_desc(unit + 3u * stride);
-                uint32_t   abase, bytes;
-                const bool staged = span_of(cur, abase, bytes);
-                uint32_t   bsel   = 0;
+                const uint32_t abase  = scur.abase;
+                const bool     staged = scur.staged;
+                uint32_t       bsel   = 0;
                 if (staged) {
                         bsel = seq_wait & 1u;
                         mbar_wait(bar_s + bsel * 8u, (seq_wait >> 1) & 1u);
@@ -354,9 +361,11 @@ __global__ void __launch_bounds__(kThreads) k_decode_stream_google(DevIndex ix, 
                                 ds_google_block_sparse<MAT>(stage_s + bsel * kDsStage + (cur.off - abase), n, prev, cur.last, od, of, accd, accf);
                 }
                 __syncwarp();
-                cur = nxt;
-                nxt = nn;
-                d2  = d3;
+                cur  = nxt;
+                nxt  = nn;
+                d2   = d3;
+                scur = snxt;
+                snxt = span_of(nn); // (its loads are a whole decode old)
         }
         flush();
 }
