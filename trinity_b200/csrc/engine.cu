@@ -946,8 +946,14 @@ static uint32_t flat_tree_transform(std::vector<DevStep> &steps, size_t begin, u
         uint32_t nl{0};
         for (size_t i = begin; i < steps.size(); ++i)
                 nl += steps[i].op == OP_LEAF && steps[i].mode != M_NONE;
-        if (nl < 2 || nl > 16 || nl + next_slot > 30)
-                return 0;
+        uint32_t nops{nl}; // slot operations of the transformed program: one per decoding leaf + every non-leaf step
+        for (size_t i = begin; i < steps.size(); ++i)
+                nops += steps[i].op != OP_LEAF;
+        if (nl < 2 || nl > 16 || nl + next_slot > 30 || nops > 32)
+                return 0; // (the kernel keeps leaves and slot operations in lane registers: <= 16 leaves, <= 32 operations, slots < 32)
+        for (size_t i = begin; i < steps.size(); ++i)
+                if (steps[i].op == OP_COUNT_GE && steps[i].term > 15u)
+                        return 0;
         const std::vector<DevStep> prog(steps.begin() + begin, steps.end());
         steps.resize(begin);
         uint32_t li{0};

@@ -451,6 +451,8 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
         DevQuery Q;
         Q.item_base = 0;
         Q.ntiles    = 0;
+        TreeState TS; // flat-tree plans: the current query's leaves and slot operations, in lane registers
+        TS.nleaf = TS.nops = 0;
 
         for (;;) {
                 // tickets run over THIS launch's queries only (a batch can take two launches: trees on the flat-tree path use a smaller tile)
@@ -471,6 +473,8 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
                         curq = qlo;
                         Q    = P.queries[qlo];
                         qgen = P.gen_sel ? Q.gen_base2 : Q.gen_base;
+                        if (Q.flat == 5u)
+                                tree_load(P, Q, TS, lane);
                 }
                 const uint32_t item = Q.item_base + (gitem - qgen); // batch-wide (query, tile) item: index of the segment arrays
                 if (Q.flat == 3u) { // candidate-driven conjunction: the work item is a 32-block group of the lead term
@@ -482,8 +486,10 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
                 const uint32_t lo = tile << P.exec_shift, hi = lo + W;
                 bool           dead = false;
                 int            handled = 0;
-                if (Q.flat && P.ix.codec == 0)
-                        handled = flat_exec_google(P, Q, lo, W, NW, slots, stage, lane); // flat-tree plans (5): leaves decoded, "not handled" => the slot program runs
+                if (Q.flat == 5u) { // flat-tree plan: all leaves in one pass, then its slot operations
+                        handled = tree_exec_google(P, Q, TS, lo, W, NW, slots, stage, lane) ? 2 : 1;
+                } else if (Q.flat && P.ix.codec == 0)
+                        handled = flat_exec_google(P, Q, lo, W, NW, slots, stage, lane);
                 if (handled == 2)
                         dead = true;
 
