@@ -134,7 +134,8 @@ int trn_segment_masked(trn_segment *, const uint32_t **docids, uint64_t *n);
 #define TRN_NODE_NOT 3
 #define TRN_NODE_OPTIONAL 4
 #define TRN_NODE_SOME 5
-#define TRN_NODE_PHRASE 6 /* front-end only so far: trn_exec_batch rejects it (TRN_ERR_UNSUPPORTED) until the positions path exists */
+#define TRN_NODE_PHRASE 6 /* executed on the GOOGLE codec (inline hits, google_codec.cpp:533-594); an index in the LUCENE codec keeps its hits in hits.data,
+                           * which this engine does not read yet: trn_exec_batch rejects phrase plans there (TRN_ERR_UNSUPPORTED, never a silent answer) */
 
 typedef struct trn_qnode {
         uint8_t  kind;

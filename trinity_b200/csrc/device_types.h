@@ -45,6 +45,9 @@ enum StepOp : uint8_t {
         OP_LEAFSCORE = 3, // second pass: decode term, accumulate BM25 where slot src (mask) has the doc's bit
         OP_COUNT_ADD = 4, // bit-sliced saturating counter in slots dst .. dst+mode-1 (LSB first) += slot src   (DisjunctionSome)
         OP_COUNT_GE  = 5, // dst = documents whose counter (slots src .. src+mode-1) is >= term (min-should-match)
+        OP_PHRASE    = 7, // phrase.cuh: keep the documents of slot dst that hold the phrase whose `mode` term ids follow in OP_ARG steps (four per
+                          // step); flag F_SCORE: add score(matchCnt, idf) (idf = the sum of the terms' weights) to the score tile
+        OP_ARG       = 8, // operand words of the preceding step (never executed)
         OP_TABLE     = 6, // candidate-driven trees: 4 words of the query's truth table (term, pad2, idf as two words); dst = first word index
 };
 enum StepMode : uint8_t { M_SET = 0, M_OR = 1, M_AND = 2, M_ANDNOT = 3, M_NONE = 4 };
@@ -135,6 +138,7 @@ struct ExecParams {
         uint32_t        total_items;
         uint32_t        gen_items; // number of tickets of this launch (items of the queries it runs)
         uint32_t        gen_sel;   // k_exec_docs: 0 = tickets follow DevQuery::gen_base, 1 = gen_base2
+        uint32_t        has_phrase; // some plan of the batch holds OP_PHRASE: launch the instantiation that executes it
         uint32_t        nslots; // bitmap slots per worker (CTA for k_exec_tiles, warp for k_exec_docs)
         uint32_t        stage_bytes; // per-warp staging bytes of k_exec_tiles (codec dependent)
         uint32_t        docs_stage_bytes; // per-warp staging bytes of k_exec_docs (1 or 2 gather buffers)

@@ -197,11 +197,14 @@ struct Compiler {
                 uint32_t              term;
                 double                idf;
                 std::vector<uint8_t> cond;
+                int                   phrase{-1}; // >= 0: node index of a phrase (its position check is repeated under the condition's mask)
         };
         std::vector<Deferred> deferred;
         std::string           err;
         bool                  reference_quirks{true};
         bool                  unsupported{false};
+        bool                  allow_phrase{false}; // the caller's kernels execute OP_PHRASE (GOOGLE codec: inline hits)
+        bool                  has_phrase{false};
 
         Compiler(const trn_qnode *nodes, uint32_t cnt, const std::vector<DevTerm> &t, bool sc, uint32_t r, std::vector<DevStep> &s)
             : n{nodes}, nn{cnt}, terms{t}, scored{sc}, root{r}, steps{s} {
@@ -231,6 +234,66 @@ struct Compiler {
 
         bool is_leaf(uint32_t i) const {
                 return n[i].kind == TRN_NODE_TERM;
+        }
+        bool is_phrase(uint32_t i) const {
+                return n[i].kind == TRN_NODE_PHRASE;
+        }
+        // the conjunction of a phrase's distinct terms into slot `tmp` (rarest first), then the position check in place (phrase.cuh)
+        void phrase_steps(uint32_t i, uint32_t tmp, bool score) {
+                const auto &          X = n[i];
+                std::vector<uint32_t> t(X.nchildren);
+                double                idfsum{0};
+                bool                  anyEmpty{false};
+                for (uint32_t j = 0; j < X.nchildren; ++j) {
+                        t[j] = n[X.first_child + j].term;
+                        idfsum += n[X.first_child + j].weight;
+                        anyEmpty |= t[j] == kEmptyTerm || terms[t[j]].documents == 0;
+                }
+                if (anyEmpty) { // a phrase with an unknown term matches nothing
+                        push(OP_CLEAR, 0, tmp, 0, 0, 0, 0);
+                        return;
+                }
+                std::vector<uint32_t> distinct(t);
+                std::sort(distinct.begin(), distinct.end());
+                distinct.erase(std::unique(distinct.begin(), distinct.end()), distinct.end());
+                std::stable_sort(distinct.begin(), distinct.end(), [&](uint32_t a, uint32_t b) { return terms[a].documents < terms[b].documents; });
+                bool first{true};
+                for (auto term : distinct) {
+                        postings += terms[term].documents;
+                        bytes += terms[term].chunk_len;
+                        push(OP_LEAF, first ? M_SET : M_AND, tmp, 0, 0, term, 0);
+                        first = false;
+                }
+                push(OP_PHRASE, uint8_t(X.nchildren), tmp, 0, score ? F_SCORE : 0, 0, idfsum);
+                for (uint32_t j = 0; j < X.nchildren; j += 4) { // four term ids per operand step, in phrase order
+                        DevStep a;
+                        std::memset(&a, 0, sizeof(a));
+                        a.op   = OP_ARG;
+                        a.term = t[j];
+                        a.pad2 = j + 1 < X.nchildren ? t[j + 1] : 0u;
+                        const uint64_t hi = uint64_t(j + 2 < X.nchildren ? t[j + 2] : 0u) | (uint64_t(j + 3 < X.nchildren ? t[j + 3] : 0u) << 32);
+                        std::memcpy(&a.idf, &hi, 8);
+                        steps.push_back(a);
+                }
+        }
+        // a phrase operand combined into dst with `mode` (== leaf() for a term); scores score(matchCnt, sum idf) where it holds
+        bool phrase_leaf(uint32_t i, uint8_t mode, uint32_t dst, bool scoring, const std::vector<uint8_t> &cond, uint8_t extraFlags) {
+                const bool wantScore = scored && scoring;
+                if (mode == M_NONE && !wantScore)
+                        return true; // nothing to do in this pass
+                const bool immediate = wantScore && cond.empty();
+                if (wantScore && !immediate)
+                        deferred.push_back({0, 0.0, cond, int(i)});
+                if (mode == M_NONE && !immediate)
+                        return true; // the deferred pass does it all
+                const int tmp = alloc_slot();
+                if (tmp < 0)
+                        return false;
+                phrase_steps(i, uint32_t(tmp), immediate);
+                if (mode != M_NONE)
+                        push(OP_SLOT, mode, dst, uint32_t(tmp), extraFlags, 0, 0);
+                release_slot(uint32_t(tmp));
+                return true;
         }
         uint32_t df(uint32_t i) const {
                 const auto t = n[i].term;
@@ -306,7 +369,10 @@ struct Compiler {
                                         const uint8_t fl = isRoot ? F_BREAK_IF_EMPTY : 0;
                                         if (is_leaf(c))
                                                 leaf(c, first ? M_SET : M_AND, s, scoring, cond, fl);
-                                        else {
+                                        else if (is_phrase(c)) {
+                                                if (!phrase_leaf(c, first ? M_SET : M_AND, s, scoring, cond, fl))
+                                                        return -1;
+                                        } else {
                                                 const int cs = node(c, scoring, cond);
                                                 if (cs < 0)
                                                         return -1;
@@ -321,7 +387,10 @@ struct Compiler {
                                 for (auto c : kids) {
                                         if (is_leaf(c))
                                                 leaf(c, M_OR, s, scoring, cond, 0);
-                                        else {
+                                        else if (is_phrase(c)) {
+                                                if (!phrase_leaf(c, M_OR, s, scoring, cond, 0))
+                                                        return -1;
+                                        } else {
                                                 // a non-leaf child of a disjunction contributes its score only for documents it matches itself
                                                 // (Disjunction scorer sums children positioned on the doc, docset_iterators_scorers.cpp)
                                                 const uint32_t willBe = next_slot;
@@ -342,7 +411,10 @@ struct Compiler {
                                 const uint8_t fl = isRoot ? F_BREAK_IF_EMPTY : 0;
                                 if (is_leaf(kids[0]))
                                         leaf(kids[0], M_SET, s, scoring, cond, fl);
-                                else {
+                                else if (is_phrase(kids[0])) {
+                                        if (!phrase_leaf(kids[0], M_SET, s, scoring, cond, fl))
+                                                return -1;
+                                } else {
                                         const int cs = node(kids[0], scoring, cond);
                                         if (cs < 0)
                                                 return -1;
@@ -353,7 +425,10 @@ struct Compiler {
                                         // Filter: excluded side never scores (docset_iterators_scorers.cpp Filter -> req only)
                                         if (is_leaf(kids[1]))
                                                 leaf(kids[1], M_ANDNOT, s, false, cond, 0);
-                                        else {
+                                        else if (is_phrase(kids[1])) {
+                                                if (!phrase_leaf(kids[1], M_ANDNOT, s, false, cond, 0))
+                                                        return -1;
+                                        } else {
                                                 const int cs = node(kids[1], false, cond);
                                                 if (cs < 0)
                                                         return -1;
@@ -364,7 +439,10 @@ struct Compiler {
                                         // Optional: main drives; opt only adds its score when it is on the document
                                         if (is_leaf(kids[1]))
                                                 leaf(kids[1], M_NONE, s, true, cond, 0);
-                                        else {
+                                        else if (is_phrase(kids[1])) {
+                                                if (!phrase_leaf(kids[1], M_NONE, s, true, cond, 0))
+                                                        return -1;
+                                        } else {
                                                 const uint32_t willBe = next_slot;
                                                 if (node(kids[1], true, child_cond(willBe)) < 0)
                                                         return -1;
@@ -399,6 +477,10 @@ struct Compiler {
                                         uint32_t src;
                                         if (is_leaf(c)) {
                                                 leaf(c, M_SET, t, scoring, child_cond(s), 0);
+                                                src = t;
+                                        } else if (is_phrase(c)) {
+                                                if (!phrase_leaf(c, M_SET, t, scoring, child_cond(s), 0))
+                                                        return -1;
                                                 src = t;
                                         } else {
                                                 auto cc = child_cond(s);
@@ -436,10 +518,11 @@ struct Compiler {
                 }
                 if (X.kind == TRN_NODE_NOT || X.kind == TRN_NODE_OPTIONAL)
                         return range(X.first_child);
-                bool first{true};
+                const bool conj = X.kind == TRN_NODE_AND || X.kind == TRN_NODE_PHRASE; // a phrase needs all of its terms
+                bool       first{true};
                 for (uint32_t c = 0; c < X.nchildren; ++c) {
                         const Range cr = range(X.first_child + c);
-                        if (X.kind == TRN_NODE_AND) {
+                        if (conj) {
                                 if (cr.empty())
                                         return Range{};
                                 if (first)
@@ -472,10 +555,11 @@ struct Compiler {
                         return df(i);
                 if (X.kind == TRN_NODE_NOT || X.kind == TRN_NODE_OPTIONAL)
                         return bound(X.first_child);
-                uint64_t b = X.kind == TRN_NODE_AND ? ~0ull : 0ull;
+                const bool conj = X.kind == TRN_NODE_AND || X.kind == TRN_NODE_PHRASE;
+                uint64_t   b    = conj ? ~0ull : 0ull;
                 for (uint32_t c = 0; c < X.nchildren; ++c) {
                         const uint64_t cb = bound(X.first_child + c);
-                        b                 = X.kind == TRN_NODE_AND ? std::min(b, cb) : b + cb;
+                        b                 = conj ? std::min(b, cb) : b + cb;
                 }
                 return b;
         }
@@ -496,10 +580,22 @@ struct Compiler {
                                         return false;
                                 }
                         } else if (n[i].kind == TRN_NODE_PHRASE) {
-                                err         = "phrase nodes need the positions path (materialize_hits), which this engine does not execute yet";
-                                unsupported = true;
-                                return false;
-                        } else if (n[i].kind > TRN_NODE_SOME) {
+                                if (!allow_phrase) {
+                                        err         = "phrase nodes need the positions path (materialize_hits): executed on the GOOGLE codec's inline hits only (LUCENE hits.data: not yet)";
+                                        unsupported = true;
+                                        return false;
+                                }
+                                if (n[i].nchildren < 2 || n[i].nchildren > 16 || n[i].first_child <= i || uint32_t(n[i].first_child) + n[i].nchildren > nn) {
+                                        err = "a phrase holds 2..16 terms behind it in the node array";
+                                        return false;
+                                }
+                                for (uint32_t k = 0; k < n[i].nchildren; ++k)
+                                        if (n[n[i].first_child + k].kind != TRN_NODE_TERM) {
+                                                err = "the children of a phrase are terms";
+                                                return false;
+                                        }
+                                has_phrase = true;
+                        } else if (n[i].kind > TRN_NODE_PHRASE) {
                                 err = "unknown node kind";
                                 return false;
                         } else {
@@ -525,6 +621,8 @@ struct Compiler {
                         return df(i);
                 if (X.kind == TRN_NODE_NOT || X.kind == TRN_NODE_OPTIONAL)
                         return cost(X.first_child);
+                if (X.kind == TRN_NODE_PHRASE) // docset_iterators.cpp:50-55: cost(its[0]) + UINT32_MAX + UINT16_MAX * size
+                        return cost(X.first_child) + 0xffffffffull + 0xffffull * X.nchildren;
                 if (X.kind == TRN_NODE_SOME) { // DisjunctionSome::cost_: the (size - min + 1) cheapest children (docset_iterators.cpp:733-742)
                         std::vector<uint64_t> cs;
                         for (uint32_t k = 0; k < X.nchildren; ++k)
@@ -570,6 +668,10 @@ struct Compiler {
                 if (is_leaf(root)) {
                         rs = int(next_slot++);
                         leaf(root, M_SET, uint32_t(rs), true, {}, 0);
+                } else if (is_phrase(root)) {
+                        rs = int(next_slot++);
+                        if (!phrase_leaf(root, M_SET, uint32_t(rs), true, {}, 0))
+                                return -1;
                 } else
                         rs = node(root, true, {});
                 if (rs < 0)
@@ -586,6 +688,29 @@ struct Compiler {
                                 push(OP_SLOT, M_SET, mask, d.cond[0], 0, 0, 0);
                                 for (size_t j = 1; j < d.cond.size(); ++j)
                                         push(OP_SLOT, M_AND, mask, d.cond[j], 0, 0, 0);
+                        }
+                        if (d.phrase >= 0) { // the phrase again, restricted to the condition's documents, scoring this time
+                                if (next_slot >= 14) {
+                                        err = "query needs more than 14 docset slots";
+                                        return -1;
+                                }
+                                const uint32_t tmp = next_slot++;
+                                // (phrase_steps starts with SET/CLEAR into tmp; the mask narrows the candidates before the position check)
+                                const size_t at = steps.size();
+                                phrase_steps(uint32_t(d.phrase), tmp, true);
+                                // insert [SLOT AND tmp, mask] in front of the OP_PHRASE step
+                                for (size_t z = at; z < steps.size(); ++z)
+                                        if (steps[z].op == OP_PHRASE) {
+                                                DevStep a;
+                                                std::memset(&a, 0, sizeof(a));
+                                                a.op   = OP_SLOT;
+                                                a.mode = M_AND;
+                                                a.dst  = uint8_t(tmp);
+                                                a.src  = uint8_t(mask);
+                                                steps.insert(steps.begin() + z, a);
+                                                break;
+                                        }
+                                continue;
                         }
                         push(OP_LEAFSCORE, M_NONE, 0, mask, 0, d.term, d.idf);
                 }
@@ -1087,16 +1212,18 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         uint32_t               treeSlots{1};
         uint32_t               maxRuns{0};
         uint32_t              maxSlots{1};
-        bool                  anyCandidate{false}, anyMembership{false};
+        bool                  anyCandidate{false}, anyMembership{false}, anyPhrase{false};
         uint64_t              items{0}, segCap{0}, candTotal{0}, postings{0}, bytes{0};
         for (uint32_t q = 0; q < nq; ++q) {
                 const auto &Q = queries[q];
                 if (!Q.nodes || !Q.nnodes)
                         return fail(c, TRN_ERR_ARG, "empty query");
                 Compiler cc(Q.nodes, Q.nnodes, c->h_terms, scored, Q.root, steps);
+                cc.allow_phrase = c->codec == TRN_CODEC_GOOGLE;
                 auto &   dq     = hq[q];
                 dq.step_begin   = uint32_t(steps.size());
                 const int rs    = cc.run();
+                anyPhrase |= cc.has_phrase;
                 if (rs < 0)
                         return fail(c, cc.unsupported ? TRN_ERR_UNSUPPORTED : TRN_ERR_ARG, "query " + std::to_string(q) + ": " + cc.err);
                 dq.nsteps    = uint32_t(steps.size()) - dq.step_begin;
@@ -1164,7 +1291,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 // The boolean function of the tree over its (<= 8 distinct) terms is tabulated here; the device probes every term for
                 // each candidate and looks the membership bits up.
                 bool candidate{false};
-                if (!scored && c->codec == TRN_CODEC_GOOGLE && c->cand_cost > 0 && !r.empty()) {
+                if (!scored && c->codec == TRN_CODEC_GOOGLE && c->cand_cost > 0 && !r.empty() && !cc.has_phrase) {
                         // distinct non-empty terms below the effective root (at most 8)
                         uint32_t tv[8];
                         uint32_t n{0};
@@ -1277,7 +1404,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 // The per-leaf groups of the step-program path ran at 10 of 32 lanes with up to 8 live bitmaps per warp (profiles/r01_u); here
                 // the lanes are packed across leaves, and a smaller tile pays for the extra bitmaps.
                 bool treeFlat{false};
-                if (!scored && !candidate && dq.flat == 0u && c->codec == TRN_CODEC_GOOGLE && c->tree_shift && !r.empty()) {
+                if (!scored && !candidate && dq.flat == 0u && c->codec == TRN_CODEC_GOOGLE && c->tree_shift && !r.empty() && !cc.has_phrase) {
                         const uint32_t nl = flat_tree_transform(steps, dq.step_begin, cc.next_slot);
                         if (nl) {
                                 dq.nsteps = uint32_t(steps.size()) - dq.step_begin;
@@ -1405,6 +1532,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         P.nq           = nq;
         P.total_items  = totalItems;
         P.gen_items    = uint32_t(genItems);
+        P.has_phrase   = anyPhrase ? 1u : 0u;
         P.nslots       = maxSlots;
         P.exec_shift   = execShift;
         P.stage_bytes  = exec_stage_bytes(c->codec);

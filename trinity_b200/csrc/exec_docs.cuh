@@ -438,7 +438,7 @@ __device__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
 #include "exec_docs_cand.cuh"
 
 // min 7 CTAs/SM: shared memory allows 7 at the default tile; without the bound ptxas stops at 64 registers and spills
-__global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) {
+template <bool PH> __global__ void __launch_bounds__(kDocsWarps * 32, PH ? 4 : 7) k_exec_docs(ExecParams P) { // PH: see k_exec_tiles
         const uint32_t W  = 1u << P.exec_shift;
         const uint32_t NW = W >> 5;
         const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -535,6 +535,9 @@ __global__ void __launch_bounds__(kDocsWarps * 32, 7) k_exec_docs(ExecParams P) 
                                         }
                                         dst[i] = gt | eq;
                                 }
+                        } else if (st.op == OP_PHRASE) {
+                                if constexpr (PH)
+                                        phrase_check(P.ix, P.steps + Q.step_begin + si + 1u, st.mode, lo, NW, dst, nullptr, 0.0, lane, 32); // phrase.cuh
                         } else if (st.op == OP_LEAF && st.mode != M_NONE) {
                                 uint32_t *tmp      = slots + size_t(P.nslots - 1) * NW;
                                 const int mode     = st.mode;
@@ -710,19 +713,21 @@ size_t exec_docs_smem_bytes(uint32_t exec_shift, uint32_t nslots, uint32_t stage
 
 int exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots, uint32_t stageBytes) {
         const size_t smem = exec_docs_smem_bytes(exec_shift, nslots, stageBytes);
-        if (cudaFuncSetAttribute(k_exec_docs, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_exec_docs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess ||
+            cudaFuncSetAttribute(k_exec_docs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
                 return 0;
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_exec_docs, kDocsWarps * 32, smem) != cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_exec_docs<false>, kDocsWarps * 32, smem) != cudaSuccess)
                 return 0;
         return n;
 }
 
 cudaError_t launch_exec_docs(const ExecParams &P, int grid, cudaStream_t stream) {
         const size_t smem = exec_docs_smem_bytes(P.exec_shift, P.nslots, P.docs_stage_bytes);
-        cudaError_t  e    = cudaFuncSetAttribute(k_exec_docs, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        const void * fn   = P.has_phrase ? (const void *)k_exec_docs<true> : (const void *)k_exec_docs<false>;
+        cudaError_t  e    = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess)
                 return e;
-        k_exec_docs<<<grid, kDocsWarps * 32, smem, stream>>>(P);
-        return cudaGetLastError();
+        void *args[] = {(void *)&P};
+        return cudaLaunchKernel(fn, dim3(grid), dim3(kDocsWarps * 32), args, smem, stream);
 }

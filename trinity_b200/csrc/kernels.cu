@@ -448,10 +448,14 @@ __device__ __forceinline__ unsigned long long make_key(float score, uint32_t doc
         return (static_cast<unsigned long long>(__float_as_uint(score)) << 32) | static_cast<unsigned long long>(~doc);
 }
 
+#include "phrase.cuh"
+
 // ------------------------------------------------------------------------------------------------ the fused kernel
 extern __shared__ __align__(16) uint8_t dyn_smem[];
 
-__global__ void __launch_bounds__(kThreads) k_exec_tiles(ExecParams P) {
+// PH: the instantiation that also executes OP_PHRASE (position checks, phrase.cuh) — used only for batches that hold phrase nodes, so that
+// the cursor code costs the common instantiation neither registers nor a stack frame
+template <bool PH> __global__ void __launch_bounds__(kThreads) k_exec_tiles(ExecParams P) {
         const uint32_t W     = 1u << P.exec_shift;
         const uint32_t NW    = W >> 5; // bitmap words per slot
         const bool     scored = P.mode != 0;
@@ -538,6 +542,12 @@ __global__ void __launch_bounds__(kThreads) k_exec_tiles(ExecParams P) {
                                         }
                                         dst[i] = gt | eq;
                                 }
+                        } else if (st.op == OP_PHRASE) {
+                                // position filter over the candidates of dst (+ the phrase's score where it holds); phrase.cuh
+                                if constexpr (PH)
+                                        phrase_check(P.ix, P.steps + Q.step_begin + si + 1u, st.mode, lo, NW, dst, (scored && (st.flags & F_SCORE)) ? acc : nullptr, st.idf, tid, kThreads);
+                        } else if (st.op == OP_ARG) {
+                                // operand words of the preceding step
                         } else {
                                 // OP_LEAF / OP_LEAFSCORE
                                 const bool     second   = st.op == OP_LEAFSCORE;
@@ -1075,21 +1085,25 @@ size_t exec_smem_bytes(uint32_t tile_shift, uint32_t nslots, int mode, int codec
 
 cudaError_t launch_exec_tiles(const ExecParams &P, int grid, cudaStream_t stream) {
         const size_t smem = exec_smem_bytes(P.exec_shift, P.nslots, P.mode, P.ix.codec);
-        cudaError_t  e    = cudaFuncSetAttribute(k_exec_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        const void * fn   = P.has_phrase ? (const void *)k_exec_tiles<true> : (const void *)k_exec_tiles<false>;
+        cudaError_t  e    = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess)
                 return e;
-        k_exec_tiles<<<grid, kThreads, smem, stream>>>(P);
-        return cudaGetLastError();
+        void *args[] = {(void *)&P};
+        return cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream);
 }
 
 int exec_max_ctas_per_sm(uint32_t tile_shift, uint32_t nslots, int mode, int codec) {
         const size_t smem = exec_smem_bytes(tile_shift, nslots, mode, codec);
-        if (cudaFuncSetAttribute(k_exec_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+        // (the phrase instantiation needs at least as many registers: size the grid for it when in doubt — a smaller grid is still correct)
+        if (cudaFuncSetAttribute(k_exec_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess ||
+            cudaFuncSetAttribute(k_exec_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
                 return 0;
-        int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_exec_tiles, kThreads, smem) != cudaSuccess)
+        int n = 0, m = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_exec_tiles<false>, kThreads, smem) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, k_exec_tiles<true>, kThreads, smem) != cudaSuccess)
                 return 0;
-        return n;
+        return std::min(n, m);
 }
 
 cudaError_t launch_query_scan(const unsigned long long *match_counts, uint32_t nq, uint64_t *q_offsets, cudaStream_t stream) {
