@@ -254,6 +254,70 @@ __device__ __forceinline__ void google_block_docs_vote(unsigned m, const uint8_t
                 bs.add(last - lo);
 }
 
+// Per-lane decoder into an OwnAcc — no votes: every lane walks ITS block through 32-bit windows of its gather slot, four 1-byte codes per
+// window when it can, else up to two codes of 1-2 bytes (two such codes always fit a window); a longer code sends the lane to global
+// memory for the rest of the block.  Used where the lanes of a group belong to different lists (flat-tree plans: profiles/r02_f shows the
+// warp-voted decoder above paying its one-code-per-step path for the whole warp whenever ONE lane holds a 2-byte code): a lane in a
+// sparse list then costs the lanes in dense lists an idle step, not a slow step.
+__device__ __forceinline__ void google_block_docs_lane(const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n, uint32_t prev,
+                                                       uint32_t last, uint32_t lo, uint32_t W, OwnAcc &bs) {
+        const uint32_t mis  = off & 15u;
+        const uint32_t base = uint32_t(__cvta_generic_to_shared(buf + lane * kGatherBytes)) + mis; // shared address of the first delta byte
+        const uint32_t nd   = n - 1u;
+        uint32_t       sp = base, rel = prev - lo, i = 0;
+        while (i < nd) {
+                const uint32_t a = sp & ~3u;
+                const uint32_t w = __funnelshift_r(lds_u32(a), lds_u32(a + 4u), (sp & 3u) * 8u); // bytes sp .. sp+3
+                if ((w & 0x80808080u) == 0u && i + 4u <= nd) {
+                        const uint32_t r0 = rel + (w & 0xffu), r1 = r0 + __byte_perm(w, 0u, 0x4441u), r2 = r1 + __byte_perm(w, 0u, 0x4442u), r3 = r2 + (w >> 24);
+                        rel = r3;
+                        sp += 4u;
+                        i += 4u;
+                        if (r0 < W && r3 < W) {
+                                bs.add(r0);
+                                bs.add(r1);
+                                bs.add(r2);
+                                bs.add(r3);
+                        } else {
+                                if (r0 < W) bs.add(r0);
+                                if (r1 < W) bs.add(r1);
+                                if (r2 < W) bs.add(r2);
+                                if (r3 < W) bs.add(r3);
+                        }
+                        continue;
+                }
+                const uint32_t b0 = w & 0xffu;
+                if (b0 >= 0xc0u)
+                        break; // 3..5-byte code: the section may leave the slot
+                const uint32_t two = b0 >> 7;
+                uint32_t       len = 1u + two;
+                rel += two ? (((b0 & 0x3fu) << 8) | __byte_perm(w, 0u, 0x4441u)) : b0;
+                if (rel < W)
+                        bs.add(rel);
+                ++i;
+                const uint32_t w2 = w >> (8u * len), c0 = w2 & 0xffu;
+                if (i < nd && c0 < 0xc0u) { // the second code of the window
+                        const uint32_t two2 = c0 >> 7;
+                        rel += two2 ? (((c0 & 0x3fu) << 8) | ((w2 >> 8) & 0xffu)) : c0;
+                        if (rel < W)
+                                bs.add(rel);
+                        ++i;
+                        len += 1u + two2;
+                }
+                sp += len;
+        }
+        if (i < nd) {
+                const uint8_t *g = index + off + (sp - base);
+                for (; i < nd; ++i) {
+                        rel += varbyte_get(g);
+                        if (rel < W)
+                                bs.add(rel);
+                }
+        }
+        if (last - lo < W)
+                bs.add(last - lo);
+}
+
 // generic sinks (BitSink of the step programs, BitAcc of flat disjunctions): the byte-wise decoder over the lane's gather slot
 template <class SINK>
 __device__ __forceinline__ void google_block_docs_gather(unsigned, const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n,

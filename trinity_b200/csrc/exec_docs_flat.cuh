@@ -286,8 +286,9 @@ __device__ bool tree_exec_google(const ExecParams &P, const DevQuery &Q, const T
                 const unsigned m = __ballot_sync(0xffffffffu, cur.active);
                 OwnAcc         bs;
                 bs.init(slots_s + cur.j * NW * 4u, dummy);
+                (void)m;
                 if (cur.active)
-                        google_block_docs_vote(m, P.ix.index, cur.off, stage, lane, cur.n, cur.prev, cur.last, lo, W, bs);
+                        google_block_docs_lane(P.ix.index, cur.off, stage, lane, cur.n, cur.prev, cur.last, lo, W, bs);
                 __syncwarp();
                 if (tail_bits) // the previous group's last words, after every block that can share them has stored
                         asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(tail_a), "r"(tail_bits) : "memory");
