@@ -19,7 +19,7 @@ GpuAccessProxy::GpuAccessProxy(int device, Codecs::AccessProxy *ap, size_t index
                 t.push_back({tctx.documents, tctx.indexChunk.offset, tctx.indexChunk.size()});
         }
         const auto ci    = ap->codec_identifier();
-        const int  codec = (ci.size() == 6 && !memcmp(ci.data(), "GOOGLE", 6)) ? TRN_CODEC_GOOGLE : TRN_CODEC_LUCENE;
+        codec            = (ci.size() == 6 && !memcmp(ci.data(), "GOOGLE", 6)) ? TRN_CODEC_GOOGLE : TRN_CODEC_LUCENE;
         if (trn_upload_index(ctx, codec, ap->indexPtr, indexSize, t.data(), uint32_t(t.size()), maxDocID) != TRN_OK) {
                 const std::string m = trn_last_error(ctx);
                 trn_destroy(ctx);
@@ -79,6 +79,18 @@ namespace {
                         }
                         n.push_back(x);
                         return int(n.size()) - 1;
+                }
+                // the engine checks positions on the device for the GOOGLE codec (inline hits); a LUCENE source keeps them in hits.data, which the
+                // engine does not hold: such plans stay with the reference's own span
+                int phrase_node(const compilation_ctx::phrase *p) {
+                        if (gap.codec != TRN_CODEC_GOOGLE) {
+                                unsupported = true;
+                                return term_node(p->termIDs[0]);
+                        }
+                        std::vector<int> kids;
+                        for (uint8_t i = 0; i < p->size; ++i)
+                                kids.push_back(term_node(p->termIDs[i]));
+                        return group(TRN_NODE_PHRASE, std::move(kids));
                 }
                 int group(uint8_t kind, std::vector<int> kids, uint32_t min = 0) {
                         PNode x;
@@ -160,7 +172,17 @@ namespace {
                                                 kids.push_back(emit(g->nodes[i]));
                                         return group(TRN_NODE_SOME, std::move(kids), g->min);
                                 }
-                                default: // phrases need the positions path: this span does not take them (the caller falls back to the CPU span)
+                                case ENT::matchphrase: // -> Phrase(PLIs in phrase order), exec.cpp:284-297
+                                        return phrase_node(static_cast<const compilation_ctx::phrase *>(e.ptr));
+                                case ENT::matchanyphrases:   // -> Disjunction of Phrases, exec.cpp:298-312
+                                case ENT::matchallphrases: { // -> Conjuction of Phrases, exec.cpp:313-327
+                                        const auto       run = static_cast<const compilation_ctx::phrasesrun *>(e.ptr);
+                                        std::vector<int> kids;
+                                        for (uint16_t i = 0; i < run->size; ++i)
+                                                kids.push_back(phrase_node(run->phrases[i]));
+                                        return kids.size() == 1 ? kids[0] : group(e.fp == ENT::matchallphrases ? TRN_NODE_AND : TRN_NODE_OR, std::move(kids));
+                                }
+                                default: // anything else (constfalse survivors, ...) stays with the reference's own span
                                         unsupported = true;
                                         return term_node(0);
                         }

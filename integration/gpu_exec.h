@@ -25,6 +25,7 @@ struct GpuAccessProxy final {
         trn_ctx *                                 ctx{nullptr};
         std::unordered_map<std::string, uint32_t> idOf; // term -> trn term id
         uint64_t                                  spansExecuted{0};
+        int                                       codec{0}; // TRN_CODEC_*
 
         // `terms`: every (term, term_index_ctx) of the source, e.g. from SegmentTerms iteration (terms.h:27-37)
         GpuAccessProxy(int device, Codecs::AccessProxy *ap, size_t indexSize, const std::vector<std::pair<std::string, term_index_ctx>> &terms, isrc_docid_t maxDocID);
@@ -37,7 +38,7 @@ void            gpu_proxy_register(IndexSource *src, GpuAccessProxy *gap);
 GpuAccessProxy *gpu_proxy_for(IndexSource *src);
 
 // exec_query()'s span factory for sources that have a device twin; returns nullptr when the plan holds something the GPU span does
-// not execute (phrases) or the source has no twin: the caller then builds the reference's own span.
+// not execute (phrases over a LUCENE source: hits.data is not on the device) or the source has no twin: the caller then builds the reference's own span.
 std::unique_ptr<DocsSetSpan> b200_gpu_span(queryexec_ctx &rctx, const exec_node root, const uint32_t execFlags, IndexSource *idxsrc, Similarity::IndexSourceTermsScorer *scorer);
 
 } // namespace Trinity

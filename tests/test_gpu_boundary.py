@@ -63,3 +63,55 @@ def test_exec_query_through_the_gpu_span_equals_stock_exec_query(ref, codec):
                     assert_close_scores(gs, ws, f"[{q}] masked")
     finally:
         refg.L.tref_gpu_detach(gpu.h)
+
+
+def _phrase_twins(rl_stock, rl_gpu, codec, ndocs, vocab=9, seed=33, lo=3, hi=40):
+    rng = np.random.default_rng(seed)
+    prob = 1.0 / np.arange(1, vocab + 1)
+    prob /= prob.sum()
+    per_term = [dict() for _ in range(vocab)]
+    for d in range(1, ndocs + 1):
+        toks = rng.choice(vocab, size=int(rng.integers(lo, hi)), p=prob)
+        for pos, t in enumerate(toks, start=1):
+            per_term[int(t)].setdefault(d, []).append(pos)
+    out = []
+    for rl in (rl_stock, rl_gpu):
+        r = RefIndex(rl, codec)
+        for t in range(vocab):
+            docs = np.array(sorted(per_term[t]), np.uint32)
+            freqs = np.array([len(per_term[t][int(d)]) for d in docs], np.uint32)
+            flat = np.array([p for d in docs for p in per_term[t][int(d)]], np.uint32)
+            r.add_term(f"w{t + 1}", docs, freqs, flat)
+        r.finish(ndocs)
+        out.append(r)
+    return out
+
+
+def test_phrases_through_the_gpu_span(ref):
+    """ENT::matchphrase / matchanyphrases / matchallphrases -> TRN_NODE_PHRASE on a GOOGLE source (positions checked on the device); on a
+    LUCENE source the binding declines (hits.data is not on the device) and the reference's own span runs: same stream either way"""
+    from test_phrase_cpu import QUERIES
+    refg = load_ref_gpu()
+    ndocs = 20_000
+    for codec, on_gpu in ((tb.CODEC_GOOGLE, True), (tb.CODEC_LUCENE, False)):
+        stock, gpu = _phrase_twins(ref, refg, codec, ndocs)
+        assert refg.L.tref_gpu_attach(gpu.h, 0, ndocs) == 0, refg.err()
+        try:
+            before = refg.L.tref_gpu_spans_executed(gpu.h)
+            nonempty = 0
+            for q in QUERIES:
+                for scored in (False, True):
+                    wd, ws = stock.exec(q, scored, ndocs + 1)
+                    gd, gs = gpu.exec(q, scored, ndocs + 1)
+                    assert_same_docs(gd, wd, f"[{q}] scored={scored} codec={codec}")
+                    if scored:
+                        assert_close_scores(gs, ws, f"[{q}] codec={codec}")
+                    nonempty += len(wd) > 0
+            executed = refg.L.tref_gpu_spans_executed(gpu.h) - before
+            assert nonempty >= 9
+            if on_gpu:  # '"w1 nosuch"' collapses before the span site; '"w1"' is a term (DocumentsOnly: exec_query's own specialisation)
+                assert executed >= 2 * len(QUERIES) - 4, (executed, len(QUERIES))
+            else:  # only '"w1"' (a plain term) may have gone to the device
+                assert executed <= 2, executed
+        finally:
+            refg.L.tref_gpu_detach(gpu.h)
