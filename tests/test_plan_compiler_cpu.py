@@ -76,3 +76,47 @@ def test_flat_tree_programs_match_the_structural_evaluator(built):
         want_m, _ = evaluate(nodes, lists, NDOCS, weights=None)
         assert np.array_equal(np.flatnonzero(got_m), np.flatnonzero(want_m)), (q, m)
     assert transformed >= 20
+
+
+TREE8 = ["({0} OR {1}) AND ({2} OR {3}) AND {4} NOT ({5} OR {6} OR {7})", "{0} AND {1} AND {2} NOT {3} NOT {4}",
+         "({0} AND {1}) OR ({2} AND {3}) OR ({4} AND {5}) NOT {6} NOT {7}", "{0} AND ({1} OR {2} OR {3}) NOT ({4} AND {5}) AND ({6} OR {7})",
+         "{0} AND {1}", "({0} OR {1}) AND {2}", "{0} NOT ({1} AND {2})", "({0} AND ({1} OR ({2} AND {3}))) NOT {4}", "{0} OR ({1} AND {2} AND {3})"]
+
+
+def test_flat_tree_masked_second_pass_matches_the_structural_evaluator():
+    """flat-tree programs with the masked second decode pass (engine.cu flat_tree_masks): frequent leaves keep only the postings inside
+    a mask computed from the other leaves — whatever subset of the postings outside the mask survives, the documents must not change"""
+    ndocs = 300_000
+    rng = np.random.default_rng(77)
+    dfs = [150_000, 100_000, 60_000, 20_000, 6_000, 2_000, 700, 200, 50, 10, 90_000, 3_000]
+    lists = []
+    for df in dfs:
+        d = np.sort(rng.choice(ndocs, size=df, replace=False).astype(np.uint32) + 1)
+        lists.append((d, np.ones(df, np.uint32)))
+    b = tb.IndexBuilder(tb.CODEC_GOOGLE)
+    for d, f in lists:
+        b.add_term(d, f)
+    index, terms = b.index(), b.terms_array()
+    names = [f"t{i + 1}" for i in range(len(lists))]
+    tdict = tb.TermDictionary(names)
+    queries = [(q, m) for q, m in ALL]
+    for _ in range(40):
+        for tpl in TREE8:
+            pick = rng.choice(len(names), size=8, replace=False)
+            queries.append((tpl.format(*[names[i] for i in pick]), None))
+    masked_programs = masked_leaves = 0
+    for q, m in queries:
+        nodes = tb.parse_query(q, tdict, min_match=m)
+        steps, root_slot, nslots = tb.debug_compile(tb.CODEC_GOOGLE, index, terms, nodes, 3)
+        nm = sum(1 for s in steps if int(s["op"]) == stepsim.OP_LEAF and (int(s["flags"]) & stepsim.F_MASKED))
+        masked_programs += nm > 0
+        masked_leaves += nm
+        assert nslots <= 31 and sum(1 for s in steps if int(s["flags"]) & stepsim.F_MASKOP) <= 32
+        for s in steps:  # a mask is never a second-pass leaf's bitmap
+            if int(s["op"]) == stepsim.OP_LEAF and (int(s["flags"]) & stepsim.F_MASKED):
+                assert not any(int(x["op"]) == stepsim.OP_LEAF and (int(x["flags"]) & stepsim.F_MASKED) and int(x["dst"]) == int(s["src"]) for x in steps)
+        want_m, _ = evaluate(nodes, lists, ndocs, weights=None)
+        for r in (None, np.random.default_rng(5), np.random.default_rng(6)):
+            got_m, _ = stepsim.run(steps, root_slot, nslots, lists, ndocs, tree=True, rng=r)
+            assert np.array_equal(np.flatnonzero(got_m), np.flatnonzero(want_m)), (q, m)
+    assert masked_programs >= 100 and masked_leaves >= 200, (masked_programs, masked_leaves)

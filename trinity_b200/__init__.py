@@ -205,7 +205,7 @@ def parse_query(text: str, tdict: TermDictionary, min_match: Optional[int] = Non
 
 def debug_compile(codec: int, index: np.ndarray, terms: np.ndarray, nodes: np.ndarray, scored):
     """(steps, root_slot, nslots): the bitmap-path step program of one plan, compiled on the host (no GPU needed).
-    scored: False / True, or 2 = the DocumentsOnly program in its flat-tree form"""
+    scored: False / True, 2 = the DocumentsOnly program in its flat-tree form, 3 = flat-tree form with the masked second decode pass"""
     from ._ffi import STEP_DTYPE
     index = np.ascontiguousarray(index, dtype=np.uint8)
     terms = np.ascontiguousarray(terms, dtype=TERM_DTYPE)

@@ -51,7 +51,12 @@ enum StepOp : uint8_t {
         OP_TABLE     = 6, // candidate-driven trees: 4 words of the query's truth table (term, pad2, idf as two words); dst = first word index
 };
 enum StepMode : uint8_t { M_SET = 0, M_OR = 1, M_AND = 2, M_ANDNOT = 3, M_NONE = 4 };
-enum StepFlags : uint8_t { F_SCORE = 1, F_BREAK_IF_EMPTY = 2 };
+enum StepFlags : uint8_t {
+        F_SCORE          = 1,
+        F_BREAK_IF_EMPTY = 2,
+        F_MASKED         = 4, // flat-tree leaf marker: decoded in the SECOND pass, only the blocks that hold a docID of the bitmap in slot `src`
+        F_MASKOP         = 8  // flat-tree slot operation of the mask section (runs between the two decode passes)
+};
 
 struct DevStep {
         uint8_t  op, mode, dst, src;

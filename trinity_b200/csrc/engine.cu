@@ -17,7 +17,9 @@
 #include <cstring>
 #include <stdexcept>
 #include <functional>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <thread>
 #include <vector>
 
@@ -91,6 +93,7 @@ struct trn_ctx {
         uint32_t             min_docid{1}; // smallest docID any term holds (a docID-range shard does not start at 1)
         uint32_t             nterms{0}, max_docid{0}, tile_shift{13}, ntiles{0}; // tile_shift: directory granularity == scored tile (8192 docs, the reference's window docset_spans.h:74)
         uint32_t             docs_shift{14}; // docID tile (log2) of the warp-per-tile DocumentsOnly kernel
+        bool                 tree_masks{true}; // TRN_TREE_MASKS=0: flat-tree queries decode every leaf in one pass (no masked second pass)
         uint32_t             tree_shift{12}; // TRN_TREE_SHIFT: docID tile (log2) of the flat-tree launch of k_exec_docs (0 = flat-tree path off)
         uint32_t             run_tiles{128};  // TRN_RUN_TILES: consecutive tiles per work item of the flat scored kernel (top-k state lives across a run)
         int                  flat_threads{320}; // TRN_SF_THREADS: CTA size of k_score_flat (256/320/384: two CTAs per SM; 512/640: one)
@@ -205,6 +208,7 @@ struct Compiler {
         bool                  unsupported{false};
         bool                  allow_phrase{false}; // the caller's kernels execute OP_PHRASE (GOOGLE codec: inline hits)
         bool                  has_phrase{false};
+        std::vector<uint32_t> leaf_nodes;          // node index of every OP_LEAF step, in program order (flat_tree_masks)
 
         Compiler(const trn_qnode *nodes, uint32_t cnt, const std::vector<DevTerm> &t, bool sc, uint32_t r, std::vector<DevStep> &s)
             : n{nodes}, nn{cnt}, terms{t}, scored{sc}, root{r}, steps{s} {
@@ -330,6 +334,7 @@ struct Compiler {
                 }
                 if (mode == M_NONE && !(flags & F_SCORE))
                         return; // nothing to do in this pass
+                leaf_nodes.push_back(i);
                 push(OP_LEAF, mode, dst, 0, flags, n[i].term, n[i].weight);
         }
 
@@ -754,6 +759,8 @@ extern "C" int trn_create(int device, trn_ctx **out) {
                 if (v == 0 || (v >= 10 && v <= 14))
                         c->tree_shift = uint32_t(v);
         }
+        if (const char *e = getenv("TRN_TREE_MASKS"))
+                c->tree_masks = atoi(e) != 0;
         if (const char *e = getenv("TRN_RUN_TILES")) {
                 const int v = atoi(e);
                 if (v >= 1 && v <= 4096)
@@ -1114,6 +1121,234 @@ static uint32_t flat_tree_transform(std::vector<DevStep> &steps, size_t begin, u
         return nl;
 }
 
+// Masked second decode pass of the flat-tree path.  A leaf whose blocks are short in docID terms (a frequent term) does not have to be
+// decoded where the rest of the tree already rules a match out: if x sits under a conjunction next to S, the value of x outside S cannot
+// reach the root (the conjunction is false there whatever x says), and the same holds for the excluded side of a Filter outside its
+// required side, through any number of operators above.  So the frequent leaves are decoded in a SECOND pass, and of their blocks only
+// those whose docID range holds a set bit of a mask bitmap: the conjunction of the constraint subtrees on the leaf's path to the root,
+// evaluated over the first-pass leaf bitmaps (any superset is a valid mask: an operand of a conjunction that is itself second-pass is
+// left out, a disjunction with such an operand is not usable).  This is Conjuction::next's advance() on the longer list
+// (docset_iterators.cpp:282-348) at block granularity.  The tree semantics used here are the compiler's (Compiler::node), from its
+// effective root.  Layout of the program afterwards: [leaf markers] [mask operations, F_MASKOP] [the unchanged slot operations].
+// Returns the number of slots the masks add.
+static uint32_t flat_tree_masks(std::vector<DevStep> &steps, size_t begin, uint32_t nl, uint32_t slotsInUse, const trn_qnode *n, uint32_t nn, uint32_t root,
+                                const std::vector<uint32_t> &leafNodes, const std::vector<DevTerm> &terms, uint32_t tileShift, double width) {
+        if (leafNodes.size() != nl || nl > 16 || width <= 0)
+                return 0;
+        std::vector<int> leafOf(nn, -1), parent(nn, -1);
+        for (uint32_t j = 0; j < nl; ++j)
+                leafOf[leafNodes[j]] = int(j);
+        {
+                std::vector<uint32_t> st{root};
+                while (!st.empty()) {
+                        const uint32_t i = st.back();
+                        st.pop_back();
+                        if (n[i].kind == TRN_NODE_TERM)
+                                continue;
+                        for (uint32_t c = 0; c < n[i].nchildren; ++c) {
+                                parent[n[i].first_child + c] = int(i);
+                                st.push_back(n[i].first_child + c);
+                        }
+                }
+        }
+        auto blocksOf = [&](uint32_t j) -> double {
+                const uint32_t t = n[leafNodes[j]].term;
+                return t == kEmptyTerm ? 0.0 : double(terms[t].nblocks);
+        };
+        auto densOf = [&](uint32_t j) -> double {
+                const uint32_t t = n[leafNodes[j]].term;
+                return t == kEmptyTerm ? 0.0 : std::min(1.0, double(terms[t].documents) / width);
+        };
+        std::vector<uint8_t> masked(nl, 0);
+        // density of the superset of node i computable from first-pass leaves (-1: unusable)
+        std::function<double(uint32_t)> sup = [&](uint32_t i) -> double {
+                const auto &X = n[i];
+                switch (X.kind) {
+                        case TRN_NODE_TERM:
+                                return (leafOf[i] >= 0 && !masked[leafOf[i]]) ? densOf(uint32_t(leafOf[i])) : -1.0;
+                        case TRN_NODE_AND: {
+                                double d{1.0};
+                                bool   any{false};
+                                for (uint32_t c = 0; c < X.nchildren; ++c) {
+                                        const double x = sup(X.first_child + c);
+                                        if (x >= 0) {
+                                                d *= x;
+                                                any = true;
+                                        }
+                                }
+                                return any ? d : -1.0;
+                        }
+                        case TRN_NODE_OR: {
+                                double d{1.0};
+                                for (uint32_t c = 0; c < X.nchildren; ++c) {
+                                        const double x = sup(X.first_child + c);
+                                        if (x < 0)
+                                                return -1.0;
+                                        d *= 1.0 - x;
+                                }
+                                return 1.0 - d;
+                        }
+                        case TRN_NODE_NOT:
+                        case TRN_NODE_OPTIONAL:
+                                return sup(X.first_child);
+                        default:
+                                return -1.0;
+                }
+        };
+        // constraint subtrees of leaf j
+        auto constraints = [&](uint32_t j) {
+                std::vector<uint32_t> out;
+                int                   c = int(leafNodes[j]);
+                while (uint32_t(c) != root && parent[c] >= 0) {
+                        const int   p = parent[c];
+                        const auto &X = n[p];
+                        if (X.kind == TRN_NODE_AND) {
+                                for (uint32_t k = 0; k < X.nchildren; ++k)
+                                        if (int(X.first_child + k) != c)
+                                                out.push_back(X.first_child + k);
+                        } else if (X.kind == TRN_NODE_NOT && int(X.first_child) + 1 == c)
+                                out.push_back(X.first_child);
+                        c = p;
+                }
+                return out;
+        };
+        const double W = double(1ull << tileShift);
+        auto         need = [&](uint32_t j) { // estimated share of leaf j's blocks a mask leaves over
+                double d{1.0};
+                bool   any{false};
+                for (auto cn : constraints(j)) {
+                        const double x = sup(cn);
+                        if (x >= 0) {
+                                d *= x;
+                                any = true;
+                        }
+                }
+                if (!any)
+                        return 1.0;
+                const double span = width / std::max(1.0, blocksOf(j)); // docIDs a block covers
+                return 1.0 - std::pow(1.0 - std::min(d, 1.0), span);
+        };
+        std::vector<uint32_t> order(nl);
+        for (uint32_t j = 0; j < nl; ++j)
+                order[j] = j;
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return blocksOf(a) > blocksOf(b); });
+        bool anyMasked{false};
+        for (auto j : order) {
+                if (blocksOf(j) * W / width < 2.0)
+                        break; // (sorted) blocks as wide as the tile: nothing to skip
+                masked[j] = 1;
+                if (need(j) > 0.6)
+                        masked[j] = 0;
+                anyMasked |= masked[j] != 0;
+        }
+        for (auto j : order) // a later choice may have taken a constraint away
+                if (masked[j] && need(j) > 0.75)
+                        masked[j] = 0;
+        if (!anyMasked)
+                return 0;
+        // ---- emission
+        std::vector<DevStep>                      mops;
+        std::unordered_map<uint32_t, int>         slotOfNode;
+        std::map<std::vector<int>, int>           slotOfAnd;
+        uint32_t                                  extra{0};
+        const uint32_t                            kMaxExtra = 6;
+        auto                                      newSlot   = [&]() -> int { return (extra < kMaxExtra && slotsInUse + extra < 30u) ? int(slotsInUse + extra++) : -1; };
+        auto                                      op        = [&](uint8_t mode, int dst, int src) {
+                DevStep S;
+                std::memset(&S, 0, sizeof(S));
+                S.op    = OP_SLOT;
+                S.mode  = mode;
+                S.dst   = uint8_t(dst);
+                S.src   = uint8_t(src);
+                S.flags = F_MASKOP;
+                mops.push_back(S);
+        };
+        std::function<int(uint32_t)> emit = [&](uint32_t i) -> int { // slot holding a superset of node i, -1: unusable (or out of slots)
+                const auto it = slotOfNode.find(i);
+                if (it != slotOfNode.end())
+                        return it->second;
+                const auto &X = n[i];
+                int         r{-1};
+                if (X.kind == TRN_NODE_TERM)
+                        r = (leafOf[i] >= 0 && !masked[leafOf[i]]) ? leafOf[i] : -1;
+                else if (X.kind == TRN_NODE_NOT || X.kind == TRN_NODE_OPTIONAL)
+                        r = emit(X.first_child);
+                else if (X.kind == TRN_NODE_AND || X.kind == TRN_NODE_OR) {
+                        std::vector<int> kids;
+                        bool             ok{true};
+                        for (uint32_t c = 0; c < X.nchildren && ok; ++c) {
+                                const int k = sup(X.first_child + c) >= 0 ? emit(X.first_child + c) : -1;
+                                if (k >= 0)
+                                        kids.push_back(k);
+                                else if (X.kind == TRN_NODE_OR)
+                                        ok = false;
+                        }
+                        if (ok && kids.size() == 1)
+                                r = kids[0];
+                        else if (ok && kids.size() > 1) {
+                                r = newSlot();
+                                if (r >= 0) {
+                                        op(M_SET, r, kids[0]);
+                                        for (size_t k = 1; k < kids.size(); ++k)
+                                                op(X.kind == TRN_NODE_AND ? M_AND : M_OR, r, kids[k]);
+                                }
+                        }
+                }
+                slotOfNode[i] = r;
+                return r;
+        };
+        std::vector<int> maskSlot(nl, -1);
+        for (uint32_t j = 0; j < nl; ++j) {
+                if (!masked[j])
+                        continue;
+                std::vector<int> cs;
+                for (auto cn : constraints(j))
+                        if (sup(cn) >= 0) {
+                                const int k = emit(cn);
+                                if (k >= 0)
+                                        cs.push_back(k);
+                        }
+                std::sort(cs.begin(), cs.end());
+                cs.erase(std::unique(cs.begin(), cs.end()), cs.end());
+                if (cs.empty()) {
+                        masked[j] = 0; // (cannot be relied on by anybody: it was never usable)
+                        continue;
+                }
+                int m;
+                if (cs.size() == 1)
+                        m = cs[0];
+                else {
+                        const auto it = slotOfAnd.find(cs);
+                        if (it != slotOfAnd.end())
+                                m = it->second;
+                        else {
+                                m = newSlot();
+                                if (m >= 0) {
+                                        op(M_SET, m, cs[0]);
+                                        for (size_t k = 1; k < cs.size(); ++k)
+                                                op(M_AND, m, cs[k]);
+                                        slotOfAnd[cs] = m;
+                                } else
+                                        m = cs[0]; // out of slots: one constraint alone is a (weaker) mask
+                        }
+                }
+                maskSlot[j] = m;
+        }
+        if (mops.size() > 32)
+                return 0;
+        anyMasked = false;
+        for (uint32_t j = 0; j < nl; ++j)
+                if (masked[j] && maskSlot[j] >= 0) {
+                        steps[begin + j].flags |= F_MASKED;
+                        steps[begin + j].src = uint8_t(maskSlot[j]);
+                        anyMasked            = true;
+                }
+        if (!anyMasked)
+                return 0;
+        steps.insert(steps.begin() + std::ptrdiff_t(begin + nl), mops.begin(), mops.end());
+        return extra;
+}
+
 extern "C" int trn_debug_compile(int codec, const uint8_t *index, uint64_t nbytes, const trn_term *terms, uint32_t nterms, const trn_qnode *nodes, uint32_t nnodes,
                                  uint32_t root, int scored, trn_debug_step *out, uint32_t cap, uint32_t *nsteps, uint32_t *root_slot, uint32_t *nslots, char *err,
                                  size_t errcap) {
@@ -1157,16 +1392,27 @@ extern "C" int trn_debug_compile(int codec, const uint8_t *index, uint64_t nbyte
         if (rs < 0)
                 return seterr(cc.err, cc.unsupported ? TRN_ERR_UNSUPPORTED : TRN_ERR_ARG);
         uint32_t treeLeaves{0};
-        if (scored == 2) { // DocumentsOnly program in its flat-tree form (what the second k_exec_docs launch runs)
+        uint32_t maskSlots{0};
+        if (scored >= 2) { // DocumentsOnly program in its flat-tree form (what the second k_exec_docs launch runs); 3: with the masked second pass
                 treeLeaves = flat_tree_transform(steps, 0, cc.next_slot);
                 rs += int(treeLeaves);
+                if (scored == 3 && treeLeaves) {
+                        uint32_t lo{0xffffffffu}, hi{0};
+                        for (const auto &T : ht)
+                                if (T.nblocks) {
+                                        lo = std::min(lo, T.first_doc);
+                                        hi = std::max(hi, T.last_doc);
+                                }
+                        if (hi >= lo)
+                                maskSlots = flat_tree_masks(steps, 0, treeLeaves, treeLeaves + cc.next_slot, nodes, nnodes, cc.root, cc.leaf_nodes, ht, 12, double(hi) - double(lo) + 1.0);
+                }
         }
         if (steps.size() > cap)
                 return seterr("step buffer too small", TRN_ERR_CAPACITY);
         std::memcpy(out, steps.data(), steps.size() * sizeof(DevStep));
         *nsteps    = uint32_t(steps.size());
         *root_slot = uint32_t(rs);
-        *nslots    = cc.next_slot + 1 + treeLeaves; // + the scratch slot of the kernels
+        *nslots    = cc.next_slot + 1 + treeLeaves + maskSlots; // + the scratch slot of the kernels
         return TRN_OK;
 }
 
@@ -1407,10 +1653,15 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 if (!scored && !candidate && dq.flat == 0u && c->codec == TRN_CODEC_GOOGLE && c->tree_shift && !r.empty() && !cc.has_phrase) {
                         const uint32_t nl = flat_tree_transform(steps, dq.step_begin, cc.next_slot);
                         if (nl) {
+                                uint32_t extra{0};
+                                if (c->tree_masks) {
+                                        const double width = double(c->max_docid) - double(std::min(c->min_docid, c->max_docid)) + 1.0; // docID span of THIS source
+                                        extra = flat_tree_masks(steps, dq.step_begin, nl, nl + cc.next_slot, Q.nodes, Q.nnodes, cc.root, cc.leaf_nodes, c->h_terms, c->tree_shift, width);
+                                }
                                 dq.nsteps = uint32_t(steps.size()) - dq.step_begin;
                                 dq.root_slot += nl;
                                 dq.flat   = 5u;
-                                treeSlots = std::max(treeSlots, nl + cc.next_slot);
+                                treeSlots = std::max(treeSlots, nl + cc.next_slot + extra);
                                 treeFlat  = true;
                         }
                 }
@@ -1608,7 +1859,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                         P2.gen_items  = uint32_t(genItems2);
                         P2.gen_sel    = 1;
                         P2.ticket     = reinterpret_cast<uint32_t *>(small + 4);
-                        const int perSM = exec_docs_max_ctas_per_sm(P2.exec_shift, P2.nslots, exec_docs_stage_bytes());
+                        const int perSM = exec_docs_max_ctas_per_sm(P2.exec_shift, P2.nslots, exec_docs_stage_bytes(), true);
                         if (perSM <= 0)
                                 return fail(c, TRN_ERR_CUDA, "the flat-tree launch does not fit on an SM with this many docset slots");
                         const int grid = int(std::min<uint64_t>(uint64_t(c->num_sms) * perSM, std::max<uint64_t>(1, (genItems2 + 3) / 4)));

@@ -502,7 +502,10 @@ __device__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
 #include "exec_docs_cand.cuh"
 
 // min 7 CTAs/SM: shared memory allows 7 at the default tile; without the bound ptxas stops at 64 registers and spills
-template <bool PH> __global__ void __launch_bounds__(kDocsWarps * 32, PH ? 4 : 7) k_exec_docs(ExecParams P) { // PH: see k_exec_tiles
+// TREE: the flat-tree launch (every query of its ticket space is a flat-tree plan) — that instantiation holds nothing but the tree
+// executor, and the other one does not carry it (the tree state lives in registers across the tile loop: in one kernel with the
+// candidate and flat paths it pushed them over the 72-register bound)
+template <bool PH, bool TREE> __global__ void __launch_bounds__(kDocsWarps * 32, PH ? 4 : (TREE ? 5 : 7)) k_exec_docs(ExecParams P) { // PH: see k_exec_tiles
         const uint32_t W  = 1u << P.exec_shift;
         const uint32_t NW = W >> 5;
         const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -537,27 +540,29 @@ template <bool PH> __global__ void __launch_bounds__(kDocsWarps * 32, PH ? 4 : 7
                         curq = qlo;
                         Q    = P.queries[qlo];
                         qgen = P.gen_sel ? Q.gen_base2 : Q.gen_base;
-                        if (Q.flat == 5u)
+                        if constexpr (TREE)
                                 tree_load(P, Q, TS, lane);
                 }
                 const uint32_t item = Q.item_base + (gitem - qgen); // batch-wide (query, tile) item: index of the segment arrays
-                if (Q.flat == 3u) { // candidate-driven conjunction: the work item is a 32-block group of the lead term
-                        __syncwarp();
-                        cand_exec_google(P, Q, curq, item, item - Q.item_base, slots, lane);
-                        continue;
+                if constexpr (!TREE) {
+                        if (Q.flat == 3u) { // candidate-driven conjunction: the work item is a 32-block group of the lead term
+                                __syncwarp();
+                                cand_exec_google(P, Q, curq, item, item - Q.item_base, slots, lane);
+                                continue;
+                        }
                 }
                 const uint32_t tile = Q.tile_lo + (item - Q.item_base);
                 const uint32_t lo = tile << P.exec_shift, hi = lo + W;
                 bool           dead = false;
                 int            handled = 0;
-                if (Q.flat == 5u) { // flat-tree plan: all leaves in one pass, then its slot operations
+                if constexpr (TREE) { // flat-tree plan: its leaves in (at most) two decode passes, then its slot operations
                         handled = tree_exec_google(P, Q, TS, lo, W, NW, slots, stage, lane) ? 2 : 1;
                 } else if (Q.flat && P.ix.codec == 0)
                         handled = flat_exec_google(P, Q, lo, W, NW, slots, stage, lane);
                 if (handled == 2)
                         dead = true;
 
-                for (uint32_t si = 0; si < Q.nsteps && !dead && handled == 0; ++si) {
+                for (uint32_t si = 0; !TREE && si < Q.nsteps && !dead && handled == 0; ++si) {
                         const DevStep st  = P.steps[Q.step_begin + si];
                         uint32_t *    dst = slots + size_t(st.dst) * NW;
                         __syncwarp();
@@ -775,20 +780,27 @@ size_t exec_docs_smem_bytes(uint32_t exec_shift, uint32_t nslots, uint32_t stage
         return size_t(kDocsWarps) * (size_t(nslots) * NW * 4 + stageBytes);
 }
 
-int exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots, uint32_t stageBytes) {
+int exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots, uint32_t stageBytes, bool tree) {
         const size_t smem = exec_docs_smem_bytes(exec_shift, nslots, stageBytes);
-        if (cudaFuncSetAttribute(k_exec_docs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess ||
-            cudaFuncSetAttribute(k_exec_docs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+        const void *fns[3] = {(const void *)k_exec_docs<false, false>, (const void *)k_exec_docs<true, false>, (const void *)k_exec_docs<false, true>};
+        if (tree) {
+                if (cudaFuncSetAttribute(fns[2], cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+                        return 0;
+        } else if (cudaFuncSetAttribute(fns[0], cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess ||
+                   cudaFuncSetAttribute(fns[1], cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
                 return 0;
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_exec_docs<false>, kDocsWarps * 32, smem) != cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_exec_docs<false, false>, kDocsWarps * 32, smem) != cudaSuccess)
+                return 0;
+        if (tree && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_exec_docs<false, true>, kDocsWarps * 32, smem) != cudaSuccess)
                 return 0;
         return n;
 }
 
 cudaError_t launch_exec_docs(const ExecParams &P, int grid, cudaStream_t stream) {
         const size_t smem = exec_docs_smem_bytes(P.exec_shift, P.nslots, P.docs_stage_bytes);
-        const void * fn   = P.has_phrase ? (const void *)k_exec_docs<true> : (const void *)k_exec_docs<false>;
+        // gen_sel == 1: the flat-tree launch (its ticket space holds flat-tree plans only; phrase plans never take that path)
+        const void *fn = P.gen_sel ? (const void *)k_exec_docs<false, true> : (P.has_phrase ? (const void *)k_exec_docs<true, false> : (const void *)k_exec_docs<false, false>);
         cudaError_t  e    = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess)
                 return e;
