@@ -1074,7 +1074,17 @@ extern "C" int trn_query_truth_table(const trn_qnode *nodes, uint32_t nnodes, ui
 // announced by one [OP_LEAF M_NONE dst = leaf slot] marker each, at the front of the program) that ONE flat (leaf, block) pass over the tile
 // fills; the rest of the program becomes slot operations on them, the compiler's own slots moved behind the leaf bitmaps.
 // Returns the number of leaves (0: the program stays as it is).
-static uint32_t flat_tree_transform(std::vector<DevStep> &steps, size_t begin, uint32_t next_slot) {
+// Leaf bitmaps are numbered by descending block count: the (leaf, block) list of a tile is then ordered from the frequent terms (blocks
+// of 1-byte deltas, four codes per decoder step) to the rare ones (2-byte deltas, blocks that straddle the tile), so that the 32 lanes
+// of a group mostly walk blocks of the same kind — a rare term's lane among frequent ones kept the whole warp in the loop for its 16-31
+// slow steps (profiles/r02_g: the slow steps ran at 5.8 of 32 lanes and were as many instructions as the fast ones).
+// Afterwards the copies are coalesced (flat_tree_coalesce): `SET d <- s` where s is not read again becomes a renaming of d, so a chain
+// like SET t <- leaf; AND t, leaf2; OR acc, t runs in the leaf's own bitmap: fewer operations per tile and — what matters more — fewer
+// bitmaps per warp (13 -> 8 for the 8-term trees of the benchmark), i.e. more resident warps.
+// rootSlot: in = the compiler's root slot, out = the slot that holds the root docset; slotsInUse: out.
+static void     flat_tree_coalesce(std::vector<DevStep> &steps, size_t opsBegin, uint32_t nl, uint32_t &rootSlot, uint32_t &slotsInUse);
+static uint32_t flat_tree_transform(std::vector<DevStep> &steps, size_t begin, uint32_t next_slot, const std::vector<DevTerm> &terms, std::vector<uint32_t> *leafNodes,
+                                    uint32_t &rootSlot, uint32_t &slotsInUse) {
         uint32_t nl{0};
         for (size_t i = begin; i < steps.size(); ++i)
                 nl += steps[i].op == OP_LEAF && steps[i].mode != M_NONE;
@@ -1088,17 +1098,30 @@ static uint32_t flat_tree_transform(std::vector<DevStep> &steps, size_t begin, u
                         return 0;
         const std::vector<DevStep> prog(steps.begin() + begin, steps.end());
         steps.resize(begin);
-        uint32_t li{0};
+        std::vector<DevStep> leaves;
         for (const auto &st : prog)
-                if (st.op == OP_LEAF && st.mode != M_NONE) { // decode marker: term -> leaf bitmap li
-                        DevStep L = st;
-                        L.mode    = M_NONE;
-                        L.dst     = uint8_t(li++);
-                        L.src     = 0;
-                        L.flags   = 0;
-                        steps.push_back(L);
-                }
-        li = 0;
+                if (st.op == OP_LEAF && st.mode != M_NONE)
+                        leaves.push_back(st);
+        std::vector<uint32_t> order(nl), slotOf(nl); // order[k]: program leaf held by bitmap k; slotOf: its inverse
+        for (uint32_t j = 0; j < nl; ++j)
+                order[j] = j;
+        auto blocksOf = [&](uint32_t j) { return leaves[j].term == kEmptyTerm ? 0u : terms[leaves[j].term].nblocks; };
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return blocksOf(a) > blocksOf(b); });
+        for (uint32_t k = 0; k < nl; ++k) {
+                slotOf[order[k]] = k;
+                DevStep L        = leaves[order[k]]; // decode marker: term -> leaf bitmap k
+                L.mode           = M_NONE;
+                L.dst            = uint8_t(k);
+                L.src            = 0;
+                L.flags          = 0;
+                steps.push_back(L);
+        }
+        if (leafNodes && leafNodes->size() == nl) {
+                const std::vector<uint32_t> was(*leafNodes);
+                for (uint32_t k = 0; k < nl; ++k)
+                        (*leafNodes)[k] = was[order[k]];
+        }
+        uint32_t li{0};
         for (auto st : prog) {
                 if (st.op == OP_LEAF) {
                         if (st.mode == M_NONE)
@@ -1108,7 +1131,7 @@ static uint32_t flat_tree_transform(std::vector<DevStep> &steps, size_t begin, u
                         S.op    = OP_SLOT;
                         S.mode  = st.mode;
                         S.dst   = uint8_t(st.dst + nl);
-                        S.src   = uint8_t(li++);
+                        S.src   = uint8_t(slotOf[li++]);
                         S.flags = st.flags;
                         steps.push_back(S);
                         continue;
@@ -1118,7 +1141,130 @@ static uint32_t flat_tree_transform(std::vector<DevStep> &steps, size_t begin, u
                         st.src = uint8_t(st.src + nl);
                 steps.push_back(st);
         }
+        rootSlot += nl;
+        slotsInUse = nl + next_slot;
+        flat_tree_coalesce(steps, begin + nl, nl, rootSlot, slotsInUse);
         return nl;
+}
+
+static void flat_tree_coalesce(std::vector<DevStep> &steps, size_t opsBegin, uint32_t nl, uint32_t &rootSlot, uint32_t &slotsInUse) {
+        std::vector<DevStep> ops(steps.begin() + std::ptrdiff_t(opsBegin), steps.end());
+        for (const auto &o : ops)
+                if (o.op != OP_SLOT && o.op != OP_CLEAR)
+                        return; // (counter planes address slot RANGES: left alone)
+        auto reads = [](const DevStep &o, uint32_t x) { // does o read slot x?
+                if (o.op != OP_SLOT)
+                        return false;
+                if (o.mode == M_NONE)
+                        return o.dst == x; // emptiness test only
+                return o.src == x || (o.mode != M_SET && o.dst == x);
+        };
+        auto overwrites = [](const DevStep &o, uint32_t x) { return o.dst == x && (o.op == OP_CLEAR || (o.op == OP_SLOT && o.mode == M_SET)); };
+        // x is dead behind operation i: nothing reads it before it is overwritten, and it is not the root
+        auto dead = [&](size_t i, uint32_t x) {
+                for (size_t j = i + 1; j < ops.size(); ++j) {
+                        if (reads(ops[j], x))
+                                return false;
+                        if (overwrites(ops[j], x))
+                                return true;
+                }
+                return x != rootSlot;
+        };
+        // CLEAR d ... OR d, x (nothing touching d in between)  ==  SET d <- x
+        std::vector<uint8_t> drop(ops.size(), 0);
+        for (size_t i = 0; i < ops.size(); ++i) {
+                if (ops[i].op != OP_CLEAR)
+                        continue;
+                const uint32_t d = ops[i].dst;
+                for (size_t j = i + 1; j < ops.size(); ++j) {
+                        const bool touches = ops[j].dst == d || (ops[j].op == OP_SLOT && ops[j].src == d);
+                        if (!touches)
+                                continue;
+                        if (ops[j].op == OP_SLOT && ops[j].mode == M_OR && ops[j].dst == d && ops[j].src != d) {
+                                ops[j].mode = M_SET;
+                                drop[i]     = 1;
+                        }
+                        break;
+                }
+        }
+        // forward renaming: ren[name] = the physical slot that holds it, holder[slot] = the name it holds (the compiler hands slot numbers
+        // out again, so a name that is overwritten must not land in a slot that meanwhile carries another live name)
+        uint32_t ren[32], holder[32];
+        for (uint32_t i = 0; i < 32; ++i)
+                ren[i] = holder[i] = i;
+        auto deadFrom = [&](size_t i, uint32_t x) { // like dead(), operation i included
+                if (x >= 32u)
+                        return true;
+                if (i < ops.size() && reads(ops[i], x))
+                        return false;
+                if (i < ops.size() && overwrites(ops[i], x))
+                        return true;
+                return dead(i, x);
+        };
+        std::vector<DevStep> out;
+        for (size_t i = 0; i < ops.size(); ++i) {
+                if (drop[i])
+                        continue;
+                DevStep o = ops[i];
+                if (o.op == OP_SLOT && o.mode == M_SET && o.src != o.dst && dead(i, o.src)) {
+                        const uint32_t p = ren[o.src];
+                        if (holder[ren[o.dst]] == o.dst)
+                                holder[ren[o.dst]] = 0xffu;
+                        ren[o.dst] = p;
+                        holder[p]  = o.dst;
+                        if (o.flags & F_BREAK_IF_EMPTY) { // the emptiness test stays, on the slot that now carries the name
+                                o.mode = M_NONE;
+                                o.dst  = uint8_t(p);
+                                o.src  = uint8_t(p);
+                                out.push_back(o);
+                        }
+                        continue;
+                }
+                if (o.op == OP_SLOT)
+                        o.src = uint8_t(ren[o.src]);
+                if (o.op == OP_CLEAR || (o.op == OP_SLOT && o.mode == M_SET)) { // a full overwrite: the name needs a slot nobody lives in
+                        uint32_t p = ren[o.dst];
+                        if (holder[p] != o.dst && !deadFrom(i, holder[p])) {
+                                p = 0xffu;
+                                for (uint32_t k = 0; k < 31u && p == 0xffu; ++k) {
+                                        const uint32_t q = k + nl < 31u ? k + nl : k + nl - 31u; // compiler slots first, then leaf bitmaps already consumed
+                                        if (deadFrom(i, holder[q]) && !(o.op == OP_SLOT && q == o.src))
+                                                p = q;
+                                }
+                                if (p == 0xffu)
+                                        return; // (cannot happen: the program had a slot for every live name) leave the program as it was
+                        }
+                        ren[o.dst] = p;
+                        holder[p]  = o.dst;
+                }
+                o.dst = uint8_t(ren[o.dst]);
+                out.push_back(o);
+        }
+        rootSlot = ren[rootSlot];
+        // compiler slots still in use, renumbered densely behind the leaf bitmaps
+        uint32_t map[32];
+        uint32_t next = nl;
+        for (uint32_t i = 0; i < 32; ++i)
+                map[i] = i < nl ? i : 0xffu;
+        auto use = [&](uint32_t x) {
+                if (x >= nl && map[x] == 0xffu)
+                        map[x] = next++;
+        };
+        for (const auto &o : out) {
+                use(o.dst);
+                if (o.op == OP_SLOT)
+                        use(o.src);
+        }
+        use(rootSlot);
+        for (auto &o : out) {
+                o.dst = uint8_t(map[o.dst]);
+                if (o.op == OP_SLOT)
+                        o.src = uint8_t(map[o.src]);
+        }
+        rootSlot   = map[rootSlot];
+        slotsInUse = next;
+        steps.resize(opsBegin);
+        steps.insert(steps.end(), out.begin(), out.end());
 }
 
 // Masked second decode pass of the flat-tree path.  A leaf whose blocks are short in docID terms (a frequent term) does not have to be
@@ -1392,10 +1538,12 @@ extern "C" int trn_debug_compile(int codec, const uint8_t *index, uint64_t nbyte
         if (rs < 0)
                 return seterr(cc.err, cc.unsupported ? TRN_ERR_UNSUPPORTED : TRN_ERR_ARG);
         uint32_t treeLeaves{0};
-        uint32_t maskSlots{0};
+        uint32_t maskSlots{0}, treeSlotsInUse{0};
         if (scored >= 2) { // DocumentsOnly program in its flat-tree form (what the second k_exec_docs launch runs); 3: with the masked second pass
-                treeLeaves = flat_tree_transform(steps, 0, cc.next_slot);
-                rs += int(treeLeaves);
+                uint32_t root2 = uint32_t(rs);
+                treeLeaves     = flat_tree_transform(steps, 0, cc.next_slot, ht, &cc.leaf_nodes, root2, treeSlotsInUse);
+                if (treeLeaves)
+                        rs = int(root2);
                 if (scored == 3 && treeLeaves) {
                         uint32_t lo{0xffffffffu}, hi{0};
                         for (const auto &T : ht)
@@ -1404,7 +1552,7 @@ extern "C" int trn_debug_compile(int codec, const uint8_t *index, uint64_t nbyte
                                         hi = std::max(hi, T.last_doc);
                                 }
                         if (hi >= lo)
-                                maskSlots = flat_tree_masks(steps, 0, treeLeaves, treeLeaves + cc.next_slot, nodes, nnodes, cc.root, cc.leaf_nodes, ht, 12, double(hi) - double(lo) + 1.0);
+                                maskSlots = flat_tree_masks(steps, 0, treeLeaves, treeSlotsInUse, nodes, nnodes, cc.root, cc.leaf_nodes, ht, 12, double(hi) - double(lo) + 1.0);
                 }
         }
         if (steps.size() > cap)
@@ -1412,7 +1560,7 @@ extern "C" int trn_debug_compile(int codec, const uint8_t *index, uint64_t nbyte
         std::memcpy(out, steps.data(), steps.size() * sizeof(DevStep));
         *nsteps    = uint32_t(steps.size());
         *root_slot = uint32_t(rs);
-        *nslots    = cc.next_slot + 1 + treeLeaves + maskSlots; // + the scratch slot of the kernels
+        *nslots    = (treeLeaves ? treeSlotsInUse + maskSlots : cc.next_slot) + 1; // + the scratch slot of the kernels
         return TRN_OK;
 }
 
@@ -1651,17 +1799,18 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 // the lanes are packed across leaves, and a smaller tile pays for the extra bitmaps.
                 bool treeFlat{false};
                 if (!scored && !candidate && dq.flat == 0u && c->codec == TRN_CODEC_GOOGLE && c->tree_shift && !r.empty() && !cc.has_phrase) {
-                        const uint32_t nl = flat_tree_transform(steps, dq.step_begin, cc.next_slot);
+                        uint32_t       root2 = dq.root_slot, inUse{0};
+                        const uint32_t nl    = flat_tree_transform(steps, dq.step_begin, cc.next_slot, c->h_terms, &cc.leaf_nodes, root2, inUse);
                         if (nl) {
                                 uint32_t extra{0};
                                 if (c->tree_masks) {
                                         const double width = double(c->max_docid) - double(std::min(c->min_docid, c->max_docid)) + 1.0; // docID span of THIS source
-                                        extra = flat_tree_masks(steps, dq.step_begin, nl, nl + cc.next_slot, Q.nodes, Q.nnodes, cc.root, cc.leaf_nodes, c->h_terms, c->tree_shift, width);
+                                        extra = flat_tree_masks(steps, dq.step_begin, nl, inUse, Q.nodes, Q.nnodes, cc.root, cc.leaf_nodes, c->h_terms, c->tree_shift, width);
                                 }
                                 dq.nsteps = uint32_t(steps.size()) - dq.step_begin;
-                                dq.root_slot += nl;
-                                dq.flat   = 5u;
-                                treeSlots = std::max(treeSlots, nl + cc.next_slot + extra);
+                                dq.root_slot = root2;
+                                dq.flat      = 5u;
+                                treeSlots    = std::max(treeSlots, inUse + extra);
                                 treeFlat  = true;
                         }
                 }

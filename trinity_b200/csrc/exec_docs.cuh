@@ -259,8 +259,10 @@ __device__ __forceinline__ void google_block_docs_vote(unsigned m, const uint8_t
 // memory for the rest of the block.  Used where the lanes of a group belong to different lists (flat-tree plans: profiles/r02_f shows the
 // warp-voted decoder above paying its one-code-per-step path for the whole warp whenever ONE lane holds a 2-byte code): a lane in a
 // sparse list then costs the lanes in dense lists an idle step, not a slow step.
+// `past`: 2^31 - W when every docID of the source is below 2^31 (a docID relative to the tile start in [W, 2^31) then lies BEHIND the tile
+// and the rest of the block with it: a rare term's block straddles many tiles, its lane leaves the walk there), else 0 (never).
 __device__ __forceinline__ void google_block_docs_lane(const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n, uint32_t prev,
-                                                       uint32_t last, uint32_t lo, uint32_t W, OwnAcc &bs) {
+                                                       uint32_t last, uint32_t lo, uint32_t W, OwnAcc &bs, uint32_t past) {
         const uint32_t mis  = off & 15u;
         const uint32_t base = uint32_t(__cvta_generic_to_shared(buf + lane * kGatherBytes)) + mis; // shared address of the first delta byte
         const uint32_t nd   = n - 1u;
@@ -305,6 +307,8 @@ __device__ __forceinline__ void google_block_docs_lane(const uint8_t *__restrict
                         len += 1u + two2;
                 }
                 sp += len;
+                if (rel - W < past)
+                        return; // behind the tile (its last docID too)
         }
         if (i < nd) {
                 const uint8_t *g = index + off + (sp - base);
@@ -505,7 +509,7 @@ __device__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
 // TREE: the flat-tree launch (every query of its ticket space is a flat-tree plan) — that instantiation holds nothing but the tree
 // executor, and the other one does not carry it (the tree state lives in registers across the tile loop: in one kernel with the
 // candidate and flat paths it pushed them over the 72-register bound)
-template <bool PH, bool TREE> __global__ void __launch_bounds__(kDocsWarps * 32, PH ? 4 : (TREE ? 5 : 7)) k_exec_docs(ExecParams P) { // PH: see k_exec_tiles
+template <bool PH, bool TREE> __global__ void __launch_bounds__(kDocsWarps * 32, PH ? 4 : (TREE ? 6 : 7)) k_exec_docs(ExecParams P) { // PH: see k_exec_tiles
         const uint32_t W  = 1u << P.exec_shift;
         const uint32_t NW = W >> 5;
         const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

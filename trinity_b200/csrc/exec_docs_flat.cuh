@@ -252,6 +252,7 @@ __device__ bool tree_exec_google(const ExecParams &P, const DevQuery &Q, const T
         const uint32_t slots_s = uint32_t(__cvta_generic_to_shared(slots));
         uint32_t *     queue   = reinterpret_cast<uint32_t *>(stage + kGatherBufBytes + 128u); // 64 entries: the needed (leaf, block) pairs of pass 1
         const uint32_t NW4     = NW >> 2;
+        const uint32_t past    = P.ix.max_docid < 0x80000000u ? 0x80000000u - W : 0u;
         __syncwarp(); // the clears above are visible before the first store
         for (uint32_t pass = 0; pass < 2u; ++pass) {
                 const bool masked = pass != 0u;
@@ -359,7 +360,7 @@ __device__ bool tree_exec_google(const ExecParams &P, const DevQuery &Q, const T
                                 OwnAcc bs;
                                 bs.init(slots_s + cur.j * NW * 4u, dummy);
                                 if (cur.active)
-                                        google_block_docs_lane(P.ix.index, cur.off, stage, lane, cur.n, cur.prev, cur.last, lo, W, bs);
+                                        google_block_docs_lane(P.ix.index, cur.off, stage, lane, cur.n, cur.prev, cur.last, lo, W, bs, past);
                                 __syncwarp();
                                 if (tail_bits) // the previous group's last words, after every block that can share them has stored
                                         asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(tail_a), "r"(tail_bits) : "memory");
