@@ -199,10 +199,7 @@ def full_size_parity(res, mode, k, counts, sums, tid, tsc, n):
     import trinity_b200 as tb
     out = {"queries_checked": int(n), "match_counts_equal": bool(np.array_equal(np.asarray(res.match_counts[:n], np.uint64), counts[:n]))}
     if mode == tb.MODE_DOCS_ONLY:
-        off = np.asarray(res.offsets[: n + 1], np.int64)
-        ids = np.asarray(res.docids[: off[-1]], np.uint64)
-        cs = np.concatenate([np.zeros(1, np.uint64), np.cumsum(ids, dtype=np.uint64)])  # (a Python 0 would promote the array to float64)
-        got = cs[off[1:]] - cs[off[:-1]]
+        got = res.checksums()[:n]  # exact in uint64; a compact result is replayed through trn_result_decode first
         out["docid_checksums_equal"] = bool(np.array_equal(got, sums[:n]))
     elif mode == tb.MODE_SCORED_TOPK:
         worst = 0.0
@@ -324,6 +321,8 @@ class Job:
         tdict = tb.TermDictionary(synth.names)
         plans = [tb.parse_query(q, tdict) for q in texts]
         full_df = synth_dfs(args.ndocs, args.nterms)
+        # the mode the product calls run in: DocumentsOnly workloads return their matches in the compact encoding unless told otherwise
+        emode = tb.MODE_DOCS_COMPACT if (mode == tb.MODE_DOCS_ONLY and args.result_encoding == "compact") else mode
         if mode != tb.MODE_DOCS_ONLY:  # global BM25 weights: df summed over shards == the unsharded df (similarity.h:209-217)
             for p in plans:
                 for x in p:
@@ -351,13 +350,15 @@ class Job:
         # ---------------- warm-up (also sizes every grow-only buffer) ----------------
         packed = g.pack(plans)
         for _ in range(W):
-            res = g.exec_batch(plans, mode, args.k, copy=False, packed=packed)
+            res = g.exec_batch(plans, emode, args.k, copy=False, packed=packed)
             exchange()
         for _ in range(W):  # the device-resident form has its own (whole-batch) buffers: warm those too
-            g.exec_batch_device(plans, mode, args.k, packed=packed)
+            g.exec_batch_device(plans, emode, args.k, packed=packed)
             exchange()
         matches_per_batch = int(res.match_counts.sum())
-        out_bytes_per_batch = (matches_per_batch * 4) if mode == tb.MODE_DOCS_ONLY else args.nq * args.k * 8
+        # bytes of one batch's result as it leaves the device: matched docIDs (plain: 4 B each; compact: the encoded segments + their
+        # descriptors) or the top-k lists
+        out_bytes_per_batch = res.result_bytes() if mode == tb.MODE_DOCS_ONLY else args.nq * args.k * 8
 
         # ---------------- timed: device-resident ----------------
         sampler = ClockSampler(self.local_rank) if with_clocks else None
@@ -368,7 +369,7 @@ class Job:
         self.barrier()
         ev0.record(stream)
         for _ in range(K):
-            g.exec_batch_device(plans, mode, args.k, packed=packed)
+            g.exec_batch_device(plans, emode, args.k, packed=packed)
             exchange()
         ev1.record(stream)
         self.barrier()
@@ -378,7 +379,7 @@ class Job:
         self.barrier()
         t0 = time.perf_counter()
         for _ in range(K):
-            res = g.exec_batch(plans, mode, args.k, copy=False, packed=packed)
+            res = g.exec_batch(plans, emode, args.k, copy=False, packed=packed)
             exchange()
             kern_ms.append(res.exec_kernel_ms)
             launches += res.kernel_launches + (1 if gathered is not None else 0)
@@ -386,6 +387,21 @@ class Job:
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         clocks = sampler.stop() if sampler else None
+        # the same end-to-end step with plain 32-bit docIDs out (TRN_MODE_DOCS_ONLY), for comparison with the compact encoding
+        plain = None
+        if emode != mode:
+            for _ in range(2):
+                rp = g.exec_batch(plans, mode, args.k, copy=False, packed=packed)
+            self.barrier()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                rp = g.exec_batch(plans, mode, args.k, copy=False, packed=packed)
+            torch.cuda.synchronize()
+            tp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            plain = {"value": args.nq * K / float(tp[0]), "unit": "queries/s", "d2h_bytes_per_step": int(rp.result_bytes()) + (args.nq + 1) * 8 + args.nq * 8}
+            res = g.exec_batch(plans, emode, args.k, copy=False, packed=packed)  # the parity check below reads the compact result
 
         times = torch.tensor([dev_ms_total / 1e3, e2e_s], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -433,7 +449,10 @@ class Job:
             "decoded_postings_per_s": postings_per_batch * K / dev_s,
             "matches_per_batch_rank0": matches_per_batch,
             "e2e": {"value": args.nq * K / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": plan_bytes, "d2h_bytes_per_step": d2h,
-                    "decoded_postings_per_s": postings_per_batch * K / e2e_s, "per_rank_ms": per_rank},
+                    "decoded_postings_per_s": postings_per_batch * K / e2e_s, "per_rank_ms": per_rank,
+                    "result_encoding": ("compact (TRN_MODE_DOCS_COMPACT: per docID tile a bitmap / 16-bit offsets / docIDs, whichever is smallest; replayed on the host by trn_result_for_each)"
+                                        if emode != mode else ("u32 docIDs" if mode == tb.MODE_DOCS_ONLY else "top-k (docID, score)")),
+                    "matched_docids_per_step": matches_per_batch, "plain_u32": plain},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
@@ -450,9 +469,7 @@ class Job:
                 # per-query match counts + docID checksums of THIS rank's shard, summed over ranks (uint64 arithmetic, wrap-around is fine)
                 cnt = torch.from_numpy(np.asarray(res.match_counts, np.uint64).astype(np.int64)).cuda()
                 if mode == tb.MODE_DOCS_ONLY:
-                    off = np.asarray(res.offsets, np.int64)
-                    cs = np.concatenate([np.zeros(1, np.uint64), np.cumsum(np.asarray(res.docids[: off[-1]], np.uint64), dtype=np.uint64)])
-                    sm = torch.from_numpy((cs[off[1:]] - cs[off[:-1]]).view(np.int64).copy()).cuda()
+                    sm = torch.from_numpy(res.checksums().view(np.int64).copy()).cuda()
                 else:
                     sm = torch.zeros(args.nq, dtype=torch.int64, device="cuda")
                 dist.all_reduce(cnt)
@@ -501,6 +518,9 @@ def main():
     ap.add_argument("--nq", type=int, default=1000)
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--cpu-sample", type=int, default=0, help="(reference arm) queries per step (0 = auto)")
+    ap.add_argument("--result-encoding", default="compact", choices=["compact", "u32"],
+                    help="DocumentsOnly workloads: how the matched docIDs leave the device — TRN_MODE_DOCS_COMPACT (per tile: bitmap / 16-bit offsets / docIDs, "
+                         "replayed by trn_result_decode) or plain 32-bit docIDs (TRN_MODE_DOCS_ONLY)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")
     args = ap.parse_args()

@@ -223,6 +223,9 @@ int trn_index_info_get(trn_ctx *, trn_index_info *out);
 #define TRN_MODE_DOCS_ONLY 0    /* ExecFlags::DocumentsOnly: matched docIDs ascending == consider(docid_t) stream        */
 #define TRN_MODE_SCORED_ALL 1   /* ExecFlags::AccumulatedScoreScheme: every (docID, score) ascending == consider(id,score) */
 #define TRN_MODE_SCORED_TOPK 2  /* AccumulatedScoreScheme + the application's top-k sink fused on device                 */
+#define TRN_MODE_DOCS_COMPACT 3 /* DocumentsOnly, the same consider(docid_t) stream in a compact encoding (below): the matched docIDs of a
+                                 * large batch are what the host link carries, so dense result tiles travel as bitmaps and sparse ones as
+                                 * 16-bit offsets; trn_result_for_each / trn_result_decode replay them                                    */
 
 /* Result of a batch. Host pointers are pinned buffers owned by the ctx, valid until the next exec call.
  * DOCS_ONLY / SCORED_ALL: query q owns [offsets[q], offsets[q+1]) of docids (ascending) (+ scores).
@@ -240,7 +243,31 @@ typedef struct trn_result {
         uint32_t        kernel_launches;
         float           device_ms; /* CUDA-event time of the device part of this call (plan H2D + all kernels) */
         float           exec_kernel_ms; /* CUDA-event time of the fused k_exec_tiles launch alone (roofline denominator) */
+        /* TRN_MODE_DOCS_COMPACT (null / 0 otherwise): `docids` is null; query q owns the 32-bit words [offsets[q], offsets[q+1]) of `words`,
+         * made of the segments of its work items qitems[q].item_base .. + nitems, in ascending docID order.  Segment i holds
+         * item_desc[i] & 0x3fffffff documents in the encoding item_desc[i] >> 30 and takes that many words:
+         *   TRN_ENC_U32    docIDs, one per word                                                              (count words)
+         *   TRN_ENC_U16    offsets from the first docID of the item's tile, two per word, low half first      ((count + 1) / 2 words)
+         *   TRN_ENC_BITMAP the tile's bitmap, bit b of word w = docID tile_first + 32 w + b                   (2^tile_shift / 32 words)
+         * the tile of item j of query q starts at docID (qitems[q].tile_lo + j) << qitems[q].tile_shift (U16 / BITMAP segments only). */
+        const uint32_t *         words;
+        uint64_t                 total_words;
+        const uint32_t *         item_desc;
+        const struct trn_qitems *qitems;
 } trn_result;
+#define TRN_ENC_U32 0u
+#define TRN_ENC_U16 1u
+#define TRN_ENC_BITMAP 2u
+typedef struct trn_qitems {
+        uint32_t item_base, nitems;
+        uint32_t tile_lo, tile_shift;
+} trn_qitems;
+/* Replay of query q's matches, ascending, exactly once each == the MatchesProxy::process / consider(docid_t) stream (docset_spans.h:14-21,
+ * matches.h:149-171); works for DOCS_ONLY and DOCS_COMPACT results.  `fn` returning non-zero stops the replay (aborted_search_exception). */
+typedef int (*trn_consider_fn)(void *ctx, uint32_t docid);
+int trn_result_for_each(const trn_result *r, uint32_t q, trn_consider_fn fn, void *ctx);
+/* query q's matched docIDs into out[0..cap); *n = their number (== match_counts[q]); TRN_ERR_CAPACITY if cap is too small */
+int trn_result_decode(const trn_result *r, uint32_t q, uint32_t *out, uint64_t cap, uint64_t *n);
 
 /* == exec_query(query, IndexSource*, masked_documents_registry*, MatchedIndexDocumentsFilter*, ..., flags, scorer) (exec.h:50-52),
  * batched (gpu_exec_queries).  H2D of the plans and D2H of the results are part of the call. */

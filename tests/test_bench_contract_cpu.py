@@ -50,7 +50,10 @@ def test_full_size_parity_checker_is_exact_in_uint64(ref):
     big = np.repeat(ids, 1)  # one copy is enough: prepend a huge constant through a fake first query below
     off = np.concatenate([np.zeros(1, np.int64), np.cumsum(counts).astype(np.int64)])
     sums = np.array([int(big[off[q]:off[q + 1]].astype(np.uint64).sum()) for q in range(nq)], np.uint64)
-    res = types.SimpleNamespace(match_counts=counts.copy(), offsets=off, docids=big.copy())
+    def result(match_counts, offsets, docids):  # what bench.py holds: a BatchResult (its checksums() is the code under test)
+        return tb.BatchResult(len(match_counts), tb.MODE_DOCS_ONLY, 0, offsets, docids, None, match_counts, 0, 0, 0, 0.0)
+
+    res = result(counts.copy(), off, big.copy())
     out = bench.full_size_parity(res, tb.MODE_DOCS_ONLY, 100, counts, sums, None, None, nq)
     assert out == {"queries_checked": nq, "match_counts_equal": True, "docid_checksums_equal": True}
     res.docids[5] ^= 1
@@ -59,7 +62,7 @@ def test_full_size_parity_checker_is_exact_in_uint64(ref):
     n = 3_000_000
     d = np.full(n, 3_999_999_999, np.uint32)
     d[-1] = 3_999_999_998
-    res = types.SimpleNamespace(match_counts=np.array([n - 1, 1], np.uint64), offsets=np.array([0, n - 1, n], np.int64), docids=d)
+    res = result(np.array([n - 1, 1], np.uint64), np.array([0, n - 1, n], np.int64), d)
     sums = np.array([int(d[: n - 1].astype(np.uint64).sum()), 3_999_999_998], np.uint64)
     assert bench.full_size_parity(res, tb.MODE_DOCS_ONLY, 100, res.match_counts, sums, None, None, 2)["docid_checksums_equal"] is True
     sums[1] += 1

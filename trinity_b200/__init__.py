@@ -16,6 +16,7 @@ from ._ffi import QNODE_DTYPE, TERM_DTYPE, TrnIndexInfo, TrnQuery, TrnResult, Tr
 
 CODEC_GOOGLE, CODEC_LUCENE = 0, 1
 MODE_DOCS_ONLY, MODE_SCORED_ALL, MODE_SCORED_TOPK = 0, 1, 2  # == ExecFlags::DocumentsOnly / AccumulatedScoreScheme (+ fused top-k sink)
+MODE_DOCS_COMPACT = 3  # DocumentsOnly, compact result segments (bitmap / 16-bit offsets / docIDs per tile): trn_result_decode replays them
 NODE_TERM, NODE_AND, NODE_OR, NODE_NOT, NODE_OPTIONAL, NODE_SOME, NODE_PHRASE = 0, 1, 2, 3, 4, 5, 6
 EMPTY_TERM = 0xFFFFFFFF
 DOC_IDS_END = 0xFFFFFFFF  # DocIDsEND, common.h:43
@@ -257,9 +258,40 @@ class BatchResult:
     kernel_launches: int
     device_ms: float
     exec_kernel_ms: float = 0.0
+    # MODE_DOCS_COMPACT: what travelled from the device (the decoded docIDs above are produced on the host by trn_result_decode)
+    total_words: int = 0
+    nitems: int = 0
+    raw: object = None  # copy=False: the TrnResult (ctx-owned buffers, valid until the next exec call); docids is None until decoded
+
+    def result_bytes(self) -> int:
+        """bytes of the result as it left the device: docIDs (+ scores) or compact words + segment descriptors"""
+        if self.mode == MODE_DOCS_COMPACT:
+            return 4 * self.total_words + 4 * self.nitems
+        return 4 * int(self.offsets[-1]) * (1 if self.scores is None else 2)
+
+    def decode_query(self, q: int, buf: Optional[np.ndarray] = None) -> np.ndarray:
+        """MODE_DOCS_COMPACT with copy=False: query q's docIDs through trn_result_decode (== the consider() replay)"""
+        n = int(self.match_counts[q])
+        out = buf if buf is not None and len(buf) >= n else np.empty(max(n, 1), np.uint32)
+        got = C.c_uint64()
+        rc = lib().trn_result_decode(C.byref(self.raw), q, _ptr(out), len(out), C.byref(got))
+        if rc != 0 or int(got.value) != n:
+            raise TrinityError(f"trn_result_decode: rc={rc}, {got.value} docIDs, match_counts says {n}")
+        return out[:n]
+
+    def checksums(self) -> np.ndarray:
+        """per-query sum of the matched docIDs (uint64, wrap-around): the full-size parity probe of bench.py"""
+        if self.docids is not None:
+            off = np.asarray(self.offsets, np.int64)
+            cs = np.concatenate([np.zeros(1, np.uint64), np.cumsum(np.asarray(self.docids[: off[-1]], np.uint64), dtype=np.uint64)])
+            return cs[off[1:]] - cs[off[:-1]]
+        buf = np.empty(max(1, int(np.max(self.match_counts)) if self.nq else 1), np.uint32)
+        return np.array([int(self.decode_query(q, buf).sum(dtype=np.uint64)) for q in range(self.nq)], np.uint64)
 
     def query(self, q: int):
         """(docids, scores) of query q.  top-k mode: only the valid entries, (score desc, docID asc)."""
+        if self.docids is None:
+            return self.decode_query(q).copy(), None
         a, b = int(self.offsets[q]), int(self.offsets[q + 1])
         d = self.docids[a:b]
         s = None if self.scores is None else self.scores[a:b]
@@ -347,6 +379,20 @@ class GpuIndexSource:
         keep = (lambda a: a.copy()) if copy else (lambda a: a)
         offsets = keep(np.ctypeslib.as_array(r.offsets, shape=(nq + 1,)))
         n = int(offsets[nq])
+        if mode == MODE_DOCS_COMPACT:
+            counts = keep(np.ctypeslib.as_array(r.match_counts, shape=(nq,)))
+            nitems = 0
+            if nq and r.qitems:
+                qi = np.ctypeslib.as_array(C.cast(r.qitems, C.POINTER(C.c_uint32)), shape=(nq, 4))
+                nitems = int((qi[:, 0] + qi[:, 1]).max())
+            br = BatchResult(nq, mode, k, offsets, None, None, counts, int(r.postings_scanned), int(r.index_bytes_touched), int(r.kernel_launches),
+                             float(r.device_ms), float(r.exec_kernel_ms), total_words=int(r.total_words), nitems=nitems, raw=r)
+            if copy:  # decode now: the ctx-owned buffers may be reused by the next call
+                per = [br.decode_query(q).copy() for q in range(nq)]
+                br.docids = np.concatenate(per) if per else np.zeros(0, np.uint32)
+                br.offsets = np.concatenate([[0], np.cumsum([len(x) for x in per])]).astype(np.uint64)
+                br.raw = None
+            return br
         docids = keep(np.ctypeslib.as_array(r.docids, shape=(max(n, 1),))[:n])
         scores = None
         if mode != MODE_DOCS_ONLY:

@@ -20,7 +20,7 @@ EXPORTS = [
     "trn_segment_masked", "trn_parse_query", "trn_query_truth_table", "trn_debug_compile", "trn_bm25_idf", "trn_bm25_score",
     "trn_create", "trn_destroy", "trn_last_error", "trn_set_stream", "trn_upload_index", "trn_set_masked_documents", "trn_index_info_get",
     "trn_exec_batch", "trn_exec_batch_device", "trn_last_topk_device", "trn_merge_topk", "trn_fetch_results", "trn_last_timings",
-    "trn_decode_terms",
+    "trn_decode_terms", "trn_result_for_each", "trn_result_decode",
 ]
 
 TERM_DTYPE = np.dtype([("documents", "<u4"), ("chunk_off", "<u4"), ("chunk_len", "<u4")])
@@ -47,7 +47,11 @@ class TrnResult(C.Structure):
     _fields_ = [("nq", C.c_uint32), ("total", C.c_uint64), ("offsets", C.POINTER(C.c_uint64)),
                 ("docids", C.POINTER(C.c_uint32)), ("scores", C.POINTER(C.c_float)),
                 ("match_counts", C.POINTER(C.c_uint64)), ("postings_scanned", C.c_uint64),
-                ("index_bytes_touched", C.c_uint64), ("kernel_launches", C.c_uint32), ("device_ms", C.c_float), ("exec_kernel_ms", C.c_float)]
+                ("index_bytes_touched", C.c_uint64), ("kernel_launches", C.c_uint32), ("device_ms", C.c_float), ("exec_kernel_ms", C.c_float),
+                ("words", C.POINTER(C.c_uint32)), ("total_words", C.c_uint64), ("item_desc", C.POINTER(C.c_uint32)), ("qitems", C.c_void_p)]
+
+
+CONSIDER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32)  # trn_consider_fn
 
 
 class TrnTimings(C.Structure):
@@ -126,6 +130,8 @@ def lib() -> C.CDLL:
     sig("trn_last_topk_device", i32, vp, P(vp), P(vp), P(vp))
     sig("trn_merge_topk", i32, vp, vp, vp, u32, u32, u32, vp, vp)
     sig("trn_fetch_results", i32, vp, P(TrnResult))
+    sig("trn_result_decode", i32, P(TrnResult), u32, vp, C.c_uint64, P(C.c_uint64))
+    sig("trn_result_for_each", i32, P(TrnResult), u32, CONSIDER_FN, vp)
     sig("trn_last_timings", i32, vp, P(TrnTimings))
     sig("trn_decode_terms", i32, vp, vp, u32, i32, vp, vp, vp, P(C.c_float))
     _lib = L

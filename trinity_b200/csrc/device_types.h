@@ -51,6 +51,9 @@ enum StepOp : uint8_t {
         OP_TABLE     = 6, // candidate-driven trees: 4 words of the query's truth table (term, pad2, idf as two words); dst = first word index
 };
 enum StepMode : uint8_t { M_SET = 0, M_OR = 1, M_AND = 2, M_ANDNOT = 3, M_NONE = 4 };
+// encodings of a compact result segment (trn_result::item_desc bits 30-31 == TRN_ENC_*)
+static constexpr uint32_t kEncU32 = 0, kEncU16 = 1, kEncBitmap = 2;
+
 enum StepFlags : uint8_t {
         F_SCORE          = 1,
         F_BREAK_IF_EMPTY = 2,
@@ -157,7 +160,11 @@ struct ExecParams {
         uint32_t *          seg_docids;
         float *             seg_scores;
         uint64_t *          item_off; // per work item: offset of its segment
-        uint32_t *          item_cnt; // per work item: number of matches
+        uint32_t *          item_cnt; // per work item: number of matches (compact results: 32-bit words of its segment)
+        // compact DocumentsOnly results (TRN_MODE_DOCS_COMPACT): a tile's matches leave the device as the tile's bitmap, as 16-bit offsets
+        // from the tile's first docID, or as plain docIDs — whichever is smallest
+        uint32_t *          item_desc;   // null unless compact: per work item, matches | encoding << 30 (trn_result::item_desc)
+        unsigned long long *word_counts; // per query: words of its segments
         // top-k
         unsigned long long *match_counts; // per query
         uint32_t *          theta;        // per query: lower bound (float bits) of the k-th best score

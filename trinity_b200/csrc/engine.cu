@@ -93,8 +93,10 @@ struct trn_ctx {
         uint32_t             min_docid{1}; // smallest docID any term holds (a docID-range shard does not start at 1)
         uint32_t             nterms{0}, max_docid{0}, tile_shift{13}, ntiles{0}; // tile_shift: directory granularity == scored tile (8192 docs, the reference's window docset_spans.h:74)
         uint32_t             docs_shift{14}; // docID tile (log2) of the warp-per-tile DocumentsOnly kernel
-        bool                 tree_masks{true}; // TRN_TREE_MASKS=0: flat-tree queries decode every leaf in one pass (no masked second pass)
-        uint32_t             tree_shift{12}; // TRN_TREE_SHIFT: docID tile (log2) of the flat-tree launch of k_exec_docs (0 = flat-tree path off)
+        bool                 tree_masks{false}; // TRN_TREE_MASKS=1: flat-tree queries decode their frequent leaves in a masked second pass (flat_tree_masks). Measured
+                                                // (profiles/r02_i..k): halves the DRAM bytes, but the needed blocks of a tile fill a fraction of a 32-lane group, so
+                                                // the warp-instruction count does not drop: 8.5-9.0K vs 9.2-11.1K q/s on the benchmark's trees. Off by default.
+        uint32_t             tree_shift{13}; // TRN_TREE_SHIFT: docID tile (log2) of the flat-tree launch of k_exec_docs (0 = flat-tree path off)
         uint32_t             run_tiles{128};  // TRN_RUN_TILES: consecutive tiles per work item of the flat scored kernel (top-k state lives across a run)
         int                  flat_threads{320}; // TRN_SF_THREADS: CTA size of k_score_flat (256/320/384: two CTAs per SM; 512/640: one)
         uint32_t             scored_shift{13};  // TRN_SCORED_SHIFT: log2 of k_score_flat's tile (13 = the reference's window, 14)
@@ -106,13 +108,19 @@ struct trn_ctx {
         // batch scratch (grow-only)
         DevBuf d_queries, d_steps, d_small[2], d_item_off, d_item_cnt, d_item_dst, d_seg_docids, d_seg_scores, d_out_docids[2], d_out_scores[2], d_q_offsets[2], d_cand,
             d_topk_docids, d_topk_scores, d_topk_counts, d_fq, d_leaves, d_luts, d_dec_units, d_dec_a, d_dec_b, d_dec_c, d_dec_docids, d_dec_freqs, d_dec_sums, d_merge_docids, d_merge_scores;
-        PinBuf h_offsets, h_docids, h_scores, h_counts, h_small, h_chunk;
+        PinBuf h_offsets, h_docids, h_scores, h_counts, h_small, h_chunk, h_item_desc;
+        DevBuf d_item_desc[2];                 // compact results: per work item, matches | encoding << 30 (double-buffered like the outputs)
+        std::vector<trn_qitems> qitems_set[2]; // compact results: the per-query item ranges of the last exec_device_impl call of each set
+        std::vector<trn_qitems> h_qitems;      // ... of the whole batch, item_base rebased (what trn_result::qitems points to)
+        std::vector<std::vector<trn_qitems>> qitems_chunk; // pipelined call: per chunk, until its results have been queued for the copy
+        uint64_t                last_items_hint{0};
         cudaEvent_t ev0{nullptr}, ev1{nullptr}, evk0{nullptr}, evk1{nullptr};
         bool        have_kernel_events{false};
         // pipelined host-buffer path (trn_exec_batch): kernels of chunk i+1 overlap the D2H of chunk i
         cudaStream_t copy_stream{nullptr};
         cudaEvent_t  ev_done[2]{nullptr, nullptr}, ev_d2h[2]{nullptr, nullptr}, ev_ck0[16]{}, ev_ck1[16]{};
         uint32_t     pipeline_chunks{4};
+        uint32_t     last_items{0}; // work items of the last exec_device_impl call (compact results: entries of item_desc)
         uint64_t     last_total_hint{0};
         // host-side breakdown of the last trn_exec_batch / trn_exec_batch_device call (trn_last_timings)
         trn_timings tm{};
@@ -805,7 +813,7 @@ extern "C" void trn_destroy(trn_ctx *c) {
                           &c->d_topk_docids, &c->d_topk_scores, &c->d_topk_counts, &c->d_fq, &c->d_leaves, &c->d_luts, &c->d_dec_units, &c->d_dec_a, &c->d_dec_b, &c->d_dec_c, &c->d_dec_docids, &c->d_dec_freqs,
                           &c->d_dec_sums, &c->d_merge_docids, &c->d_merge_scores})
                 b->release();
-        for (PinBuf *b : {&c->h_offsets, &c->h_docids, &c->h_scores, &c->h_counts, &c->h_small, &c->h_chunk})
+        for (PinBuf *b : {&c->h_offsets, &c->h_docids, &c->h_scores, &c->h_counts, &c->h_small, &c->h_chunk, &c->h_item_desc})
                 b->release();
         for (cudaEvent_t e : {c->ev0, c->ev1, c->evk0, c->evk1, c->ev_done[0], c->ev_done[1], c->ev_d2h[0], c->ev_d2h[1]})
                 if (e)
@@ -1584,8 +1592,11 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 return TRN_ERR_ARG;
         if (!c->have_index)
                 return fail(c, TRN_ERR_STATE, "no index uploaded");
-        if (!queries || !nq || mode < 0 || mode > 2)
+        if (!queries || !nq || mode < 0 || mode > 3)
                 return fail(c, TRN_ERR_ARG, "trn_exec_batch: bad arguments");
+        const bool compact = mode == TRN_MODE_DOCS_COMPACT; // DocumentsOnly with compact result segments; everything else is the same plan
+        if (compact)
+                mode = TRN_MODE_DOCS_ONLY;
         if (c->block_docs != (c->codec == TRN_CODEC_GOOGLE ? 32u : 128u))
                 return fail(c, TRN_ERR_UNSUPPORTED, "the uploaded index was built with a block size other than the reference format's (decode sweep only)");
         if (mode == TRN_MODE_SCORED_TOPK && (k == 0 || k > kernel_max_k()))
@@ -1882,7 +1893,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         // ---- device buffers
         CK(c->d_queries.ensure(nq * sizeof(DevQuery)));
         CK(c->d_steps.ensure(std::max<size_t>(sizeof(DevStep), steps.size() * sizeof(DevStep))));
-        const size_t smallBytes = 64 + size_t(nq) * (8 + 4 + 4);
+        const size_t smallBytes = 64 + size_t(nq) * (8 + 4 + 4 + 8);
         CK(c->d_small[set].ensure(smallBytes));
         CK(c->d_q_offsets[set].ensure((size_t(nq) + 1) * 8));
         if (mode != TRN_MODE_SCORED_TOPK) {
@@ -1916,9 +1927,19 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         auto *   match_counts = reinterpret_cast<unsigned long long *>(small + 64);
         auto *   theta        = reinterpret_cast<uint32_t *>(small + 64 + size_t(nq) * 8);
         auto *   cand_cursor  = reinterpret_cast<uint32_t *>(small + 64 + size_t(nq) * 12);
+        auto *   word_counts  = reinterpret_cast<unsigned long long *>(small + 64 + size_t(nq) * 16);
 
         if (set < 0 || set > 1)
                 return TRN_ERR_ARG;
+        if (compact) {
+                CK(c->d_item_desc[set].ensure(std::max<size_t>(4, size_t(totalItems) * 4)));
+                auto &qi = c->qitems_set[set];
+                qi.resize(nq);
+                for (uint32_t q = 0; q < nq; ++q) {
+                        const DevQuery &dq = hq[q];
+                        qi[q] = trn_qitems{dq.item_base, dq.ntiles, dq.tile_lo, dq.flat == 5u ? c->tree_shift : execShift};
+                }
+        }
         CK(cudaMemcpyAsync(c->d_queries.p, hq.data(), nq * sizeof(DevQuery), cudaMemcpyHostToDevice, c->stream));
         if (!steps.empty())
                 CK(cudaMemcpyAsync(c->d_steps.p, steps.data(), steps.size() * sizeof(DevStep), cudaMemcpyHostToDevice, c->stream));
@@ -1946,6 +1967,8 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         P.seg_scores   = scored ? c->d_seg_scores.as<float>() : nullptr;
         P.item_off     = c->d_item_off.as<uint64_t>();
         P.item_cnt     = c->d_item_cnt.as<uint32_t>();
+        P.item_desc    = compact ? c->d_item_desc[set].as<uint32_t>() : nullptr;
+        P.word_counts  = word_counts;
         P.match_counts = match_counts;
         P.theta        = theta;
         P.cand_cursor  = cand_cursor;
@@ -2022,7 +2045,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 CK(cudaEventRecord(k1, c->stream));
         }
         if (mode != TRN_MODE_SCORED_TOPK) {
-                CK(launch_query_scan(match_counts, nq, c->d_q_offsets[set].as<uint64_t>(), c->stream));
+                CK(launch_query_scan(compact ? word_counts : match_counts, nq, c->d_q_offsets[set].as<uint64_t>(), c->stream)); // compact: offsets in words
                 ++launches;
                 if (totalItems) {
                         CK(launch_item_scan(P.queries, nq, P.item_cnt, c->d_q_offsets[set].as<uint64_t>(), c->d_item_dst.as<uint64_t>(), c->stream));
@@ -2036,7 +2059,8 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 ++launches;
         }
         c->tm.enqueue_ms += float(now_ms() - tEnqueue0);
-        c->last_mode     = mode;
+        c->last_mode     = compact ? TRN_MODE_DOCS_COMPACT : mode;
+        c->last_items    = totalItems;
         c->last_nq       = nq;
         c->last_k        = k;
         c->last_launches = launches;
@@ -2099,9 +2123,26 @@ extern "C" int trn_fetch_results(trn_ctx *c, trn_result *out) {
                                 CK(cudaMemcpyAsync(c->h_scores.p, c->d_out_scores[0].p, total * 4, cudaMemcpyDeviceToHost, c->stream));
                         out->scores = c->h_scores.as<float>();
                 }
+                if (c->last_mode == TRN_MODE_DOCS_COMPACT) {
+                        CK(c->h_item_desc.ensure(std::max<size_t>(4, size_t(c->last_items) * 4)));
+                        if (c->last_items)
+                                CK(cudaMemcpyAsync(c->h_item_desc.p, c->d_item_desc[0].p, size_t(c->last_items) * 4, cudaMemcpyDeviceToHost, c->stream));
+                }
                 CK(cudaStreamSynchronize(c->stream));
-                out->total  = total;
-                out->docids = c->h_docids.as<uint32_t>();
+                if (c->last_mode == TRN_MODE_DOCS_COMPACT) {
+                        c->h_qitems      = c->qitems_set[0];
+                        out->words       = c->h_docids.as<uint32_t>();
+                        out->total_words = total;
+                        out->item_desc   = c->h_item_desc.as<uint32_t>();
+                        out->qitems      = c->h_qitems.data();
+                        uint64_t matches{0};
+                        for (uint32_t q = 0; q < nq; ++q)
+                                matches += c->h_counts.as<uint64_t>()[q];
+                        out->total = matches;
+                } else {
+                        out->total  = total;
+                        out->docids = c->h_docids.as<uint32_t>();
+                }
         } else {
                 const uint32_t k = c->last_k;
                 CK(c->h_docids.ensure(size_t(nq) * k * 4));
@@ -2144,6 +2185,7 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
         if (!c || !out)
                 return TRN_ERR_ARG;
         uint32_t nchunks = c->pipeline_chunks;
+        const bool compact = mode == TRN_MODE_DOCS_COMPACT;
         if (mode == TRN_MODE_SCORED_TOPK || nq < 8 * nchunks || nchunks <= 1) {
                 const double t0 = now_ms();
                 const int    r  = trn_exec_batch_device(c, queries, nq, mode, k, nullptr);
@@ -2166,8 +2208,11 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
         const uint32_t per = (nq + nchunks - 1) / nchunks;
         CK(c->h_chunk.ensure(2 * (64 + (size_t(per) + 1) * 16)));
         uint64_t *hoff = c->h_offsets.as<uint64_t>(), *hcnt = c->h_counts.as<uint64_t>();
-        uint64_t  running{0}, postings{0}, bytes{0};
+        uint64_t  running{0}, postings{0}, bytes{0}, runningItems{0}, matches{0};
         uint32_t  launches{0};
+        std::vector<uint32_t> chunkItems; // compact: work items of every chunk (entries of its item_desc)
+        if (compact)
+                c->h_qitems.resize(nq);
         float     ksum{0};
         struct Chunk {
                 uint32_t q0, n;
@@ -2228,10 +2273,23 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                         if (scored)
                                 CK(cudaMemcpyAsync(c->h_scores.as<float>() + running, c->d_out_scores[set].p, total * 4, cudaMemcpyDeviceToHost, c->copy_stream));
                 }
+                if (compact) { // the chunk's segment descriptors; its queries' item ranges move behind the earlier chunks' items
+                        const uint32_t ni = chunkItems[j];
+                        CK(grow(c->h_item_desc, std::max<size_t>(4, std::max<uint64_t>(runningItems + ni, c->last_items_hint) * 4), runningItems * 4));
+                        if (ni)
+                                CK(cudaMemcpyAsync(c->h_item_desc.as<uint32_t>() + runningItems, c->d_item_desc[set].p, size_t(ni) * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+                        for (uint32_t i = 0; i < C.n; ++i) {
+                                trn_qitems qi = c->qitems_chunk[j][i];
+                                qi.item_base += uint32_t(runningItems);
+                                c->h_qitems[C.q0 + i] = qi;
+                        }
+                        runningItems += ni;
+                }
                 CK(cudaEventRecord(c->ev_d2h[set], c->copy_stream));
                 for (uint32_t i = 0; i < C.n; ++i) {
                         hoff[C.q0 + i] = running + o[i];
                         hcnt[C.q0 + i] = m[i];
+                        matches += m[i];
                 }
                 running += total;
                 return TRN_OK;
@@ -2254,6 +2312,14 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                 if (r != TRN_OK)
                         return r;
                 CK(cudaEventRecord(c->ev_done[set], c->stream));
+                if (compact) {
+                        if (chunkItems.size() <= i) {
+                                chunkItems.resize(i + 1);
+                                c->qitems_chunk.resize(i + 1);
+                        }
+                        chunkItems[i]      = c->last_items;
+                        c->qitems_chunk[i] = c->qitems_set[set];
+                }
                 postings += part.postings_scanned;
                 bytes += part.index_bytes_touched;
                 launches += part.kernel_launches;
@@ -2281,10 +2347,17 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
         c->last_total_hint = running + running / 16;
         std::memset(out, 0, sizeof(*out));
         out->nq                  = nq;
-        out->total               = running;
+        out->total               = compact ? matches : running;
         out->offsets             = hoff;
-        out->docids              = c->h_docids.as<uint32_t>();
+        out->docids              = compact ? nullptr : c->h_docids.as<uint32_t>();
         out->scores              = scored ? c->h_scores.as<float>() : nullptr;
+        if (compact) {
+                out->words         = c->h_docids.as<uint32_t>();
+                out->total_words   = running;
+                out->item_desc     = c->h_item_desc.as<uint32_t>();
+                out->qitems        = c->h_qitems.data();
+                c->last_items_hint = runningItems + runningItems / 16;
+        }
         out->match_counts        = hcnt;
         out->postings_scanned    = postings;
         out->index_bytes_touched = bytes;

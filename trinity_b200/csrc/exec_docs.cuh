@@ -743,6 +743,48 @@ template <bool PH, bool TREE> __global__ void __launch_bounds__(kDocsWarps * 32,
                 const uint32_t incl  = warp_incl_scan(c, lane);
                 const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
                 unsigned long long base = 0;
+                if (P.item_desc) {
+                        // ---- compact results: the tile's bitmap when more than 1 document in 16 matches, else 16-bit offsets from the tile's
+                        // first docID (a tile holds at most 2^16 documents), two per word
+                        const bool     bitmap = total * 2u > W / 8u || W > 65536u;
+                        const uint32_t words  = total ? (bitmap ? NW : (total + 1u) >> 1) : 0u;
+                        if (lane == 0) {
+                                if (total) {
+                                        base = atomicAdd(P.seg_cursor, static_cast<unsigned long long>(words));
+                                        atomicAdd(&P.match_counts[curq], static_cast<unsigned long long>(total));
+                                        atomicAdd(&P.word_counts[curq], static_cast<unsigned long long>(words));
+                                        if (base + words > P.seg_capacity) {
+                                                *P.overflow = 1;
+                                                base        = ~0ull;
+                                        }
+                                }
+                                P.item_off[item]  = base;
+                                P.item_cnt[item]  = base == ~0ull ? 0u : words;
+                                P.item_desc[item] = base == ~0ull ? 0u : (total | (bitmap ? kEncBitmap : kEncU16) << 30);
+                        }
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (total && base != ~0ull) {
+                                if (bitmap) {
+                                        for (uint32_t i = lane; i < NW; i += 32)
+                                                P.seg_docids[base + i] = root[i];
+                                } else {
+                                        uint16_t *out = reinterpret_cast<uint16_t *>(P.seg_docids + base);
+                                        uint32_t  pos = incl - c;
+                                        for (uint32_t i = 0; i < wpl; ++i) {
+                                                const uint32_t wi = lane * wpl + i;
+                                                uint32_t       w  = root[wi];
+                                                while (w) {
+                                                        const uint32_t bit = uint32_t(__ffs(int(w)) - 1);
+                                                        w &= w - 1;
+                                                        out[pos++] = uint16_t(wi * 32u + bit);
+                                                }
+                                        }
+                                        if (lane == 31 && (total & 1u))
+                                                out[total] = 0; // the pad half-word travels too
+                                }
+                        }
+                        continue;
+                }
                 if (lane == 0) {
                         if (total) {
                                 base = atomicAdd(P.seg_cursor, static_cast<unsigned long long>(total));

@@ -232,6 +232,8 @@ __device__ void cand_exec_google(const ExecParams &P, const DevQuery &Q, uint32_
                         if (lane == 0) {
                                 P.item_off[item] = 0;
                                 P.item_cnt[item] = 0;
+                                if (P.item_desc)
+                                        P.item_desc[item] = 0;
                         }
                         return;
                 }
@@ -268,6 +270,11 @@ __device__ void cand_exec_google(const ExecParams &P, const DevQuery &Q, uint32_
                 }
                 P.item_off[item] = base;
                 P.item_cnt[item] = base == ~0ull ? 0u : total;
+                if (P.item_desc) { // compact results: a lead-block group is not a docID tile — plain docIDs (kEncU32), one word each
+                        P.item_desc[item] = base == ~0ull ? 0u : total;
+                        if (total)
+                                atomicAdd(&P.word_counts[curq], static_cast<unsigned long long>(total));
+                }
         }
         base = __shfl_sync(0xffffffffu, base, 0);
         if (!total || base == ~0ull)

@@ -916,3 +916,76 @@ static int parse_query_impl(const char *text, const std::unordered_map<std::stri
         *root   = 0;
         return TRN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ result replay
+// == the MatchesProxy::process / consider(docid_t) stream of one query (docset_spans.h:14-21, matches.h:149-171), from either result form
+template <class F> static int replay_query(const trn_result *r, uint32_t q, F &&f) {
+        if (!r || q >= r->nq || !r->offsets)
+                return TRN_ERR_ARG;
+        if (r->docids) { // TRN_MODE_DOCS_ONLY / SCORED_*: plain docIDs
+                for (uint64_t i = r->offsets[q]; i < r->offsets[q + 1]; ++i)
+                        if (f(r->docids[i]))
+                                return TRN_OK;
+                return TRN_OK;
+        }
+        if (!r->words || !r->item_desc || !r->qitems)
+                return r->offsets[q] == r->offsets[q + 1] ? TRN_OK : TRN_ERR_ARG;
+        const trn_qitems &Q = r->qitems[q];
+        const uint32_t *  w = r->words + r->offsets[q];
+        for (uint32_t j = 0; j < Q.nitems; ++j) {
+                const uint32_t d = r->item_desc[Q.item_base + j], n = d & 0x3fffffffu, enc = d >> 30;
+                if (!n)
+                        continue;
+                const uint32_t base = (Q.tile_lo + j) << Q.tile_shift;
+                if (enc == TRN_ENC_U32) {
+                        for (uint32_t i = 0; i < n; ++i)
+                                if (f(w[i]))
+                                        return TRN_OK;
+                        w += n;
+                } else if (enc == TRN_ENC_U16) {
+                        for (uint32_t i = 0; i < n; ++i)
+                                if (f(base + ((w[i >> 1] >> ((i & 1u) * 16u)) & 0xffffu)))
+                                        return TRN_OK;
+                        w += (n + 1u) >> 1;
+                } else if (enc == TRN_ENC_BITMAP) {
+                        const uint32_t nw = (1u << Q.tile_shift) >> 5;
+                        for (uint32_t k = 0; k < nw; ++k) {
+                                uint32_t x = w[k];
+                                while (x) {
+                                        const uint32_t b = uint32_t(__builtin_ctz(x));
+                                        x &= x - 1u;
+                                        if (f(base + 32u * k + b))
+                                                return TRN_OK;
+                                }
+                        }
+                        w += nw;
+                } else
+                        return TRN_ERR_FORMAT;
+        }
+        return w == r->words + r->offsets[q + 1] ? TRN_OK : TRN_ERR_FORMAT; // the segments must add up to the query's words
+}
+
+extern "C" int trn_result_for_each(const trn_result *r, uint32_t q, trn_consider_fn fn, void *ctx) {
+        if (!fn)
+                return TRN_ERR_ARG;
+        return replay_query(r, q, [&](uint32_t id) { return fn(ctx, id) != 0; });
+}
+
+extern "C" int trn_result_decode(const trn_result *r, uint32_t q, uint32_t *out, uint64_t cap, uint64_t *n) {
+        if (!n || (!out && cap))
+                return TRN_ERR_ARG;
+        uint64_t  k{0};
+        bool      over{false};
+        const int rc = replay_query(r, q, [&](uint32_t id) {
+                if (k < cap)
+                        out[k] = id;
+                else
+                        over = true;
+                ++k;
+                return false;
+        });
+        *n = k;
+        if (rc != TRN_OK)
+                return rc;
+        return over ? TRN_ERR_CAPACITY : TRN_OK;
+}
