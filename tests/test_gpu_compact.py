@@ -35,13 +35,16 @@ def test_compact_equals_plain_and_reference(ref, codec):
         r.add_term(n, d, f)
     r.finish(NDOCS)
     g = _index(codec, lists)
-    qs = [q for q in TEMPLATES + EXTRA + OPTIONAL_QUERIES if "nosuchterm" not in q]
+    qs = [q for q in TEMPLATES + EXTRA if "nosuchterm" not in q]
+    nplain = len(qs)
+    qs += OPTIONAL_QUERIES  # (the reference parses '<t>' as optional only with parser flag 8)
     rng = np.random.default_rng(4)
     for tpl in TREE8:
         for _ in range(3):
             qs.append(tpl.format(*[names[i] for i in rng.choice(len(names), size=8, replace=False)]))
     plans = [tb.parse_query(q, tdict) for q in qs]
-    want = [r.exec(q, False, NDOCS + 1)[0] for q in qs]
+    flags = [8 if nplain <= i < nplain + len(OPTIONAL_QUERIES) else 0 for i in range(len(qs))]
+    want = [r.exec(q, False, NDOCS + 1, parser_flags=f)[0] for q, f in zip(qs, flags)]
     encodings = set()
     for batch in (plans, plans[:5]):  # pipelined call (>= 32 queries) and the single-call form
         plain = g.exec_batch(batch, tb.MODE_DOCS_ONLY)
