@@ -112,8 +112,8 @@ def test_sparse_table_lookup_equals_brute_force(codec):
         assert len(bad) == 0, f"{name}: docID {probes[bad[0]]} -> block {got[bad[0]]}, want {want[bad[0]]} (tf_shift {shift})"
         if nblocks <= 8:
             assert shift == 32 and entries == 0
-        else:  # never more table entries than blocks (+ the closing entry), never finer than the 8192-document window
-            assert 13 <= shift <= 31 and entries <= nblocks + 1, (name, shift, entries, nblocks)
+        else:  # at most one table entry per two blocks (+ the closing entry), never finer than 512 docIDs
+            assert 9 <= shift <= 31 and entries <= nblocks // 2 + 1, (name, shift, entries, nblocks)
 
 
 @pytest.mark.parametrize("codec", [tb.CODEC_GOOGLE, tb.CODEC_LUCENE])

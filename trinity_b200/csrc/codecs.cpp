@@ -667,7 +667,7 @@ void build_block_directory(Codec codec, const uint8_t *index, uint64_t nbytes, c
                 if (td.nblocks <= kDirNoTableBlocks)
                         continue;
                 uint32_t s = kDirMinShift;
-                while (s < 31 && uint64_t(td.last_doc >> s) - (td.first_doc >> s) + 1 > td.nblocks)
+                while (s < 31 && (uint64_t(td.last_doc >> s) - (td.first_doc >> s) + 1) * kDirBlocksPerEntry > td.nblocks)
                         ++s;
                 td.tf_shift = s;
                 td.tf_base  = td.first_doc >> s;

@@ -119,7 +119,7 @@ struct trn_ctx {
         // pipelined host-buffer path (trn_exec_batch): kernels of chunk i+1 overlap the D2H of chunk i
         cudaStream_t copy_stream{nullptr};
         cudaEvent_t  ev_done[2]{nullptr, nullptr}, ev_d2h[2]{nullptr, nullptr}, ev_ck0[16]{}, ev_ck1[16]{};
-        uint32_t     pipeline_chunks{4};
+        uint32_t     pipeline_chunks{8}; // TRN_PIPELINE_CHUNKS (profiles/r02_n: 4 -> 38.4K, 6 -> 40.1K, 8 -> 40.7K, 12 -> 40.1K q/s end to end on the headline batch)
         uint32_t     last_items{0}; // work items of the last exec_device_impl call (compact results: entries of item_desc)
         uint64_t     last_total_hint{0};
         // host-side breakdown of the last trn_exec_batch / trn_exec_batch_device call (trn_last_timings)

@@ -25,33 +25,34 @@ static constexpr uint32_t kCandSmem    = kCandBytes + kGatherBufBytes;          
 static constexpr uint32_t kCandSmemMask = kCandSmem + kCandMaskBytes;                   // ... | membership bytes (only queries with terms that are not necessary)
 static constexpr uint32_t kCandInvalid = 0xffffffffu;
 
-// one lane decodes the doc section of ITS staged block into out[0..n)
+// one lane decodes the doc section of ITS staged block into out[0..n).  Branch-free per code: the 32 lanes of a group hold blocks with
+// different mixes of 1-, 2- and 3-byte codes, and a loop that branches on the code length (with early exits) does not reconverge before
+// its end — profiles/r02_n: this function ran at 2.1 of 32 lanes.  Every lane runs the same 31 steps; a lane whose block ends, whose next
+// code may leave its 80-byte slot or is longer than 3 bytes goes idle and finishes from global memory afterwards.
 __device__ __forceinline__ void google_block_to_array(const uint8_t *__restrict__ index, uint32_t off, const uint8_t *buf, int lane, uint32_t n, uint32_t prev,
                                                       uint32_t last, uint32_t *out) {
         const uint32_t mis = off & 15u;
-        uint32_t       sp  = uint32_t(__cvta_generic_to_shared(buf + lane * kGatherBytes)) + mis;
+        const uint32_t sp  = uint32_t(__cvta_generic_to_shared(buf + lane * kGatherBytes)) + mis;
         const uint32_t nd  = n - 1u;
         uint32_t       doc = prev, i = 0, p = 0;
-        for (; i < nd; ++i) {
+        bool           live = true;
+#pragma unroll 1
+        for (uint32_t it = 0; it < 31u; ++it) {
+                const uint32_t at = sp + p, a = at & ~3u;
+                const uint32_t w  = __funnelshift_r(lds_u32(a), lds_u32(a + 4u), (at & 3u) * 8u); // bytes p .. p+3 (reads stay inside the staging area)
+                const uint32_t b0 = w & 0xffu;
+                const uint32_t two = b0 >= 0x80u ? 1u : 0u, three = b0 >= 0xc0u ? 1u : 0u;
+                const uint32_t v2 = ((b0 & 0x3fu) << 8) | ((w >> 8) & 0xffu), v3 = ((b0 & 0x1fu) << 16) | ((w >> 8) & 0xffffu);
+                const uint32_t v  = three ? v3 : (two ? v2 : b0);
                 // 3-byte codes (gaps >= 16384: the sparsest leads) are decoded in place too, so the 31 x 2 + 15 <= 80 bound of the other
                 // decoders does not hold here: every code (<= 3 bytes) is checked against the end of the slot
-                if (mis + p + 3u > kGatherBytes)
-                        break;
-                const uint32_t b0 = lds_u8(sp + p);
-                uint32_t       v;
-                if (b0 < 0x80u) {
-                        v = b0;
-                        p += 1u;
-                } else if (b0 < 0xc0u) {
-                        v = ((b0 & 0x3fu) << 8) | lds_u8(sp + p + 1u);
-                        p += 2u;
-                } else if (b0 < 0xe0u) {
-                        v = ((b0 & 0x1fu) << 16) | lds_u8(sp + p + 1u) | (lds_u8(sp + p + 2u) << 8);
-                        p += 3u;
-                } else
-                        break; // 4- and 5-byte codes: continue from global memory
-                doc += v;
-                out[i] = doc;
+                live = live && it < nd && b0 < 0xe0u && mis + p + 3u <= kGatherBytes;
+                if (live) {
+                        doc += v;
+                        out[it] = doc;
+                        p += 1u + two + three;
+                        i = it + 1u;
+                }
         }
         if (i < nd) {
                 const uint8_t *g = index + off + p;
