@@ -231,10 +231,36 @@ namespace {
                 isrc_docid_t process(MatchesProxy *mp, const isrc_docid_t min, const isrc_docid_t max) override final {
                         trn_query  q{plan.data(), uint32_t(plan.size()), 0};
                         trn_result r;
-                        if (trn_exec_batch(gap.ctx, &q, 1, scored ? TRN_MODE_SCORED_ALL : TRN_MODE_DOCS_ONLY, 0, &r) != TRN_OK)
+                        // DocumentsOnly: the compact result form (a docID tile's matches as bitmap / 16-bit offsets / docIDs) — what a batch
+                        // of queries would use to keep the host link out of the way; replayed below by trn_result_for_each
+                        if (trn_exec_batch(gap.ctx, &q, 1, scored ? TRN_MODE_SCORED_ALL : TRN_MODE_DOCS_COMPACT, 0, &r) != TRN_OK)
                                 throw Switch::system_error(trn_last_error(gap.ctx));
                         ++gap.spansExecuted;
                         relevant_document rd; // docset_iterators.h:456-497: carries (id, score_) to the Handler
+                        if (!scored) {
+                                struct Replay {
+                                        MatchesProxy *     mp;
+                                        relevant_document *rd;
+                                        isrc_docid_t       min, max, stoppedAt;
+                                } st{mp, &rd, min, max, DocIDsEND};
+                                // ascending docID, exactly once per match; an exception thrown by consider() (aborted_search_exception) unwinds
+                                // through the replay like it unwinds through the reference's own span
+                                const int rc = trn_result_for_each(&r, 0, [](void *ctx, uint32_t id) -> int {
+                                        auto &S = *static_cast<Replay *>(ctx);
+                                        if (id < S.min)
+                                                return 0;
+                                        if (id >= S.max) {
+                                                S.stoppedAt = id;
+                                                return 1;
+                                        }
+                                        S.rd->set_document(id);
+                                        S.mp->process(S.rd); // -> Handler::process -> maskedDocs / consider(id) (exec.cpp:1095-1345)
+                                        return 0;
+                                }, &st);
+                                if (rc != TRN_OK)
+                                        throw Switch::data_error("malformed compact result");
+                                return st.stoppedAt;
+                        }
                         for (uint64_t i = r.offsets[0]; i < r.offsets[1]; ++i) { // ascending docID, exactly once per match
                                 const auto id = r.docids[i];
                                 if (id < min)
@@ -242,9 +268,8 @@ namespace {
                                 if (id >= max)
                                         return id;
                                 rd.set_document(id);
-                                if (scored)
-                                        rd.score_ = r.scores[i];
-                                mp->process(&rd); // -> Handler::process -> maskedDocs / consider(id[, score]) (exec.cpp:1095-1345)
+                                rd.score_ = r.scores[i];
+                                mp->process(&rd); // -> Handler::process -> maskedDocs / consider(id, score) (exec.cpp:1095-1345)
                         }
                         return DocIDsEND;
                 }
