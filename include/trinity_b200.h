@@ -134,8 +134,8 @@ int trn_segment_masked(trn_segment *, const uint32_t **docids, uint64_t *n);
 #define TRN_NODE_NOT 3
 #define TRN_NODE_OPTIONAL 4
 #define TRN_NODE_SOME 5
-#define TRN_NODE_PHRASE 6 /* executed on the GOOGLE codec (inline hits, google_codec.cpp:533-594); an index in the LUCENE codec keeps its hits in hits.data,
-                           * which this engine does not read yet: trn_exec_batch rejects phrase plans there (TRN_ERR_UNSUPPORTED, never a silent answer) */
+#define TRN_NODE_PHRASE 6 /* executed on the GOOGLE codec (inline hits, google_codec.cpp:533-594) and, once trn_upload_hits has handed over hits.data, on the
+                           * LUCENE codec (lucene_codec.cpp:767-856); a LUCENE source without its hits rejects phrase plans (TRN_ERR_UNSUPPORTED, never a silent answer) */
 
 typedef struct trn_qnode {
         uint8_t  kind;
@@ -183,6 +183,10 @@ typedef struct trn_debug_step {
         uint32_t pad2;
         double   idf;
 } trn_debug_step;
+/* the kernels' position cursors (csrc/hitcursor.h) run on the host over one term: positions of the listed documents (counts[i] each), for
+ * the CPU tests; `hits` = hits.data (LUCENE), ignored for GOOGLE */
+int trn_debug_positions(int codec, const uint8_t *index, uint64_t nbytes, const uint8_t *hits, uint64_t hits_bytes, const trn_term *term, const uint32_t *docids, uint32_t n,
+                        uint32_t *counts, uint32_t *positions, uint64_t cap, uint64_t *total, char *err, size_t errcap);
 int trn_debug_compile(int codec, const uint8_t *index, uint64_t nbytes, const trn_term *terms, uint32_t nterms, const trn_qnode *nodes, uint32_t nnodes, uint32_t root,
                       int scored, trn_debug_step *out, uint32_t cap, uint32_t *nsteps, uint32_t *root_slot, uint32_t *nslots, char *err, size_t errcap);
 
@@ -218,6 +222,11 @@ typedef struct trn_index_info {
         uint64_t index_bytes, directory_bytes, total_blocks, total_postings;
 } trn_index_info;
 int trn_index_info_get(trn_ctx *, trn_index_info *out);
+
+/* LUCENE positions == Lucene AccessProxy::hitsDataPtr (lucene_codec.h:204-218): hits.data of the index uploaded before, for phrase plans
+ * (TRN_NODE_PHRASE).  `index` = the bytes trn_upload_index received (read again on the host to lay out the hits directory).  The GOOGLE
+ * codec keeps its hits inline and needs no such call. */
+int trn_upload_hits(trn_ctx *, const uint8_t *index, uint64_t nbytes, const uint8_t *hits, uint64_t hits_bytes);
 
 /* execution modes == ExecFlags (exec.h:12-43) + where top-k lives */
 #define TRN_MODE_DOCS_ONLY 0    /* ExecFlags::DocumentsOnly: matched docIDs ascending == consider(docid_t) stream        */

@@ -1,11 +1,13 @@
 // See gpu_exec.h.  Reference-side binding: everything here speaks the reference's types on one side and the C ABI on the other.
 #include "gpu_exec.h"
+#include "lucene_codec.h"
 #include <mutex>
 #include <stdexcept>
 
 namespace Trinity {
 
-GpuAccessProxy::GpuAccessProxy(int device, Codecs::AccessProxy *ap, size_t indexSize, const std::vector<std::pair<std::string, term_index_ctx>> &terms, isrc_docid_t maxDocID) {
+GpuAccessProxy::GpuAccessProxy(int device, Codecs::AccessProxy *ap, size_t indexSize, const std::vector<std::pair<std::string, term_index_ctx>> &terms, isrc_docid_t maxDocID,
+                               const uint8_t *hitsData, size_t hitsSize) {
         if (trn_create(device, &ctx) != TRN_OK) {
                 const std::string m = ctx ? trn_last_error(ctx) : "trn_create failed";
                 if (ctx)
@@ -25,6 +27,24 @@ GpuAccessProxy::GpuAccessProxy(int device, Codecs::AccessProxy *ap, size_t index
                 trn_destroy(ctx);
                 throw Switch::data_error(m.c_str());
         }
+        // LUCENE keeps positions in hits.data (Lucene::AccessProxy::hitsDataPtr, lucene_codec.h:204-218): with them on the device the span
+        // takes phrase plans too; without them those stay with the reference's own span
+        if (codec == TRN_CODEC_LUCENE) {
+                if (!hitsData) {
+                        const auto lap = static_cast<Codecs::Lucene::AccessProxy *>(ap);
+                        hitsData       = lap->hitsDataPtr;
+                        hitsSize       = lap->hitsDataSize; // (0 when the proxy was handed a pointer: pass the size to this constructor then)
+                }
+                if (hitsData && hitsSize) {
+                        if (trn_upload_hits(ctx, ap->indexPtr, indexSize, hitsData, hitsSize) != TRN_OK) {
+                                const std::string m = trn_last_error(ctx);
+                                trn_destroy(ctx);
+                                throw Switch::data_error(m.c_str());
+                        }
+                        havePositions = true;
+                }
+        } else
+                havePositions = true; // GOOGLE: inline
 }
 
 GpuAccessProxy::~GpuAccessProxy() {
@@ -80,10 +100,10 @@ namespace {
                         n.push_back(x);
                         return int(n.size()) - 1;
                 }
-                // the engine checks positions on the device for the GOOGLE codec (inline hits); a LUCENE source keeps them in hits.data, which the
-                // engine does not hold: such plans stay with the reference's own span
+                // the engine checks positions on the device: GOOGLE has them inline, a LUCENE source needs its hits.data uploaded (constructor);
+                // without it such plans stay with the reference's own span
                 int phrase_node(const compilation_ctx::phrase *p) {
-                        if (gap.codec != TRN_CODEC_GOOGLE) {
+                        if (!gap.havePositions) {
                                 unsupported = true;
                                 return term_node(p->termIDs[0]);
                         }

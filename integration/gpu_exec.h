@@ -26,9 +26,13 @@ struct GpuAccessProxy final {
         std::unordered_map<std::string, uint32_t> idOf; // term -> trn term id
         uint64_t                                  spansExecuted{0};
         int                                       codec{0}; // TRN_CODEC_*
+        bool                                      havePositions{false}; // GOOGLE: inline hits; LUCENE: hits.data uploaded
 
         // `terms`: every (term, term_index_ctx) of the source, e.g. from SegmentTerms iteration (terms.h:27-37)
-        GpuAccessProxy(int device, Codecs::AccessProxy *ap, size_t indexSize, const std::vector<std::pair<std::string, term_index_ctx>> &terms, isrc_docid_t maxDocID);
+        // LUCENE: hits.data is taken from the Lucene::AccessProxy (hitsDataPtr / hitsDataSize); a proxy that was handed a bare pointer does not
+        // know the size: pass both here
+        GpuAccessProxy(int device, Codecs::AccessProxy *ap, size_t indexSize, const std::vector<std::pair<std::string, term_index_ctx>> &terms, isrc_docid_t maxDocID,
+                       const uint8_t *hitsData = nullptr, size_t hitsSize = 0);
         ~GpuAccessProxy();
         GpuAccessProxy(const GpuAccessProxy &) = delete;
 };
@@ -38,7 +42,7 @@ void            gpu_proxy_register(IndexSource *src, GpuAccessProxy *gap);
 GpuAccessProxy *gpu_proxy_for(IndexSource *src);
 
 // exec_query()'s span factory for sources that have a device twin; returns nullptr when the plan holds something the GPU span does
-// not execute (phrases over a LUCENE source: hits.data is not on the device) or the source has no twin: the caller then builds the reference's own span.
+// not execute (phrases over a LUCENE source whose hits.data was not uploaded) or the source has no twin: the caller then builds the reference's own span.
 std::unique_ptr<DocsSetSpan> b200_gpu_span(queryexec_ctx &rctx, const exec_node root, const uint32_t execFlags, IndexSource *idxsrc, Similarity::IndexSourceTermsScorer *scorer);
 
 } // namespace Trinity

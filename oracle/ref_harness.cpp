@@ -828,13 +828,19 @@ extern "C" void *tref_synth_build(int codec, uint32_t ndocs, uint32_t nterms, ui
 namespace {
         std::unordered_map<void *, std::unique_ptr<Trinity::GpuAccessProxy>> g_gaps;
 }
+extern "C" int tref_gpu_attach2(void *h, int device, uint64_t maxDocID, int withHits);
 extern "C" int tref_gpu_attach(void *h, int device, uint64_t maxDocID) {
+        return tref_gpu_attach2(h, device, maxDocID, 1);
+}
+extern "C" int tref_gpu_attach2(void *h, int device, uint64_t maxDocID, int withHits) { // withHits = 0: a LUCENE source whose hits.data stays on the host
         auto x = static_cast<RefIndex *>(h);
         return guarded([&] {
                 std::vector<std::pair<std::string, term_index_ctx>> terms;
                 for (size_t i = 0; i < x->names.size(); ++i)
                         terms.emplace_back(x->names[i], x->tctx[i]);
-                auto gap = std::make_unique<Trinity::GpuAccessProxy>(device, x->ap.get(), x->index.size(), terms, isrc_docid_t(maxDocID));
+                const bool hits = withHits && !x->hits.empty();
+                auto       gap  = std::make_unique<Trinity::GpuAccessProxy>(device, x->ap.get(), x->index.size(), terms, isrc_docid_t(maxDocID), hits ? x->hits.data() : nullptr,
+                                                                     hits ? x->hits.size() : 0);
                 Trinity::gpu_proxy_register(x->src, gap.get());
                 g_gaps[h] = std::move(gap);
         });

@@ -3,7 +3,7 @@
 # unsharded reference on rank 0, per-rank e2e breakdown, NUMA binding
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/r02_h_topo.txt 2>&1
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02_h_bench_8gpu.log 2> gpurun_out/r02_h_bench_8gpu.err
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/r02_h_bench_8gpu.log 2> gpurun_out/r02_h_bench_8gpu.err
 echo "rc=$?"
 tail -1 gpurun_out/r02_h_bench_8gpu.log | python -c "
 import json,sys

@@ -4,6 +4,8 @@ span-building call site of exec_query() (exec.cpp:1083-1086) going through the r
 tree is turned into a plan by PlanBuilder (not by this repo's parser), runs through trn_exec_batch, and is replayed through
 MatchesProxy::process -> the stock exec Handlers -> MatchedIndexDocumentsFilter::consider().  The stream consider() sees must equal the
 stock library's, for every golden query shape, both ExecFlags modes, both codecs, with and without masked documents."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -88,14 +90,17 @@ def _phrase_twins(rl_stock, rl_gpu, codec, ndocs, vocab=9, seed=33, lo=3, hi=40)
 
 
 def test_phrases_through_the_gpu_span(ref):
-    """ENT::matchphrase / matchanyphrases / matchallphrases -> TRN_NODE_PHRASE on a GOOGLE source (positions checked on the device); on a
-    LUCENE source the binding declines (hits.data is not on the device) and the reference's own span runs: same stream either way"""
+    """ENT::matchphrase / matchanyphrases / matchallphrases -> TRN_NODE_PHRASE: positions checked on the device for a GOOGLE source (inline
+    hits) and for a LUCENE source whose hits.data the binding uploaded; a LUCENE source WITHOUT its hits on the device makes the binding
+    decline and the reference's own span runs: the same stream in all three cases"""
     from test_phrase_cpu import QUERIES
     refg = load_ref_gpu()
+    refg.L.tref_gpu_attach2.restype = C.c_int
+    refg.L.tref_gpu_attach2.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int]
     ndocs = 20_000
-    for codec, on_gpu in ((tb.CODEC_GOOGLE, True), (tb.CODEC_LUCENE, False)):
+    for codec, with_hits in ((tb.CODEC_GOOGLE, 1), (tb.CODEC_LUCENE, 1), (tb.CODEC_LUCENE, 0)):
         stock, gpu = _phrase_twins(ref, refg, codec, ndocs)
-        assert refg.L.tref_gpu_attach(gpu.h, 0, ndocs) == 0, refg.err()
+        assert refg.L.tref_gpu_attach2(gpu.h, 0, ndocs, with_hits) == 0, refg.err()
         try:
             before = refg.L.tref_gpu_spans_executed(gpu.h)
             nonempty = 0
@@ -103,13 +108,13 @@ def test_phrases_through_the_gpu_span(ref):
                 for scored in (False, True):
                     wd, ws = stock.exec(q, scored, ndocs + 1)
                     gd, gs = gpu.exec(q, scored, ndocs + 1)
-                    assert_same_docs(gd, wd, f"[{q}] scored={scored} codec={codec}")
+                    assert_same_docs(gd, wd, f"[{q}] scored={scored} codec={codec} hits={with_hits}")
                     if scored:
-                        assert_close_scores(gs, ws, f"[{q}] codec={codec}")
+                        assert_close_scores(gs, ws, f"[{q}] codec={codec} hits={with_hits}")
                     nonempty += len(wd) > 0
             executed = refg.L.tref_gpu_spans_executed(gpu.h) - before
             assert nonempty >= 9
-            if on_gpu:  # '"w1 nosuch"' collapses before the span site; '"w1"' is a term (DocumentsOnly: exec_query's own specialisation)
+            if with_hits:  # '"w1 nosuch"' collapses before the span site; '"w1"' is a term (DocumentsOnly: exec_query's own specialisation)
                 assert executed >= 2 * len(QUERIES) - 4, (executed, len(QUERIES))
             else:  # only '"w1"' (a plain term) may have gone to the device
                 assert executed <= 2, executed

@@ -2,7 +2,8 @@
 google_codec.cpp:533-594 materialize_hits + Phrase::consider_phrase_match docset_iterators.cpp:66-158).  The corpus is generated
 DOCUMENT-major (one term per position: the reference's DocWordsSpace keeps one term per position).  Documents bit-exact in DocumentsOnly and
 scored mode, phrase scores (score(matchCnt, sum idf), docset_iterators_scorers.cpp:195-228) within 1e-5, top-k per assert_topk_equal.
-The LUCENE codec keeps hits in hits.data, which the engine does not read: phrase plans are refused there, loudly."""
+The LUCENE codec keeps its hits in hits.data (lucene_codec.cpp:401-513, :767-856): executed once trn_upload_hits has handed it over; without
+it phrase plans are refused, loudly."""
 import numpy as np
 import pytest
 
@@ -14,7 +15,7 @@ from util import assert_close_scores, assert_same_docs, assert_topk_equal
 pytestmark = pytest.mark.gpu
 
 
-def _corpus(ref, codec, ndocs, vocab, seed, minlen, maxlen):
+def _corpus(ref, codec, ndocs, vocab, seed, minlen, maxlen, with_hits=True):
     rng = np.random.default_rng(seed)
     prob = 1.0 / np.arange(1, vocab + 1)
     prob /= prob.sum()
@@ -35,14 +36,18 @@ def _corpus(ref, codec, ndocs, vocab, seed, minlen, maxlen):
     r.finish(ndocs)
     g = tb.GpuIndexSource(0)
     g.upload(codec, b.index(), b.terms_array(), ndocs)
+    if codec == tb.CODEC_LUCENE and with_hits:
+        g.upload_hits(b.index(), b.hits())
     return r, g, tb.TermDictionary(names)
 
 
+@pytest.mark.parametrize("codec", [tb.CODEC_GOOGLE, tb.CODEC_LUCENE], ids=["google", "lucene"])
 @pytest.mark.parametrize("shape", ["short", "long"])
-def test_phrases_match_reference_google(ref, shape):
-    # "long": documents of up to 300 tokens over 9 terms => hundreds of hits per (term, document): the 64-position chunks of the checker
+def test_phrases_match_reference(ref, shape, codec):
+    # "long": documents of up to 300 tokens over 9 terms => hundreds of hits per (term, document): the 64-position chunks of the checker,
+    # and (LUCENE) runs of hits that cross 128-hit blocks and reach into the varbyte tail
     ndocs, vocab, lo, hi = (60_000, 9, 3, 30) if shape == "short" else (3_000, 9, 80, 300)
-    r, g, tdict = _corpus(ref, tb.CODEC_GOOGLE, ndocs, vocab, 21, lo, hi)
+    r, g, tdict = _corpus(ref, codec, ndocs, vocab, 21, lo, hi)
     qs = [q for q in QUERIES]
     plans = [tb.parse_query(q, tdict) for q in qs]
     res = g.exec_batch(plans, tb.MODE_DOCS_ONLY)
@@ -65,8 +70,8 @@ def test_phrases_match_reference_google(ref, shape):
     g.close()
 
 
-def test_phrases_are_refused_on_lucene(ref):
-    r, g, tdict = _corpus(ref, tb.CODEC_LUCENE, 2_000, 9, 21, 3, 20)
+def test_phrases_are_refused_on_lucene_without_its_hits(ref):
+    r, g, tdict = _corpus(ref, tb.CODEC_LUCENE, 2_000, 9, 21, 3, 20, with_hits=False)
     with pytest.raises(tb.TrinityError, match="rc=-7"):
         g.exec_batch([tb.parse_query('"w1 w2"', tdict)], tb.MODE_DOCS_ONLY)
     res = g.exec_batch([tb.parse_query("w1 AND w2", tdict)], tb.MODE_DOCS_ONLY)  # everything else keeps working

@@ -204,6 +204,32 @@ def parse_query(text: str, tdict: TermDictionary, min_match: Optional[int] = Non
     return out
 
 
+def debug_positions(codec: int, index: np.ndarray, hits: np.ndarray, term, docids) -> list:
+    """per listed document the positions the kernels' own cursor code (csrc/hitcursor.h, run on the host) reads for one term"""
+    index = np.ascontiguousarray(index, dtype=np.uint8)
+    hits = np.ascontiguousarray(hits if hits is not None else np.zeros(0, np.uint8), dtype=np.uint8)
+    t = TrnTerm(int(term[0]), int(term[1]), int(term[2]))
+    d = _u32(list(docids))
+    counts = np.zeros(max(len(d), 1), np.uint32)
+    cap = 1 << 16
+    while True:
+        pos = np.zeros(cap, np.uint32)
+        total = C.c_uint64()
+        err = C.create_string_buffer(256)
+        rc = lib().trn_debug_positions(codec, _ptr(index), index.size, _ptr(hits) if hits.size else None, hits.size, C.byref(t), _ptr(d), len(d), _ptr(counts),
+                                       _ptr(pos), cap, C.byref(total), err, 256)
+        if rc == -6:
+            cap = int(total.value)
+            continue
+        if rc != 0:
+            raise TrinityError(err.value.decode("utf-8", "replace") or f"rc={rc}")
+        out, at = [], 0
+        for i in range(len(d)):
+            out.append(pos[at: at + int(counts[i])].copy())
+            at += int(counts[i])
+        return out
+
+
 def debug_compile(codec: int, index: np.ndarray, terms: np.ndarray, nodes: np.ndarray, scored):
     """(steps, root_slot, nslots): the bitmap-path step program of one plan, compiled on the host (no GPU needed).
     scored: False / True, 2 = the DocumentsOnly program in its flat-tree form, 3 = flat-tree form with the masked second decode pass"""
@@ -330,6 +356,12 @@ class GpuIndexSource:
         self.terms = terms.copy()
         self.docs_cnt = max_docid
         self.codec = codec
+
+    def upload_hits(self, index: np.ndarray, hits: np.ndarray):
+        """LUCENE: hits.data of the uploaded index (== Lucene AccessProxy::hitsDataPtr) — needed for phrase plans"""
+        index = np.ascontiguousarray(index, dtype=np.uint8)
+        hits = np.ascontiguousarray(hits, dtype=np.uint8)
+        self._ck(self._L.trn_upload_hits(self._h, _ptr(index), index.size, _ptr(hits) if hits.size else None, hits.size))
 
     def set_masked_documents(self, docids=None):
         """== masked_documents_registry: these docIDs never reach consider() / the top-k (None or empty clears)"""

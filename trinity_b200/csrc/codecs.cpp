@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -705,6 +706,139 @@ void build_block_directory(Codec codec, const uint8_t *index, uint64_t nbytes, c
                 for (auto &t : fths)
                         t.join();
         }
+}
+
+} // namespace trn
+
+namespace trn {
+
+void build_hits_directory(const uint8_t *index, uint64_t nbytes, const uint8_t *hits, uint64_t hbytes, const term_index_ctx *terms, uint32_t nterms,
+                          const BlockDirectory &dir, int threads, HitsDirectory &out) {
+        using Codecs::Lucene::BLOCK_SIZE;
+        if (dir.terms.size() != nterms)
+                throw std::runtime_error("hits directory: block directory of another index");
+        out.hit_base.assign(dir.blk_last.size(), 0);
+        out.hb_begin.assign(nterms, 0);
+        out.sum_hits.assign(nterms, 0);
+        // entries of hblk_off per term are known from the chunk headers
+        uint64_t total{0};
+        for (uint32_t i = 0; i < nterms; ++i) {
+                const auto &t = terms[i];
+                out.hb_begin[i] = uint32_t(total);
+                if (!t.documents || !t.size)
+                        continue;
+                if (uint64_t(t.offset) + t.size > nbytes || t.size < 14)
+                        throw std::runtime_error("lucene: term chunk outside the index");
+                out.sum_hits[i] = get_u32(index + t.offset + 4);
+                total += uint64_t(out.sum_hits[i] / BLOCK_SIZE) + 2;
+                if (total >= (1ull << 32))
+                        throw std::runtime_error("hits directory: more than 2^32 hit blocks");
+        }
+        out.hblk_off.assign(total, 0);
+        std::atomic<uint32_t> next{0};
+        std::atomic<bool>     failed{false};
+        std::string           err;
+        std::mutex            mu;
+        auto                  worker = [&] {
+                uint32_t vals[BLOCK_SIZE];
+                for (;;) {
+                        const uint32_t i = next.fetch_add(1);
+                        if (i >= nterms || failed.load())
+                                break;
+                        const auto &t = terms[i];
+                        if (!t.documents || !t.size)
+                                continue;
+                        try {
+                                const auto &   td       = dir.terms[i];
+                                const uint8_t *base     = index + t.offset;
+                                const uint32_t hitsOff  = get_u32(base), sumHits = out.sum_hits[i], skipn = uint32_t(base[12]) | (uint32_t(base[13]) << 8);
+                                const uint8_t *chunkEnd = base + t.size - size_t(skipn) * 22;
+                                // ---- hits before every document block: the freqs of the block walk
+                                const uint32_t nfull = t.documents / BLOCK_SIZE, tail = t.documents % BLOCK_SIZE;
+                                if (td.nblocks != nfull + (tail ? 1u : 0u))
+                                        throw std::runtime_error("hits directory: block count disagrees with the block directory");
+                                uint64_t run{0};
+                                for (uint32_t b = 0; b < nfull; ++b) {
+                                        const uint8_t *p = index + dir.blk_off[td.dir_begin + b];
+                                        out.hit_base[td.dir_begin + b] = uint32_t(run);
+                                        // the deltas int-block is skipped by its length byte, the freqs int-block decoded
+                                        if (p >= chunkEnd)
+                                                throw std::runtime_error("lucene: int-block past chunk end");
+                                        const uint32_t L = *p++;
+                                        if (L == 0)
+                                                (void)vb_checked(p, chunkEnd, "lucene");
+                                        else
+                                                p += size_t(L) * 4;
+                                        (void)lucene_ints_decode(p, chunkEnd, vals);
+                                        for (uint32_t k = 0; k < BLOCK_SIZE; ++k)
+                                                run += vals[k];
+                                }
+                                if (tail) {
+                                        const uint8_t *p = index + dir.blk_off[td.dir_begin + nfull];
+                                        out.hit_base[td.dir_begin + nfull] = uint32_t(run);
+                                        for (uint32_t k = 0; k < tail; ++k) {
+                                                (void)vb_checked(p, chunkEnd, "lucene");
+                                                run += vb_checked(p, chunkEnd, "lucene");
+                                        }
+                                }
+                                out.hit_base[td.dir_begin + td.nblocks] = uint32_t(run); // sentinel
+                                if (run != sumHits)
+                                        throw std::runtime_error("lucene: the freqs of a term do not add up to its sumHits");
+                                // ---- the term's hit blocks
+                                if (!sumHits)
+                                        continue;
+                                if (uint64_t(hitsOff) >= hbytes)
+                                        throw std::runtime_error("lucene: hits offset outside hits.data");
+                                const uint8_t *hend = hits + hbytes, *p = hits + hitsOff;
+                                uint32_t *     o    = out.hblk_off.data() + out.hb_begin[i];
+                                auto           hop  = [&](const uint8_t *&q) {
+                                        if (q >= hend)
+                                                throw std::runtime_error("lucene: hit block past the end of hits.data");
+                                        const uint32_t L = *q++;
+                                        if (L == 0)
+                                                (void)vb_checked(q, hend, "lucene hits");
+                                        else {
+                                                if (size_t(L) * 4 > size_t(hend - q))
+                                                        throw std::runtime_error("lucene: hit block past the end of hits.data");
+                                                q += size_t(L) * 4;
+                                        }
+                                };
+                                const uint32_t nfh = sumHits / BLOCK_SIZE;
+                                for (uint32_t h = 0; h < nfh; ++h) {
+                                        o[h] = uint32_t(p - hits);
+                                        hop(p); // position deltas
+                                        hop(p); // payload sizes
+                                        const uint32_t plen = vb_checked(p, hend, "lucene hits");
+                                        if (plen > size_t(hend - p))
+                                                throw std::runtime_error("lucene: payloads past the end of hits.data");
+                                        p += plen;
+                                }
+                                o[nfh] = uint32_t(p - hits);
+                                for (uint32_t k = 0; k < sumHits % BLOCK_SIZE; ++k) {
+                                        const uint32_t v = vb_checked(p, hend, "lucene hits");
+                                        if (v & 1u) {
+                                                if (p >= hend)
+                                                        throw std::runtime_error("lucene: hit tail past the end of hits.data");
+                                                ++p;
+                                        }
+                                }
+                                o[nfh + 1] = uint32_t(p - hits);
+                        } catch (const std::exception &e) {
+                                std::lock_guard<std::mutex> g(mu);
+                                if (!failed.exchange(true))
+                                        err = std::string("term ") + std::to_string(i) + ": " + e.what();
+                        }
+                }
+        };
+        std::vector<std::thread> pool;
+        const int                n = std::max(1, std::min(threads, 64));
+        for (int k = 1; k < n; ++k)
+                pool.emplace_back(worker);
+        worker();
+        for (auto &th : pool)
+                th.join();
+        if (failed.load())
+                throw std::runtime_error(err);
 }
 
 } // namespace trn

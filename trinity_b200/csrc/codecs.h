@@ -161,6 +161,24 @@ struct BlockDirectory {
         }
 };
 
+// LUCENE positions (lucene_codec.cpp:401-513 refill_hits / :767-856 materialize_hits): a term's hits live in hits.data, 128 per PFor
+// block (position deltas int-block, payload sizes int-block, varbyte payload length, payloads) + a varbyte tail, documents owning
+// consecutive runs of freq(doc) hits.  The reference reaches a document's hits through the skiplist entry of its block
+// ({hits block offset, hits already consumed}, one entry per block for <= 65535 blocks) and by decoding forward; here, like the block
+// directory, every block gets its entry at load time:
+//   hit_base[dir_begin + b] = hits owned by the term's documents before block b (sentinel entry: the term's sumHits), and
+//   hblk_off[hb_begin + h]  = byte offset in hits.data of the term's h-th 128-hit block; entry nfull = the varbyte tail, entry nfull + 1 = its end.
+struct HitsDirectory {
+        std::vector<uint32_t> hit_base, hblk_off;
+        std::vector<uint32_t> hb_begin, sum_hits; // per term
+        uint64_t              bytes() const {
+                return (hit_base.size() + hblk_off.size() + hb_begin.size() + sum_hits.size()) * 4ull;
+        }
+};
+// throws std::runtime_error on malformed chunks / hit streams
+void build_hits_directory(const uint8_t *index, uint64_t nbytes, const uint8_t *hits, uint64_t hbytes, const term_index_ctx *terms, uint32_t nterms,
+                          const BlockDirectory &dir, int threads, HitsDirectory &out);
+
 // throws std::runtime_error on malformed chunks
 void build_block_directory(Codec codec, const uint8_t *index, uint64_t nbytes, const term_index_ctx *terms, uint32_t nterms, int threads, BlockDirectory &out);
 

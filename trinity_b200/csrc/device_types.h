@@ -4,6 +4,8 @@
 
 namespace trn {
 
+struct HitTerm;
+
 static constexpr uint32_t kEmptyTerm = 0xffffffffu;
 
 // one per dictionary term (36 B)
@@ -35,6 +37,11 @@ struct DevIndex {
         uint32_t        max_docid;
         uint32_t        block_docs; // documents per full block (GOOGLE: google_codec.h:18 N = 32 — other values only for the decode sweep; LUCENE: 128)
         int             codec;
+        // LUCENE positions (trn_upload_hits; null otherwise): hits.data and its load-time directory (codecs.h HitsDirectory)
+        const uint8_t * hits;
+        const uint32_t *hit_base; // parallel to blk_last: hits of the term's documents before the block
+        const uint32_t *hblk_off; // per term: byte offsets of its 128-hit blocks in hits.data, then of its varbyte tail, then the end
+        const struct HitTerm *hit_term; // per term: {first entry in hblk_off, sumHits} (hitcursor.h)
 };
 
 // ---- per-query step program (built on the host from the trn_qnode tree) ----

@@ -8,6 +8,7 @@
 #include "../../include/trinity_b200.h"
 #include "codecs.h"
 #include "device_types.h"
+#include "hitcursor.h"
 #include "kernels.h"
 #include <algorithm>
 #include <array>
@@ -109,6 +110,10 @@ struct trn_ctx {
         DevBuf d_queries, d_steps, d_small[2], d_item_off, d_item_cnt, d_item_dst, d_seg_docids, d_seg_scores, d_out_docids[2], d_out_scores[2], d_q_offsets[2], d_cand,
             d_topk_docids, d_topk_scores, d_topk_counts, d_fq, d_leaves, d_luts, d_dec_units, d_dec_a, d_dec_b, d_dec_c, d_dec_docids, d_dec_freqs, d_dec_sums, d_merge_docids, d_merge_scores;
         PinBuf h_offsets, h_docids, h_scores, h_counts, h_small, h_chunk, h_item_desc;
+        DevBuf d_hits, d_hit_base, d_hblk_off, d_hit_term; // LUCENE positions (trn_upload_hits)
+        bool   have_hits{false};
+        BlockDirectory              h_dir;     // LUCENE: kept for trn_upload_hits (the hits directory is laid out like the block directory)
+        std::vector<term_index_ctx> h_termctx; // ...
         DevBuf d_item_desc[2];                 // compact results: per work item, matches | encoding << 30 (double-buffered like the outputs)
         std::vector<trn_qitems> qitems_set[2]; // compact results: the per-query item ranges of the last exec_device_impl call of each set
         std::vector<trn_qitems> h_qitems;      // ... of the whole batch, item_base rebased (what trn_result::qitems points to)
@@ -594,7 +599,7 @@ struct Compiler {
                                 }
                         } else if (n[i].kind == TRN_NODE_PHRASE) {
                                 if (!allow_phrase) {
-                                        err         = "phrase nodes need the positions path (materialize_hits): executed on the GOOGLE codec's inline hits only (LUCENE hits.data: not yet)";
+                                        err         = "phrase nodes need the positions (materialize_hits): a LUCENE source executes them once its hits.data has been uploaded (trn_upload_hits)";
                                         unsupported = true;
                                         return false;
                                 }
@@ -916,9 +921,72 @@ extern "C" int trn_upload_index(trn_ctx *c, int codec, const uint8_t *index, uin
         c->index_bytes = nbytes;
         c->dir_bytes   = dir.bytes();
         c->have_index  = true;
+        c->have_hits   = false; // positions belong to the index they were uploaded for
+        c->h_dir       = BlockDirectory{};
+        c->h_termctx.clear();
+        if (codec == TRN_CODEC_LUCENE) {
+                try {
+                        c->h_termctx.resize(nterms);
+                        for (uint32_t i = 0; i < nterms; ++i) {
+                                c->h_termctx[i].documents = terms[i].documents;
+                                c->h_termctx[i].offset    = terms[i].chunk_off;
+                                c->h_termctx[i].size      = terms[i].chunk_len;
+                        }
+                        dir.tile_first.clear();
+                        dir.tile_first.shrink_to_fit();
+                        c->h_dir = std::move(dir);
+                } catch (const std::bad_alloc &) {
+                        c->h_termctx.clear(); // trn_upload_hits will say so
+                }
+        }
         // the masked-documents bitmap belongs to the index it was set for (its size follows that index's max_docid): a new upload
         // starts with an empty registry, callers set it again (trn_set_masked_documents)
         c->have_masked = false;
+        return TRN_OK;
+}
+
+// LUCENE positions: hits.data of the uploaded index (lucene_codec.cpp:401-513).  `index` = the bytes trn_upload_index received (they are
+// read again on the host: the freqs give every block's first hit number); without this call phrase plans on a LUCENE source are refused.
+extern "C" int trn_upload_hits(trn_ctx *c, const uint8_t *index, uint64_t nbytes, const uint8_t *hits, uint64_t hbytes) {
+        if (!c || !index || (!hits && hbytes))
+                return c ? fail(c, TRN_ERR_ARG, "trn_upload_hits: bad arguments") : TRN_ERR_ARG;
+        if (!c->have_index)
+                return fail(c, TRN_ERR_STATE, "no index uploaded");
+        if (c->codec != TRN_CODEC_LUCENE)
+                return fail(c, TRN_ERR_ARG, "trn_upload_hits: the GOOGLE codec keeps its hits inline (nothing to upload)");
+        if (nbytes != c->index_bytes || c->h_termctx.size() != c->nterms)
+                return fail(c, TRN_ERR_ARG, "trn_upload_hits: not the index this context holds");
+        if (hbytes >= (1ull << 32))
+                return fail(c, TRN_ERR_ARG, "hits.data larger than 4 GiB");
+        CK(cudaSetDevice(c->device));
+        HitsDirectory hd;
+        try {
+                const int threads = int(std::max(1u, std::min(64u, std::thread::hardware_concurrency())));
+                build_hits_directory(index, nbytes, hits, hbytes, c->h_termctx.data(), c->nterms, c->h_dir, threads, hd);
+        } catch (const std::bad_alloc &) {
+                return fail(c, TRN_ERR_CAPACITY, "trn_upload_hits: out of host memory");
+        } catch (const std::exception &e) {
+                return fail(c, TRN_ERR_FORMAT, e.what());
+        }
+        std::vector<HitTerm> ht(c->nterms);
+        for (uint32_t i = 0; i < c->nterms; ++i)
+                ht[i] = HitTerm{hd.hb_begin[i], hd.sum_hits[i]};
+        c->have_hits = false;
+        CK(c->d_hits.ensure(hbytes + 256));
+        CK(cudaMemsetAsync(c->d_hits.p, 0, hbytes + 256, c->stream));
+        if (hbytes)
+                CK(cudaMemcpyAsync(c->d_hits.p, hits, hbytes, cudaMemcpyHostToDevice, c->stream));
+        CK(c->d_hit_base.ensure(std::max<size_t>(4, hd.hit_base.size() * 4)));
+        CK(c->d_hblk_off.ensure(std::max<size_t>(4, hd.hblk_off.size() * 4)));
+        CK(c->d_hit_term.ensure(std::max<size_t>(8, ht.size() * 8)));
+        if (!hd.hit_base.empty())
+                CK(cudaMemcpyAsync(c->d_hit_base.p, hd.hit_base.data(), hd.hit_base.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        if (!hd.hblk_off.empty())
+                CK(cudaMemcpyAsync(c->d_hblk_off.p, hd.hblk_off.data(), hd.hblk_off.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        if (!ht.empty())
+                CK(cudaMemcpyAsync(c->d_hit_term.p, ht.data(), ht.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->have_hits = true;
         return TRN_OK;
 }
 
@@ -983,6 +1051,10 @@ static DevIndex dev_index(trn_ctx *c) {
         ix.max_docid  = c->max_docid;
         ix.block_docs = c->block_docs;
         ix.codec      = c->codec;
+        ix.hits       = c->have_hits ? c->d_hits.as<uint8_t>() : nullptr;
+        ix.hit_base   = c->have_hits ? c->d_hit_base.as<uint32_t>() : nullptr;
+        ix.hblk_off   = c->have_hits ? c->d_hblk_off.as<uint32_t>() : nullptr;
+        ix.hit_term   = c->have_hits ? c->d_hit_term.as<HitTerm>() : nullptr;
         return ix;
 }
 
@@ -1624,7 +1696,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                 if (!Q.nodes || !Q.nnodes)
                         return fail(c, TRN_ERR_ARG, "empty query");
                 Compiler cc(Q.nodes, Q.nnodes, c->h_terms, scored, Q.root, steps);
-                cc.allow_phrase = c->codec == TRN_CODEC_GOOGLE;
+                cc.allow_phrase = c->codec == TRN_CODEC_GOOGLE || c->have_hits; // GOOGLE: inline hits; LUCENE: hits.data uploaded (trn_upload_hits)
                 auto &   dq     = hq[q];
                 dq.step_begin   = uint32_t(steps.size());
                 const int rs    = cc.run();

@@ -15,6 +15,7 @@
 //   k_decode_terms whole-list decode (microbench + parity probe) == PostingsListIterator::next() over a list.
 #include "device_types.h"
 #include "dirlookup.h"
+#include "hitcursor.h"
 #include "kernels.h"
 #include "varbyte.h"
 #include <algorithm>

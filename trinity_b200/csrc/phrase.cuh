@@ -13,10 +13,7 @@
 // verdicts of up to 64 positions of t0 travel in a bit mask; documents with more hits of t0 are handled in chunks of 64.
 #pragma once
 
-struct PhraseTerm { // a term of the phrase as the cursor needs it
-        uint32_t dir, nb, docs, first, last, tfb, tfbase, tfs;
-};
-
+// (the cursors themselves: hitcursor.h, shared with the host and included by kernels.cu ahead of namespace trn)
 __device__ __forceinline__ PhraseTerm phrase_term(const DevIndex &ix, uint32_t term) {
         PhraseTerm    t;
         const DevTerm T = ix.terms[term];
@@ -28,6 +25,7 @@ __device__ __forceinline__ PhraseTerm phrase_term(const DevIndex &ix, uint32_t t
         t.tfb    = T.tf_begin;
         t.tfbase = T.tf_base;
         t.tfs    = T.tf_shift;
+        t.id     = term;
         return t;
 }
 
@@ -41,75 +39,26 @@ __device__ __forceinline__ uint32_t phrase_arg(const DevStep *args, uint32_t j) 
         return s == 2u ? uint32_t(w) : uint32_t(w >> 32);
 }
 
-// the hits of ONE document of one term: positions are cumulative deltas, a hit = varbyte((delta << 1) | payloadSizeChanged) [u8 size] payload
-struct HitCursor {
-        const uint8_t *p;
-        uint32_t       left; // hits not yet read
-        uint32_t       pos;
-        uint32_t       psize; // current payload size (restarts at 0 for every document)
-        __device__ __forceinline__ uint32_t next() {
-                const uint32_t step = varbyte_get(p);
-                if (step & 1u)
-                        psize = *p++;
-                pos += step >> 1;
-                p += psize;
-                --left;
-                return pos;
-        }
-};
 
-// cursor on the hits of document d of the term (left == 0: the term does not hold d)
-__device__ HitCursor hit_cursor_google(const DevIndex &ix, const PhraseTerm &t, uint32_t d) {
-        HitCursor c;
-        c.p    = nullptr;
-        c.left = c.pos = c.psize = 0;
-        if (!t.nb || d < t.first || d > t.last)
-                return c;
-        const uint32_t b = dir_first_block_ge(ix.blk_last + t.dir, ix.tile_first + t.tfb, t.nb, t.first, t.last, t.tfbase, t.tfs, d);
-        if (b >= t.nb)
-                return c;
-        const uint32_t last = __ldg(ix.blk_last + t.dir + b), prev = b ? __ldg(ix.blk_last + t.dir + b - 1u) : 0u;
-        const uint32_t n    = (b + 1u == t.nb) ? (t.docs - 32u * (t.nb - 1u)) : 32u;
-        const uint8_t *p    = ix.index + __ldg(ix.blk_off + t.dir + b); // first doc-delta byte
-        // doc deltas: all n-1 of them (the freqs start behind them); the block's last document comes from the directory
-        uint32_t idx = 0xffffffffu, doc = prev;
-        for (uint32_t i = 0; i + 1u < n; ++i) {
-                doc += varbyte_get(p);
-                if (doc == d)
-                        idx = i;
-        }
-        if (last == d)
-                idx = n - 1u;
-        if (idx == 0xffffffffu)
-                return c;
-        // freqs: the document's own, and (through a second pointer into the same section) those of the documents before it
-        const uint8_t *pf   = p;
-        uint32_t       mine = 0;
-        for (uint32_t i = 0; i < n; ++i) {
-                const uint32_t f = varbyte_get(p);
-                if (i == idx)
-                        mine = f;
-        }
-        // p is at the block's hits now: skip the hits of the documents before ours
-        for (uint32_t i = 0; i < idx; ++i) {
-                const uint32_t f = varbyte_get(pf);
-                uint32_t       ps = 0;
-                for (uint32_t h = 0; h < f; ++h) {
-                        const uint32_t step = varbyte_get(p);
-                        if (step & 1u)
-                                ps = *p++;
-                        p += ps;
-                }
-        }
-        c.p    = p;
-        c.left = mine & 0xffffu; // freq is uint16_t in the reference (codecs.h:217)
-        return c;
+__device__ __forceinline__ HitsView hits_view(const DevIndex &ix) {
+        HitsView v;
+        v.index      = ix.index;
+        v.blk_last   = ix.blk_last;
+        v.blk_off    = ix.blk_off;
+        v.tile_first = ix.tile_first;
+        v.hits       = ix.hits;
+        v.hit_base   = ix.hit_base;
+        v.hblk_off   = ix.hblk_off;
+        v.hit_term   = ix.hit_term;
+        v.codec      = ix.codec;
+        return v;
 }
 
 // number of non-zero positions q of t0 in document d with t(j) at q + j for all j < k (0: d does not hold the phrase)
 __device__ uint32_t phrase_match_count(const DevIndex &ix, const DevStep *args, uint32_t k, uint32_t d) {
         const PhraseTerm t0 = phrase_term(ix, phrase_arg(args, 0));
-        HitCursor        c0 = hit_cursor_google(ix, t0, d);
+        const HitsView   hv = hits_view(ix);
+        HitCursor        c0 = hit_cursor(hv, t0, d);
         uint32_t         total = 0;
         while (c0.left) { // chunks of 64 positions of t0
                 const uint32_t     nchunk = min(64u, c0.left);
@@ -117,7 +66,12 @@ __device__ uint32_t phrase_match_count(const DevIndex &ix, const DevStep *args, 
                 for (uint32_t j = 1; j < k && alive; ++j) {
                         const uint32_t tj = phrase_arg(args, j);
                         HitCursor      a  = c0;
-                        HitCursor      b  = tj == 0xffffffffu ? HitCursor{nullptr, 0, 0, 0} : hit_cursor_google(ix, phrase_term(ix, tj), d);
+                        HitCursor      b;
+                        if (tj == 0xffffffffu) {
+                                b.p    = nullptr;
+                                b.left = b.pos = b.psize = b.mode = 0;
+                        } else
+                                b = hit_cursor(hv, phrase_term(ix, tj), d);
                         unsigned long long ok = 0;
                         uint32_t           pb = 0;
                         bool               have = false;
