@@ -5,6 +5,9 @@ from pathlib import Path
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
+# the host-buffer pipeline sizes its chunks by the postings a batch references (engine.cu: chunk_postings); the test indexes are tiny, so
+# without this every batch would take the single-call form and the chunked path would go untested
+os.environ.setdefault("TRN_CHUNK_POSTINGS", "1")
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 

@@ -180,4 +180,23 @@ struct ExecParams {
         uint32_t *          overflow;     // set to 1 if seg_capacity was exceeded
 };
 
+// device-side GOOGLE encoder (encode_google.cuh)
+struct EncParams {
+        const unsigned long long *term_begin; // nterms + 1: first posting of every term in docids[] / freqs[]
+        const unsigned long long *blk_begin;  // nterms + 1: first block of every term in the flat block numbering
+        uint32_t                  nterms;
+        uint64_t                  nblocks;
+        const uint32_t *          docids;
+        const uint32_t *          freqs;
+        const uint32_t *          positions; // every document's hits, concatenated in posting order; nullptr: positions 1..freq (what the synthetic builders write without hits)
+        const unsigned long long *hit_begin; // exclusive scan of freqs (with positions)
+        uint32_t                  block_docs, skiplist_step, phase0; // phase0: blocks committed so far by the session, modulo skiplist_step
+        uint32_t *                bsz;       // bytes of every block (header included)
+        uint32_t *                bterm;     // term of every block
+        const unsigned long long *boff;      // exclusive scan of bsz
+        const unsigned long long *term_off;  // nterms + 1: chunk offsets in out[]
+        uint8_t *                 out;
+        uint32_t *                error;     // != 0: an input the reference encoder throws on (docIDs not ascending / 0, positions decreasing or 0)
+};
+
 } // namespace trn

@@ -124,6 +124,7 @@ struct trn_ctx {
         // pipelined host-buffer path (trn_exec_batch): kernels of chunk i+1 overlap the D2H of chunk i
         cudaStream_t copy_stream{nullptr};
         cudaEvent_t  ev_done[2]{nullptr, nullptr}, ev_d2h[2]{nullptr, nullptr}, ev_ck0[16]{}, ev_ck1[16]{};
+        uint64_t     chunk_postings{1000000000ull}; // TRN_CHUNK_POSTINGS: referenced postings a pipeline chunk must carry (~1.1 ms of k_exec_docs)
         uint32_t     pipeline_chunks{8}; // TRN_PIPELINE_CHUNKS (profiles/r02_n: 4 -> 38.4K, 6 -> 40.1K, 8 -> 40.7K, 12 -> 40.1K q/s end to end on the headline batch)
         uint32_t     last_items{0}; // work items of the last exec_device_impl call (compact results: entries of item_desc)
         uint64_t     last_total_hint{0};
@@ -792,6 +793,11 @@ extern "C" int trn_create(int device, trn_ctx **out) {
                 const int v = atoi(e);
                 if (v >= 1 && v <= 16)
                         c->pipeline_chunks = uint32_t(v);
+        }
+        if (const char *e = getenv("TRN_CHUNK_POSTINGS")) {
+                const long long v = atoll(e);
+                if (v >= 1)
+                        c->chunk_postings = uint64_t(v);
         }
         CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
@@ -2258,6 +2264,17 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                 return TRN_ERR_ARG;
         uint32_t nchunks = c->pipeline_chunks;
         const bool compact = mode == TRN_MODE_DOCS_COMPACT;
+        if (nchunks > 1 && queries && c->have_index) {
+                // a chunk must be worth its launch tails: on a small shard (docID-sharded runs) the whole batch is a few ms of kernel time and 8
+                // chunks of it are mostly tails (profiles/r02_h: 4.4 ms in 8 launches vs 2.75 ms in one at N=8) -> as many chunks as the
+                // referenced postings pay for, at chunk_postings each
+                uint64_t est{0};
+                for (uint32_t q = 0; q < nq; ++q)
+                        for (uint32_t i = 0; i < queries[q].nnodes && queries[q].nodes; ++i)
+                                if (queries[q].nodes[i].kind == TRN_NODE_TERM && queries[q].nodes[i].term < c->nterms)
+                                        est += c->h_terms[queries[q].nodes[i].term].documents;
+                nchunks = uint32_t(std::min<uint64_t>(nchunks, std::max<uint64_t>(1, est / c->chunk_postings)));
+        }
         if (mode == TRN_MODE_SCORED_TOPK || nq < 8 * nchunks || nchunks <= 1) {
                 const double t0 = now_ms();
                 const int    r  = trn_exec_batch_device(c, queries, nq, mode, k, nullptr);
@@ -2470,6 +2487,136 @@ extern "C" int trn_merge_topk(trn_ctx *c, const void *docids, const void *scores
         CK(cudaSetDevice(c->device));
         CK(launch_topk_merge(static_cast<const uint32_t *>(docids), static_cast<const float *>(scores), nshards, nq, k, static_cast<uint32_t *>(out_docids),
                              static_cast<float *>(out_scores), c->stream));
+        return TRN_OK;
+}
+
+// =================================================================================================== device-side encoder (GOOGLE)
+extern "C" int trn_encode_google(trn_ctx *c, const uint64_t *term_begin, uint32_t nterms, const uint32_t *docids, const uint32_t *freqs, const uint32_t *positions,
+                                 uint32_t block_docs, uint32_t skiplist_step, uint32_t *countdown, uint8_t *out, uint64_t cap, uint64_t *out_bytes, trn_term *terms,
+                                 float *device_ms) {
+        if (!c)
+                return TRN_ERR_ARG;
+        if (!term_begin || !nterms || !out_bytes || !terms || block_docs == 0 || block_docs > 128 || skiplist_step == 0 ||
+            (countdown && (*countdown == 0 || *countdown > skiplist_step)))
+                return fail(c, TRN_ERR_ARG, "trn_encode_google: bad arguments");
+        const uint64_t nposts = term_begin[nterms];
+        if (term_begin[0] != 0 || (nposts && (!docids || !freqs)))
+                return fail(c, TRN_ERR_ARG, "trn_encode_google: bad arguments");
+        CK(cudaSetDevice(c->device));
+        std::vector<uint64_t> blk_begin(nterms + 1);
+        uint64_t              nblocks{0};
+        for (uint32_t t = 0; t < nterms; ++t) {
+                if (term_begin[t + 1] < term_begin[t] || term_begin[t + 1] - term_begin[t] > 0xffffffffull)
+                        return fail(c, TRN_ERR_ARG, "trn_encode_google: term_begin must ascend (at most 2^32 - 1 documents per term)");
+                blk_begin[t] = nblocks;
+                nblocks += (term_begin[t + 1] - term_begin[t] + block_docs - 1) / block_docs;
+        }
+        blk_begin[nterms] = nblocks;
+        uint64_t nhits{0};
+        if (positions)
+                for (uint64_t i = 0; i < nposts; ++i)
+                        nhits += freqs[i];
+        const uint32_t phase0 = countdown ? (skiplist_step - *countdown) % skiplist_step : 0u;
+        DevBuf d_tb, d_bb, d_doc, d_fr, d_pos, d_hb, d_bsz, d_bterm, d_boff, d_part, d_toff, d_cb, d_out, d_err;
+        struct Free {
+                std::vector<DevBuf *> v;
+                ~Free() {
+                        for (auto b : v)
+                                b->release();
+                }
+        } fr{{&d_tb, &d_bb, &d_doc, &d_fr, &d_pos, &d_hb, &d_bsz, &d_bterm, &d_boff, &d_part, &d_toff, &d_cb, &d_out, &d_err}};
+        const size_t parts = size_t(std::max(nposts, nblocks) / 4096 + 4);
+        CK(d_tb.ensure((size_t(nterms) + 1) * 8));
+        CK(d_bb.ensure((size_t(nterms) + 1) * 8));
+        CK(d_doc.ensure(std::max<size_t>(4, nposts * 4)));
+        CK(d_fr.ensure(std::max<size_t>(4, nposts * 4)));
+        CK(d_bsz.ensure(std::max<size_t>(4, nblocks * 4)));
+        CK(d_bterm.ensure(std::max<size_t>(4, nblocks * 4)));
+        CK(d_boff.ensure((nblocks + 1) * 8));
+        CK(d_part.ensure(parts * 8));
+        CK(d_toff.ensure((size_t(nterms) + 1) * 8));
+        CK(d_cb.ensure(size_t(nterms) * 8));
+        CK(d_err.ensure(4));
+        CK(cudaMemcpyAsync(d_tb.p, term_begin, (size_t(nterms) + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(d_bb.p, blk_begin.data(), (size_t(nterms) + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        if (nposts) {
+                CK(cudaMemcpyAsync(d_doc.p, docids, nposts * 4, cudaMemcpyHostToDevice, c->stream));
+                CK(cudaMemcpyAsync(d_fr.p, freqs, nposts * 4, cudaMemcpyHostToDevice, c->stream));
+        }
+        if (positions) {
+                CK(d_pos.ensure(std::max<size_t>(4, nhits * 4)));
+                CK(d_hb.ensure((nposts + 1) * 8));
+                if (nhits)
+                        CK(cudaMemcpyAsync(d_pos.p, positions, nhits * 4, cudaMemcpyHostToDevice, c->stream));
+        }
+        CK(cudaMemsetAsync(d_err.p, 0, 4, c->stream));
+        EncParams E{};
+        E.term_begin    = d_tb.as<unsigned long long>();
+        E.blk_begin     = d_bb.as<unsigned long long>();
+        E.nterms        = nterms;
+        E.nblocks       = nblocks;
+        E.docids        = d_doc.as<uint32_t>();
+        E.freqs         = d_fr.as<uint32_t>();
+        E.positions     = positions ? d_pos.as<uint32_t>() : nullptr;
+        E.hit_begin     = positions ? d_hb.as<unsigned long long>() : nullptr;
+        E.block_docs    = block_docs;
+        E.skiplist_step = skiplist_step;
+        E.phase0        = phase0;
+        E.bsz           = d_bsz.as<uint32_t>();
+        E.bterm         = d_bterm.as<uint32_t>();
+        E.boff          = d_boff.as<unsigned long long>();
+        E.term_off      = d_toff.as<unsigned long long>();
+        E.error         = d_err.as<uint32_t>();
+        cudaEvent_t e0 = c->ev0, e1 = c->ev1, e2 = c->evk0, e3 = c->evk1;
+        CK(cudaEventRecord(e0, c->stream));
+        if (positions)
+                CK(launch_enc_scan(d_fr.as<uint32_t>(), nposts, d_part.as<unsigned long long>(), d_hb.as<unsigned long long>(), c->stream));
+        CK(launch_enc_google_sizes(E, c->stream));
+        CK(launch_enc_scan(d_bsz.as<uint32_t>(), nblocks, d_part.as<unsigned long long>(), d_boff.as<unsigned long long>(), c->stream));
+        CK(launch_enc_term_sizes(E, d_cb.as<unsigned long long>(), c->stream));
+        CK(cudaEventRecord(e1, c->stream));
+        // chunk offsets: a prefix sum over the terms on the host (the output size must be known here anyway)
+        std::vector<uint64_t> chunk(nterms), toff(nterms + 1);
+        uint32_t              herr{0};
+        CK(cudaMemcpyAsync(chunk.data(), d_cb.p, size_t(nterms) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(&herr, d_err.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (herr)
+                return fail(c, TRN_ERR_ARG, "google encoder: document IDs must be > 0 and strictly ascending, positions > 0 and non-decreasing");
+        uint64_t total{0};
+        for (uint32_t t = 0; t < nterms; ++t) {
+                toff[t] = total;
+                total += chunk[t];
+        }
+        toff[nterms] = total;
+        *out_bytes   = total;
+        if (total >= (1ull << 32))
+                return fail(c, TRN_ERR_CAPACITY, "google encoder: the index of one source is limited to 4 GiB (range32_t, codecs.h:17-55)");
+        if (total > cap || !out)
+                return fail(c, TRN_ERR_CAPACITY, "trn_encode_google: output buffer too small");
+        CK(d_out.ensure(std::max<size_t>(4, total)));
+        E.out = d_out.as<uint8_t>();
+        CK(cudaMemcpyAsync(d_toff.p, toff.data(), (size_t(nterms) + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaEventRecord(e2, c->stream));
+        CK(cudaMemsetAsync(d_out.p, 0, std::max<size_t>(4, total), c->stream)); // a term without documents is its zero u16
+        CK(launch_enc_google_write(E, c->stream));
+        CK(cudaEventRecord(e3, c->stream));
+        CK(cudaMemcpyAsync(out, d_out.p, total, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (uint32_t t = 0; t < nterms; ++t) {
+                terms[t].documents = uint32_t(term_begin[t + 1] - term_begin[t]);
+                terms[t].chunk_off = uint32_t(toff[t]);
+                terms[t].chunk_len = uint32_t(chunk[t]);
+        }
+        if (countdown)
+                *countdown = skiplist_step - uint32_t((uint64_t(phase0) + nblocks) % skiplist_step);
+        if (device_ms) {
+                float a{0}, b{0};
+                CK(cudaEventElapsedTime(&a, e0, e1));
+                CK(cudaEventElapsedTime(&b, e2, e3));
+                *device_ms = a + b;
+        }
+        c->have_kernel_events = false;
         return TRN_OK;
 }
 

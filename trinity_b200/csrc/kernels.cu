@@ -1067,6 +1067,7 @@ __global__ void __launch_bounds__(kThreads) k_decode_terms(DevIndex ix, const ui
 
 #include "decode_google.cuh"
 #include "decode_stream.cuh"
+#include "encode_google.cuh"
 
 // ------------------------------------------------------------------------------------------------ launch wrappers
 uint32_t exec_stage_bytes(int codec) {

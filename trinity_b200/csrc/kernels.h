@@ -31,5 +31,9 @@ cudaError_t launch_build_luts(const FlatLeaf *leaves, uint32_t nleaves, float *l
 cudaError_t launch_score_flat(const ScoreParams &S, int threads, int num_sms, cudaStream_t stream);
 cudaError_t launch_decode_stream(const DevIndex &ix, const DecUnit *units, const uint64_t *out_base, uint32_t total_units, uint32_t *docids, uint32_t *freqs,
                                  unsigned long long *sums, int num_sms, cudaStream_t stream);
+cudaError_t launch_enc_scan(const uint32_t *in, uint64_t n, unsigned long long *partials, unsigned long long *out, cudaStream_t stream);
+cudaError_t launch_enc_google_sizes(const EncParams &E, cudaStream_t stream);
+cudaError_t launch_enc_term_sizes(const EncParams &E, unsigned long long *chunk_bytes, cudaStream_t stream);
+cudaError_t launch_enc_google_write(const EncParams &E, cudaStream_t stream);
 uint32_t    kernel_max_k();
 } // namespace trn
