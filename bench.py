@@ -422,7 +422,8 @@ class Job:
         peak, peak_src = measured_peak()
         kernel_name = "k_exec_docs" if mode == tb.MODE_DOCS_ONLY else ("k_score_flat" if codec == 1 else "k_exec_tiles")
         # the host-buffer path pipelines a set-query batch in chunks (TRN_PIPELINE_CHUNKS, default 4): one fused-kernel launch per chunk
-        nlaunch = 1 if mode == tb.MODE_SCORED_TOPK else min(int(os.environ.get("TRN_PIPELINE_CHUNKS", "8")), max(1, args.nq // 8))
+        # (as many as the referenced postings pay for, at most TRN_PIPELINE_CHUNKS = 8: the engine reports what it used)
+        nlaunch = max(1, int(round(float(np.mean([t.get("chunks", 1.0) for t in tms]))))) if tms else 1
         k_ms_step = float(np.mean(kern_ms)) if kern_ms else None          # all fused-kernel launches of one step
         k_ms = k_ms_step / nlaunch if k_ms_step else None                 # average duration of ONE launch
         traffic = ncu_traffic(f"{kernel_name}:{workload}") if (world == 1 and args.ndocs == 100_000_000 and args.nq == 1000) else None

@@ -291,6 +291,7 @@ typedef struct trn_timings {
         float final_wait_ms;   /* blocked at the end: last kernels + result D2H */
         float kernel_ms;       /* CUDA-event time of the fused exec kernels (device) */
         float total_ms;        /* the whole call */
+        float chunks;          /* pipelined call: chunks the batch was split into (sized by the postings it references); 1 = single call */
 } trn_timings;
 int trn_last_timings(trn_ctx *, trn_timings *out);
 
@@ -315,14 +316,14 @@ int trn_decode_terms(trn_ctx *, const uint32_t *term_ids, uint32_t nterms, int m
  * (SURVEY.md 8(f) row 4), byte for byte what the reference encoder writes for the same postings.  All pointers are HOST pointers:
  *   term_begin[nterms + 1]  first posting of every term in docids[] / freqs[] (term i holds [term_begin[i], term_begin[i+1]))
  *   docids[], freqs[]       ascending docIDs > 0 per term; freqs[i] = hits of posting i
- *   positions[]             the hits of all postings, concatenated in posting order (sum(freqs) entries, > 0, non-decreasing per document);
+ *   positions[]             the hits of all postings, concatenated in posting order (sum(freqs) entries, in 1..16383 = below Limits::MaxPosition, non-decreasing per document);
  *                           NULL = positions 1..freq (what an index built without positions carries)
  *   block_docs / skiplist_step  the two compile-time constants of the format (32 / 8 = the reference's; other values only for the
  *                           decode sweep, BASELINE.json configs[4]); *countdown (in/out, may be NULL = a fresh session) = the encoder
  *                           session's skiplistEntryCountdown, which carries over between terms (google_codec.h:57)
  *   out[cap]                receives the chunks of the terms back to back; *out_bytes their total (also when cap is too small:
  *                           TRN_ERR_CAPACITY, nothing written); terms[nterms] the term_index_ctx tuples
- * TRN_ERR_ARG: an input the reference encoder throws on (docID 0 / not ascending, a position 0 / decreasing).
+ * TRN_ERR_ARG: an input the reference encoder throws on (docID 0 / not ascending, a position 0 / decreasing / >= Limits::MaxPosition).
  * *device_ms (may be NULL): the device time of the encode (kernels and the two scans), without the host<->device copies. */
 int trn_encode_google(trn_ctx *, const uint64_t *term_begin, uint32_t nterms, const uint32_t *docids, const uint32_t *freqs, const uint32_t *positions,
                       uint32_t block_docs, uint32_t skiplist_step, uint32_t *countdown, uint8_t *out, uint64_t cap, uint64_t *out_bytes, trn_term *terms,

@@ -473,6 +473,27 @@ class GpuIndexSource:
                                           _ptr(f) if materialise else None, _ptr(sums), C.byref(ms)))
         return d, f, sums, float(ms.value)
 
+    def encode_google(self, lists, block_docs: int = 32, skiplist_step: int = 8, countdown: Optional[int] = None):
+        """GPU-side Encoder (== Codecs::Google::Encoder, google_codec.cpp:9-176): builds the GOOGLE index of `lists` on the device.
+        lists: one (docids, freqs[, positions]) per term — positions (all of them or none) = the hits of the term's postings, concatenated.
+        Returns (index bytes, terms array, countdown after the last term, device_ms)."""
+        lists = list(lists)
+        with_pos = len(lists) > 0 and len(lists[0]) > 2 and lists[0][2] is not None
+        tb = np.zeros(len(lists) + 1, np.uint64)
+        for i, l in enumerate(lists):
+            tb[i + 1] = tb[i] + len(l[0])
+        d = np.concatenate([_u32(l[0]) for l in lists]) if lists else np.zeros(0, np.uint32)
+        f = np.concatenate([_u32(l[1]) for l in lists]) if lists else np.zeros(0, np.uint32)
+        p = np.concatenate([_u32(l[2]) for l in lists]) if with_pos else None
+        terms = np.zeros(len(lists), dtype=TERM_DTYPE)
+        cd = C.c_uint32(countdown if countdown is not None else skiplist_step)
+        nbytes, ms = C.c_uint64(), C.c_float()
+        cap = 16 + 2 * len(lists) + int(d.size) * 11 + (int(f.sum()) * 5 if with_pos else int(f.sum())) + 8 * (int(d.size) // max(1, block_docs) + len(lists) + 1)
+        out = np.zeros(cap, np.uint8)
+        self._ck(self._L.trn_encode_google(self._h, _ptr(tb), len(lists), _ptr(d), _ptr(f), _ptr(p), block_docs, skiplist_step, C.byref(cd),
+                                           _ptr(out), cap, C.byref(nbytes), _ptr(terms), C.byref(ms)))
+        return out[:nbytes.value].copy(), terms, int(cd.value), float(ms.value)
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.trn_destroy(self._h)

@@ -184,7 +184,7 @@ template <bool WRITE> __global__ void __launch_bounds__(128) k_enc_google_blocks
                                 uint32_t       pp{0}, h{0};
                                 for (uint32_t k = 0; k < fr[q]; ++k) {
                                         const uint32_t pos = E.positions[hb + k];
-                                        bad |= pos == 0u || pos < pp;
+                                        bad |= pos == 0u || pos < pp || pos >= (1u << 14); // Limits::MaxPosition (trinity_limits.h:15; google_codec.cpp:47-49)
                                         h += vb_len_of((pos - pp) << 1);
                                         pp = pos;
                                 }

@@ -2284,6 +2284,7 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                 const int    fr = trn_fetch_results(c, out);
                 c->tm.final_wait_ms = float(now_ms() - tw);
                 c->tm.total_ms      = float(now_ms() - t0);
+                c->tm.chunks        = 1.f;
                 if (fr == TRN_OK)
                         c->tm.kernel_ms = out->exec_kernel_ms;
                 return fr;
@@ -2432,6 +2433,7 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
         }
         c->tm.total_ms     = float(now_ms() - tB0);
         c->tm.kernel_ms    = ksum;
+        c->tm.chunks       = float(ch.size());
         hoff[nq]           = running;
         c->last_total_hint = running + running / 16;
         std::memset(out, 0, sizeof(*out));
@@ -2582,7 +2584,7 @@ extern "C" int trn_encode_google(trn_ctx *c, const uint64_t *term_begin, uint32_
         CK(cudaMemcpyAsync(&herr, d_err.p, 4, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         if (herr)
-                return fail(c, TRN_ERR_ARG, "google encoder: document IDs must be > 0 and strictly ascending, positions > 0 and non-decreasing");
+                return fail(c, TRN_ERR_ARG, "google encoder: document IDs must be > 0 and strictly ascending, positions in 1..16383 and non-decreasing");
         uint64_t total{0};
         for (uint32_t t = 0; t < nterms; ++t) {
                 toff[t] = total;
