@@ -451,7 +451,7 @@ class Job:
             "matches_per_batch_rank0": matches_per_batch,
             "e2e": {"value": args.nq * K / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": plan_bytes, "d2h_bytes_per_step": d2h,
                     "decoded_postings_per_s": postings_per_batch * K / e2e_s, "per_rank_ms": per_rank,
-                    "result_encoding": ("compact (TRN_MODE_DOCS_COMPACT: per docID tile a bitmap / 16-bit offsets / docIDs, whichever is smallest; replayed on the host by trn_result_for_each)"
+                    "result_encoding": ("compact (TRN_MODE_DOCS_COMPACT: per docID tile a bitmap / bucketed 8-bit offsets / 16-bit offsets / docIDs, whichever is smallest; replayed on the host by trn_result_for_each)"
                                         if emode != mode else ("u32 docIDs" if mode == tb.MODE_DOCS_ONLY else "top-k (docID, score)")),
                     "matched_docids_per_step": matches_per_batch, "plain_u32": plain},
             "gpu_launches": launches,
@@ -520,7 +520,7 @@ def main():
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--cpu-sample", type=int, default=0, help="(reference arm) queries per step (0 = auto)")
     ap.add_argument("--result-encoding", default="compact", choices=["compact", "u32"],
-                    help="DocumentsOnly workloads: how the matched docIDs leave the device — TRN_MODE_DOCS_COMPACT (per tile: bitmap / 16-bit offsets / docIDs, "
+                    help="DocumentsOnly workloads: how the matched docIDs leave the device — TRN_MODE_DOCS_COMPACT (per tile: bitmap / bucketed 8-bit offsets / 16-bit offsets / docIDs, "
                          "replayed by trn_result_decode) or plain 32-bit docIDs (TRN_MODE_DOCS_ONLY)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")

@@ -251,7 +251,7 @@ namespace {
                 isrc_docid_t process(MatchesProxy *mp, const isrc_docid_t min, const isrc_docid_t max) override final {
                         trn_query  q{plan.data(), uint32_t(plan.size()), 0};
                         trn_result r;
-                        // DocumentsOnly: the compact result form (a docID tile's matches as bitmap / 16-bit offsets / docIDs) — what a batch
+                        // DocumentsOnly: the compact result form (a docID tile's matches as bitmap / bucketed 8-bit offsets / 16-bit offsets / docIDs) — what a batch
                         // of queries would use to keep the host link out of the way; replayed below by trn_result_for_each
                         if (trn_exec_batch(gap.ctx, &q, 1, scored ? TRN_MODE_SCORED_ALL : TRN_MODE_DOCS_COMPACT, 0, &r) != TRN_OK)
                                 throw Switch::system_error(trn_last_error(gap.ctx));

@@ -1,5 +1,6 @@
 """trn_result_for_each / trn_result_decode (the consider(docid_t) replay of a result, matches.h:149-171) over hand-built results in both
-forms: plain docIDs and the compact segments of TRN_MODE_DOCS_COMPACT (docIDs / 16-bit offsets / tile bitmaps).  No GPU involved."""
+forms: plain docIDs and the compact segments of TRN_MODE_DOCS_COMPACT (docIDs / 16-bit offsets / bucketed 8-bit offsets / tile bitmaps).
+No GPU involved."""
 import ctypes as C
 
 import numpy as np
@@ -8,7 +9,7 @@ import pytest
 import trinity_b200 as tb
 from trinity_b200._ffi import CONSIDER_FN, TrnResult, lib
 
-ENC_U32, ENC_U16, ENC_BITMAP = 0, 1, 2
+ENC_U32, ENC_U16, ENC_BITMAP, ENC_U8B = 0, 1, 2, 3
 
 
 def _compact(queries, shift):
@@ -31,6 +32,14 @@ def _compact(queries, shift):
                 if len(rel) & 1:
                     rel = np.append(rel, 0)
                 words += [int(rel[i]) | (int(rel[i + 1]) << 16) for i in range(0, len(rel), 2)]
+            elif enc == ENC_U8B:
+                rel = (ids - first).astype(np.uint32)
+                nbk = (1 << shift) >> 8
+                cnt = np.bincount(rel >> 8, minlength=nbk).astype(np.uint8)
+                assert np.bincount(rel >> 8, minlength=nbk).max() < 256
+                by = np.concatenate([cnt, (rel & 255).astype(np.uint8)])
+                by = np.concatenate([by, np.zeros((-len(by)) % 4, np.uint8)])
+                words += [int(x) for x in by.view(np.uint32)]
             else:
                 bm = np.zeros((1 << shift) // 32, np.uint32)
                 rel = ids - first
@@ -72,8 +81,10 @@ def test_compact_segments_replay_in_every_encoding():
     q1 = (0, [np.array([3, 9, 70000, 4000000000], np.uint32), np.array([4000000001], np.uint32)], [ENC_U32, ENC_U32])  # lead-block groups: any docIDs
     q2 = (0, [], [])
     q3 = (1 << 19, [tile(1 << 19, 33)], [ENC_U16])  # a tile high up in the docID space
-    r, keep = _compact([q0, q1, q2, q3], shift)
-    for q, (lo, items, _) in enumerate([q0, q1, q2, q3]):
+    # bucketed 8-bit offsets: buckets with 0, 1 and many documents, a count that is not a multiple of 4 (pad bytes), next to other forms
+    q4 = (40, [tile(40, 301), tile(41, 5), tile(42, 2000), tile(43, 64)], [ENC_U8B, ENC_U8B, ENC_BITMAP, ENC_U8B])
+    r, keep = _compact([q0, q1, q2, q3, q4], shift)
+    for q, (lo, items, _) in enumerate([q0, q1, q2, q3, q4]):
         want = np.concatenate([np.asarray(x, np.uint32) for x in items]) if items else np.zeros(0, np.uint32)
         rc, n, got = _decode(r, q, len(want) + 3)
         assert rc == 0 and n == len(want) and np.array_equal(got, want), q
@@ -108,5 +119,11 @@ def test_malformed_segments_are_reported():
     keep[3][1] += 1  # the query claims one word more than its segments hold
     assert _decode(r, 0, 8)[0] == -3
     keep[3][1] -= 1
-    keep[1][0] = 3 | (3 << 30)  # unknown encoding
+    # bucketed form whose count bytes do not add up to the item's documents
+    r, keep = _compact([(0, [np.array([1, 2, 300, 301, 302], np.uint32)], [ENC_U8B])], 12)
+    assert _decode(r, 0, 8)[0] == 0
+    by = keep[0].view(np.uint8)
+    by[1] += 1
+    assert _decode(r, 0, 8)[0] == -3
+    by[1] -= 2
     assert _decode(r, 0, 8)[0] == -3

@@ -16,7 +16,7 @@ from ._ffi import QNODE_DTYPE, TERM_DTYPE, TrnIndexInfo, TrnQuery, TrnResult, Tr
 
 CODEC_GOOGLE, CODEC_LUCENE = 0, 1
 MODE_DOCS_ONLY, MODE_SCORED_ALL, MODE_SCORED_TOPK = 0, 1, 2  # == ExecFlags::DocumentsOnly / AccumulatedScoreScheme (+ fused top-k sink)
-MODE_DOCS_COMPACT = 3  # DocumentsOnly, compact result segments (bitmap / 16-bit offsets / docIDs per tile): trn_result_decode replays them
+MODE_DOCS_COMPACT = 3  # DocumentsOnly, compact result segments (bitmap / bucketed 8-bit offsets / 16-bit offsets / docIDs per tile): trn_result_decode replays them
 NODE_TERM, NODE_AND, NODE_OR, NODE_NOT, NODE_OPTIONAL, NODE_SOME, NODE_PHRASE = 0, 1, 2, 3, 4, 5, 6
 EMPTY_TERM = 0xFFFFFFFF
 DOC_IDS_END = 0xFFFFFFFF  # DocIDsEND, common.h:43

@@ -59,7 +59,7 @@ enum StepOp : uint8_t {
 };
 enum StepMode : uint8_t { M_SET = 0, M_OR = 1, M_AND = 2, M_ANDNOT = 3, M_NONE = 4 };
 // encodings of a compact result segment (trn_result::item_desc bits 30-31 == TRN_ENC_*)
-static constexpr uint32_t kEncU32 = 0, kEncU16 = 1, kEncBitmap = 2;
+static constexpr uint32_t kEncU32 = 0, kEncU16 = 1, kEncBitmap = 2, kEncU8B = 3;
 
 enum StepFlags : uint8_t {
         F_SCORE          = 1,

@@ -735,19 +735,39 @@ template <bool PH, bool TREE> __global__ void __launch_bounds__(kDocsWarps * 32,
                         __syncwarp();
                 }
                 // ---- emission: ordered compaction of the root docset
-                uint32_t c = 0;
+                uint32_t c = 0, full = 0;
                 const uint32_t *root = slots + size_t(Q.root_slot) * NW;
-                if (!dead)
-                        for (uint32_t i = 0; i < wpl; ++i)
-                                c += __popc(root[lane * wpl + i]);
+                if (!dead) {
+                        uint32_t cb = 0; // documents of the current 256-docID bucket (8 words): 256 of them do not fit the bucketed form's count byte
+                        for (uint32_t i = 0; i < wpl; ++i) {
+                                const uint32_t pc = __popc(root[lane * wpl + i]);
+                                c += pc;
+                                cb += pc;
+                                if ((i & 7u) == 7u) {
+                                        full |= cb == 256u ? 1u : 0u;
+                                        cb = 0;
+                                }
+                        }
+                }
                 const uint32_t incl  = warp_incl_scan(c, lane);
                 const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
                 unsigned long long base = 0;
                 if (P.item_desc) {
-                        // ---- compact results: the tile's bitmap when more than 1 document in 16 matches, else 16-bit offsets from the tile's
-                        // first docID (a tile holds at most 2^16 documents), two per word
-                        const bool     bitmap = total * 2u > W / 8u || W > 65536u;
-                        const uint32_t words  = total ? (bitmap ? NW : (total + 1u) >> 1) : 0u;
+                        // ---- compact results, whichever form takes the fewest words (a tile holds at most 2^16 documents):
+                        //   bitmap   the tile's words                                                          dense tiles (> 1 document in 8)
+                        //   U8B      per 256-docID bucket a count byte, then one offset byte per document      1 in 8 .. 1 in 256
+                        //   U16      16-bit offsets from the tile's first docID, two per word                  sparse tiles
+                        const uint32_t nbk  = W >> 8;
+                        const bool     u8ok = wpl >= 8u && W <= 65536u && !__any_sync(0xffffffffu, full != 0u); // a lane owns whole buckets
+                        uint32_t       enc = kEncBitmap, words = NW;
+                        if (W <= 65536u) {
+                                if (((total + 1u) >> 1) < words)
+                                        enc = kEncU16, words = (total + 1u) >> 1;
+                                if (u8ok && ((nbk + total + 3u) >> 2) < words)
+                                        enc = kEncU8B, words = (nbk + total + 3u) >> 2;
+                        }
+                        if (!total)
+                                words = 0;
                         if (lane == 0) {
                                 if (total) {
                                         base = atomicAdd(P.seg_cursor, static_cast<unsigned long long>(words));
@@ -760,13 +780,33 @@ template <bool PH, bool TREE> __global__ void __launch_bounds__(kDocsWarps * 32,
                                 }
                                 P.item_off[item]  = base;
                                 P.item_cnt[item]  = base == ~0ull ? 0u : words;
-                                P.item_desc[item] = base == ~0ull ? 0u : (total | (bitmap ? kEncBitmap : kEncU16) << 30);
+                                P.item_desc[item] = base == ~0ull ? 0u : (total | enc << 30);
                         }
                         base = __shfl_sync(0xffffffffu, base, 0);
                         if (total && base != ~0ull) {
-                                if (bitmap) {
+                                if (enc == kEncBitmap) {
                                         for (uint32_t i = lane; i < NW; i += 32)
                                                 P.seg_docids[base + i] = root[i];
+                                } else if (enc == kEncU8B) {
+                                        uint8_t *o8  = reinterpret_cast<uint8_t *>(P.seg_docids + base);
+                                        uint32_t pos = nbk + (incl - c), cb = 0;
+                                        for (uint32_t i = 0; i < wpl; ++i) {
+                                                const uint32_t wi = lane * wpl + i;
+                                                uint32_t       w  = root[wi];
+                                                cb += __popc(w);
+                                                while (w) {
+                                                        const uint32_t bit = uint32_t(__ffs(int(w)) - 1);
+                                                        w &= w - 1;
+                                                        o8[pos++] = uint8_t((wi & 7u) * 32u + bit);
+                                                }
+                                                if ((i & 7u) == 7u) {
+                                                        o8[wi >> 3] = uint8_t(cb);
+                                                        cb          = 0;
+                                                }
+                                        }
+                                        if (lane == 31)
+                                                for (uint32_t z = nbk + total; z < words * 4u; ++z)
+                                                        o8[z] = 0; // the pad bytes travel too
                                 } else {
                                         uint16_t *out = reinterpret_cast<uint16_t *>(P.seg_docids + base);
                                         uint32_t  pos = incl - c;

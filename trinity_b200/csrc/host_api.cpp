@@ -1023,8 +1023,23 @@ template <class F> static int replay_query(const trn_result *r, uint32_t q, F &&
                                 }
                         }
                         w += nw;
-                } else
-                        return TRN_ERR_FORMAT;
+                } else { // TRN_ENC_U8B
+                        const uint32_t nbk = (1u << Q.tile_shift) >> 8, nwords = (nbk + n + 3u) >> 2;
+                        if (!nbk || w + nwords > r->words + r->offsets[q + 1])
+                                return TRN_ERR_FORMAT;
+                        const uint8_t *cnt = reinterpret_cast<const uint8_t *>(w), *off = cnt + nbk;
+                        uint32_t       k{0};
+                        for (uint32_t b = 0; b < nbk; ++b) {
+                                if (k + cnt[b] > n)
+                                        return TRN_ERR_FORMAT;
+                                for (uint32_t i = 0; i < cnt[b]; ++i)
+                                        if (f(base + 256u * b + off[k++]))
+                                                return TRN_OK;
+                        }
+                        if (k != n)
+                                return TRN_ERR_FORMAT; // the buckets must add up to the item's documents
+                        w += nwords;
+                }
         }
         return w == r->words + r->offsets[q + 1] ? TRN_OK : TRN_ERR_FORMAT; // the segments must add up to the query's words
 }
