@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — the BASELINE.json metric: queries/sec (+ decoded-postings/sec) on the synthetic Zipfian index.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload and2|or10|tree8] [--sub or10,tree8|none]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload and2|or10|tree8|and2l] [--sub or10,tree8,and2l|none]
 
 One "step" = one pass of the hot path over one batch of synthetic queries.  Default workload (BASELINE.json configs[1]): a batch of
 1000 2-term AND queries on the 100M-doc Zipfian synthetic index, GOOGLE codec, DocumentsOnly.  The same run also measures configs[2]
@@ -40,6 +40,7 @@ WORKLOADS = {
     "and2": dict(codec=0, mode=0, desc="1000 x 2-term AND, DocumentsOnly, GOOGLE codec"),
     "or10": dict(codec=1, mode=2, desc="10-term OR, BM25 top-100, LUCENE codec"),
     "tree8": dict(codec=0, mode=0, desc="8-term mixed AND/OR/NOT trees, DocumentsOnly, GOOGLE codec"),
+    "and2l": dict(codec=1, mode=0, desc="1000 x 2-term AND, DocumentsOnly, LUCENE codec (the headline batch on the other postings format)"),
 }
 BYTES_PER_POSTING = {0: 4.54, 1: 1.95}  # measured on the synthetic index (with positions): GOOGLE inline hits / LUCENE index file only
 
@@ -52,7 +53,7 @@ def gen_queries(workload: str, nq: int, nterms: int, seed: int = 0xC0FFEE):
     names = [f"t{r:04d}" for r in range(1, nterms + 1)]
     out, ranks = [], []
     for _ in range(nq):
-        if workload == "and2":
+        if workload in ("and2", "and2l"):
             t = rng.choice(nterms, size=2, replace=False, p=w)
             out.append(f"{names[t[0]]} AND {names[t[1]]}")
         elif workload == "or10":
@@ -513,7 +514,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="and2", choices=list(WORKLOADS))
-    ap.add_argument("--sub", default="auto", help="workloads measured besides the primary one at a reduced step count: 'or10,tree8', 'none', 'auto' (= or10,tree8 for the default primary at full size)")
+    ap.add_argument("--sub", default="auto", help="workloads measured besides the primary one at a reduced step count: 'or10,tree8,and2l', 'none', 'auto' (= all three for the default primary)")
     ap.add_argument("--ndocs", type=int, default=100_000_000)
     ap.add_argument("--nterms", type=int, default=4096)
     ap.add_argument("--nq", type=int, default=1000)
@@ -538,7 +539,7 @@ def main():
     line["numa"] = job.numa
     subs = []
     if args.sub == "auto":
-        subs = [w for w in ("or10", "tree8") if w != args.workload] if args.workload == "and2" else []
+        subs = [w for w in ("or10", "tree8", "and2l") if w != args.workload] if args.workload == "and2" else []
     elif args.sub != "none":
         subs = [w for w in args.sub.split(",") if w in WORKLOADS and w != args.workload]
     if subs:
