@@ -1,12 +1,8 @@
 """k_score_flat (scored flat disjunctions on the LUCENE codec: DocsSetSpanForDisjunctionsWithThreshold + Scorer::score + the top-k sink,
-docset_spans.cpp:681-790, similarity.h:228-235) in BOTH accumulation forms against the reference's exec_query:
-  * fixed point (u32 multiples of 2^-shift, native shared-memory adds) — the default when every flat query of the batch qualifies,
-  * fp32 with compare-and-swap loops — TRN_SF_FIXED=0, and automatically when a query does not qualify (a term that every document
-    holds has an idf ~1e-6: the weights' ratio exceeds what 31 bits resolve within a fifth of the 1e-5 tolerance),
-on postings with freq 0 (Scorer::score(0) == 0: the document matches with score +0 — the fixed-point form keeps those in a bitmap of
-their own), freq >= 64 (outside the per-term table), tail blocks, documents matched by every term and by one."""
-import os
-
+docset_spans.cpp:681-790, similarity.h:228-235) against the reference's exec_query on postings with freq 0 (Scorer::score(0) == 0: the
+document matches with score +0, which the -0.0f "untouched" sentinel of the score tile must tell apart), freq >= 64 (outside the per-term
+table), tail blocks, single terms, documents matched by every term and by one, sparse-only disjunctions (most tiles see no posting), and
+weights twelve orders of magnitude apart (a term that every document holds has an idf ~1e-6)."""
 import numpy as np
 import pytest
 
@@ -40,22 +36,13 @@ QUERIES = [
     " OR ".join(f"t{i}" for i in range(1, 13)),
     "t6 OR t7 OR t8",          # sparse terms only: most tiles see no posting
 ]
-INELIGIBLE = ["t13 OR t3", "t13"]  # the every-document term: fp32 path even with fixed point enabled
+EVERY_DOC = ["t13 OR t3", "t13"]  # the every-document term: weights ~1e-6 next to ~5
 
 
-@pytest.mark.parametrize("fixed", ["1", "0"], ids=["fixed-point", "fp32-cas"])
-def test_flat_scored_disjunctions_match_reference(ref, fixed):
-    old = os.environ.get("TRN_SF_FIXED")
-    os.environ["TRN_SF_FIXED"] = fixed
-    try:
-        p = Pair(ref, tb.CODEC_LUCENE, _lists(), NDOCS)
-    finally:
-        if old is None:
-            os.environ.pop("TRN_SF_FIXED", None)
-        else:
-            os.environ["TRN_SF_FIXED"] = old
+def test_flat_scored_disjunctions_match_reference(ref):
+    p = Pair(ref, tb.CODEC_LUCENE, _lists(), NDOCS)
     saw_zero = False
-    for batch in (QUERIES, QUERIES + INELIGIBLE, INELIGIBLE):
+    for batch in (QUERIES, QUERIES + EVERY_DOC, EVERY_DOC):
         plans = [p.plan(q, scored=True) for q in batch]
         allres = p.gpu.exec_batch(plans, tb.MODE_SCORED_ALL)
         top = {k: p.gpu.exec_batch(plans, tb.MODE_SCORED_TOPK, k=k) for k in (10, 100)}
@@ -63,11 +50,11 @@ def test_flat_scored_disjunctions_match_reference(ref, fixed):
             wd, ws = p.ref.exec(q, True, NDOCS + 1)
             saw_zero |= bool((ws == 0).any())
             gd, gs = allres.query(i)
-            assert_same_docs(gd, wd, f"[{q}] scored-all fixed={fixed}")
-            assert_close_scores(gs, ws, f"[{q}] scored-all fixed={fixed}")
+            assert_same_docs(gd, wd, f"[{q}] scored-all")
+            assert_close_scores(gs, ws, f"[{q}] scored-all")
             for k, res in top.items():
                 td, ts = res.query(i)
                 assert int(res.match_counts[i]) == len(wd), f"[{q}] match count"
-                assert_topk_equal(td, ts, wd, ws, k, f"[{q}] top-{k} fixed={fixed}")
+                assert_topk_equal(td, ts, wd, ws, k, f"[{q}] top-{k}")
     assert saw_zero, "the corpus is meant to hold documents that match with score 0 (freq-0 postings)"
     p.gpu.close()

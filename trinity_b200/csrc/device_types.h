@@ -98,7 +98,7 @@ struct DevQuery {
 // ---- flat scored disjunctions (k_score_flat, score_flat.cuh)
 struct FlatLeaf {
         uint32_t term; // kEmptyTerm: the query names a term this index source does not hold
-        uint32_t fx_shift; // fixed-point launch (ScoreParams::fx): scores of this leaf's query are kept as multiples of 2^-fx_shift
+        uint32_t pad;
         double   idf;
 };
 static_assert(sizeof(FlatLeaf) == 16, "FlatLeaf layout");
@@ -118,7 +118,6 @@ struct ScoreParams {
         const float *    luts; // [leaf][64]
         uint32_t         nflat, total_items, run_tiles, tile_shift;
         int              mode; // TRN_MODE_SCORED_ALL / TRN_MODE_SCORED_TOPK
-        int              fx;   // 1: every flat query of the launch qualifies for fixed-point accumulation (k_score_flat<NT, true>)
         uint32_t         k;
         uint32_t *       ticket;
         unsigned long long *match_counts;

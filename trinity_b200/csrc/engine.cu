@@ -102,7 +102,6 @@ struct trn_ctx {
         uint32_t             run_tiles{128};  // TRN_RUN_TILES: consecutive tiles per work item of the flat scored kernel (top-k state lives across a run)
         int                  flat_threads{320}; // TRN_SF_THREADS: CTA size of k_score_flat (256/320/384: two CTAs per SM; 512/640: one)
         uint32_t             scored_shift{13};  // TRN_SCORED_SHIFT: log2 of k_score_flat's tile (13 = the reference's window, 14)
-        bool                 flat_fixed{true}; // TRN_SF_FIXED=0: k_score_flat accumulates fp32 with CAS loops even when every query qualifies for fixed point (A/B switch)
         int                  flat_scored{1}; // TRN_FLAT_SCORED=0: every scored query through the general step-program kernel (A/B switch)
         uint64_t             index_bytes{0}, dir_bytes{0}, total_blocks{0}, total_postings{0};
         DevBuf               d_index, d_blk_last, d_blk_off, d_terms, d_tile_first, d_masked;
@@ -785,8 +784,6 @@ extern "C" int trn_create(int device, trn_ctx **out) {
         }
         if (const char *e = getenv("TRN_FLAT_SCORED"))
                 c->flat_scored = atoi(e) != 0;
-        if (const char *e = getenv("TRN_SF_FIXED"))
-                c->flat_fixed = atoi(e) != 0;
         if (const char *e = getenv("TRN_SF_THREADS"))
                 c->flat_threads = atoi(e);
         if (const char *e = getenv("TRN_SCORED_SHIFT")) {
@@ -1698,7 +1695,6 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
         std::vector<DevStep>   steps;
         std::vector<FlatQuery> fqs;    // queries k_score_flat runs
         std::vector<FlatLeaf>  leaves;
-        bool                   fxAll{true}; // every flat scored query of the batch qualifies for fixed-point accumulation
         uint64_t               genItems{0}, genItems2{0}, flatItems{0};
         uint32_t               treeSlots{1};
         uint32_t               maxRuns{0};
@@ -1765,28 +1761,11 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                                 fq.qid        = q;
                                 fq.leaf_begin = uint32_t(leaves.size());
                                 fq.nleaf      = nl;
-                                // fixed-point accumulation (k_score_flat<NT, true>): scores as multiples of 2^-shift.  A posting scores less than its
-                                // leaf's weight (f / (f + 1.2) < 1), so a document's sum stays below sum(w) * 2^shift < 2^31; a posting's rounding error
-                                // is 2^-(shift+1) against a smallest positive score of 0.45 * min(w) (freq 1): eligible when that ratio is <= 2e-6, a
-                                // fifth of the 1e-5 parity tolerance (10-term OR at 100M documents: shift 25, ratio 5e-8)
-                                double sumw{0}, minw{std::numeric_limits<double>::infinity()};
-                                for (uint32_t ch = 0; ch < nl; ++ch) {
-                                        sumw += Q.nodes[f0 + ch].weight;
-                                        minw = std::min(minw, Q.nodes[f0 + ch].weight);
-                                }
-                                uint32_t shift{0};
-                                bool     fxq = c->flat_fixed && minw > 0.0 && sumw < 1e9;
-                                if (fxq) {
-                                        const int e = int(std::floor(std::log2((2147483648.0 - 64.0) / sumw)));
-                                        shift       = uint32_t(std::min(60, e));
-                                        fxq         = e >= 1 && std::ldexp(0.5, -int(shift)) <= 2e-6 * 0.4545 * minw;
-                                }
-                                fxAll &= fxq;
                                 for (uint32_t ch = 0; ch < nl; ++ch) {
                                         FlatLeaf L;
-                                        L.term     = Q.nodes[f0 + ch].term;
-                                        L.fx_shift = fxq ? shift : 0u;
-                                        L.idf      = Q.nodes[f0 + ch].weight;
+                                        L.term = Q.nodes[f0 + ch].term;
+                                        L.pad  = 0;
+                                        L.idf  = Q.nodes[f0 + ch].weight;
                                         leaves.push_back(L);
                                 }
                                 fqs.push_back(fq);
@@ -2096,7 +2075,6 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                         S.total_items  = mode == TRN_MODE_SCORED_TOPK ? uint32_t(std::min<uint64_t>(uint64_t(maxRuns) * nflat, 0xffffffffull)) : uint32_t(flatItems);
                         S.tile_shift   = c->scored_shift;
                         S.mode         = mode;
-                        S.fx           = fxAll ? 1 : 0;
                         S.k            = k;
                         S.ticket       = reinterpret_cast<uint32_t *>(small + 4);
                         S.match_counts = match_counts;

@@ -124,7 +124,8 @@ __device__ __forceinline__ uint32_t lucene_intblock_v(const uint8_t *s, uint32_t
 // acc[rel[g]] += sc[g] for the postings selected by `on` (bit g), atomically (another warp may be adding another term's score to the
 // same document).  Shared memory has no native fp32 add: atomicAdd compiles to a load / add / compare-and-swap loop per posting, and four
 // of them in a row are four serialised ~100-cycle chains.  Here the four loads, adds and CAS attempts are issued side by side; a CAS that
-// lost a race (rare) retries on its own.
+// lost a race (rare) retries on its own.  (Measured alternative, profiles/r02_t: scores as u32 fixed-point units with native ATOMS.ADD — same
+// instruction count, the uncontended CAS chains cost little, and 5 % SLOWER on the 10-term OR workload: 1867 vs 1973 q/s; not kept.)
 __device__ __forceinline__ void sf_add4(float *acc, const uint32_t rel[4], const float sc[4], uint32_t on) {
         uint32_t *a = reinterpret_cast<uint32_t *>(acc);
         uint32_t  old[4], seen[4];
@@ -142,30 +143,6 @@ __device__ __forceinline__ void sf_add4(float *acc, const uint32_t rel[4], const
                         r = atomicCAS(&a[rel[g]], o, __float_as_uint(__uint_as_float(o) + sc[g]));
                 }
         }
-}
-
-// the fixed-point form (k_score_flat<NT, true>): scores are u32 multiples of 2^-shift (engine.cu picks the shift per query so that the sum of a
-// query's weights stays below 2^31 and the rounding stays two orders below the 1e-5 parity tolerance) — shared memory HAS a native u32 add:
-// four fire-and-forget ATOMS.ADD instead of four load / add / compare-and-swap chains
-__device__ __forceinline__ void sf_add4_fx(uint32_t *a, const uint32_t rel[4], const uint32_t sc[4], uint32_t on) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-                if ((on >> g) & 1u)
-                        atomicAdd(&a[rel[g]], sc[g]);
-}
-// a posting that scores 0 units (freq 0: Scorer::score(0) == 0) still matches its document: the rare case goes through a bitmap of its own
-__device__ __forceinline__ void sf_note_zero(uint32_t *zbm, uint32_t *flag, const uint32_t rel[4], const uint32_t sc[4], uint32_t on) {
-        const bool z = ((on & 1u) && !sc[0]) || ((on & 2u) && !sc[1]) || ((on & 4u) && !sc[2]) || ((on & 8u) && !sc[3]);
-        if (__any_sync(0xffffffffu, z)) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                        if (((on >> g) & 1u) && !sc[g])
-                                atomicOr(&zbm[rel[g] >> 5], 1u << (rel[g] & 31u));
-                *flag = 1;
-        }
-}
-__device__ __forceinline__ uint32_t sf_to_fx(float score, float scale) { // a positive score is at least one unit
-        return score > 0.f ? max(1u, __float2uint_rn(score * scale)) : 0u;
 }
 
 // per-term BM25 table: lut[leaf][f] = Scorer::score(f) for f < 64 (similarity.h:228-235), once per batch
@@ -201,7 +178,7 @@ template <int NT> __device__ __forceinline__ uint32_t sf_prune(unsigned long lon
 static constexpr uint32_t kSfCacheLeaves = 12;                        // leaves that own a cache slot (the others always decode)
 static constexpr uint32_t kSfCacheBytes  = kSfCacheLeaves * 128 * 8;  // per leaf: 128 docIDs + 128 scores of its cached (tile-straddling) block
 
-template <int NT, bool FX>
+template <int NT>
 __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParams S) {
         constexpr int      NWARPS       = NT / 32;
         constexpr uint32_t kSfListCap   = SfCap<NT>::value;
@@ -215,13 +192,11 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
         uint32_t *          cdoc  = reinterpret_cast<uint32_t *>(dyn_smem + size_t(W) * 4 + kSfListBytes + size_t(kSfMaxLeaves) * 256); // [leaf][128]
         float *             csc   = reinterpret_cast<float *>(cdoc + kSfCacheLeaves * 128);                        // [leaf][128]
         uint8_t *           wst   = reinterpret_cast<uint8_t *>(csc + kSfCacheLeaves * 128);                       // NWARPS x kSfWarpBytes
-        uint32_t *          zbm   = reinterpret_cast<uint32_t *>(wst + size_t(NWARPS) * kSfWarpBytes);             // fixed-point only: NW words (documents matched by score-0 postings)
 
         __shared__ __align__(8) unsigned long long s_bar[NWARPS * 2];
         __shared__ uint32_t           s_item, s_n, s_theta, s_warp[NWARPS + 1];
         __shared__ uint32_t           s_fill_blk[2][kSfMaxLeaves], s_fill_tile[2][kSfMaxLeaves]; // block cached for a leaf during tile T: slot T & 1
         __shared__ unsigned long long s_base;
-        __shared__ uint32_t           s_zero; // fixed-point: some posting of the current tile scored 0 units (freq 0): its document is in zbm
 
         const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
         uint8_t *      stage   = wst + size_t(warp) * kSfWarpBytes;
@@ -235,10 +210,7 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
         }
         __syncthreads();
         uint32_t seq_issue = 0, seq_wait = 0; // bulk copies issued / consumed by this warp: buffer = seq & 1, phase parity = (seq >> 1) & 1
-        // "no posting yet" word of the score tile: -0.0f (x + -0.0 == x; scores are >= +0.0) or, fixed-point, 0 (a posting adds >= 1)
-        constexpr uint32_t kNone = FX ? 0u : kSfSentinel;
-        const float4 sent4 = make_float4(__uint_as_float(kNone), __uint_as_float(kNone), __uint_as_float(kNone), __uint_as_float(kNone));
-        uint32_t *accu = reinterpret_cast<uint32_t *>(acc);
+        const float4 sent4 = make_float4(__uint_as_float(kSfSentinel), __uint_as_float(kSfSentinel), __uint_as_float(kSfSentinel), __uint_as_float(kSfSentinel));
 
         for (;;) {
                 __syncthreads();
@@ -292,25 +264,14 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
                                 mytfs           = T.tf_shift;
                         }
                 }
-                // fixed-point: every leaf of the query carries the query's shift; scale = 2^shift, exact in fp32
-                const float fxs   = FX ? __uint_as_float((127u + S.leaves[FQ.leaf_begin].fx_shift) << 23) : 1.f;
-                const float fxinv = FX ? __uint_as_float((127u - S.leaves[FQ.leaf_begin].fx_shift) << 23) : 1.f;
-                for (uint32_t i = tid; i < nleaf * 64u; i += NT) {
-                        const float x = S.luts[size_t(FQ.leaf_begin) * 64u + i];
-                        lut[i]        = FX ? __uint_as_float(sf_to_fx(x, fxs)) : x;
-                }
+                for (uint32_t i = tid; i < nleaf * 64u; i += NT)
+                        lut[i] = S.luts[size_t(FQ.leaf_begin) * 64u + i];
                 for (uint32_t i = tid; i < W4; i += NT)
                         reinterpret_cast<float4 *>(acc)[i] = sent4;
                 if (tid < 2 * int(kSfMaxLeaves))
                         (&s_fill_tile[0][0])[tid] = 0xffffffffu;
                 if (tid == 0)
                         s_n = 0;
-                if (FX) {
-                        for (uint32_t i = tid; i < NW; i += NT)
-                                zbm[i] = 0;
-                        if (tid == 0)
-                                s_zero = 0;
-                }
                 uint32_t thr_local = 0, nmatch = 0, n_list = 0; // n_list: s_n as of the last point where nobody was pushing (same in every thread)
                 uint32_t mycb = 0xffffffffu;                    // lane t: the block of leaf t whose documents + scores sit in the cache (same in every warp)
                 // first block of every leaf that can reach the run's first document; afterwards each tile's end lookup is the next tile's start
@@ -404,12 +365,7 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
                                                         sc[g]  = csc[tj * 128u + lane + 32 * g];
                                                         on |= (rel[g] < W ? 1u : 0u) << g;
                                                 }
-                                                if (FX) {
-                                                        const uint32_t su[4] = {__float_as_uint(sc[0]), __float_as_uint(sc[1]), __float_as_uint(sc[2]), __float_as_uint(sc[3])};
-                                                        sf_add4_fx(accu, rel, su, on);
-                                                        sf_note_zero(zbm, &s_zero, rel, su, on);
-                                                } else
-                                                        sf_add4(acc, rel, sc, on);
+                                                sf_add4(acc, rel, sc, on);
                                                 continue;
                                         }
                                         const uint32_t bsel = seq_wait & 1u;
@@ -457,11 +413,8 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
 #pragma unroll
                                                 for (int g = 0; g < 4; ++g) {
                                                         const uint32_t f16 = fr[g] & 0xffffu; // freq is uint16_t in the reference (codecs.h:217)
-                                                        if (FX) // (the table holds the units as bit patterns)
-                                                                sc[g] = (!big || f16 < 64u) ? lt[f16 & 63u] : __uint_as_float(sf_to_fx(bm25_score(idfj, f16), fxs));
-                                                        else
-                                                                sc[g] = (!big || f16 < 64u) ? lt[f16 & 63u] : bm25_score(idfj, f16);
-                                                        rel[g] = d[g] - lo;
+                                                        sc[g]              = (!big || f16 < 64u) ? lt[f16 & 63u] : bm25_score(idfj, f16);
+                                                        rel[g]             = d[g] - lo;
                                                 }
                                                 if (first - lo < W && last - lo < W)
                                                         on = 0xfu; // block completely inside the tile: no range checks
@@ -470,12 +423,7 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
                                                         for (int g = 0; g < 4; ++g)
                                                                 on |= (rel[g] < W ? 1u : 0u) << g;
                                                 }
-                                                if (FX) {
-                                                        const uint32_t su[4] = {__float_as_uint(sc[0]), __float_as_uint(sc[1]), __float_as_uint(sc[2]), __float_as_uint(sc[3])};
-                                                        sf_add4_fx(accu, rel, su, on);
-                                                        sf_note_zero(zbm, &s_zero, rel, su, on);
-                                                } else
-                                                        sf_add4(acc, rel, sc, on);
+                                                sf_add4(acc, rel, sc, on);
                                                 if (kj == 2u) { // the leaf's last block of the tile: keep it for the following tiles of the run
 #pragma unroll
                                                         for (int g = 0; g < 4; ++g) {
@@ -498,18 +446,8 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
                                                                 doc += varbyte_get(pp);
                                                                 const uint32_t f16 = varbyte_get(pp) & 0xffffu;
                                                                 const uint32_t rel = doc - lo;
-                                                                if (rel < W) {
-                                                                        if (FX) {
-                                                                                const uint32_t u = f16 < 64u ? __float_as_uint(lt[f16]) : sf_to_fx(bm25_score(idfj, f16), fxs);
-                                                                                if (u)
-                                                                                        atomicAdd(&accu[rel], u);
-                                                                                else {
-                                                                                        atomicOr(&zbm[rel >> 5], 1u << (rel & 31u));
-                                                                                        s_zero = 1;
-                                                                                }
-                                                                        } else
-                                                                                atomicAdd(&acc[rel], f16 < 64u ? lt[f16] : bm25_score(idfj, f16));
-                                                                }
+                                                                if (rel < W)
+                                                                        atomicAdd(&acc[rel], f16 < 64u ? lt[f16] : bm25_score(idfj, f16));
                                                         }
                                                 }
                                         }
@@ -519,18 +457,6 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
                         __syncthreads(); // ---- every posting of the tile has been scored
 
                         const uint32_t *mk = S.ix.masked ? S.ix.masked + (lo >> 5) : nullptr;
-                        // fixed-point words -> the bit convention of the float tile: a document nobody scored becomes the sentinel (INT_MIN as a signed
-                        // integer), a matched one keeps its units (< 2^31); documents matched by score-0 postings only are in zbm
-                        const bool zany = FX && s_zero != 0u;
-                        auto fxmap = [&](uint32_t &b0, uint32_t &b1, uint32_t &b2, uint32_t &b3, uint32_t i4) {
-                                if (!FX)
-                                        return;
-                                const uint32_t z = zany ? (zbm[i4 >> 3] >> ((i4 & 7u) * 4u)) & 0xfu : 0u;
-                                b0 = (b0 | (z & 1u)) ? b0 : kSfSentinel;
-                                b1 = (b1 | (z & 2u)) ? b1 : kSfSentinel;
-                                b2 = (b2 | (z & 4u)) ? b2 : kSfSentinel;
-                                b3 = (b3 | (z & 8u)) ? b3 : kSfSentinel;
-                        };
                         if (S.mode == 2) {
                                 // ---- threshold scan: as signed integers the sentinel is INT_MIN and scores (>= +0.0) order like their bits
                                 const int      thr      = int(max(thr_local, s_theta));
@@ -538,7 +464,6 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
                                 for (uint32_t i4 = tid; i4 < W4; i4 += NT) {
                                         float4   v  = reinterpret_cast<const float4 *>(acc)[i4];
                                         uint32_t b0 = __float_as_uint(v.x), b1 = __float_as_uint(v.y), b2 = __float_as_uint(v.z), b3 = __float_as_uint(v.w);
-                                        fxmap(b0, b1, b2, b3, i4);
                                         if (mk) { // masked documents (masked_documents_registry::test, exec.cpp:1108-1116) never reach the sink
                                                 const uint32_t m = (__ldg(mk + (i4 >> 3)) >> ((i4 & 7u) * 4u)) & 0xfu;
                                                 if (m & 1u) b0 = kSfSentinel;
@@ -577,7 +502,6 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
                                                         const int thr2 = int(max(thr_local, uint32_t(thr)));
                                                         float4    v    = reinterpret_cast<const float4 *>(acc)[i4];
                                                         uint32_t  bb[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
-                                                        fxmap(bb[0], bb[1], bb[2], bb[3], i4);
                                                         if (mk) {
                                                                 const uint32_t m = (__ldg(mk + (i4 >> 3)) >> ((i4 & 7u) * 4u)) & 0xfu;
 #pragma unroll
@@ -603,12 +527,8 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
                                         const uint32_t i4  = r4 + tid;
                                         const bool     on  = i4 < W4;
                                         const float4   v   = on ? reinterpret_cast<const float4 *>(acc)[i4] : sent4;
-                                        uint32_t       b0 = __float_as_uint(v.x), b1 = __float_as_uint(v.y), b2 = __float_as_uint(v.z), b3 = __float_as_uint(v.w);
-                                        if (on)
-                                                fxmap(b0, b1, b2, b3, i4);
-                                        else if (FX)
-                                                b0 = b1 = b2 = b3 = kSfSentinel;
-                                        uint32_t nib = ((~b0) >> 31) | (((~b1) >> 31) << 1) | (((~b2) >> 31) << 2) | (((~b3) >> 31) << 3);
+                                        uint32_t       nib = ((~__float_as_uint(v.x)) >> 31) | (((~__float_as_uint(v.y)) >> 31) << 1) | (((~__float_as_uint(v.z)) >> 31) << 2) |
+                                                       (((~__float_as_uint(v.w)) >> 31) << 3);
                                         nib <<= (i4 & 7u) * 4u;
                                         nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
                                         nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
@@ -662,7 +582,7 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
                                                         w &= w - 1;
                                                         const uint32_t rel = wi * 32u + bit;
                                                         S.seg_docids[pos]  = lo + rel;
-                                                        S.seg_scores[pos]  = FX ? float(accu[rel]) * fxinv : acc[rel];
+                                                        S.seg_scores[pos]  = acc[rel];
                                                         ++pos;
                                                 }
                                         }
@@ -672,12 +592,6 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
                         n_list = s_n;
                         for (uint32_t i = tid; i < W4; i += NT) // the next tile starts from an untouched score tile
                                 reinterpret_cast<float4 *>(acc)[i] = sent4;
-                        if (zany) {
-                                for (uint32_t i = tid; i < NW; i += NT)
-                                        zbm[i] = 0;
-                                if (tid == 0)
-                                        s_zero = 0;
-                        }
                         __syncthreads();
                 }
 
@@ -692,8 +606,7 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
                                 if (uint32_t(key >> 32) >= theta0) {
                                         const uint32_t pos = atomicAdd(&S.cand_cursor[q], 1u);
                                         if (pos < FQ.cand_cap)
-                                                S.cand[size_t(FQ.cand_base) + pos] = // (fixed-point units leave as the float they stand for)
-                                                        make_uint2(FX ? __float_as_uint(float(uint32_t(key >> 32)) * fxinv) : uint32_t(key >> 32), ~uint32_t(key));
+                                                S.cand[size_t(FQ.cand_base) + pos] = make_uint2(uint32_t(key >> 32), ~uint32_t(key));
                                 }
                         }
                         if (n >= k && tid == 0)
@@ -708,8 +621,7 @@ __global__ void __launch_bounds__(NT, NT <= 384 ? 2 : 1) k_score_flat(ScoreParam
 
 size_t score_flat_smem_bytes(uint32_t tile_shift, int threads) {
         const size_t listBytes = (threads <= 384 ? 2048u : 4096u) * 8u;
-        return (size_t(1) << tile_shift) * 4 + listBytes + size_t(kSfMaxLeaves) * 256 + kSfCacheBytes + size_t(threads / 32) * kSfWarpBytes +
-               ((size_t(1) << tile_shift) >> 5) * 4; // (+ the fixed-point form's bitmap of documents matched by score-0 postings)
+        return (size_t(1) << tile_shift) * 4 + listBytes + size_t(kSfMaxLeaves) * 256 + kSfCacheBytes + size_t(threads / 32) * kSfWarpBytes;
 }
 
 uint32_t score_flat_max_leaves() {
@@ -725,14 +637,8 @@ cudaError_t launch_build_luts(const FlatLeaf *leaves, uint32_t nleaves, float *l
 
 // threads: CTA size (256 / 320: two CTAs per SM on 2^13-document tiles; 512 / 640: one CTA per SM, for 2^14-document tiles)
 cudaError_t launch_score_flat(const ScoreParams &S, int threads, int num_sms, cudaStream_t stream) {
-        const void *fn = S.fx ? (threads == 320   ? (const void *)k_score_flat<320, true>
-                                 : threads == 512 ? (const void *)k_score_flat<512, true>
-                                 : threads == 640 ? (const void *)k_score_flat<640, true>
-                                                  : (const void *)k_score_flat<256, true>)
-                              : (threads == 320   ? (const void *)k_score_flat<320, false>
-                                 : threads == 512 ? (const void *)k_score_flat<512, false>
-                                 : threads == 640 ? (const void *)k_score_flat<640, false>
-                                                  : (const void *)k_score_flat<256, false>);
+        const void *fn = threads == 320 ? (const void *)k_score_flat<320> : threads == 512 ? (const void *)k_score_flat<512>
+                                                                         : threads == 640 ? (const void *)k_score_flat<640> : (const void *)k_score_flat<256>;
         if (threads != 320 && threads != 512 && threads != 640)
                 threads = 256;
         const size_t smem = score_flat_smem_bytes(S.tile_shift, threads);
