@@ -2095,7 +2095,7 @@ static int exec_device_impl(trn_ctx *c, const trn_query *queries, uint32_t nq, i
                         launches += 2;
                 }
                 if (ownItems) {
-                        const int perSM = warpKernel ? exec_docs_max_ctas_per_sm(execShift, maxSlots, exec_docs_stage_bytes()) : exec_max_ctas_per_sm(execShift, maxSlots, mode, c->codec);
+                        const int perSM = warpKernel ? exec_docs_max_ctas_per_sm(execShift, maxSlots, exec_docs_stage_bytes(), false, c->codec == TRN_CODEC_LUCENE) : exec_max_ctas_per_sm(execShift, maxSlots, mode, c->codec);
                         if (perSM <= 0)
                                 return fail(c, TRN_ERR_CUDA, "the exec kernel does not fit on an SM with this many docset slots");
                         const uint64_t workers = warpKernel ? (ownItems + 3) / 4 : ownItems; // 4 warp-workers per CTA

@@ -432,72 +432,134 @@ __device__ void google_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
         bs.flush();
 }
 
-// Lucene: the warp decodes one 128-doc block at a time
+// LUCENE leaf: the blocks [bA, bB] of a term into the sink, one 128-document block at a time per warp (lucene_codec.cpp:515-594 refill_documents
+// + FastPFor<4> __decodeArray fastpfor.h:222-270; block skipping == Decoder::advance's skiplist step, lucene_codec.cpp:596-656).
+//   * 32 blocks are examined at once (lane = block): which of them can hold a document of the tile that the filter still wants;
+//   * a needed block's bytes arrive by ONE 1-D bulk copy (cp.async.bulk + mbarrier, issued by lane 0) — and the NEXT needed block's copy is
+//     issued as soon as the current block's values sit in registers, so it travels while the prefix sum runs and the bits are set
+//     (a single staging buffer: a second one would cost resident warps);
+//   * the page is unpacked vertically (lane l owns values l, l+32, l+64, l+96: lucene_intblock_v of score_flat.cuh), the freq int-block
+//     behind it is never touched in DocumentsOnly mode.
 __device__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t bA, uint32_t bB, uint32_t lo, uint32_t hi, BitSink &bs, const uint32_t *skipfilt,
-                                 uint8_t *stage, int lane) {
-        const uint32_t *bl    = ix.blk_last + T.dir_begin;
-        const uint32_t *bo    = ix.blk_off + T.dir_begin;
-        const uint32_t  nfull = T.documents >> 7;
-        for (uint32_t b = bA; b <= bB; ++b) {
-                const uint32_t off = bo[b], offn = bo[b + 1], last = bl[b], prev = b ? bl[b - 1] : 0u;
-                if (skipfilt) {
-                        const uint32_t d0 = max(prev + 1u, lo), d1 = min(last, hi - 1u);
-                        if (d1 < d0)
-                                continue;
-                        const uint32_t r0 = d0 - lo, r1 = d1 - lo, w0 = r0 >> 5, w1 = r1 >> 5;
-                        if (w1 - w0 < 32u) {
-                                uint32_t       m = 0;
-                                const uint32_t w = w0 + uint32_t(lane);
-                                if (w <= w1) {
-                                        m = skipfilt[w];
-                                        if (w == w0)
-                                                m &= 0xffffffffu << (r0 & 31u);
-                                        if (w == w1)
-                                                m &= 0xffffffffu >> (31u - (r1 & 31u));
+                                 uint8_t *stage, int lane, uint32_t bar_s, uint32_t &seq) {
+        const uint32_t *bl      = ix.blk_last + T.dir_begin;
+        const uint32_t *bo      = ix.blk_off + T.dir_begin;
+        const uint32_t  nfull   = T.documents >> 7;
+        const uint32_t  stage_s = uint32_t(__cvta_generic_to_shared(stage));
+        uint32_t *      scratch = reinterpret_cast<uint32_t *>(stage + kGatherBufBytes);
+        const uint32_t  W       = hi - lo; // (hi wraps to 0 only for the last tile of a 2^32 docID space: hi - lo is still the tile size)
+        for (uint32_t b0 = bA; b0 <= bB; b0 += 32u) {
+                // ---- lane = block b0 + lane: its bytes, its docID range, and whether the tile / the filter needs it
+                const uint32_t b    = b0 + uint32_t(lane);
+                bool           need = b <= bB;
+                uint32_t       off = 0, offn = 0, prev = 0;
+                if (need) {
+                        off  = __ldg(bo + b);
+                        offn = __ldg(bo + b + 1u);
+                        prev = b ? __ldg(bl + b - 1u) : 0u;
+                        const uint32_t last = __ldg(bl + b);
+                        const uint32_t d0 = max(prev + 1u, lo), d1 = min(last - lo, W - 1u) + lo; // documents of the block inside the tile
+                        if (last < lo || d1 < d0)
+                                need = false;
+                        else if (skipfilt) {
+                                const uint32_t r0 = d0 - lo, r1 = d1 - lo, w0 = r0 >> 5, w1 = r1 >> 5;
+                                if (w1 - w0 <= 15u) { // (a block spanning more of the tile than that is simply decoded)
+                                        uint32_t any = 0;
+                                        for (uint32_t w = w0; w <= w1; ++w) {
+                                                uint32_t m = skipfilt[w];
+                                                if (w == w0)
+                                                        m &= 0xffffffffu << (r0 & 31u);
+                                                if (w == w1)
+                                                        m &= 0xffffffffu >> (31u - (r1 & 31u));
+                                                any |= m;
+                                        }
+                                        need = any != 0u;
                                 }
-                                if (!__any_sync(0xffffffffu, m != 0))
-                                        continue;
                         }
                 }
-                const uint32_t len = offn - off;
-                if (b < nfull) {
-                        const uint32_t skew = stage_copy(ix.index, off, len, stage, lane);
-                        __syncwarp();
-                        uint32_t d[4];
-                        (void)lucene_intblock(stage, skew, lane, d, reinterpret_cast<uint32_t *>(stage + 2560));
-                        d[1] += d[0];
-                        d[2] += d[1];
-                        d[3] += d[2];
-                        const uint32_t incl = warp_incl_scan(d[3], lane);
-                        const uint32_t base = prev + incl - d[3];
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                                const uint32_t doc = base + d[t];
-                                if (doc >= lo && doc < hi)
-                                        bs.add(doc - lo);
-                        }
-                } else {
-                        const uint32_t tail = T.documents & 127u;
-                        const uint8_t *p;
-                        if (len + 32u <= kGatherBufBytes) {
-                                const uint32_t skew = stage_copy(ix.index, off, len, stage, lane);
-                                __syncwarp();
-                                p = stage + skew;
-                        } else
-                                p = ix.index + off;
+                uint32_t mask = __ballot_sync(0xffffffffu, need);
+                auto issue = [&](uint32_t j) { // bulk copy of lane j's block into the staging buffer
+                        const uint32_t o = __shfl_sync(0xffffffffu, off, int(j)), on = __shfl_sync(0xffffffffu, offn, int(j));
+                        const uint32_t abase = o & ~15u, bytes = min(((on + 15u) & ~15u) - abase, kGatherBufBytes);
                         if (lane == 0) {
-                                uint32_t doc = prev;
-                                for (uint32_t i = 0; i < tail; ++i) {
-                                        doc += varbyte_get(p);
-                                        (void)varbyte_get(p);
-                                        if (doc >= hi)
-                                                break;
-                                        if (doc >= lo)
-                                                bs.add(doc - lo);
+                                mbar_expect_tx(bar_s, bytes);
+                                bulk_g2s(stage_s, ix.index + abase, bytes, bar_s);
+                        }
+                };
+                if (mask)
+                        issue(uint32_t(__ffs(int(mask)) - 1));
+                while (mask) {
+                        const uint32_t j = uint32_t(__ffs(int(mask)) - 1);
+                        mask &= mask - 1u;
+                        const uint32_t bj = b0 + j, oj = __shfl_sync(0xffffffffu, off, int(j)), onj = __shfl_sync(0xffffffffu, offn, int(j));
+                        const uint32_t pj = __shfl_sync(0xffffffffu, prev, int(j));
+                        mbar_wait(bar_s, seq & 1u);
+                        ++seq;
+                        const uint32_t skew = oj & 15u;
+                        if (bj < nfull) {
+                                uint32_t d[4], dbits;
+                                (void)lucene_intblock_v(stage, skew, lane, d, scratch, dbits);
+                                __syncwarp(); // every lane has read the staging buffer: the next block may land in it
+                                if (mask)
+                                        issue(uint32_t(__ffs(int(mask)) - 1));
+                                // docIDs = prev + inclusive prefix sum over the block (update_curdoc, lucene_codec.cpp:568-594), group by group
+                                if (dbits <= 11u) { // 32 values below 2048 sum to less than 65536: two groups share one scan
+                                        const uint32_t sa = warp_incl_scan(d[0] | (d[1] << 16), lane), sb = warp_incl_scan(d[2] | (d[3] << 16), lane);
+                                        const uint32_t ta = __shfl_sync(0xffffffffu, sa, 31), tb = __shfl_sync(0xffffffffu, sb, 31);
+                                        const uint32_t b1 = pj + (ta & 0xffffu), b2 = b1 + (ta >> 16), b3 = b2 + (tb & 0xffffu);
+                                        d[0] = pj + (sa & 0xffffu);
+                                        d[1] = b1 + (sa >> 16);
+                                        d[2] = b2 + (sb & 0xffffu);
+                                        d[3] = b3 + (sb >> 16);
+                                } else {
+                                        uint32_t base = pj;
+#pragma unroll
+                                        for (int g = 0; g < 4; ++g) {
+                                                const uint32_t sc = warp_incl_scan(d[g], lane);
+                                                d[g]              = base + sc;
+                                                base += __shfl_sync(0xffffffffu, sc, 31);
+                                        }
                                 }
+                                // the lane's four documents sit 32 documents apart (vertical layout): nothing to merge per lane, so they go straight
+                                // into the sink's bitmap — the (up to) four filter / target words are loaded side by side first, and only a
+                                // document the filter still wants costs an atomic
+                                uint32_t rel[4], f[4];
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                        rel[g] = d[g] - lo;
+                                        f[g]   = rel[g] < W ? (bs.mode == M_ANDNOT ? bs.bm[rel[g] >> 5] : (bs.filt ? bs.filt[rel[g] >> 5] : 0xffffffffu)) : 0u;
+                                }
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                        const uint32_t bit = 1u << (rel[g] & 31u);
+                                        if (f[g] & bit) {
+                                                if (bs.mode == M_ANDNOT)
+                                                        atomicAnd(&bs.bm[rel[g] >> 5], ~bit);
+                                                else
+                                                        atomicOr(&bs.bm[rel[g] >> 5], bit);
+                                        }
+                                }
+                        } else {
+                                // the term's tail: (varbyte delta, varbyte freq) pairs (lucene_codec.cpp:527-550), at most 127 of them
+                                const uint32_t tail = T.documents & 127u;
+                                const bool     fits = ((onj + 15u) & ~15u) - (oj & ~15u) <= kGatherBufBytes; // (10 bytes per pair at most: 1285 > the buffer never happens, but stay safe)
+                                if (lane == 0) {
+                                        const uint8_t *p   = fits ? stage + skew : ix.index + oj;
+                                        uint32_t       doc = pj;
+                                        for (uint32_t i = 0; i < tail; ++i) {
+                                                doc += varbyte_get(p);
+                                                (void)varbyte_get(p);
+                                                if (doc - lo >= W && doc >= lo)
+                                                        break;
+                                                if (doc - lo < W)
+                                                        bs.add(doc - lo);
+                                        }
+                                }
+                                __syncwarp();
+                                if (mask)
+                                        issue(uint32_t(__ffs(int(mask)) - 1));
                         }
                 }
-                __syncwarp();
         }
         bs.flush();
 }
@@ -509,7 +571,18 @@ __device__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
 // TREE: the flat-tree launch (every query of its ticket space is a flat-tree plan) — that instantiation holds nothing but the tree
 // executor, and the other one does not carry it (the tree state lives in registers across the tile loop: in one kernel with the
 // candidate and flat paths it pushed them over the 72-register bound)
-template <bool PH, bool TREE> __global__ void __launch_bounds__(kDocsWarps * 32, PH ? 4 : (TREE ? 6 : 7)) k_exec_docs(ExecParams P) { // PH: see k_exec_tiles
+// LUC: the launch runs over a LUCENE index (the codec is a property of the uploaded index, so of the launch): that instantiation carries the
+// bulk-copy block decoder and none of the GOOGLE-only paths (candidate-driven, flat, flat-tree), and the GOOGLE ones do not carry it
+template <bool PH, bool TREE, bool LUC> __global__ void __launch_bounds__(kDocsWarps * 32, PH ? 4 : (TREE ? 6 : 7)) k_exec_docs(ExecParams P) { // PH: see k_exec_tiles
+        __shared__ __align__(8) unsigned long long s_lbar[kDocsWarps]; // LUCENE: one mbarrier per warp for its block copies
+        uint32_t lseq = 0;                                            // ... and how many copies the warp has consumed (phase parity)
+        if constexpr (LUC) {
+                if ((threadIdx.x & 31) == 0) {
+                        mbar_init(uint32_t(__cvta_generic_to_shared(&s_lbar[threadIdx.x >> 5])), 1);
+                        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                }
+                __syncthreads();
+        }
         const uint32_t W  = 1u << P.exec_shift;
         const uint32_t NW = W >> 5;
         const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -548,7 +621,7 @@ template <bool PH, bool TREE> __global__ void __launch_bounds__(kDocsWarps * 32,
                                 tree_load(P, Q, TS, lane);
                 }
                 const uint32_t item = Q.item_base + (gitem - qgen); // batch-wide (query, tile) item: index of the segment arrays
-                if constexpr (!TREE) {
+                if constexpr (!TREE && !LUC) {
                         if (Q.flat == 3u) { // candidate-driven conjunction: the work item is a 32-block group of the lead term
                                 __syncwarp();
                                 cand_exec_google(P, Q, curq, item, item - Q.item_base, slots, lane);
@@ -561,7 +634,7 @@ template <bool PH, bool TREE> __global__ void __launch_bounds__(kDocsWarps * 32,
                 int            handled = 0;
                 if constexpr (TREE) { // flat-tree plan: its leaves in (at most) two decode passes, then its slot operations
                         handled = tree_exec_google(P, Q, TS, lo, W, NW, slots, stage, lane) ? 2 : 1;
-                } else if (Q.flat && P.ix.codec == 0)
+                } else if (!LUC && Q.flat)
                         handled = flat_exec_google(P, Q, lo, W, NW, slots, stage, lane);
                 if (handled == 2)
                         dead = true;
@@ -625,7 +698,7 @@ template <bool PH, bool TREE> __global__ void __launch_bounds__(kDocsWarps * 32,
                                 BitSink         bs;
                                 // Google operands that are decoded in full go through the plain-store word builder into a bitmap of their
                                 // own (dst itself for SET, the scratch slot otherwise) and are combined word-wise afterwards
-                                const bool ownOk = P.ix.codec == 0 && haveTerm && bA <= bB;
+                                const bool ownOk = !LUC && haveTerm && bA <= bB;
                                 const uint32_t dummy = uint32_t(__cvta_generic_to_shared(stage + kGatherBufBytes)) + uint32_t(lane) * 4u;
                                 if (ownOk && mode != M_AND) {
                                         uint32_t *out = mode == M_SET ? dst : tmp;
@@ -705,8 +778,10 @@ template <bool PH, bool TREE> __global__ void __launch_bounds__(kDocsWarps * 32,
                                 }
                                 __syncwarp();
                                 if (haveTerm && bA <= bB) {
-                                        if (P.ix.codec == 0) google_leaf_warp(P.ix, T, bA, bB, lo, hi, bs, skipfilt, stage, P.docs_stage_bytes, lane);
-                                        else lucene_leaf_warp(P.ix, T, bA, bB, lo, hi, bs, skipfilt, stage, lane);
+                                        if constexpr (!LUC)
+                                                google_leaf_warp(P.ix, T, bA, bB, lo, hi, bs, skipfilt, stage, P.docs_stage_bytes, lane);
+                                        else
+                                                lucene_leaf_warp(P.ix, T, bA, bB, lo, hi, bs, skipfilt, stage, lane, uint32_t(__cvta_generic_to_shared(&s_lbar[warp])), lseq);
                                 }
                                 if (mode == M_AND) {
                                         __syncwarp();
@@ -866,27 +941,40 @@ size_t exec_docs_smem_bytes(uint32_t exec_shift, uint32_t nslots, uint32_t stage
         return size_t(kDocsWarps) * (size_t(nslots) * NW * 4 + stageBytes);
 }
 
-int exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots, uint32_t stageBytes, bool tree) {
+int exec_docs_max_ctas_per_sm(uint32_t exec_shift, uint32_t nslots, uint32_t stageBytes, bool tree, bool lucene) {
         const size_t smem = exec_docs_smem_bytes(exec_shift, nslots, stageBytes);
-        const void *fns[3] = {(const void *)k_exec_docs<false, false>, (const void *)k_exec_docs<true, false>, (const void *)k_exec_docs<false, true>};
-        if (tree) {
-                if (cudaFuncSetAttribute(fns[2], cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+        const void *fns[2];
+        if (lucene) {
+                fns[0] = (const void *)k_exec_docs<false, false, true>;
+                fns[1] = (const void *)k_exec_docs<true, false, true>;
+        } else if (tree) {
+                fns[0] = fns[1] = (const void *)k_exec_docs<false, true, false>;
+        } else {
+                fns[0] = (const void *)k_exec_docs<false, false, false>;
+                fns[1] = (const void *)k_exec_docs<true, false, false>;
+        }
+        int best = 0;
+        for (int i = 0; i < 2; ++i) {
+                if (cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
                         return 0;
-        } else if (cudaFuncSetAttribute(fns[0], cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess ||
-                   cudaFuncSetAttribute(fns[1], cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
-                return 0;
-        int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_exec_docs<false, false>, kDocsWarps * 32, smem) != cudaSuccess)
-                return 0;
-        if (tree && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_exec_docs<false, true>, kDocsWarps * 32, smem) != cudaSuccess)
-                return 0;
-        return n;
+                int n = 0;
+                if (i == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fns[i], kDocsWarps * 32, smem) != cudaSuccess)
+                        return 0;
+                if (i == 0)
+                        best = n;
+        }
+        return best;
 }
 
 cudaError_t launch_exec_docs(const ExecParams &P, int grid, cudaStream_t stream) {
         const size_t smem = exec_docs_smem_bytes(P.exec_shift, P.nslots, P.docs_stage_bytes);
-        // gen_sel == 1: the flat-tree launch (its ticket space holds flat-tree plans only; phrase plans never take that path)
-        const void *fn = P.gen_sel ? (const void *)k_exec_docs<false, true> : (P.has_phrase ? (const void *)k_exec_docs<true, false> : (const void *)k_exec_docs<false, false>);
+        // gen_sel == 1: the flat-tree launch (its ticket space holds flat-tree plans only; phrase plans never take that path; GOOGLE only)
+        const void *fn;
+        if (P.ix.codec != 0)
+                fn = P.has_phrase ? (const void *)k_exec_docs<true, false, true> : (const void *)k_exec_docs<false, false, true>;
+        else
+                fn = P.gen_sel ? (const void *)k_exec_docs<false, true, false>
+                               : (P.has_phrase ? (const void *)k_exec_docs<true, false, false> : (const void *)k_exec_docs<false, false, false>);
         cudaError_t  e    = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess)
                 return e;
