@@ -440,8 +440,12 @@ __device__ void google_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
 //     (a single staging buffer: a second one would cost resident warps);
 //   * the page is unpacked vertically (lane l owns values l, l+32, l+64, l+96: lucene_intblock_v of score_flat.cuh), the freq int-block
 //     behind it is never touched in DocumentsOnly mode.
-__device__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t bA, uint32_t bB, uint32_t lo, uint32_t hi, BitSink &bs, const uint32_t *skipfilt,
-                                 uint8_t *stage, int lane, uint32_t bar_s, uint32_t &seq) {
+// SINK: how a document reaches the bitmap (uniform per call, so decided once): 0 = or-in, 1 = or-in when the filter bitmap holds it (AND),
+// 2 = clear when set (AND NOT)
+template <int SINK>
+__device__ void lucene_leaf_warp_t(const DevIndex &ix, const DevTerm &T, uint32_t bA, uint32_t bB, uint32_t lo, uint32_t hi, BitSink &bs, const uint32_t *skipfilt,
+                                   uint8_t *stage, int lane, uint32_t bar_s, uint32_t &seq) {
+        const uint32_t *const fw = SINK == 2 ? bs.bm : bs.filt; // the words a document is tested against (SINK 0: none)
         const uint32_t *bl      = ix.blk_last + T.dir_begin;
         const uint32_t *bo      = ix.blk_off + T.dir_begin;
         const uint32_t  nfull   = T.documents >> 7;
@@ -527,13 +531,16 @@ __device__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
 #pragma unroll
                                 for (int g = 0; g < 4; ++g) {
                                         rel[g] = d[g] - lo;
-                                        f[g]   = rel[g] < W ? (bs.mode == M_ANDNOT ? bs.bm[rel[g] >> 5] : (bs.filt ? bs.filt[rel[g] >> 5] : 0xffffffffu)) : 0u;
+                                        if (SINK == 0)
+                                                f[g] = rel[g] < W ? 0xffffffffu : 0u;
+                                        else
+                                                f[g] = rel[g] < W ? fw[rel[g] >> 5] : 0u;
                                 }
 #pragma unroll
                                 for (int g = 0; g < 4; ++g) {
                                         const uint32_t bit = 1u << (rel[g] & 31u);
                                         if (f[g] & bit) {
-                                                if (bs.mode == M_ANDNOT)
+                                                if (SINK == 2)
                                                         atomicAnd(&bs.bm[rel[g] >> 5], ~bit);
                                                 else
                                                         atomicOr(&bs.bm[rel[g] >> 5], bit);
@@ -562,6 +569,15 @@ __device__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t 
                 }
         }
         bs.flush();
+}
+__device__ __forceinline__ void lucene_leaf_warp(const DevIndex &ix, const DevTerm &T, uint32_t bA, uint32_t bB, uint32_t lo, uint32_t hi, BitSink &bs,
+                                                 const uint32_t *skipfilt, uint8_t *stage, int lane, uint32_t bar_s, uint32_t &seq) {
+        if (bs.mode == M_ANDNOT)
+                lucene_leaf_warp_t<2>(ix, T, bA, bB, lo, hi, bs, skipfilt, stage, lane, bar_s, seq);
+        else if (bs.filt)
+                lucene_leaf_warp_t<1>(ix, T, bA, bB, lo, hi, bs, skipfilt, stage, lane, bar_s, seq);
+        else
+                lucene_leaf_warp_t<0>(ix, T, bA, bB, lo, hi, bs, skipfilt, stage, lane, bar_s, seq);
 }
 
 #include "exec_docs_flat.cuh"
