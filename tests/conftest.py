@@ -8,6 +8,7 @@ ROOT = Path(__file__).resolve().parent.parent
 # the host-buffer pipeline sizes its chunks by the postings a batch references (engine.cu: chunk_postings); the test indexes are tiny, so
 # without this every batch would take the single-call form and the chunked path would go untested
 os.environ.setdefault("TRN_CHUNK_POSTINGS", "1")
+os.environ.setdefault("TRN_CHUNK_RULE", "postings")  # (and keep it from being resized by the previous batch's tiny result)
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 

@@ -127,6 +127,10 @@ struct trn_ctx {
         cudaEvent_t  ev_done[2]{nullptr, nullptr}, ev_d2h[2]{nullptr, nullptr}, ev_ck0[16]{}, ev_ck1[16]{};
         uint64_t     chunk_postings{1000000000ull}; // TRN_CHUNK_POSTINGS: referenced postings a pipeline chunk must carry (~1.1 ms of k_exec_docs)
         bool         taper_chunks{true};             // TRN_TAPER_CHUNKS=0: equal chunks only
+        bool         chunk_rule_sqrt{true};          // TRN_CHUNK_RULE=postings: chunk count from the referenced postings alone
+        uint64_t     hint_bytes{0}, hint_postings{0}; // result bytes / referenced postings of the previous host-buffer batch ...
+        uint32_t     hint_nq{0};                     // ... and its shape: the next batch of the same shape sizes its chunks from them
+        int          hint_mode{-1};
         uint32_t     pipeline_chunks{8}; // TRN_PIPELINE_CHUNKS (profiles/r02_n: 4 -> 38.4K, 6 -> 40.1K, 8 -> 40.7K, 12 -> 40.1K q/s end to end on the headline batch)
         uint32_t     last_items{0}; // work items of the last exec_device_impl call (compact results: entries of item_desc)
         uint64_t     last_total_hint{0};
@@ -798,6 +802,8 @@ extern "C" int trn_create(int device, trn_ctx **out) {
         }
         if (const char *e = getenv("TRN_TAPER_CHUNKS"))
                 c->taper_chunks = atoi(e) != 0;
+        if (const char *e = getenv("TRN_CHUNK_RULE"))
+                c->chunk_rule_sqrt = std::string(e) != "postings";
         if (const char *e = getenv("TRN_CHUNK_POSTINGS")) {
                 const long long v = atoll(e);
                 if (v >= 1)
@@ -2267,17 +2273,31 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
         if (!c || !out)
                 return TRN_ERR_ARG;
         uint32_t nchunks = c->pipeline_chunks;
+        uint64_t estPostings{0};
         const bool compact = mode == TRN_MODE_DOCS_COMPACT;
         if (nchunks > 1 && queries && c->have_index) {
                 // a chunk must be worth its launch tails: on a small shard (docID-sharded runs) the whole batch is a few ms of kernel time and 8
                 // chunks of it are mostly tails (profiles/r02_h: 4.4 ms in 8 launches vs 2.75 ms in one at N=8) -> as many chunks as the
                 // referenced postings pay for, at chunk_postings each
-                uint64_t est{0};
+                uint64_t est{0}, leaves{0};
                 for (uint32_t q = 0; q < nq; ++q)
                         for (uint32_t i = 0; i < queries[q].nnodes && queries[q].nodes; ++i)
-                                if (queries[q].nodes[i].kind == TRN_NODE_TERM && queries[q].nodes[i].term < c->nterms)
+                                if (queries[q].nodes[i].kind == TRN_NODE_TERM && queries[q].nodes[i].term < c->nterms) {
                                         est += c->h_terms[queries[q].nodes[i].term].documents;
-                nchunks = uint32_t(std::min<uint64_t>(nchunks, std::max<uint64_t>(1, est / c->chunk_postings)));
+                                        ++leaves;
+                                }
+                estPostings = est;
+                nchunks     = uint32_t(std::min<uint64_t>(nchunks, std::max<uint64_t>(1, est / c->chunk_postings)));
+                // With the result size of the previous batch of this shape known, the chunk count balances what chunking buys against what it
+                // costs: c chunks expose 1/c of the result copy (D ms at ~45 GB/s) and add c launch tails — minimum at c = sqrt(D / tail).  A tail
+                // is the run time of the last work items of a launch: ~0.15 ms for conjunction / candidate items, ~0.9 ms for the tile items of
+                // multi-leaf trees (profiles/r02_t: tree8 97.5 ms in 10 launches vs 89.5 ms in one; and2 20.0 vs 18.6).
+                if (c->chunk_rule_sqrt && c->hint_bytes && c->hint_nq == nq && c->hint_mode == mode && est >= c->hint_postings - c->hint_postings / 4 &&
+                    est <= c->hint_postings + c->hint_postings / 4) {
+                        const double D    = double(c->hint_bytes) / 45e6; // ms
+                        const double tail = leaves > 4ull * nq ? 0.9 : 0.15;
+                        nchunks           = uint32_t(std::min<double>(c->pipeline_chunks, std::max(1.0, std::floor(std::sqrt(D / tail) + 0.5))));
+                }
         }
         if (mode == TRN_MODE_SCORED_TOPK || nq < 8 * nchunks || nchunks <= 1) {
                 const double t0 = now_ms();
@@ -2289,6 +2309,12 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                 c->tm.final_wait_ms = float(now_ms() - tw);
                 c->tm.total_ms      = float(now_ms() - t0);
                 c->tm.chunks        = 1.f;
+                if (fr == TRN_OK && mode != TRN_MODE_SCORED_TOPK) { // (a batch that took the single-call form still tells the next one its size)
+                        c->hint_bytes    = (compact ? out->total_words : out->total) * 4 * (mode == TRN_MODE_SCORED_ALL ? 2 : 1);
+                        c->hint_nq       = nq;
+                        c->hint_mode     = mode;
+                        c->hint_postings = estPostings;
+                }
                 if (fr == TRN_OK)
                         c->tm.kernel_ms = out->exec_kernel_ms;
                 return fr;
@@ -2449,6 +2475,10 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
         c->tm.chunks       = float(ch.size());
         hoff[nq]           = running;
         c->last_total_hint = running + running / 16;
+        c->hint_bytes      = running * 4 * (scored ? 2 : 1);
+        c->hint_nq         = nq;
+        c->hint_mode       = mode;
+        c->hint_postings   = estPostings;
         std::memset(out, 0, sizeof(*out));
         out->nq                  = nq;
         out->total               = compact ? matches : running;
