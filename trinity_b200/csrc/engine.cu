@@ -128,6 +128,7 @@ struct trn_ctx {
         uint64_t     chunk_postings{1000000000ull}; // TRN_CHUNK_POSTINGS: referenced postings a pipeline chunk must carry (~1.1 ms of k_exec_docs)
         bool         taper_chunks{true};             // TRN_TAPER_CHUNKS=0: equal chunks only
         bool         chunk_rule_sqrt{true};          // TRN_CHUNK_RULE=postings: chunk count from the referenced postings alone
+        double       chunk_tail_ms{0.3}, chunk_tail_tree_ms{0.9}; // TRN_CHUNK_TAIL_US / TRN_CHUNK_TAIL_TREE_US: modelled cost of one more launch
         uint64_t     hint_bytes{0}, hint_postings{0}; // result bytes / referenced postings of the previous host-buffer batch ...
         uint32_t     hint_nq{0};                     // ... and its shape: the next batch of the same shape sizes its chunks from them
         int          hint_mode{-1};
@@ -804,6 +805,10 @@ extern "C" int trn_create(int device, trn_ctx **out) {
                 c->taper_chunks = atoi(e) != 0;
         if (const char *e = getenv("TRN_CHUNK_RULE"))
                 c->chunk_rule_sqrt = std::string(e) != "postings";
+        if (const char *e = getenv("TRN_CHUNK_TAIL_US"))
+                c->chunk_tail_ms = std::max(1.0, atof(e)) / 1000.0;
+        if (const char *e = getenv("TRN_CHUNK_TAIL_TREE_US"))
+                c->chunk_tail_tree_ms = std::max(1.0, atof(e)) / 1000.0;
         if (const char *e = getenv("TRN_CHUNK_POSTINGS")) {
                 const long long v = atoll(e);
                 if (v >= 1)
@@ -2274,6 +2279,7 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                 return TRN_ERR_ARG;
         uint32_t nchunks = c->pipeline_chunks;
         uint64_t estPostings{0};
+        bool     taperOne{false};
         const bool compact = mode == TRN_MODE_DOCS_COMPACT;
         if (nchunks > 1 && queries && c->have_index) {
                 // a chunk must be worth its launch tails: on a small shard (docID-sharded runs) the whole batch is a few ms of kernel time and 8
@@ -2289,17 +2295,21 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                 estPostings = est;
                 nchunks     = uint32_t(std::min<uint64_t>(nchunks, std::max<uint64_t>(1, est / c->chunk_postings)));
                 // With the result size of the previous batch of this shape known, the chunk count balances what chunking buys against what it
-                // costs: c chunks expose 1/c of the result copy (D ms at ~45 GB/s) and add c launch tails — minimum at c = sqrt(D / tail).  A tail
-                // is the run time of the last work items of a launch: ~0.15 ms for conjunction / candidate items, ~0.9 ms for the tile items of
-                // multi-leaf trees (profiles/r02_t: tree8 97.5 ms in 10 launches vs 89.5 ms in one; and2 20.0 vs 18.6).
+                // costs: c chunks (the last one tapered, below) expose 1/(4c) of the result copy (D ms at ~45 GB/s) and add c + 2 launch tails —
+                // minimum at c = sqrt(D / (4 tail)).  A tail is the run time of the last work items of a launch plus its scan / gather kernels and
+                // what its copy fails to overlap: modelled 0.3 ms for conjunction / candidate items, 0.9 ms for the tile items of multi-leaf trees
+                // (measured, profiles/r02_t, r02_y, r02_z: and2 46.3K q/s end to end with 3 + 2 launches vs 44.7K with 8 + 2; tree8 10.66K with
+                // 2 + 2 vs 10.0K with 8 + 2; one of 8 shards: 3.84 ms with 2 + 2 launches, 4.32 with 4 + 2, 4.52 with one).
                 if (c->chunk_rule_sqrt && c->hint_bytes && c->hint_nq == nq && c->hint_mode == mode && est >= c->hint_postings - c->hint_postings / 4 &&
                     est <= c->hint_postings + c->hint_postings / 4) {
                         const double D    = double(c->hint_bytes) / 45e6; // ms
-                        const double tail = leaves > 4ull * nq ? 0.9 : 0.15;
-                        nchunks           = uint32_t(std::min<double>(c->pipeline_chunks, std::max(1.0, std::floor(std::sqrt(D / tail) + 0.5))));
+                        const double tail = leaves > 4ull * nq ? c->chunk_tail_tree_ms : c->chunk_tail_ms;
+                        nchunks           = uint32_t(std::min<double>(c->pipeline_chunks, std::max(1.0, std::floor(std::sqrt(D / (4.0 * tail)) + 0.5))));
+                        // one chunk: still worth its taper (two more launches for 3/4 of the copy off the critical path)?
+                        taperOne = c->taper_chunks && D > 8.0 / 3.0 * tail;
                 }
         }
-        if (mode == TRN_MODE_SCORED_TOPK || nq < 8 * nchunks || nchunks <= 1) {
+        if (mode == TRN_MODE_SCORED_TOPK || nq < 8 * nchunks || (nchunks <= 1 && !(taperOne && nq >= 32))) {
                 const double t0 = now_ms();
                 const int    r  = trn_exec_batch_device(c, queries, nq, mode, k, nullptr);
                 if (r != TRN_OK)
