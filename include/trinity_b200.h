@@ -258,9 +258,9 @@ typedef struct trn_result {
          *   TRN_ENC_U32    docIDs, one per word                                                              (count words)
          *   TRN_ENC_U16    offsets from the first docID of the item's tile, two per word, low half first      ((count + 1) / 2 words)
          *   TRN_ENC_BITMAP the tile's bitmap, bit b of word w = docID tile_first + 32 w + b                   (2^tile_shift / 32 words)
- *   TRN_ENC_U8B    the tile in 256-docID buckets: 2^tile_shift / 256 count bytes (documents of every bucket, < 256 each), then one
- *                  offset byte per document (docID = tile_first + 256 bucket + offset), zero-padded to a word   ((buckets + count + 3) / 4 words)
-         * the tile of item j of query q starts at docID (qitems[q].tile_lo + j) << qitems[q].tile_shift (U16 / BITMAP segments only). */
+         *   TRN_ENC_U8B    the tile in 256-docID buckets: 2^tile_shift / 256 count bytes (documents of every bucket, < 256 each), then one
+         *                  offset byte per document (docID = tile_first + 256 bucket + offset), zero-padded to a word   ((buckets + count + 3) / 4 words)
+         * the tile of item j of query q starts at docID (qitems[q].tile_lo + j) << qitems[q].tile_shift (U16 / U8B / BITMAP segments only). */
         const uint32_t *         words;
         uint64_t                 total_words;
         const uint32_t *         item_desc;

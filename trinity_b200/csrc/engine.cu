@@ -128,7 +128,7 @@ struct trn_ctx {
         uint64_t     chunk_postings{1000000000ull}; // TRN_CHUNK_POSTINGS: referenced postings a pipeline chunk must carry (~1.1 ms of k_exec_docs)
         bool         taper_chunks{true};             // TRN_TAPER_CHUNKS=0: equal chunks only
         bool         chunk_rule_sqrt{true};          // TRN_CHUNK_RULE=postings: chunk count from the referenced postings alone
-        double       chunk_tail_ms{0.3}, chunk_tail_tree_ms{0.9}; // TRN_CHUNK_TAIL_US / TRN_CHUNK_TAIL_TREE_US: modelled cost of one more launch
+        double       chunk_tail_ms{0.15}, chunk_tail_tree_ms{0.9}; // TRN_CHUNK_TAIL_US / TRN_CHUNK_TAIL_TREE_US: modelled cost of one more launch
         uint64_t     hint_bytes{0}, hint_postings{0}; // result bytes / referenced postings of the previous host-buffer batch ...
         uint32_t     hint_nq{0};                     // ... and its shape: the next batch of the same shape sizes its chunks from them
         int          hint_mode{-1};
@@ -2297,9 +2297,10 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                 // With the result size of the previous batch of this shape known, the chunk count balances what chunking buys against what it
                 // costs: c chunks (the last one tapered, below) expose 1/(4c) of the result copy (D ms at ~45 GB/s) and add c + 2 launch tails —
                 // minimum at c = sqrt(D / (4 tail)).  A tail is the run time of the last work items of a launch plus its scan / gather kernels and
-                // what its copy fails to overlap: modelled 0.3 ms for conjunction / candidate items, 0.9 ms for the tile items of multi-leaf trees
-                // (measured, profiles/r02_t, r02_y, r02_z: and2 46.3K q/s end to end with 3 + 2 launches vs 44.7K with 8 + 2; tree8 10.66K with
-                // 2 + 2 vs 10.0K with 8 + 2; one of 8 shards: 3.84 ms with 2 + 2 launches, 4.32 with 4 + 2, 4.52 with one).
+                // what its copy fails to overlap: modelled 0.15 ms for conjunction / candidate items, 0.9 ms for the tile items of multi-leaf trees
+                // (measured, profiles/r02_t, r02_y, r02_z, r02_ab: and2 at N = 1 45.3-46.3K q/s end to end with 3..6 + 2 launches vs 44.7K with 8 + 2 —
+                // flat; tree8 10.66K with 2 + 2 vs 10.0K with 8 + 2; one of 8 shards: and2 3.84 ms with 2 + 2 launches, 3.88 with 1 + 2, 4.32 with
+                // 4 + 2, 4.52 with one; the LUCENE conjunction 8.51 ms with 2 + 2 vs 8.83 with 1 + 2).
                 if (c->chunk_rule_sqrt && c->hint_bytes && c->hint_nq == nq && c->hint_mode == mode && est >= c->hint_postings - c->hint_postings / 4 &&
                     est <= c->hint_postings + c->hint_postings / 4) {
                         const double D    = double(c->hint_bytes) / 45e6; // ms
