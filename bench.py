@@ -156,8 +156,8 @@ def measured_peak():
 
 
 def ncu_traffic(kernel: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
-    of this same command (profiles/traffic.json, written from the .ncu-rep by scripts/ncu_summary.py); None if not captured"""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per 1000-query batch, from the committed ncu --set full capture
+    of this same command (profiles/traffic.json, values copied from the ncu summaries it names); None if not captured"""
     p = ROOT / "profiles" / "traffic.json"
     if p.exists():
         try:
@@ -428,6 +428,8 @@ class Job:
         k_ms_step = float(np.mean(kern_ms)) if kern_ms else None          # all fused-kernel launches of one step
         k_ms = k_ms_step / nlaunch if k_ms_step else None                 # average duration of ONE launch
         traffic = ncu_traffic(f"{kernel_name}:{workload}") if (world == 1 and args.ndocs == 100_000_000 and args.nq == 1000) else None
+        if traffic is not None:
+            traffic = int(traffic) // nlaunch  # the capture is per 1000-query batch; the line reports per launch, like `achieved`
         algo_bytes = (int(res.index_bytes_touched) + out_bytes_per_batch) // nlaunch   # algorithmic bytes of ONE launch
         achieved = algo_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None
 
