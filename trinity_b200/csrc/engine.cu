@@ -98,6 +98,8 @@ struct trn_ctx {
         bool                 tree_masks{false}; // TRN_TREE_MASKS=1: flat-tree queries decode their frequent leaves in a masked second pass (flat_tree_masks). Measured
                                                 // (profiles/r02_i..k): halves the DRAM bytes, but the needed blocks of a tile fill a fraction of a 32-lane group, so
                                                 // the warp-instruction count does not drop: 8.5-9.0K vs 9.2-11.1K q/s on the benchmark's trees. Off by default.
+                                                // (profiles/r02_ag: not a matter of WHICH leaves are admitted — 8.2-8.4K q/s with TRN_TREE_MASK_NEED 0.6 ... 0.05 vs
+                                                // 11.2K off: a few masked queries raise the launch-wide slot count and take resident warps from every query.)
         uint32_t             tree_shift{13}; // TRN_TREE_SHIFT: docID tile (log2) of the flat-tree launch of k_exec_docs (0 = flat-tree path off)
         uint32_t             run_tiles{128};  // TRN_RUN_TILES: consecutive tiles per work item of the flat scored kernel (top-k state lives across a run)
         int                  flat_threads{320}; // TRN_SF_THREADS: CTA size of k_score_flat (256/320/384: two CTAs per SM; 512/640: one)
@@ -156,6 +158,9 @@ struct trn_ctx {
 static inline double now_ms() {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+
+// flat_tree_masks: a leaf is decoded in the masked pass when at most this share of its blocks is expected to survive its mask (TRN_TREE_MASK_NEED)
+static double g_tree_mask_need = 0.6;
 
 static int fail(trn_ctx *c, int code, const std::string &m) {
         c->err = m;
@@ -782,6 +787,11 @@ extern "C" int trn_create(int device, trn_ctx **out) {
         }
         if (const char *e = getenv("TRN_TREE_MASKS"))
                 c->tree_masks = atoi(e) != 0;
+        if (const char *e = getenv("TRN_TREE_MASK_NEED")) {
+                const double v = atof(e);
+                if (v > 0.0 && v <= 1.0)
+                        g_tree_mask_need = v;
+        }
         if (const char *e = getenv("TRN_RUN_TILES")) {
                 const int v = atoi(e);
                 if (v >= 1 && v <= 4096)
@@ -1484,12 +1494,12 @@ static uint32_t flat_tree_masks(std::vector<DevStep> &steps, size_t begin, uint3
                 if (blocksOf(j) * W / width < 2.0)
                         break; // (sorted) blocks as wide as the tile: nothing to skip
                 masked[j] = 1;
-                if (need(j) > 0.6)
+                if (need(j) > g_tree_mask_need)
                         masked[j] = 0;
                 anyMasked |= masked[j] != 0;
         }
         for (auto j : order) // a later choice may have taken a constraint away
-                if (masked[j] && need(j) > 0.75)
+                if (masked[j] && need(j) > g_tree_mask_need + 0.15)
                         masked[j] = 0;
         if (!anyMasked)
                 return 0;
