@@ -297,6 +297,13 @@ typedef struct trn_timings {
         float chunks;          /* pipelined call: chunks the batch was split into (sized by the postings it references); 1 = single call */
 } trn_timings;
 int trn_last_timings(trn_ctx *, trn_timings *out);
+/* Host-only view of the pipeline planner (tests, tooling): the launches trn_exec_batch would split a DocumentsOnly / SCORED_ALL batch into, from
+ * what it knows before the first launch — referenced postings and TERM nodes of the batch, the knobs (TRN_PIPELINE_CHUNKS, TRN_CHUNK_POSTINGS,
+ * TRN_CHUNK_RULE, TRN_TAPER_CHUNKS, TRN_CHUNK_TAIL_US, TRN_CHUNK_TAIL_TREE_US) and the previous batch's result bytes / postings / shape.
+ * sizes[] receives the queries per launch, *n their number, *single_call whether the batch takes the one-call form. */
+int trn_debug_chunk_plan(uint32_t nq, int topk, uint64_t est_postings, uint64_t leaves, uint32_t max_chunks, uint64_t chunk_postings, int rule_sqrt, int taper,
+                         double tail_ms, double tail_tree_ms, uint64_t hint_bytes, uint64_t hint_postings, int hint_same_shape, uint32_t *sizes, uint32_t cap,
+                         uint32_t *n, int *single_call);
 
 /* Split form used by bench.py / multi-GPU: run on device only, results stay in HBM ... */
 int trn_exec_batch_device(trn_ctx *, const trn_query *queries, uint32_t nq, int mode, uint32_t k, trn_result *out_counts_only);

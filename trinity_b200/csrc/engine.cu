@@ -9,6 +9,7 @@
 #include "codecs.h"
 #include "device_types.h"
 #include "hitcursor.h"
+#include "chunkplan.h"
 #include "kernels.h"
 #include <algorithm>
 #include <array>
@@ -2287,40 +2288,33 @@ extern "C" int trn_fetch_results(trn_ctx *c, trn_result *out) {
 extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq, int mode, uint32_t k, trn_result *out) {
         if (!c || !out)
                 return TRN_ERR_ARG;
-        uint32_t nchunks = c->pipeline_chunks;
-        uint64_t estPostings{0};
-        bool     taperOne{false};
-        const bool compact = mode == TRN_MODE_DOCS_COMPACT;
-        if (nchunks > 1 && queries && c->have_index) {
-                // a chunk must be worth its launch tails: on a small shard (docID-sharded runs) the whole batch is a few ms of kernel time and 8
-                // chunks of it are mostly tails (profiles/r02_h: 4.4 ms in 8 launches vs 2.75 ms in one at N=8) -> as many chunks as the
-                // referenced postings pay for, at chunk_postings each
-                uint64_t est{0}, leaves{0};
+        // how the batch is split into pipelined launches: chunkplan.h (a pure function of what is known here, pinned on the CPU by
+        // tests/test_chunk_plan_cpu.py).  Measured (profiles/r02_t, r02_y, r02_z, r02_ab, r02_ac): and2 at N = 1 45.3-46.3K q/s end to end with
+        // 3..6 + 2 launches vs 44.7K with 8 + 2; tree8 10.66K with 2 + 2 vs 10.0K with 8 + 2; one of 8 shards: and2 3.84 ms with 2 + 2 launches,
+        // 3.88 with 1 + 2, 4.32 with 4 + 2, 4.52 with one; the LUCENE conjunction 8.51 ms with 2 + 2 vs 8.83 with 1 + 2.
+        ChunkPlanIn pin;
+        pin.nq   = nq;
+        pin.topk = mode == TRN_MODE_SCORED_TOPK;
+        if (queries && c->have_index)
                 for (uint32_t q = 0; q < nq; ++q)
                         for (uint32_t i = 0; i < queries[q].nnodes && queries[q].nodes; ++i)
                                 if (queries[q].nodes[i].kind == TRN_NODE_TERM && queries[q].nodes[i].term < c->nterms) {
-                                        est += c->h_terms[queries[q].nodes[i].term].documents;
-                                        ++leaves;
+                                        pin.est_postings += c->h_terms[queries[q].nodes[i].term].documents;
+                                        ++pin.leaves;
                                 }
-                estPostings = est;
-                nchunks     = uint32_t(std::min<uint64_t>(nchunks, std::max<uint64_t>(1, est / c->chunk_postings)));
-                // With the result size of the previous batch of this shape known, the chunk count balances what chunking buys against what it
-                // costs: c chunks (the last one tapered, below) expose 1/(4c) of the result copy (D ms at ~45 GB/s) and add c + 2 launch tails —
-                // minimum at c = sqrt(D / (4 tail)).  A tail is the run time of the last work items of a launch plus its scan / gather kernels and
-                // what its copy fails to overlap: modelled 0.15 ms for conjunction / candidate items, 0.9 ms for the tile items of multi-leaf trees
-                // (measured, profiles/r02_t, r02_y, r02_z, r02_ab: and2 at N = 1 45.3-46.3K q/s end to end with 3..6 + 2 launches vs 44.7K with 8 + 2 —
-                // flat; tree8 10.66K with 2 + 2 vs 10.0K with 8 + 2; one of 8 shards: and2 3.84 ms with 2 + 2 launches, 3.88 with 1 + 2, 4.32 with
-                // 4 + 2, 4.52 with one; the LUCENE conjunction 8.51 ms with 2 + 2 vs 8.83 with 1 + 2).
-                if (c->chunk_rule_sqrt && c->hint_bytes && c->hint_nq == nq && c->hint_mode == mode && est >= c->hint_postings - c->hint_postings / 4 &&
-                    est <= c->hint_postings + c->hint_postings / 4) {
-                        const double D    = double(c->hint_bytes) / 45e6; // ms
-                        const double tail = leaves > 4ull * nq ? c->chunk_tail_tree_ms : c->chunk_tail_ms;
-                        nchunks           = uint32_t(std::min<double>(c->pipeline_chunks, std::max(1.0, std::floor(std::sqrt(D / (4.0 * tail)) + 0.5))));
-                        // one chunk: still worth its taper (two more launches for 3/4 of the copy off the critical path)?
-                        taperOne = c->taper_chunks && D > 8.0 / 3.0 * tail;
-                }
-        }
-        if (mode == TRN_MODE_SCORED_TOPK || nq < 8 * nchunks || (nchunks <= 1 && !(taperOne && nq >= 32))) {
+        pin.max_chunks      = (queries && c->have_index) ? c->pipeline_chunks : 1u;
+        pin.chunk_postings  = c->chunk_postings;
+        pin.rule_sqrt       = c->chunk_rule_sqrt;
+        pin.taper           = c->taper_chunks;
+        pin.tail_ms         = c->chunk_tail_ms;
+        pin.tail_tree_ms    = c->chunk_tail_tree_ms;
+        pin.hint_bytes      = c->hint_bytes;
+        pin.hint_postings   = c->hint_postings;
+        pin.hint_same_shape = c->hint_nq == nq && c->hint_mode == mode;
+        const ChunkPlan plan        = plan_chunks(pin);
+        const uint64_t  estPostings = pin.est_postings;
+        const bool      compact     = mode == TRN_MODE_DOCS_COMPACT;
+        if (plan.single_call) {
                 const double t0 = now_ms();
                 const int    r  = trn_exec_batch_device(c, queries, nq, mode, k, nullptr);
                 if (r != TRN_OK)
@@ -2346,7 +2340,7 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
         const bool scored = mode == TRN_MODE_SCORED_ALL;
         CK(c->h_offsets.ensure((size_t(nq) + 1) * 8));
         CK(c->h_counts.ensure(size_t(nq) * 8));
-        const uint32_t per = (nq + nchunks - 1) / nchunks;
+        const uint32_t per = *std::max_element(plan.sizes.begin(), plan.sizes.end()); // queries of the largest launch
         CK(c->h_chunk.ensure(2 * (64 + (size_t(per) + 1) * 16)));
         uint64_t *hoff = c->h_offsets.as<uint64_t>(), *hcnt = c->h_counts.as<uint64_t>();
         uint64_t  running{0}, postings{0}, bytes{0}, runningItems{0}, matches{0};
@@ -2359,16 +2353,12 @@ extern "C" int trn_exec_batch(trn_ctx *c, const trn_query *queries, uint32_t nq,
                 uint32_t q0, n;
         };
         std::vector<Chunk> ch;
-        for (uint32_t q0 = 0; q0 < nq; q0 += per)
-                ch.push_back({q0, std::min(per, nq - q0)});
-        if (c->taper_chunks && ch.back().n >= 32) {
-                // nothing overlaps the LAST chunk's result copy: taper the end of the batch (1/2, 1/4, 1/4 of a chunk) so that what is copied after
-                // the last kernel is a quarter of a chunk — two more launch tails (~0.1 ms each) against 3/4 of a chunk's D2H (profiles/r02_s: 1.6 ms)
-                const Chunk    L = ch.back();
-                const uint32_t a = L.n / 2, b = L.n / 4;
-                ch.back()       = {L.q0, a};
-                ch.push_back({L.q0 + a, b});
-                ch.push_back({L.q0 + a + b, L.n - a - b});
+        {
+                uint32_t q0{0};
+                for (const uint32_t n : plan.sizes) {
+                        ch.push_back({q0, n});
+                        q0 += n;
+                }
         }
         auto grow = [&](PinBuf &b, size_t need, size_t keep) -> cudaError_t {
                 if (need <= b.cap)

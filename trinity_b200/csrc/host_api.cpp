@@ -1,6 +1,7 @@
 // Host-side half of the C ABI: index builder, synthetic workload generator, query front-end, BM25 weights.
 // (The device half lives in engine.cu.)  No reference code is linked here; formats are pinned by tests against oracle/_ref.
 #include "../../include/trinity_b200.h"
+#include "chunkplan.h"
 #include "codecs.h"
 #include "dirlookup.h"
 #include "hitcursor.h"
@@ -979,6 +980,37 @@ static int parse_query_impl(const char *text, const std::unordered_map<std::stri
         *nnodes = uint32_t(out.size());
         *root   = 0;
         return TRN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ pipeline plan (host only: tests, tooling)
+// The launches trn_exec_batch would split a DocumentsOnly / SCORED_ALL batch into (csrc/chunkplan.h — the same function the engine calls), from
+// the quantities it knows before the first launch.  sizes[] receives the queries per launch (at most cap), *n their number, *single_call
+// whether the batch takes the one-call form.
+extern "C" int trn_debug_chunk_plan(uint32_t nq, int topk, uint64_t est_postings, uint64_t leaves, uint32_t max_chunks, uint64_t chunk_postings, int rule_sqrt,
+                                    int taper, double tail_ms, double tail_tree_ms, uint64_t hint_bytes, uint64_t hint_postings, int hint_same_shape,
+                                    uint32_t *sizes, uint32_t cap, uint32_t *n, int *single_call) {
+        if (!n || !single_call || (cap && !sizes))
+                return TRN_ERR_ARG;
+        ChunkPlanIn in;
+        in.nq              = nq;
+        in.topk            = topk != 0;
+        in.est_postings    = est_postings;
+        in.leaves          = leaves;
+        in.max_chunks      = max_chunks;
+        in.chunk_postings  = chunk_postings;
+        in.rule_sqrt       = rule_sqrt != 0;
+        in.taper           = taper != 0;
+        in.tail_ms         = tail_ms;
+        in.tail_tree_ms    = tail_tree_ms;
+        in.hint_bytes      = hint_bytes;
+        in.hint_postings   = hint_postings;
+        in.hint_same_shape = hint_same_shape != 0;
+        const ChunkPlan P  = plan_chunks(in);
+        *n                 = uint32_t(P.sizes.size());
+        *single_call       = P.single_call ? 1 : 0;
+        for (uint32_t i = 0; i < *n && i < cap; ++i)
+                sizes[i] = P.sizes[i];
+        return *n <= cap ? TRN_OK : TRN_ERR_CAPACITY;
 }
 
 // ------------------------------------------------------------------------------------------------ result replay
